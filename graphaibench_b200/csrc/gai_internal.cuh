@@ -1,0 +1,52 @@
+// Internal helpers shared by the sm_100a translation units behind include/gai_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "gai_b200.h"
+
+namespace gai {
+
+int set_error(int code, const char* what, const char* detail);
+
+#define GAI_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) return gai::set_error(GAI_ERR_CUDA, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define GAI_CHECK_ARG(cond)                                                        \
+  do {                                                                             \
+    if (!(cond)) return gai::set_error(GAI_ERR_ARG, "invalid argument", #cond);   \
+  } while (0)
+
+#define GAI_LAUNCH_CHECK() GAI_CUDA(cudaGetLastError())
+
+static inline cudaStream_t S(gai_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (148 on B200); cached.
+int sm_count();
+
+// Library-owned scratch (split-K partials, reductions). Grown on demand, never shrunk; one per device.
+int workspace(size_t bytes, void** out);
+
+constexpr uint32_t HUB_DEGREE = 1024;  // rows longer than this go to the CTA-per-row kernel
+
+}  // namespace gai
+
+// Device graph. Plain struct of device pointers, passed by value into kernels (as the reference passes its
+// LearningGraph, include/gnn/graph_operations.h:85).
+struct gai_csr {
+  uint32_t nv = 0;
+  uint64_t nnz = 0;
+  uint32_t* rowptr = nullptr;
+  uint32_t* colidx = nullptr;
+  float* norm_gcn = nullptr;   // 1/sqrt(deg)
+  float* norm_mean = nullptr;  // 1/deg
+  uint32_t* hub_rows = nullptr;
+  uint32_t n_hub = 0;
+  uint32_t* tperm = nullptr;  // e -> e^T
+  bool owns_csr = false;
+};

@@ -1,0 +1,308 @@
+// GAT attention for sm_100a: scores + edge-softmax (forward); SDDMM, softmax/LeakyReLU backward, attention-vector
+// gradients and the transposed aggregation (backward).
+// Replaces compute_attn_score_warp / compute_scores_grad_warp / compute_alpha_grad_warp / csr2csc
+// (include/gnn/graph_operations.h:190-467, src/gnn/gconv/gat_aggregator.cu:7-115) and restates the CPU path
+// (src/gnn/gconv/gat_aggregator.cpp:57-200) with these changes of schedule, not of math:
+//   * el_i = <alpha_l, z_i>, er_i = <alpha_r, z_i> are computed once per VERTEX (the reference recomputes
+//     <alpha_r, z_j> once per EDGE, gat_aggregator.cpp:70);
+//   * d_alpha_r = sum_e ds_e z_{dst(e)} is regrouped as Z^T·colsum with colsum_j = sum of ds over the edges that
+//     point at j (read through the cached e->e^T permutation), d_alpha_l = Z^T·rowsum: one pass over Z instead of
+//     an nnz x F gather, reduced in two deterministic stages (the reference GPU kernel uses float atomics);
+//   * the transposed attention matrix is never materialised: the final SpMM reads vals[perm[e]].
+// The per-edge aggregation itself goes through the bit-exact SpMM family in spmm.cu.
+#include "gai_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Row-cooperative reductions: a warp (light rows) or a whole CTA (hub rows).
+template <bool CTA>
+__device__ __forceinline__ float coop_sum(float v, float* red) {
+  v = warp_sum(v);
+  if (!CTA) return v;
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; i++) t += red[i];
+  return t;
+}
+template <bool CTA>
+__device__ __forceinline__ float coop_max(float v, float* red) {
+  v = warp_max(v);
+  if (!CTA) return v;
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < nw; i++) t = fmaxf(t, red[i]);
+  return t;
+}
+
+struct RowSel {
+  const uint32_t* rowptr;
+  const uint32_t* hub_rows;
+  uint32_t nv, n_hub, hub_threshold;
+};
+
+// Resolves which row this warp / CTA owns; returns false if none.
+template <bool CTA>
+__device__ __forceinline__ bool pick_row(const RowSel& r, uint32_t& row, uint32_t& s, uint32_t& e, int& tid, int& nthr) {
+  if (CTA) {
+    if (blockIdx.x >= r.n_hub) return false;
+    row = r.hub_rows[blockIdx.x];
+    tid = threadIdx.x; nthr = blockDim.x;
+  } else {
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= r.nv) return false;
+    row = (uint32_t)w;
+    tid = threadIdx.x & 31; nthr = 32;
+  }
+  s = __ldg(r.rowptr + row); e = __ldg(r.rowptr + row + 1);
+  if (!CTA && (e - s) > r.hub_threshold) return false;
+  return true;
+}
+
+// el/er per vertex: one warp per row, coalesced.
+__global__ void el_er_kernel(uint32_t nv, int F, const float* __restrict__ z, const float* __restrict__ al, const float* __restrict__ ar,
+                             float* __restrict__ el, float* __restrict__ er) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nv) return;
+  const float* x = z + (size_t)w * F;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < F; k += 32) { const float v = x[k]; a += __ldg(al + k) * v; b += __ldg(ar + k) * v; }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { el[w] = a; er[w] = b; }
+}
+
+// temp_scores[e] = el_i + er_j; norm_scores = softmax_row(LeakyReLU(temp_scores))   (gat_aggregator.cpp:62-77)
+template <bool CTA>
+__global__ void scores_kernel(const RowSel r, const uint32_t* __restrict__ colidx, const float* __restrict__ el, const float* __restrict__ er,
+                              float slope, float* __restrict__ temp_scores, float* __restrict__ norm_scores) {
+  __shared__ float red[32];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const float eli = __ldg(el + row);
+  float mx = -INFINITY;
+  for (uint32_t k = s + tid; k < e; k += nthr) {
+    const float t = eli + __ldg(er + __ldg(colidx + k));
+    temp_scores[k] = t;
+    const float sc = t > 0.f ? t : slope * t;
+    mx = fmaxf(mx, sc);
+  }
+  mx = coop_max<CTA>(mx, red);
+  float sum = 0.f;
+  for (uint32_t k = s + tid; k < e; k += nthr) {
+    const float t = temp_scores[k];
+    const float sc = t > 0.f ? t : slope * t;
+    const float p = expf(sc - mx);
+    norm_scores[k] = p;
+    sum += p;
+  }
+  sum = coop_sum<CTA>(sum, red);
+  for (uint32_t k = s + tid; k < e; k += nthr) norm_scores[k] = norm_scores[k] / sum;
+}
+
+// SDDMM dS[e] = <g_i, z_j>. One warp per edge-slice: light rows = one warp per row; hub rows = CTA per row, warps split the edges.
+template <bool CTA>
+__global__ void sddmm_kernel(const RowSel r, const uint32_t* __restrict__ colidx, int F, const float* __restrict__ grad, const float* __restrict__ z,
+                             float* __restrict__ ds, int vec) {
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = CTA ? (threadIdx.x >> 5) : 0;
+  const int nwarps = CTA ? (blockDim.x >> 5) : 1;
+  const float* g = grad + (size_t)row * F;
+  if (vec == 4) {
+    const int nch = F / 4;
+    // keep up to 4 chunks of g_i in registers (F <= 512); further chunks are re-read (L1)
+    float4 gr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) gr[k] = (lane + 32 * k < nch) ? __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * k) : make_float4(0, 0, 0, 0);
+    for (uint32_t k0 = s + warp * 2; k0 < e; k0 += nwarps * 2) {
+      float d[2] = {0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (k0 + u < e) {
+          const float4* x = reinterpret_cast<const float4*>(z + (size_t)__ldg(colidx + k0 + u) * F);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (lane + 32 * k < nch) { const float4 v = __ldg(x + lane + 32 * k); d[u] += gr[k].x * v.x + gr[k].y * v.y + gr[k].z * v.z + gr[k].w * v.w; }
+          }
+          for (int c = lane + 128; c < nch; c += 32) { const float4 v = __ldg(x + c); const float4 q = __ldg(reinterpret_cast<const float4*>(g) + c); d[u] += q.x * v.x + q.y * v.y + q.z * v.z + q.w * v.w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const float t = warp_sum(d[u]);
+        if (lane == 0 && k0 + u < e) ds[k0 + u] = t;
+      }
+    }
+  } else {
+    for (uint32_t k0 = s + warp; k0 < e; k0 += nwarps) {
+      const float* x = z + (size_t)__ldg(colidx + k0) * F;
+      float d = 0.f;
+      for (int c = lane; c < F; c += 32) d += __ldg(g + c) * __ldg(x + c);
+      d = warp_sum(d);
+      if (lane == 0) ds[k0] = d;
+    }
+  }
+}
+
+// In place on ds: softmax backward (closed form of math_functions.cpp:496-514), LeakyReLU backward
+// (gat_aggregator.cpp:144); rowsum[i] = sum_e ds_e (the reference's src_score_grad, :149).
+template <bool CTA>
+__global__ void softmax_bwd_kernel(const RowSel r, float slope, const float* __restrict__ temp_scores, const float* __restrict__ p,
+                                   float* __restrict__ ds, float* __restrict__ rowsum) {
+  __shared__ float red[32];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  float dot = 0.f;
+  for (uint32_t k = s + tid; k < e; k += nthr) dot += p[k] * ds[k];
+  dot = coop_sum<CTA>(dot, red);
+  float rs = 0.f;
+  for (uint32_t k = s + tid; k < e; k += nthr) {
+    const float dy = p[k] * (ds[k] - dot);
+    const float v = dy * (temp_scores[k] > 0.f ? 1.0f : slope);
+    ds[k] = v;
+    rs += v;
+  }
+  rs = coop_sum<CTA>(rs, red);
+  if (tid == 0) rowsum[row] = rs;
+}
+
+// colsum[j] = sum over edges e' pointing at j of ds[e'] = sum_{e in row j} ds[perm[e]]  (symmetric pattern)
+template <bool CTA>
+__global__ void colsum_kernel(const RowSel r, const uint32_t* __restrict__ perm, const float* __restrict__ ds, float* __restrict__ colsum) {
+  __shared__ float red[32];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  float cs = 0.f;
+  for (uint32_t k = s + tid; k < e; k += nthr) cs += __ldg(ds + __ldg(perm + k));
+  cs = coop_sum<CTA>(cs, red);
+  if (tid == 0) colsum[row] = cs;
+}
+
+// Stage 1 of d_alpha = Z^T·[rowsum colsum]: each CTA reduces a slab of rows; thread (tx, ty): column tx (+CW*q), rows ty, ty+RH, ...
+__global__ void alpha_grad_stage1(uint32_t nv, int F, const float* __restrict__ z, const float* __restrict__ rowsum, const float* __restrict__ colsum,
+                                  uint32_t rows_per_cta, int CW, float* __restrict__ partial /*[grid][2][F]*/) {
+  extern __shared__ float sm[];  // [RH][2][CW]
+  const int tx = threadIdx.x % CW, ty = threadIdx.x / CW, RH = blockDim.x / CW;
+  const uint32_t r0 = blockIdx.x * rows_per_cta;
+  const uint32_t r1 = (r0 + rows_per_cta < nv) ? r0 + rows_per_cta : nv;
+  for (int c0 = 0; c0 < F; c0 += CW) {
+    const int c = c0 + tx;
+    float al = 0.f, ar = 0.f;
+    if (c < F) {
+      for (uint32_t i = r0 + ty; i < r1; i += RH) {
+        const float v = __ldg(z + (size_t)i * F + c);
+        al += __ldg(rowsum + i) * v;
+        ar += __ldg(colsum + i) * v;
+      }
+    }
+    sm[(ty * 2 + 0) * CW + tx] = al;
+    sm[(ty * 2 + 1) * CW + tx] = ar;
+    __syncthreads();
+    if (ty == 0 && c < F) {
+      float sl = 0.f, sr = 0.f;
+      for (int q = 0; q < RH; q++) { sl += sm[(q * 2 + 0) * CW + tx]; sr += sm[(q * 2 + 1) * CW + tx]; }
+      partial[((size_t)blockIdx.x * 2 + 0) * F + c] = sl;
+      partial[((size_t)blockIdx.x * 2 + 1) * F + c] = sr;
+    }
+    __syncthreads();
+  }
+}
+__global__ void alpha_grad_stage2(int F, int nparts, const float* __restrict__ partial, float* __restrict__ dal, float* __restrict__ dar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * F) return;
+  const int which = i / F, c = i % F;
+  float s = 0.f;
+  for (int p = 0; p < nparts; p++) s += partial[((size_t)p * 2 + which) * F + c];
+  (which ? dar : dal)[c] = s;
+}
+
+RowSel make_sel(gai_csr_t g) {
+  RowSel r;
+  r.rowptr = g->rowptr; r.hub_rows = g->hub_rows; r.nv = g->nv; r.n_hub = g->n_hub;
+  r.hub_threshold = g->n_hub ? gai::HUB_DEGREE : 0xffffffffu;
+  return r;
+}
+inline unsigned warp_grid(uint32_t nv) { return (unsigned)(((uint64_t)nv * 32 + 255) / 256); }
+
+}  // namespace
+
+extern "C" {
+
+int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
+                    float* norm_scores, float* out, int flags, gai_stream_t stream) {
+  GAI_CHECK_ARG(g && z && alpha_l && alpha_r && temp_scores && norm_scores && out && F > 0);
+  if (g->nv == 0) return GAI_OK;
+  cudaStream_t st = gai::S(stream);
+  void* ws = nullptr;
+  int rc = gai::workspace(sizeof(float) * 2 * (size_t)g->nv, &ws);
+  if (rc != GAI_OK) return rc;
+  float* el = reinterpret_cast<float*>(ws);
+  float* er = el + g->nv;
+  el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, z, alpha_l, alpha_r, el, er);
+  GAI_LAUNCH_CHECK();
+  const RowSel r = make_sel(g);
+  scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
+  GAI_LAUNCH_CHECK();
+  if (g->n_hub) {
+    scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
+    GAI_LAUNCH_CHECK();
+  }
+  return gai_spmm_edge(g, F, norm_scores, nullptr, z, F, out, F, flags, nullptr, stream);
+}
+
+int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, float slope, const float* temp_scores, const float* norm_scores,
+                     float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, gai_stream_t stream) {
+  GAI_CHECK_ARG(g && z && grad_in && temp_scores && norm_scores && ds && d_alpha_l && d_alpha_r && dz && F > 0);
+  if (g->nv == 0) return GAI_OK;
+  int rc = gai_csr_build_transpose(g, stream);
+  if (rc != GAI_OK) return rc;
+  cudaStream_t st = gai::S(stream);
+  const int sms = gai::sm_count();
+  const int nparts = (int)((g->nv + 255) / 256 < (uint32_t)(4 * sms) ? (g->nv + 255) / 256 : (uint32_t)(4 * sms));
+  void* ws = nullptr;
+  rc = gai::workspace(sizeof(float) * (2 * (size_t)g->nv + (size_t)nparts * 2 * F), &ws);
+  if (rc != GAI_OK) return rc;
+  float* rowsum = reinterpret_cast<float*>(ws);
+  float* colsum = rowsum + g->nv;
+  float* partial = colsum + g->nv;
+  const RowSel r = make_sel(g);
+  const int vec = (F % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 && reinterpret_cast<uintptr_t>(grad_in) % 16 == 0) ? 4 : 1;
+  sddmm_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, F, grad_in, z, ds, vec);
+  GAI_LAUNCH_CHECK();
+  if (g->n_hub) { sddmm_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, F, grad_in, z, ds, vec); GAI_LAUNCH_CHECK(); }
+  softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, slope, temp_scores, norm_scores, ds, rowsum);
+  GAI_LAUNCH_CHECK();
+  if (g->n_hub) { softmax_bwd_kernel<true><<<g->n_hub, 256, 0, st>>>(r, slope, temp_scores, norm_scores, ds, rowsum); GAI_LAUNCH_CHECK(); }
+  colsum_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->tperm, ds, colsum);
+  GAI_LAUNCH_CHECK();
+  if (g->n_hub) { colsum_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->tperm, ds, colsum); GAI_LAUNCH_CHECK(); }
+  int CW = 1;
+  while (CW < F && CW < 256) CW <<= 1;
+  const uint32_t rows_per_cta = (g->nv + nparts - 1) / nparts;
+  alpha_grad_stage1<<<nparts, 256, sizeof(float) * 2 * 256, st>>>(g->nv, F, z, rowsum, colsum, rows_per_cta, CW, partial);
+  GAI_LAUNCH_CHECK();
+  alpha_grad_stage2<<<(2 * F + 255) / 256, 256, 0, st>>>(F, nparts, partial, d_alpha_l, d_alpha_r);
+  GAI_LAUNCH_CHECK();
+  // dZ = P^T · G  (update_all with transposed scores, gat_aggregator.cpp:175-199); z is dead from here on, dz may alias it
+  return gai_spmm_edge(g, F, norm_scores, g->tperm, grad_in, F, dz, F, GAI_EPI_NONE, nullptr, stream);
+}
+
+}  // extern "C"

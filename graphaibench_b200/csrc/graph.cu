@@ -1,0 +1,177 @@
+// Device CSR for the GNN path: upload, degree normalisers, hub-row list, transpose permutation.
+// Replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data (src/gnn/lgraph.cu:51-105) and the
+// per-backward cusparseCsr2cscEx2 call (src/utilities/math_functions.cu:345-358, src/gnn/gconv/gat_aggregator.cu:86-89).
+#include <vector>
+#include "gai_internal.cuh"
+
+namespace {
+
+// One thread per vertex. Both normalisers reproduce the reference's mixed float/double expressions exactly:
+//   lgraph.cpp:29-32        temp = sqrtf(float(deg)); v = temp == 0 ? 0 : float(1.0 / double(temp))
+//   sage_aggregator.cpp:17  b = float(1.0 / double(float(deg)))        (inf for deg == 0, never used by a row of its own)
+__global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, float* __restrict__ norm_gcn,
+                             float* __restrict__ norm_mean, uint32_t* __restrict__ hub_rows, uint32_t* __restrict__ hub_count,
+                             uint32_t hub_cap) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  uint32_t deg = rowptr[v + 1] - rowptr[v];
+  float fdeg = __uint2float_rn(deg);
+  float t = __fsqrt_rn(fdeg);
+  norm_gcn[v] = (t == 0.0f) ? 0.0f : __double2float_rn(__ddiv_rn(1.0, (double)t));
+  norm_mean[v] = __double2float_rn(__ddiv_rn(1.0, (double)fdeg));
+  if (deg > gai::HUB_DEGREE) {
+    uint32_t slot = atomicAdd(hub_count, 1u);
+    if (slot < hub_cap) hub_rows[slot] = v;
+  }
+}
+
+// One warp per row; each lane binary-searches its edges' mirror position. Pattern must be symmetric
+// with sorted rows (what the reference's symmetric_csr_transpose assumes, math_functions.cpp:32-74).
+__global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+                                      uint32_t* __restrict__ perm, uint32_t* __restrict__ bad) {
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  if (warp >= nv) return;
+  uint32_t src = warp;
+  uint32_t b = rowptr[src], e = rowptr[src + 1];
+  for (uint32_t k = b + lane; k < e; k += 32) {
+    uint32_t dst = colidx[k];
+    int64_t l = rowptr[dst], r = (int64_t)rowptr[dst + 1] - 1;
+    int64_t found = -1;
+    while (r >= l) {
+      int64_t mid = l + (r - l) / 2;
+      uint32_t val = colidx[mid];
+      if (val == src) { found = mid; break; }
+      if (val < src) l = mid + 1; else r = mid - 1;
+    }
+    if (found < 0) { atomicAdd(bad, 1u); perm[k] = (uint32_t)k; }
+    else perm[k] = (uint32_t)found;
+  }
+}
+
+int finish_create(gai_csr* g, cudaStream_t st) {
+  GAI_CUDA(cudaMalloc(&g->norm_gcn, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
+  GAI_CUDA(cudaMalloc(&g->norm_mean, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
+  uint32_t hub_cap = (uint32_t)(g->nnz / gai::HUB_DEGREE) + 1;
+  GAI_CUDA(cudaMalloc(&g->hub_rows, sizeof(uint32_t) * (size_t)(hub_cap + 1)));
+  uint32_t* d_count = g->hub_rows + hub_cap;
+  GAI_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
+  if (g->nv) {
+    norms_kernel<<<(g->nv + 255) / 256, 256, 0, st>>>(g->nv, g->rowptr, g->norm_gcn, g->norm_mean, g->hub_rows, d_count, hub_cap);
+    GAI_LAUNCH_CHECK();
+  }
+  uint32_t n_hub = 0;
+  GAI_CUDA(cudaMemcpyAsync(&n_hub, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  GAI_CUDA(cudaStreamSynchronize(st));
+  g->n_hub = n_hub < hub_cap ? n_hub : hub_cap;
+  return GAI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gai_add_selfloop_h(uint32_t nv, const uint32_t* rowptr, const uint32_t* colidx, uint32_t* rowptr_out, uint32_t* colidx_out) {
+  GAI_CHECK_ARG(rowptr && rowptr_out && (colidx || rowptr[nv] == 0) && colidx_out);
+  // Row i of the output is row i of the input with `i` placed in front of the first neighbour larger than i
+  // (at the end if there is none) — the placement LearningGraph::add_selfloop makes (lgraph.h:185-218).
+  for (uint32_t i = 0; i < nv; i++) {
+    const uint32_t b = rowptr[i], e = rowptr[i + 1];
+    uint32_t pos = e;
+    for (uint32_t k = b; k < e; k++) {
+      if (colidx[k] > i) { pos = k; break; }
+    }
+    uint32_t* o = colidx_out + (size_t)b + i;
+    if (pos > b) memcpy(o, colidx + b, sizeof(uint32_t) * (pos - b));
+    o[pos - b] = i;
+    if (e > pos) memcpy(o + (pos - b) + 1, colidx + pos, sizeof(uint32_t) * (e - pos));
+  }
+  for (uint32_t i = nv + 1; i-- > 0;) rowptr_out[i] = rowptr[i] + i;  // descending: rowptr_out may alias rowptr
+  return GAI_OK;
+}
+
+int gai_csr_create(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_h, const uint32_t* colidx_h, gai_stream_t stream, gai_csr_t* out) {
+  GAI_CHECK_ARG(out && rowptr_h && (colidx_h || nnz == 0));
+  GAI_CHECK_ARG(nnz < (uint64_t(1) << 32));
+  GAI_CHECK_ARG(rowptr_h[nv] == nnz);
+  cudaStream_t st = gai::S(stream);
+  gai_csr* g = new gai_csr();
+  g->nv = nv; g->nnz = nnz; g->owns_csr = true;
+  int rc = GAI_OK;
+  do {
+    if (cudaMalloc(&g->rowptr, sizeof(uint32_t) * ((size_t)nv + 1)) != cudaSuccess ||
+        cudaMalloc(&g->colidx, sizeof(uint32_t) * (size_t)(nnz ? nnz : 1)) != cudaSuccess) {
+      rc = gai::set_error(GAI_ERR_CUDA, "gai_csr_create", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (cudaMemcpyAsync(g->rowptr, rowptr_h, sizeof(uint32_t) * ((size_t)nv + 1), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        (nnz && cudaMemcpyAsync(g->colidx, colidx_h, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st) != cudaSuccess)) {
+      rc = gai::set_error(GAI_ERR_CUDA, "gai_csr_create upload", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    rc = finish_create(g, st);
+  } while (0);
+  if (rc != GAI_OK) { gai_csr_destroy(g); return rc; }
+  *out = g;
+  return GAI_OK;
+}
+
+int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, const uint32_t* colidx_d, gai_stream_t stream, gai_csr_t* out) {
+  GAI_CHECK_ARG(out && rowptr_d && (colidx_d || nnz == 0));
+  GAI_CHECK_ARG(nnz < (uint64_t(1) << 32));
+  gai_csr* g = new gai_csr();
+  g->nv = nv; g->nnz = nnz; g->owns_csr = false;
+  g->rowptr = const_cast<uint32_t*>(rowptr_d);
+  g->colidx = const_cast<uint32_t*>(colidx_d);
+  int rc = finish_create(g, gai::S(stream));
+  if (rc != GAI_OK) { gai_csr_destroy(g); return rc; }
+  *out = g;
+  return GAI_OK;
+}
+
+int gai_csr_destroy(gai_csr_t g) {
+  if (!g) return GAI_OK;
+  if (g->owns_csr) { cudaFree(g->rowptr); cudaFree(g->colidx); }
+  cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->hub_rows); cudaFree(g->tperm);
+  delete g;
+  return GAI_OK;
+}
+
+uint32_t gai_csr_nv(gai_csr_t g) { return g ? g->nv : 0; }
+uint64_t gai_csr_nnz(gai_csr_t g) { return g ? g->nnz : 0; }
+const uint32_t* gai_csr_rowptr(gai_csr_t g) { return g ? g->rowptr : nullptr; }
+const uint32_t* gai_csr_colidx(gai_csr_t g) { return g ? g->colidx : nullptr; }
+const float* gai_csr_vertex_norm(gai_csr_t g) { return g ? g->norm_gcn : nullptr; }
+uint32_t gai_csr_num_hub_rows(gai_csr_t g) { return g ? g->n_hub : 0; }
+
+int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr);
+  if (norm_gcn_d) GAI_CUDA(cudaMemcpyAsync(g->norm_gcn, norm_gcn_d, sizeof(float) * (size_t)g->nv, cudaMemcpyDeviceToDevice, gai::S(stream)));
+  if (norm_mean_d) GAI_CUDA(cudaMemcpyAsync(g->norm_mean, norm_mean_d, sizeof(float) * (size_t)g->nv, cudaMemcpyDeviceToDevice, gai::S(stream)));
+  return GAI_OK;
+}
+
+int gai_csr_build_transpose(gai_csr_t g, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr);
+  if (g->tperm) return GAI_OK;
+  cudaStream_t st = gai::S(stream);
+  GAI_CUDA(cudaMalloc(&g->tperm, sizeof(uint32_t) * (size_t)(g->nnz + 1)));
+  uint32_t* bad = g->tperm + g->nnz;
+  GAI_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
+  if (g->nv) {
+    uint64_t threads = (uint64_t)g->nv * 32;
+    transpose_perm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g->nv, g->rowptr, g->colidx, g->tperm, bad);
+    GAI_LAUNCH_CHECK();
+  }
+  uint32_t nbad = 0;
+  GAI_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  GAI_CUDA(cudaStreamSynchronize(st));
+  if (nbad) {
+    cudaFree(g->tperm); g->tperm = nullptr;
+    return gai::set_error(GAI_ERR_ARG, "gai_csr_build_transpose", "pattern is not structurally symmetric");
+  }
+  return GAI_OK;
+}
+const uint32_t* gai_csr_transpose_perm(gai_csr_t g) { return g ? g->tperm : nullptr; }
+
+}  // extern "C"

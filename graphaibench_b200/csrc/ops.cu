@@ -1,0 +1,317 @@
+// Elementwise ops, row-wise L2 normalisation, masked softmax cross-entropy, Adam and the matmul entry point.
+// Replaces relu_gpu/d_relu_gpu/init_const_gpu/l2norm/d_l2norm/softmax_cross_entropy/d_softmax_cross_entropy/
+// masked_avg_loss/masked_accuracy_single (src/utilities/math_functions.cu) and adam::update_gpu (optimizer.cu:5-36).
+#include "gai_internal.cuh"
+
+namespace gai {
+int gemm_simt(size_t M, size_t N, size_t K, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int ta, int tb,
+              int accum, int flags, cudaStream_t st);
+int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int ta, int tb,
+            int accum, int flags, int passes, cudaStream_t st);  // returns GAI_ERR_UNSUPPORTED when the shape is not taken
+static int g_gemm_mode = 0;
+}  // namespace gai
+
+namespace {
+
+inline unsigned grid_for(size_t n, int threads, int per_thread = 1) {
+  size_t blocks = (n + (size_t)threads * per_thread - 1) / ((size_t)threads * per_thread);
+  size_t cap = (size_t)gai::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+__global__ void relu_kernel(size_t n, const float* __restrict__ in, float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
+    for (size_t k = i; k < n4; k += stride) {
+      float4 v = reinterpret_cast<const float4*>(in)[k];
+      v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+      reinterpret_cast<float4*>(out)[k] = v;
+    }
+    for (size_t k = n4 * 4 + i; k < n; k += stride) out[k] = in[k] > 0.f ? in[k] : 0.f;
+  } else {
+    for (size_t k = i; k < n; k += stride) out[k] = in[k] > 0.f ? in[k] : 0.f;
+  }
+}
+
+// out = data > 0 ? grad : 0   (d_relu_cpu, math_functions.cpp:453-463)
+__global__ void d_relu_kernel(size_t n, const float* __restrict__ grad, const float* __restrict__ data, float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  if ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
+    for (size_t k = i; k < n4; k += stride) {
+      const float4 g = reinterpret_cast<const float4*>(grad)[k];
+      const float4 d = reinterpret_cast<const float4*>(data)[k];
+      float4 v;
+      v.x = d.x > 0.f ? g.x : 0.f; v.y = d.y > 0.f ? g.y : 0.f; v.z = d.z > 0.f ? g.z : 0.f; v.w = d.w > 0.f ? g.w : 0.f;
+      reinterpret_cast<float4*>(out)[k] = v;
+    }
+    for (size_t k = n4 * 4 + i; k < n; k += stride) out[k] = data[k] > 0.f ? grad[k] : 0.f;
+  } else {
+    for (size_t k = i; k < n; k += stride) out[k] = data[k] > 0.f ? grad[k] : 0.f;
+  }
+}
+
+__global__ void fill_kernel(size_t n, float value, float* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = value;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// One warp per row (the reference GPU kernel is thread-per-row with strided, uncoalesced access: math_functions.cu:158-205).
+__global__ void l2norm_kernel(int n, int dim, const float* __restrict__ in, float* __restrict__ out) {
+  const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = in + (size_t)row * dim;
+  float s = 0.f;
+  for (int j = lane; j < dim; j += 32) s += x[j] * x[j];
+  s = warp_sum(s);
+  s = s < 1.0e-12f ? 1.0e-12f : s;  // l2norm_layer.cpp:29
+  s = sqrtf(s);
+  for (int j = lane; j < dim; j += 32) out[(size_t)row * dim + j] = x[j] / s;
+}
+
+// l2norm_layer.cpp:45-62: grad_out = x*coef0*coef1 + g*sum_x2*coef1, coef0 = -<x,g>, coef1 = sum_x2^-1.5
+__global__ void d_l2norm_kernel(int n, int dim, const float* __restrict__ feat_in, const float* __restrict__ grad_in, float* __restrict__ grad_out) {
+  const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = feat_in + (size_t)row * dim;
+  const float* g = grad_in + (size_t)row * dim;
+  float sx = 0.f, c0 = 0.f;
+  for (int j = lane; j < dim; j += 32) { sx += x[j] * x[j]; c0 -= x[j] * g[j]; }
+  sx = warp_sum(sx);
+  c0 = warp_sum(c0);
+  sx = sx < 1.0e-12f ? 1.0e-12f : sx;
+  const float c1 = powf(sx, -1.5f);
+  for (int j = lane; j < dim; j += 32) grad_out[(size_t)row * dim + j] = x[j] * c0 * c1 + g[j] * sx * c1;
+}
+
+// Masked softmax + cross entropy, one warp per row in [begin, end).
+__global__ void softmax_ce_fwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                      const float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ losses) {
+  const size_t row = begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= end) return;
+  if (masks && masks[row] != 1) return;
+  const float* x = logits + row * ncls;
+  float mx = -INFINITY;
+  for (int j = lane; j < ncls; j += 32) mx = fmaxf(mx, x[j]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < ncls; j += 32) s += expf(x[j] - mx);
+  s = warp_sum(s);
+  const int lab = labels[row];
+  for (int j = lane; j < ncls; j += 32) {
+    const float p = expf(x[j] - mx) / s;
+    probs[row * ncls + j] = p;
+    if (j == lab) losses[row] = -((p == 0.f) ? logf(1e-10f) : logf(p));  // math_functions.cpp:531-542
+  }
+}
+
+__global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                      const float* __restrict__ probs, float* __restrict__ grad) {
+  const size_t n = (end - begin) * ncls;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const double inv_range = (double)(end - begin);
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const size_t row = begin + k / ncls;
+    const int j = (int)(k % ncls);
+    if (masks && masks[row] != 1) continue;
+    // softmax_loss_layer.cpp:31: (pred - onehot) / (end - begin), evaluated in double then rounded
+    grad[row * ncls + j] = (float)(((double)probs[row * ncls + j] - (labels[row] == j ? 1.0 : 0.0)) / inv_range);
+  }
+}
+
+// Single CTA, fixed-order tree: deterministic run to run. stats = {mean loss, accuracy, count}.
+__global__ void loss_acc_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                const float* __restrict__ logits, const float* __restrict__ losses, float* __restrict__ stats) {
+  __shared__ float s_loss[1024];
+  __shared__ float s_corr[1024];
+  __shared__ float s_cnt[1024];
+  float l = 0.f, c = 0.f, n = 0.f;
+  for (size_t row = begin + threadIdx.x; row < end; row += blockDim.x) {
+    if (masks && masks[row] != 1) continue;
+    l += losses[row];
+    n += 1.f;
+    const float* x = logits + row * ncls;
+    int am = -1; float mx = -INFINITY;
+    for (int j = 0; j < ncls; j++) if (x[j] > mx) { mx = x[j]; am = j; }  // argmax, math_functions.cpp:129-139
+    if (am == (int)labels[row]) c += 1.f;
+  }
+  s_loss[threadIdx.x] = l; s_corr[threadIdx.x] = c; s_cnt[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
+      s_corr[threadIdx.x] += s_corr[threadIdx.x + o];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float cnt = s_cnt[0];
+    stats[0] = cnt > 0.f ? s_loss[0] / cnt : 0.f;
+    stats[1] = s_corr[0] / cnt;
+    stats[2] = cnt;
+  }
+}
+
+// optimizer.cpp:22-35 — eps inside the sqrt; b1_t/b2_t are the powers BEFORE this call's post-multiply.
+__global__ void adam_kernel(size_t n, const float* __restrict__ dW, float* __restrict__ W, float* __restrict__ m, float* __restrict__ v,
+                            float lr, float b1, float b2, float b1_t, float b2_t, float eps) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float g = dW[i];
+    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(__fsub_rn(1.0f, b1), g));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), g), g));
+    m[i] = mi; v[i] = vi;
+    const float num = __fmul_rn(lr, __fdiv_rn(mi, __fsub_rn(1.0f, b1_t)));
+    const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(vi, __fsub_rn(1.0f, b2_t)), eps));
+    W[i] = __fsub_rn(W[i], __fdiv_rn(num, den));
+  }
+}
+
+__global__ void gather_rows_kernel(size_t n_ids, const uint32_t* __restrict__ ids, int F, const float* __restrict__ src, int ld_src,
+                                   float* __restrict__ dst, int ld_dst, int vec) {
+  // one warp per row; 128-bit loads when the layout allows (src may be a peer-mapped NVLink pointer)
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r = warp; r < n_ids; r += nwarps) {
+    const float* s = src + (size_t)ids[r] * ld_src;
+    float* d = dst + r * ld_dst;
+    if (vec == 4) {
+      for (int j = lane; j < F / 4; j += 32) reinterpret_cast<float4*>(d)[j] = reinterpret_cast<const float4*>(s)[j];
+    } else {
+      for (int j = lane; j < F; j += 32) d[j] = s[j];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gai_relu(size_t n, const float* in, float* out, gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(in && out);
+  relu_kernel<<<grid_for(n, 256, 4), 256, 0, gai::S(stream)>>>(n, in, out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_d_relu(size_t n, const float* grad, const float* data, float* out, gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(grad && data && out);
+  d_relu_kernel<<<grid_for(n, 256, 4), 256, 0, gai::S(stream)>>>(n, grad, data, out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_fill(size_t n, float value, float* out, gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(out != nullptr);
+  fill_kernel<<<grid_for(n, 256, 4), 256, 0, gai::S(stream)>>>(n, value, out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream) {
+  if (n <= 0) return GAI_OK;
+  GAI_CHECK_ARG(in && out && dim > 0);
+  l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, in, out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_d_l2norm(int n, int dim, const float* feat_in, const float* grad_in, float* grad_out, gai_stream_t stream) {
+  if (n <= 0) return GAI_OK;
+  GAI_CHECK_ARG(feat_in && grad_in && grad_out && dim > 0);
+  d_l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, feat_in, grad_in, grad_out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+
+int gai_softmax_ce_forward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits, float* probs,
+                           float* losses, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && probs && losses);
+  if (begin == end) return GAI_OK;
+  softmax_ce_fwd_kernel<<<(unsigned)(((end - begin) * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, probs, losses);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs, float* grad_out,
+                            gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out);
+  if (begin == end) return GAI_OK;
+  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                             const float* losses, float* stats_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && losses && stats_d);
+  loss_acc_kernel<<<1, 1024, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, losses, stats_d);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+
+int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, float lr, float b1, float b2, float b1_t, float b2_t, float eps,
+                    gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(dW && W && m && v);
+  adam_kernel<<<grid_for(n, 256), 256, 0, gai::S(stream)>>>(n, dW, W, m, v, lr, b1, b2, b1_t, b2_t, eps);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+
+int gai_gather_rows(size_t n_ids, const uint32_t* ids, int F, const float* src, int ld_src, float* dst, int ld_dst, gai_stream_t stream) {
+  if (n_ids == 0) return GAI_OK;
+  GAI_CHECK_ARG(ids && src && dst && F > 0 && ld_src >= F && ld_dst >= F);
+  const bool v4 = (F % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  gather_rows_kernel<<<grid_for(n_ids * 32, 256), 256, 0, gai::S(stream)>>>(n_ids, ids, F, src, ld_src, dst, ld_dst, v4 ? 4 : 1);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+
+int gai_set_gemm_mode(int mode) {
+  GAI_CHECK_ARG(mode >= 0 && mode <= 3);
+  gai::g_gemm_mode = mode;
+  return GAI_OK;
+}
+int gai_get_gemm_mode(void) { return gai::g_gemm_mode; }
+
+int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int transA,
+                  int transB, int accum, int flags, gai_stream_t stream) {
+  if (x == 0 || y == 0) return GAI_OK;
+  GAI_CHECK_ARG(A && B && C);
+  GAI_CHECK_ARG(lda >= (transA ? x : z) && ldb >= (transB ? z : y) && ldc >= y);
+  cudaStream_t st = gai::S(stream);
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    int rc = gai::gemm_tc(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED) return rc;
+    if (mode >= 2) return rc;  // an explicit tensor-core request must not silently degrade
+  }
+  return gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, st);
+}
+
+int gai_matmul(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, int transA, int transB, int accum, int flags,
+               gai_stream_t stream) {
+  // reference layout (math_functions.cpp:142-151): lda = transA ? x : z, ldb = transB ? z : y, ldc = y
+  return gai_matmul_ld(x, y, z, A, transA ? x : z, B, transB ? z : y, C, y, transA, transB, accum, flags, stream);
+}
+
+}  // extern "C"

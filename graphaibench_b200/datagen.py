@@ -1,0 +1,77 @@
+"""Synthetic inputs in the reference's on-disk conventions: R-MAT power-law graphs, symmetrised, sorted,
+deduplicated, no self-loops; N(0,1) features; uniform labels; range splits. Host-side numpy (input generation only)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def rmat_csr(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 0.19, 0.19, 0.05), permute: bool = False):
+    """Undirected R-MAT: draw directed pairs, drop loops, symmetrise, sort, dedupe. Returns (rowptr int64[n+1], colidx u32[nnz]).
+    nnz lands within a few percent of the target (duplicates are removed, so we oversample and trim whole pairs)."""
+    rng = np.random.default_rng(seed)
+    scale = int(np.ceil(np.log2(max(n_vertices, 2))))
+    a, b, c, _ = abcd
+    want_pairs = target_nnz // 2
+    keys = np.empty(0, np.int64)
+    draw = int(want_pairs * 1.25) + 16
+    for _ in range(8):
+        src = np.zeros(draw, np.int64)
+        dst = np.zeros(draw, np.int64)
+        for _lvl in range(scale):
+            r = rng.random(draw)
+            sb = (r >= a + b).astype(np.int64)                       # lower half (c or d quadrant)
+            db = (((r >= a) & (r < a + b)) | (r >= a + b + c)).astype(np.int64)  # right half (b or d quadrant)
+            src = (src << 1) | sb
+            dst = (dst << 1) | db
+        ok = (src < n_vertices) & (dst < n_vertices) & (src != dst)
+        lo = np.minimum(src[ok], dst[ok])
+        hi = np.maximum(src[ok], dst[ok])
+        keys = np.unique(np.concatenate([keys, lo * n_vertices + hi]))
+        if len(keys) >= want_pairs:
+            break
+        draw = int((want_pairs - len(keys)) * 1.6) + 16
+    if len(keys) > want_pairs:
+        keys = keys[np.sort(rng.choice(len(keys), want_pairs, replace=False))]
+    lo, hi = keys // n_vertices, keys % n_vertices
+    if permute:
+        perm = rng.permutation(n_vertices)
+        lo, hi = perm[lo], perm[hi]
+    s = np.concatenate([lo, hi])
+    d = np.concatenate([hi, lo])
+    order = np.lexsort((d, s))
+    s, d = s[order], d[order]
+    rowptr = np.zeros(n_vertices + 1, np.int64)
+    np.cumsum(np.bincount(s, minlength=n_vertices), out=rowptr[1:])
+    return rowptr, d.astype(np.uint32)
+
+
+def features(n, f, seed=2):
+    return np.random.default_rng(seed).standard_normal((n, f), dtype=np.float32)
+
+
+def labels(n, ncls, seed=3):
+    return np.random.default_rng(seed).integers(0, ncls, n, dtype=np.uint8)
+
+
+def split_ranges(n):
+    """first 50% train / next 25% val / rest test, as graph.meta.txt ranges (begin, end, count) x 3."""
+    t, v = n // 2, n // 2 + n // 4
+    return np.array([0, t, t, t, v, v - t, v, n, n - v], np.int64)
+
+
+def write_dataset(path, rowptr64, colidx, feats, labs, ncls, split9):
+    """Write the reference .bin set (reader.cpp:414-457): graph.meta.txt, graph.vertex.bin (int64), graph.edge.bin (u32),
+    graph.feats.bin (f32), graph.vlabel.bin (u8)."""
+    os.makedirs(path, exist_ok=True)
+    nv, ne = len(rowptr64) - 1, len(colidx)
+    deg = np.diff(rowptr64)
+    meta = [nv, ne, 4, 8, 1, 2, int(deg.max()) if nv else 0, feats.shape[1], ncls, 0] + [int(x) for x in split9]
+    with open(os.path.join(path, "graph.meta.txt"), "w") as f:
+        f.write("\n".join(str(m) for m in meta[:10]) + "\n")
+        f.write(" ".join(str(m) for m in meta[10:13]) + "\n" + " ".join(str(m) for m in meta[13:16]) + "\n" + " ".join(str(m) for m in meta[16:19]) + "\n")
+    np.asarray(rowptr64, np.int64).tofile(os.path.join(path, "graph.vertex.bin"))
+    np.asarray(colidx, np.uint32).tofile(os.path.join(path, "graph.edge.bin"))
+    np.asarray(feats, np.float32).tofile(os.path.join(path, "graph.feats.bin"))
+    np.asarray(labs, np.uint8).tofile(os.path.join(path, "graph.vlabel.bin"))

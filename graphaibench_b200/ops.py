@@ -1,0 +1,240 @@
+"""Torch-tensor front end over the C ABI (torch is plumbing: device memory + streams). Every function launches the
+hand-written sm_100a kernels in libgai_b200.so on torch's current stream; nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._abi import check, lib
+
+EPI_NONE, EPI_RELU, EPI_ADD = 0, 1, 2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and (t.dim() == 0 or t.stride(-1) == 1), "device tensors with unit inner stride only"
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    assert t.dtype == torch.float32
+    return _p(t)
+
+
+class DeviceGraph:
+    """gai_csr handle (device CSR + degree normalisers + hub list + cached transpose permutation)."""
+
+    def __init__(self, rowptr, colidx, device_arrays=False):
+        L = lib()
+        self._h = C.c_void_p()
+        if device_arrays:
+            assert rowptr.dtype == torch.int32 or rowptr.dtype == torch.uint32
+            self._keep = (rowptr, colidx)
+            nv, nnz = rowptr.numel() - 1, colidx.numel()
+            check(L.gai_csr_create_device(nv, nnz, _p(rowptr), _p(colidx), _stream(), C.byref(self._h)), "gai_csr_create_device")
+        else:
+            rp = np.ascontiguousarray(rowptr, np.uint32)
+            ci = np.ascontiguousarray(colidx, np.uint32)
+            nv, nnz = len(rp) - 1, len(ci)
+            check(L.gai_csr_create(nv, nnz, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), _stream(), C.byref(self._h)),
+                  "gai_csr_create")
+        self.nv, self.nnz = nv, nnz
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().gai_csr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def n_hub(self):
+        return lib().gai_csr_num_hub_rows(self._h)
+
+    def vertex_norm(self):
+        out = torch.empty(self.nv, dtype=torch.float32, device="cuda")
+        check(lib().gai_memcpy_d2d(_p(out), lib().gai_csr_vertex_norm(self._h), 4 * self.nv, _stream()))
+        return out
+
+    def csr(self):
+        rp = torch.empty(self.nv + 1, dtype=torch.int32, device="cuda")
+        ci = torch.empty(max(self.nnz, 1), dtype=torch.int32, device="cuda")
+        check(lib().gai_memcpy_d2d(_p(rp), lib().gai_csr_rowptr(self._h), 4 * (self.nv + 1), _stream()))
+        check(lib().gai_memcpy_d2d(_p(ci), lib().gai_csr_colidx(self._h), 4 * self.nnz, _stream()))
+        return rp, ci[: self.nnz]
+
+    def transpose_perm(self):
+        check(lib().gai_csr_build_transpose(self._h, _stream()), "gai_csr_build_transpose")
+        out = torch.empty(max(self.nnz, 1), dtype=torch.int32, device="cuda")
+        check(lib().gai_memcpy_d2d(_p(out), lib().gai_csr_transpose_perm(self._h), 4 * self.nnz, _stream()))
+        return out[: self.nnz]
+
+    def set_norms(self, norm_gcn=None, norm_mean=None):
+        check(lib().gai_csr_set_norms(self._h, _f32(norm_gcn) if norm_gcn is not None else None,
+                                      _f32(norm_mean) if norm_mean is not None else None, _stream()))
+
+
+def add_selfloop(rowptr, colidx):
+    rp = np.ascontiguousarray(rowptr, np.uint32)
+    ci = np.ascontiguousarray(colidx, np.uint32)
+    nv = len(rp) - 1
+    rpo = np.empty(nv + 1, np.uint32)
+    cio = np.empty(len(ci) + nv, np.uint32)
+    check(lib().gai_add_selfloop_h(nv, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), rpo.ctypes.data_as(C.c_void_p),
+                                   cio.ctypes.data_as(C.c_void_p)), "gai_add_selfloop_h")
+    return rpo, cio
+
+
+def _ld(t):
+    return t.stride(0) if t.dim() == 2 else t.numel()
+
+
+def spmm_gcn(g, x, out=None, flags=0, addend=None, rows=None):
+    F = x.shape[1]
+    if out is None:
+        out = torch.empty(g.nv, F, dtype=torch.float32, device=x.device)
+    if rows is None:
+        check(lib().gai_spmm_gcn(g.handle, F, _f32(x), x.stride(0), _f32(out), out.stride(0), flags, _p(addend), _stream()), "gai_spmm_gcn")
+    else:
+        check(lib().gai_spmm_gcn_rows(g.handle, rows[0], rows[1], F, _f32(x), x.stride(0), _f32(out), out.stride(0), flags, _p(addend), _stream()),
+              "gai_spmm_gcn_rows")
+    return out
+
+
+def spmm_mean(g, x, out=None, transposed=False, flags=0, addend=None, rows=None):
+    F = x.shape[1]
+    if out is None:
+        out = torch.empty(g.nv, F, dtype=torch.float32, device=x.device)
+    if rows is None:
+        check(lib().gai_spmm_mean(g.handle, F, _f32(x), x.stride(0), _f32(out), out.stride(0), int(transposed), flags, _p(addend), _stream()),
+              "gai_spmm_mean")
+    else:
+        check(lib().gai_spmm_mean_rows(g.handle, rows[0], rows[1], F, _f32(x), x.stride(0), _f32(out), out.stride(0), int(transposed), flags,
+                                       _p(addend), _stream()), "gai_spmm_mean_rows")
+    return out
+
+
+def spmm_edge(g, vals, x, out=None, perm=None, flags=0, addend=None):
+    F = x.shape[1]
+    if out is None:
+        out = torch.empty(g.nv, F, dtype=torch.float32, device=x.device)
+    check(lib().gai_spmm_edge(g.handle, F, _f32(vals), _p(perm), _f32(x), x.stride(0), _f32(out), out.stride(0), flags, _p(addend), _stream()),
+          "gai_spmm_edge")
+    return out
+
+
+def matmul(A, B, out=None, transA=False, transB=False, accum=False, flags=0):
+    """Reference matmul(x,y,z,A,B,C,transA,transB,accum): C[x,y] = op(A)[x,z] @ op(B)[z,y] (+C)."""
+    x, z = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
+    y = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == z
+    if out is None:
+        assert not accum
+        out = torch.empty(x, y, dtype=torch.float32, device=A.device)
+    check(lib().gai_matmul_ld(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), int(transA), int(transB),
+                              int(accum), flags, _stream()), "gai_matmul_ld")
+    return out
+
+
+def relu(x, out=None):
+    out = torch.empty_like(x) if out is None else out
+    check(lib().gai_relu(x.numel(), _f32(x), _f32(out), _stream()), "gai_relu")
+    return out
+
+
+def d_relu(grad, data, out=None):
+    out = torch.empty_like(grad) if out is None else out
+    check(lib().gai_d_relu(grad.numel(), _f32(grad), _f32(data), _f32(out), _stream()), "gai_d_relu")
+    return out
+
+
+def l2norm(x, out=None):
+    out = torch.empty_like(x) if out is None else out
+    check(lib().gai_l2norm(x.shape[0], x.shape[1], _f32(x), _f32(out), _stream()), "gai_l2norm")
+    return out
+
+
+def d_l2norm(feat_in, grad_in, out=None):
+    out = torch.empty_like(feat_in) if out is None else out
+    check(lib().gai_d_l2norm(feat_in.shape[0], feat_in.shape[1], _f32(feat_in), _f32(grad_in), _f32(out), _stream()), "gai_d_l2norm")
+    return out
+
+
+def softmax_ce_forward(logits, labels, masks, begin, end, probs, losses):
+    check(lib().gai_softmax_ce_forward(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), _f32(probs), _f32(losses), _stream()),
+          "gai_softmax_ce_forward")
+
+
+def softmax_ce_backward(probs, labels, masks, begin, end, grad):
+    check(lib().gai_softmax_ce_backward(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), _f32(grad), _stream()),
+          "gai_softmax_ce_backward")
+
+
+def masked_loss_accuracy(logits, labels, masks, begin, end, losses, stats=None):
+    stats = torch.empty(3, dtype=torch.float32, device=logits.device) if stats is None else stats
+    check(lib().gai_masked_loss_accuracy(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), _f32(losses), _f32(stats), _stream()),
+          "gai_masked_loss_accuracy")
+    return stats
+
+
+def adam_update(dW, W, m, v, lr, b1_t, b2_t, b1=0.9, b2=0.999, eps=1e-8):
+    check(lib().gai_adam_update(W.numel(), _f32(dW), _f32(W), _f32(m), _f32(v), lr, b1, b2, b1_t, b2_t, eps, _stream()), "gai_adam_update")
+
+
+def gat_forward(g, z, alpha_l, alpha_r, slope=0.2, flags=0):
+    F = z.shape[1]
+    temp = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=z.device)
+    norm = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=z.device)
+    out = torch.empty(g.nv, F, dtype=torch.float32, device=z.device)
+    check(lib().gai_gat_forward(g.handle, F, _f32(z), _f32(alpha_l), _f32(alpha_r), slope, _f32(temp), _f32(norm), _f32(out), flags, _stream()),
+          "gai_gat_forward")
+    return out, temp, norm
+
+
+def gat_backward(g, z, grad_in, temp, norm, slope=0.2, dz=None):
+    F = z.shape[1]
+    ds = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=z.device)
+    dal = torch.empty(F, dtype=torch.float32, device=z.device)
+    dar = torch.empty(F, dtype=torch.float32, device=z.device)
+    dz = torch.empty_like(z) if dz is None else dz
+    check(lib().gai_gat_backward(g.handle, F, _f32(z), _f32(grad_in), slope, _f32(temp), _f32(norm), _f32(ds), _f32(dal), _f32(dar), _f32(dz),
+                                 _stream()), "gai_gat_backward")
+    return dz, dal, dar, ds
+
+
+def gather_rows(ids, src, out=None):
+    F = src.shape[1]
+    out = torch.empty(ids.numel(), F, dtype=torch.float32, device=ids.device) if out is None else out
+    check(lib().gai_gather_rows(ids.numel(), _p(ids), F, _f32(src), src.stride(0), _f32(out), out.stride(0), _stream()), "gai_gather_rows")
+    return out
+
+
+def partition1d(rowptr64, colidx, nparts, part):
+    """Host-side 1D master+halo partition (bit-exact vs the reference partitioner). Returns dict of numpy arrays."""
+    rp = np.ascontiguousarray(rowptr64, np.int64)
+    ci = np.ascontiguousarray(colidx, np.uint32)
+    nv = len(rp) - 1
+    m, ne = C.c_int64(), C.c_int64()
+    lb, le = C.c_uint32(), C.c_uint32()
+    L = lib()
+    check(L.gai_partition1d_h(nv, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), nparts, part, None, None, None,
+                              C.byref(m), C.byref(ne), C.byref(lb), C.byref(le)), "gai_partition1d_h")
+    idx = np.empty(m.value, np.uint32)
+    srp = np.empty(m.value + 1, np.int64)
+    sci = np.empty(max(ne.value, 1), np.uint32)
+    check(L.gai_partition1d_h(nv, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), nparts, part, idx.ctypes.data_as(C.c_void_p),
+                              srp.ctypes.data_as(C.c_void_p), sci.ctypes.data_as(C.c_void_p), C.byref(m), C.byref(ne), C.byref(lb), C.byref(le)),
+          "gai_partition1d_h")
+    return dict(idx_map=idx, rowptr=srp, colidx=sci[: ne.value], local_begin=lb.value, local_end=le.value)

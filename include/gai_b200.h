@@ -1,0 +1,163 @@
+/* gai_b200.h — C ABI of the B200-native GNN-layer hot path (drop-in boundary).
+ *
+ * The reference (chenxuhao/GraphAIBench) has no FFI: its CPU and GPU builds are two object sets behind the
+ * same C++ declarations, chosen at link time (src/gnn/Makefile:56-79).  This ABI is the thin layer a third
+ * object set calls: every entry point below replaces one reference routine (cited as file:line, paths relative
+ * to the reference root) and is what graphaibench_b200/host/*.{h,cpp} — the C++ mirror of the reference's
+ * LearningGraph / *_Aggregator / *_layer / loss / optimizer classes — binds to.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (GAI_OK == 0); gai_last_error() gives the text.
+ *   - pointers are DEVICE pointers unless the name ends in _h (host).  Matrices are dense row-major fp32 with
+ *     an explicit leading dimension where one is given (ld == number of columns for the reference's layout).
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it (no device-wide syncs:
+ *     the reference's CudaTest() after every launch, include/utils/cutils.h:18-28, is not reproduced).
+ *   - sparse fp32 accumulation is sequential in CSR edge order with a rounded multiply then a rounded add, i.e.
+ *     bit-identical to the reference CPU path (src/gnn/gconv/gcn_aggregator.cpp:56-73), for every row length.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns GAI_ERR_CUDA.
+ */
+#ifndef GAI_B200_H
+#define GAI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  GAI_OK = 0,
+  GAI_ERR_CUDA = 1,        /* a CUDA runtime/driver call failed (includes "no device") */
+  GAI_ERR_ARG = 2,         /* invalid argument */
+  GAI_ERR_NOMEM = 3,
+  GAI_ERR_UNSUPPORTED = 4
+};
+
+typedef struct gai_csr* gai_csr_t; /* opaque device graph: replaces LearningGraph's d_* members (include/gnn/lgraph.h:38-44) */
+typedef void* gai_stream_t;        /* cudaStream_t */
+
+const char* gai_last_error(void);
+int gai_version(void);
+int gai_device_count(int* n);
+int gai_set_device(int dev);
+
+/* ---- device memory / transfers: replace float_malloc_device, copy_float_device, uint8_malloc_device, ...
+ *      (include/utils/math_functions.hh:14-174, src/utilities/math_functions.cu:56-111) ------------------- */
+int gai_malloc(void** p, size_t bytes);
+int gai_free(void* p);
+int gai_memset(void* p, int value, size_t bytes, gai_stream_t stream);
+int gai_memcpy_h2d(void* dst, const void* src_h, size_t bytes, gai_stream_t stream);
+int gai_memcpy_d2h(void* dst_h, const void* src, size_t bytes, gai_stream_t stream);
+int gai_memcpy_d2d(void* dst, const void* src, size_t bytes, gai_stream_t stream);
+int gai_stream_sync(gai_stream_t stream);
+int gai_host_alloc_pinned(void** p_h, size_t bytes);
+int gai_host_free_pinned(void* p_h);
+
+/* ---- host-side graph construction (integer work, bit-exact) ---------------------------------------- */
+/* LearningGraph::add_selfloop (include/gnn/lgraph.h:185-218). colidx_out_h has nnz+nv entries. */
+int gai_add_selfloop_h(uint32_t nv, const uint32_t* rowptr_h, const uint32_t* colidx_h, uint32_t* rowptr_out_h, uint32_t* colidx_out_h);
+
+/* ---- device CSR: replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data/compute_edge_data
+ *      (src/gnn/lgraph.cu:51-140) and the role of GraphGPU::init (include/graph_gpu.h:207-243). -------------
+ * Uploads rowptr (u32, nv+1) and colidx (u32, nnz), then on the device computes
+ *    norm_gcn[v]  = (float)(1.0 / (double)sqrtf((float)deg_v))   (0 if deg_v == 0)   — lgraph.cpp:22-34
+ *    norm_mean[v] = (float)(1.0 / (double)(float)deg_v)                               — sage_aggregator.cpp:17,41
+ * and the hub-row list used by the CTA-per-row kernel.  Row lengths are taken from rowptr, so call this on the
+ * graph the layers will see (i.e. after add_selfloop for GCN/GAT). */
+int gai_csr_create(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_h, const uint32_t* colidx_h, gai_stream_t stream, gai_csr_t* out);
+/* Same, from arrays already resident in device memory (borrowed, not copied; must outlive the handle). */
+int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, const uint32_t* colidx_d, gai_stream_t stream, gai_csr_t* out);
+int gai_csr_destroy(gai_csr_t g);
+uint32_t gai_csr_nv(gai_csr_t g);
+uint64_t gai_csr_nnz(gai_csr_t g);
+const uint32_t* gai_csr_rowptr(gai_csr_t g);   /* LearningGraph::row_start_ptr (lgraph.h:173) */
+const uint32_t* gai_csr_colidx(gai_csr_t g);   /* LearningGraph::edge_dst_ptr  (lgraph.h:175) */
+const float* gai_csr_vertex_norm(gai_csr_t g); /* LearningGraph::vertex_data_ptr (lgraph.h:179) */
+/* Override the per-vertex normalisers with values computed elsewhere (1D partition: norms come from GLOBAL degrees). */
+int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream);
+uint32_t gai_csr_num_hub_rows(gai_csr_t g);
+/* e -> e^T permutation on a structurally symmetric pattern (binary search per edge, as
+ * symmetric_csr_transpose, src/utilities/math_functions.cpp:46-74); built once, cached in the handle. */
+int gai_csr_build_transpose(gai_csr_t g, gai_stream_t stream);
+const uint32_t* gai_csr_transpose_perm(gai_csr_t g);
+
+/* ---- neighbour aggregation (SpMM) -------------------------------------------------------------------
+ * out[i, 0:F] = epilogue( sum_{e in row i} w_e * in[col_e, 0:F] ), i in [row_begin, row_end).
+ * flags: GAI_EPI_ADD  -> add `addend[i, :]` (ld = ld_out) after the sum;  GAI_EPI_RELU -> max(.,0) last. */
+enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2 };
+/* GCN_Aggregator::aggregate == d_aggregate (src/gnn/gconv/gcn_aggregator.cpp:23-77): w_e = norm_i * norm_j. */
+int gai_spmm_gcn(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
+/* SAGE_Aggregator::aggregate (transposed=0, w_e = 1/deg_i) / d_aggregate (transposed=1, w_e = 1/deg_j)
+ * (src/gnn/gconv/sage_aggregator.cpp:7-54). */
+int gai_spmm_mean(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend, gai_stream_t stream);
+/* update_all with explicit per-edge values (src/gnn/gconv/gat_aggregator.cpp:26-45; spmm(), math_functions.cpp:206-219).
+ * If perm != NULL the value used for edge e is vals[perm[e]] (transposed attention without materialising it). */
+int gai_spmm_edge(gai_csr_t g, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
+/* Row-range variants for the 1D partition (interior rows first, boundary rows after the halo arrives). */
+int gai_spmm_gcn_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
+int gai_spmm_mean_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend, gai_stream_t stream);
+
+/* ---- GAT attention (src/gnn/gconv/gat_aggregator.cpp:57-200) ----------------------------------------
+ * forward:  t_e = <alpha_l, z_i> + <alpha_r, z_j>;  s_e = LeakyReLU_slope(t_e);  p = softmax over row i;
+ *           out_i = sum_e p_e z_j.   temp_scores (t) and norm_scores (p) are saved for the backward (nnz each). */
+int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, const float* alpha_r, float slope,
+                    float* temp_scores, float* norm_scores, float* out, int flags, gai_stream_t stream);
+/* backward: dS_e = <g_i, z_j> (SDDMM); softmax-bwd + LeakyReLU-bwd; d_alpha_l/r (deterministic two-stage reduce,
+ *           no atomics); dZ_i = sum_e p^T_e g_j  (transpose through the cached permutation).
+ *           dz may alias z (the reference writes dZ over out_temp, gat_layer.cpp:33-36): z is fully consumed first. */
+int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, float slope, const float* temp_scores,
+                     const float* norm_scores, float* scores_grad_ws, float* d_alpha_l, float* d_alpha_r, float* dz, gai_stream_t stream);
+
+/* ---- dense transform: matmul(x,y,z,A,B,C,transA,transB,accum) (src/utilities/math_functions.cpp:142-171;
+ *      GPU twin cublasSgemm, math_functions.cu:321-343).  C[x×y] = op(A)[x×z] · op(B)[z×y] (+ C if accum).
+ *      fp32 in/out; tensor-core path = tcgen05 kind::tf32 with 3xTF32 error compensation (≈fp32 accuracy).
+ *      flags: GAI_EPI_RELU applies max(.,0) in the epilogue.  ---------------------------------------------- */
+int gai_matmul(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, int transA, int transB, int accum, int flags, gai_stream_t stream);
+/* Same with explicit leading dimensions (lda/ldb are those of the STORED matrices). */
+int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc,
+                  int transA, int transB, int accum, int flags, gai_stream_t stream);
+/* Select the dense path: 0 = auto, 1 = fp32 SIMT FFMA, 2 = tcgen05 3xTF32, 3 = tcgen05 1xTF32 (fast, ~1e-3). */
+int gai_set_gemm_mode(int mode);
+int gai_get_gemm_mode(void);
+
+/* ---- elementwise (src/utilities/math_functions.cpp:442-463; .cu:242-269) ---------------------------- */
+int gai_relu(size_t n, const float* in, float* out, gai_stream_t stream);
+int gai_d_relu(size_t n, const float* grad, const float* data, float* out, gai_stream_t stream);
+int gai_fill(size_t n, float value, float* out, gai_stream_t stream); /* init_const_gpu, math_functions.cu:12-19 */
+
+/* ---- l2norm_layer (src/layers/l2norm_layer.cpp:19-64; l2norm/d_l2norm math_functions.cu:158-205) ---- */
+int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream);
+int gai_d_l2norm(int n, int dim, const float* feat_in, const float* grad_in, float* grad_out, gai_stream_t stream);
+
+/* ---- softmax_loss_layer (src/layers/softmax_loss_layer.cpp:4-55) + masked_accuracy_single (math_functions.cpp:79-92)
+ * forward : rows i in [begin,end) with masks[i]==1 (masks NULL = all): probs_i = softmax(logits_i);
+ *           losses[i] = -log(probs_i[label_i]) (log(1e-10) if 0).
+ * backward: grad_i = (probs_i - onehot)/(end-begin) on the same rows; other rows untouched.
+ * reduce  : stats_d[0] = mean loss over masked rows, stats_d[1] = accuracy (argmax of LOGITS == label), stats_d[2] = count. */
+int gai_softmax_ce_forward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                           float* probs, float* losses, gai_stream_t stream);
+int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
+                            float* grad_out, gai_stream_t stream);
+int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                             const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
+
+/* ---- adam::update (src/utilities/optimizer.cpp:22-35; GPU twin optimizer.cu:5-36).  The caller owns m, v and
+ *      the running powers b1_t/b2_t (they advance once per update() call on the reference's optimiser object). */
+int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, float lr, float b1, float b2, float b1_t, float b2_t,
+                    float eps, gai_stream_t stream);
+
+/* ---- 1D vertex partition: PartitionedGraph::edgecut_induced_partition1D + generate_induced_subgraph
+ *      (src/partitioner/graph_partition.cc:70-178), host side, integer, bit-exact.
+ * Two-call protocol: with idx_map_h == NULL returns the sizes (*m_out = |masters ∪ halo|, *ne_out = induced nnz);
+ * then fills idx_map_h[m], sub_rowptr_h[m+1] (int64, as eidType), sub_colidx_h[ne], local_begin/local_end. */
+int gai_partition1d_h(uint32_t nv, const int64_t* rowptr_h, const uint32_t* colidx_h, int nparts, int part, uint32_t* idx_map_h,
+                      int64_t* sub_rowptr_h, uint32_t* sub_colidx_h, int64_t* m_out, int64_t* ne_out, uint32_t* local_begin, uint32_t* local_end);
+
+/* ---- halo exchange over NVLink peer memory (multi-GPU; no reference counterpart: the reference GNN path is
+ *      single-GPU).  dst_rows[k, 0:F] = src[ids[k], 0:F] where `src` may be a peer-mapped pointer. */
+int gai_gather_rows(size_t n_ids, const uint32_t* ids, int F, const float* src, int ld_src, float* dst, int ld_dst, gai_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAI_B200_H */

@@ -177,3 +177,46 @@ class RefModel:
         arr = np.ascontiguousarray(arr, np.float32).ravel()
         if self.L.ref_model_set(self.h, name.encode(), layer, arr, arr.size) < 0:
             raise KeyError(name)
+
+
+_librefpart = None
+
+
+def ref_partition1d(rowptr64, colidx, nparts, part):
+    """The reference's edgecut_induced_partition1D (src/partitioner/graph_partition.cc:128-178) on an in-memory CSR."""
+    global _librefpart
+    if _librefpart is None:
+        _librefpart = C.CDLL(_LIBREFPART_PATH)
+        _librefpart.refpart_new.argtypes = [C.c_uint32, i64p, u32p, C.c_int]
+        _librefpart.refpart_new.restype = C.c_void_p
+        _librefpart.refpart_sizes.argtypes = [C.c_void_p, C.c_int, i64p]
+        _librefpart.refpart_get.argtypes = [C.c_void_p, C.c_int, u32p, i64p, u32p]
+    P = _librefpart
+    rp = np.ascontiguousarray(rowptr64, np.int64)
+    ci = np.ascontiguousarray(colidx, np.uint32)
+    key = (rp.ctypes.data, len(rp), nparts)
+    cache = ref_partition1d.__dict__.setdefault("cache", {})
+    if key not in cache:
+        cache.clear()
+        cache[key] = (P.refpart_new(len(rp) - 1, rp, ci, nparts), rp, ci)
+    h = cache[key][0]
+    sz = np.zeros(4, np.int64)
+    P.refpart_sizes(h, part, sz)
+    idx = np.zeros(sz[0], np.uint32); srp = np.zeros(sz[0] + 1, np.int64); sci = np.zeros(max(sz[1], 1), np.uint32)
+    P.refpart_get(h, part, idx, srp, sci)
+    return dict(idx_map=idx, rowptr=srp, colidx=sci[: sz[1]], local_begin=int(sz[2]), local_end=int(sz[3]))
+
+
+def orc_partition1d(rowptr64, colidx, nparts, part):
+    """C restatement of the same (gnn_oracle.c: orc_partition1d)."""
+    L = liborc()
+    rp = np.ascontiguousarray(rowptr64, np.int64)
+    ci = np.ascontiguousarray(colidx, np.uint32)
+    nv = len(rp) - 1
+    ne = C.c_int64()
+    m = L.orc_partition1d(nv, rp, ci, nparts, part, None, None, None, C.byref(ne), None, None)
+    idx = np.zeros(m, np.uint32); srp = np.zeros(m + 1, np.int64); sci = np.zeros(max(ne.value, 1), np.uint32)
+    lb, le = C.c_uint32(), C.c_uint32()
+    L.orc_partition1d(nv, rp, ci, nparts, part, idx.ctypes.data_as(C.c_void_p), srp.ctypes.data_as(C.c_void_p), sci.ctypes.data_as(C.c_void_p),
+                      C.byref(ne), C.byref(lb), C.byref(le))
+    return dict(idx_map=idx, rowptr=srp, colidx=sci[: ne.value], local_begin=lb.value, local_end=le.value)

@@ -1,0 +1,76 @@
+"""CPU suite, part 2: the C-ABI library loads, exports every symbol include/gai_b200.h declares, and its host-side
+(integer) entry points are bit-exact against the golden vectors. No compute entry point is called here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, sha
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from graphaibench_b200 import build, _abi
+    build.build_cuda()
+    return _abi
+
+
+def test_header_symbols_exported(abi):
+    hdr = open(os.path.join(ROOT, "include", "gai_b200.h")).read()
+    declared = set(re.findall(r"\b(gai_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = abi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in gai_b200.h but not exported by libgai_b200.so"
+    assert declared == set(abi.EXPORTED), (declared ^ set(abi.EXPORTED))
+    assert L.gai_version() >= 100
+
+
+def test_library_is_sm100a_and_has_no_cpu_fallback(abi):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+    # with no GPU present compute entry points fail loudly instead of silently computing on the host
+    import torch
+    if not torch.cuda.is_available():
+        n = C.c_int(-1)
+        rc = abi.lib().gai_device_count(C.byref(n))
+        assert rc != 0 or n.value == 0
+        p = C.c_void_p()
+        assert abi.lib().gai_malloc(C.byref(p), 1024) != 0
+        assert abi.lib().gai_last_error()
+
+
+def test_add_selfloop_h_bit_exact(abi, golden, small_graph, cora):
+    from graphaibench_b200 import ops
+    rp, ci = ops.add_selfloop(small_graph["rowptr"], small_graph["colidx"])
+    assert np.array_equal(rp, golden["sg_loop_rowptr"]) and sha(ci) == str(golden["sg_loop_colidx_sha"])
+    # empty graph and single isolated vertex
+    rp, ci = ops.add_selfloop(np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+    assert list(rp) == [0] and len(ci) == 0
+    rp, ci = ops.add_selfloop(np.zeros(2, np.uint32), np.zeros(0, np.uint32))
+    assert list(rp) == [0, 1] and list(ci) == [0]
+    # against the oracle on cora
+    from oracle import model as om
+    g = om.Graph(cora["rowptr"], cora["colidx"]); g.add_selfloop()
+    rp, ci = ops.add_selfloop(cora["rowptr"], cora["colidx"])
+    assert np.array_equal(rp, g.rowptr) and np.array_equal(ci, g.colidx)
+
+
+def test_partition1d_h_bit_exact(abi, golden, cora, small_graph):
+    from graphaibench_b200 import ops
+    for name, (rp, ci) in (("cora", (cora["rowptr64"], cora["colidx"])), ("sg", (small_graph["rowptr64"], small_graph["colidx"]))):
+        for nparts in (2, 4):
+            for part in range(nparts):
+                r = ops.partition1d(rp, ci, nparts, part)
+                key = f"part_{name}_{nparts}_{part}"
+                assert list(golden[key + "_lb_le_m_ne"]) == [r["local_begin"], r["local_end"], len(r["idx_map"]), len(r["colidx"])]
+                assert sha(r["idx_map"]) == str(golden[key + "_idx_sha"])
+                assert sha(r["rowptr"]) == str(golden[key + "_rowptr_sha"])
+                assert sha(r["colidx"]) == str(golden[key + "_colidx_sha"])
+    # ragged: more parts than vertices, empty trailing partitions
+    rp = np.array([0, 1, 2], np.int64); ci = np.array([1, 0], np.uint32)
+    r = ops.partition1d(rp, ci, 4, 3)
+    assert len(r["idx_map"]) == 0 and r["local_begin"] == r["local_end"] == 0

@@ -1,0 +1,243 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every kernel behind the C ABI against the CPU oracle on the same
+seeded inputs and against the golden vectors generated from the reference. Bit-exact for index work and for the sparse
+fp32 aggregation (same operation order and roundings as the reference CPU path); stated tolerances elsewhere."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import require_cuda, sha
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north-star fp32 tolerance, applied norm-wise: max|a-b| <= REL_TOL * max|ref|
+
+
+def close(a, ref, tol=REL_TOL):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    scale = max(np.abs(ref).max(), 1e-30)
+    err = np.abs(a - ref).max() / scale
+    assert err <= tol, f"norm-wise relative error {err:.3e} > {tol}"
+
+
+@pytest.fixture(scope="module")
+def T():
+    require_cuda()
+    import torch
+    from graphaibench_b200 import build
+    build.build_cuda()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops(T):
+    from graphaibench_b200 import ops
+    return ops
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_csr_norms_bit_exact(T, ops, golden, small_graph):
+    rp, ci = ops.add_selfloop(small_graph["rowptr"], small_graph["colidx"])
+    g = ops.DeviceGraph(rp, ci)
+    assert g.n_hub >= 1  # the fixture has a hub row (> 1024 neighbours)
+    assert np.array_equal(g.vertex_norm().cpu().numpy(), golden["sg_loop_vdata"])
+    drp, dci = g.csr()
+    assert np.array_equal(drp.cpu().numpy().view(np.uint32), rp) and np.array_equal(dci.cpu().numpy().view(np.uint32), ci)
+
+
+@pytest.mark.parametrize("F", [7, 16, 47, 100, 256])
+def test_spmm_bit_exact_vs_reference_goldens(T, ops, golden, small_graph, F):
+    x = dev(T, small_graph["x"][F])
+    rp, ci = ops.add_selfloop(small_graph["rowptr"], small_graph["colidx"])
+    g_loop = ops.DeviceGraph(rp, ci)
+    g_raw = ops.DeviceGraph(small_graph["rowptr"], small_graph["colidx"])
+    assert sha(ops.spmm_gcn(g_loop, x).cpu().numpy()) == str(golden[f"sg_gcn_{F}_sha"])
+    assert sha(ops.spmm_mean(g_raw, x).cpu().numpy()) == str(golden[f"sg_mean_{F}_sha"])
+    assert sha(ops.spmm_mean(g_raw, x, transposed=True).cpu().numpy()) == str(golden[f"sg_meanT_{F}_sha"])
+
+
+@pytest.mark.parametrize("F", [1, 2, 5, 12, 36, 64, 130, 172, 512, 600, 1100])
+def test_spmm_bit_exact_vs_oracle_widths(T, ops, liborc, small_graph, F):
+    """All vector widths / lane-group shapes / column-block loops, incl. the hub-row kernel."""
+    from oracle import model as om
+    n = small_graph["n"]
+    rng = np.random.default_rng(F)
+    x = rng.standard_normal((n, F), dtype=np.float32)
+    g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.add_selfloop(); g.compute_vertex_data()
+    ref = np.zeros((n, F), np.float32)
+    liborc.orc_spmm_gcn(n, g.rowptr, g.colidx, g.vdata, F, x.reshape(-1), ref.reshape(-1))
+    dg = ops.DeviceGraph(g.rowptr, g.colidx)
+    out = ops.spmm_gcn(dg, dev(T, x)).cpu().numpy()
+    assert np.array_equal(out, ref)
+    vals = rng.standard_normal(g.ne, dtype=np.float32)
+    liborc.orc_spmm_edge(n, g.rowptr, g.colidx, vals, F, x.reshape(-1), ref.reshape(-1))
+    out = ops.spmm_edge(dg, dev(T, vals), dev(T, x)).cpu().numpy()
+    assert np.array_equal(out, ref)
+
+
+def test_spmm_epilogue_ld_and_row_ranges(T, ops, liborc, small_graph):
+    from oracle import model as om
+    n, F = small_graph["n"], 100
+    x = small_graph["x"][F]
+    g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.compute_vertex_data()
+    ref = np.zeros((n, F), np.float32)
+    liborc.orc_spmm_mean(n, g.rowptr, g.colidx, F, x.reshape(-1), ref.reshape(-1), 0)
+    dg = ops.DeviceGraph(g.rowptr, g.colidx)
+    add = np.random.default_rng(3).standard_normal((n, F), dtype=np.float32)
+    # fused (+addend, ReLU) epilogue == unfused reference sequence
+    out = ops.spmm_mean(dg, dev(T, x), flags=ops.EPI_ADD | ops.EPI_RELU, addend=dev(T, add)).cpu().numpy()
+    assert np.array_equal(out, np.maximum(ref + add, 0))
+    # leading dimensions: input is a column slice of a wider buffer, output lands inside a wider buffer
+    wide_in = T.zeros(n, 2 * F + 4, device="cuda"); wide_in[:, 4:4 + F] = dev(T, x)
+    wide_out = T.full((n, 3 * F), -7.0, device="cuda")
+    ops.spmm_mean(dg, wide_in[:, 4:4 + F], out=wide_out[:, F:2 * F])
+    assert np.array_equal(wide_out[:, F:2 * F].cpu().numpy(), ref)
+    assert float(wide_out[:, :F].max()) == -7.0 and float(wide_out[:, 2 * F:].min()) == -7.0
+    # row ranges (1D partition: interior / boundary split) reproduce the full result, hub row included
+    out = T.full((n, F), 5.0, device="cuda")
+    ops.spmm_mean(dg, dev(T, x), out=out, rows=(0, 700))
+    assert float(out[700:].min()) == 5.0
+    ops.spmm_mean(dg, dev(T, x), out=out, rows=(700, n))
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_spmm_empty_and_degenerate(T, ops):
+    g = ops.DeviceGraph(np.zeros(5, np.uint32), np.zeros(0, np.uint32))  # 4 isolated vertices
+    out = ops.spmm_mean(g, T.ones(4, 8, device="cuda"))
+    assert float(out.abs().max()) == 0.0
+    g0 = ops.DeviceGraph(np.zeros(1, np.uint32), np.zeros(0, np.uint32))  # empty graph
+    assert ops.spmm_gcn(g0, T.ones(0, 8, device="cuda")).shape == (0, 8)
+
+
+def test_transpose_perm_bit_exact(T, ops, small_graph):
+    from oracle import model as om
+    g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.add_selfloop()
+    dg = ops.DeviceGraph(g.rowptr, g.colidx)
+    assert np.array_equal(dg.transpose_perm().cpu().numpy().view(np.uint32), g.transpose_perm())
+    # asymmetric pattern is rejected, not silently mis-transposed
+    from graphaibench_b200 import GaiError
+    bad = ops.DeviceGraph(np.array([0, 1, 1], np.uint32), np.array([1], np.uint32))
+    with pytest.raises(GaiError):
+        bad.transpose_perm()
+
+
+@pytest.mark.parametrize("shape", [(300, 40, 70, 0, 0), (257, 7, 16, 0, 0), (1433, 16, 2708, 1, 0), (2708, 1433, 16, 0, 1),
+                                   (129, 65, 33, 1, 1), (5000, 256, 100, 0, 0), (100, 256, 5000, 1, 0)])
+@pytest.mark.parametrize("mode", [1, 0])
+def test_matmul_vs_oracle(T, ops, liborc, shape, mode):
+    from graphaibench_b200._abi import lib
+    x, y, z, ta, tb = shape
+    rng = np.random.default_rng(x + y)
+    A = rng.standard_normal((z, x) if ta else (x, z), dtype=np.float32)
+    B = rng.standard_normal((y, z) if tb else (z, y), dtype=np.float32)
+    C0 = rng.standard_normal((x, y), dtype=np.float32)
+    lib().gai_set_gemm_mode(mode)
+    try:
+        for accum in (0, 1):
+            ref = C0.copy()
+            liborc.orc_gemm(x, y, z, A.reshape(-1), B.reshape(-1), ref.reshape(-1), ta, tb, accum)
+            out = dev(T, C0.copy())
+            ops.matmul(dev(T, A), dev(T, B), out=out, transA=bool(ta), transB=bool(tb), accum=bool(accum))
+            close(out.cpu().numpy(), ref)
+        ref = np.zeros((x, y), np.float32)
+        liborc.orc_gemm(x, y, z, A.reshape(-1), B.reshape(-1), ref.reshape(-1), ta, tb, 0)
+        out = ops.matmul(dev(T, A), dev(T, B), transA=bool(ta), transB=bool(tb), flags=ops.EPI_RELU)
+        close(out.cpu().numpy(), np.maximum(ref, 0))
+    finally:
+        lib().gai_set_gemm_mode(0)
+
+
+def test_relu_drelu_bit_exact(T, ops, liborc):
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 1024, 100003):
+        x = rng.standard_normal(n, dtype=np.float32); gr = rng.standard_normal(n, dtype=np.float32)
+        r1, r2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        liborc.orc_relu(n, x, r1); liborc.orc_d_relu(n, gr, x, r2)
+        assert np.array_equal(ops.relu(dev(T, x)).cpu().numpy(), r1)
+        assert np.array_equal(ops.d_relu(dev(T, gr), dev(T, x)).cpu().numpy(), r2)
+        xd = dev(T, x)
+        ops.relu(xd, out=xd)  # in place, as the layers call it
+        assert np.array_equal(xd.cpu().numpy(), r1)
+
+
+def test_softmax_ce_vs_reference_golden(T, ops, golden):
+    logits, labs, masks = golden["loss_logits"], golden["loss_labels"], golden["loss_masks"]
+    nv, ncls = logits.shape
+    probs = T.zeros(nv, ncls, device="cuda"); losses = T.zeros(nv, device="cuda"); grad = T.zeros(nv, ncls, device="cuda")
+    dl, dlab, dm = dev(T, logits), dev(T, labs), dev(T, masks)
+    ops.softmax_ce_forward(dl, dlab, dm, 5, 40, probs, losses)
+    ops.softmax_ce_backward(probs, dlab, dm, 5, 40, grad)
+    stats = ops.masked_loss_accuracy(dl, dlab, dm, 5, 40, losses).cpu().numpy()
+    close(probs.cpu().numpy(), golden["loss_probs"], 2e-6)
+    close(grad.cpu().numpy(), golden["loss_grad"], 2e-6)
+    assert abs(stats[0] - golden["loss_value"]) <= 1e-5 * abs(golden["loss_value"])
+    assert stats[1] == golden["loss_acc"] and stats[2] == 35
+    assert float(grad[:5].abs().max()) == 0.0 and float(grad[40:].abs().max()) == 0.0  # untouched outside the range
+
+
+def test_adam_bit_exact_vs_reference_golden(T, ops, golden):
+    W = dev(T, golden["adam_W"].copy()); m = T.zeros_like(W); v = T.zeros_like(W)
+    b1t, b2t = np.float32(0.9), np.float32(0.999)
+    for s in range(golden["adam_grads"].shape[0]):
+        ops.adam_update(dev(T, golden["adam_grads"][s]), W, m, v, 0.02, float(b1t), float(b2t))
+        b1t, b2t = np.float32(b1t * np.float32(0.9)), np.float32(b2t * np.float32(0.999))
+    assert np.array_equal(W.cpu().numpy(), golden["adam_W_after"])
+
+
+def test_l2norm_vs_oracle(T, ops, liborc):
+    rng = np.random.default_rng(2)
+    n, dim = 513, 37
+    x = rng.standard_normal((n, dim), dtype=np.float32); x[3] = 0  # a zero row exercises the 1e-12 clamp
+    gin = rng.standard_normal((n, dim), dtype=np.float32)
+    r1, r2 = np.zeros((n, dim), np.float32), np.zeros((n, dim), np.float32)
+    liborc.orc_l2norm(n, dim, x.reshape(-1), r1.reshape(-1)); liborc.orc_d_l2norm(n, dim, x.reshape(-1), gin.reshape(-1), r2.reshape(-1))
+    close(ops.l2norm(dev(T, x)).cpu().numpy(), r1)
+    close(ops.d_l2norm(dev(T, x), dev(T, gin)).cpu().numpy(), r2)
+
+
+def test_gat_forward_backward_vs_reference_golden(T, ops, golden, small_graph):
+    rp, ci = ops.add_selfloop(small_graph["rowptr"], small_graph["colidx"])
+    g = ops.DeviceGraph(rp, ci)
+    z, gin = dev(T, golden["gat_z"]), dev(T, golden["gat_gin"])
+    out, temp, norm = ops.gat_forward(g, z, dev(T, golden["gat_al"]), dev(T, golden["gat_ar"]))
+    close(norm.cpu().numpy(), golden["gat_norm_scores"])
+    close(out.cpu().numpy(), golden["gat_out"])
+    dz, dal, dar, _ = ops.gat_backward(g, z, gin, temp, norm)
+    close(dz.cpu().numpy(), golden["gat_gout"])
+    close(dal.cpu().numpy(), golden["gat_dal"], 2e-5)  # long fp32 reductions in a different (deterministic) order
+    close(dar.cpu().numpy(), golden["gat_dar"], 2e-5)
+    # dz may alias z (the reference overwrites out_temp with dZ)
+    z2 = z.clone()
+    ops.gat_backward(g, z2, gin, temp, norm, dz=z2)
+    assert np.array_equal(z2.cpu().numpy(), dz.cpu().numpy())
+
+
+@pytest.mark.parametrize("F", [64, 256])
+def test_gat_wide_vs_oracle(T, ops, liborc, small_graph, F):
+    from oracle import model as om
+    g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.add_selfloop()
+    n = g.nv
+    rng = np.random.default_rng(F)
+    z = rng.standard_normal((n, F), dtype=np.float32) * 0.3; gin = rng.standard_normal((n, F), dtype=np.float32)
+    al = rng.standard_normal(F, dtype=np.float32) * 0.2; ar = rng.standard_normal(F, dtype=np.float32) * 0.2
+    ts, sc, ns, nsg = (np.zeros(g.ne, np.float32) for _ in range(4))
+    out, gout = np.zeros((n, F), np.float32), np.zeros((n, F), np.float32)
+    dal, dar = np.zeros(F, np.float32), np.zeros(F, np.float32)
+    liborc.orc_gat_forward(n, g.rowptr, g.colidx, F, al, ar, 0.2, z.reshape(-1), ts, sc, ns, out.reshape(-1))
+    liborc.orc_gat_backward(n, g.rowptr, g.colidx, F, 0.2, z.reshape(-1), gin.reshape(-1), ts, ns, sc, nsg, dal, dar, gout.reshape(-1), 1)
+    dg = ops.DeviceGraph(g.rowptr, g.colidx)
+    o, temp, norm = ops.gat_forward(dg, dev(T, z), dev(T, al), dev(T, ar))
+    close(o.cpu().numpy(), out); close(norm.cpu().numpy(), ns)
+    dz, d_al, d_ar, _ = ops.gat_backward(dg, dev(T, z), dev(T, gin), temp, norm)
+    close(dz.cpu().numpy(), gout); close(d_al.cpu().numpy(), dal, 5e-5); close(d_ar.cpu().numpy(), dar, 5e-5)
+
+
+def test_gather_rows(T, ops):
+    rng = np.random.default_rng(4)
+    src = rng.standard_normal((1000, 100), dtype=np.float32)
+    ids = rng.integers(0, 1000, 333).astype(np.int32)
+    out = ops.gather_rows(dev(T, ids), dev(T, src)).cpu().numpy()
+    assert np.array_equal(out, src[ids])
