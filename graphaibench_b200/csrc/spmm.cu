@@ -265,13 +265,14 @@ int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
                   int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
-  GAI_CHECK_ARG(g != nullptr && in != nullptr && out != nullptr);
-  GAI_CHECK_ARG(F > 0 && ld_in >= F && ld_out >= F);
+  GAI_CHECK_ARG(g != nullptr);
   GAI_CHECK_ARG(rb <= re && re <= g->nv);
+  if (re == rb) return GAI_OK;  // empty graph / empty row range: nothing to do (buffers may be NULL)
+  GAI_CHECK_ARG(in != nullptr && out != nullptr);
+  GAI_CHECK_ARG(F > 0 && ld_in >= F && ld_out >= F);
   GAI_CHECK_ARG(!(flags & GAI_EPI_ADD) || addend != nullptr);
   GAI_CHECK_ARG(mode < M_EDGE || vals != nullptr);
   GAI_CHECK_ARG(in != out);
-  if (re == rb) return GAI_OK;
   SpmmArgs a;
   a.rowptr = g->rowptr; a.colidx = g->colidx;
   a.norm = (mode == M_GCN) ? g->norm_gcn : g->norm_mean;
