@@ -137,38 +137,46 @@ __global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const 
   }
 }
 
-// Single CTA, fixed-order tree: deterministic run to run. stats = {mean loss, accuracy, count}.
-__global__ void loss_acc_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
-                                const float* __restrict__ logits, const float* __restrict__ losses, float* __restrict__ stats) {
-  __shared__ float s_loss[1024];
-  __shared__ float s_corr[1024];
-  __shared__ float s_cnt[1024];
-  float l = 0.f, c = 0.f, n = 0.f;
-  for (size_t row = begin + threadIdx.x; row < end; row += blockDim.x) {
+// Two-stage, fixed-order reduction (deterministic run to run). Stage 1: one warp per row computes argmax(logits) with the
+// reference's tie-break (first maximum, math_functions.cpp:129-139); each CTA folds its rows into one partial
+// {loss sum, correct, count}. Stage 2: one CTA adds the partials in index order. stats = {mean loss, accuracy, count}.
+__global__ void loss_acc_stage1(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                const float* __restrict__ logits, const float* __restrict__ losses, double* __restrict__ partial) {
+  __shared__ double s_l[8];
+  __shared__ unsigned s_c[8], s_n[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  double l = 0.0; unsigned c = 0, n = 0;
+  for (size_t row = begin + (size_t)blockIdx.x * 8 + warp; row < end; row += nwarps) {
     if (masks && masks[row] != 1) continue;
-    l += losses[row];
-    n += 1.f;
     const float* x = logits + row * ncls;
-    int am = -1; float mx = -INFINITY;
-    for (int j = 0; j < ncls; j++) if (x[j] > mx) { mx = x[j]; am = j; }  // argmax, math_functions.cpp:129-139
-    if (am == (int)labels[row]) c += 1.f;
-  }
-  s_loss[threadIdx.x] = l; s_corr[threadIdx.x] = c; s_cnt[threadIdx.x] = n;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      s_loss[threadIdx.x] += s_loss[threadIdx.x + o];
-      s_corr[threadIdx.x] += s_corr[threadIdx.x + o];
-      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+    float mx = -INFINITY; int am = 0x7fffffff;
+    for (int j = lane; j < ncls; j += 32) { const float v = x[j]; if (v > mx) { mx = v; am = j; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oam = __shfl_xor_sync(0xffffffffu, am, o);
+      if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
     }
-    __syncthreads();
+    if (lane == 0) { l += (double)losses[row]; n += 1; c += (am == (int)labels[row]); }
   }
+  if (lane == 0) { s_l[warp] = l; s_c[warp] = c; s_n[warp] = n; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const float cnt = s_cnt[0];
-    stats[0] = cnt > 0.f ? s_loss[0] / cnt : 0.f;
-    stats[1] = s_corr[0] / cnt;
-    stats[2] = cnt;
+    double tl = 0.0; unsigned tc = 0, tn = 0;
+    for (int w = 0; w < 8; w++) { tl += s_l[w]; tc += s_c[w]; tn += s_n[w]; }
+    partial[(size_t)blockIdx.x * 3 + 0] = tl;
+    partial[(size_t)blockIdx.x * 3 + 1] = (double)tc;
+    partial[(size_t)blockIdx.x * 3 + 2] = (double)tn;
   }
+}
+__global__ void loss_acc_stage2(int nparts, const double* __restrict__ partial, float* __restrict__ stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double tl = 0.0, tc = 0.0, tn = 0.0;
+  for (int p = 0; p < nparts; p++) { tl += partial[p * 3 + 0]; tc += partial[p * 3 + 1]; tn += partial[p * 3 + 2]; }
+  stats[0] = tn > 0.0 ? (float)(tl / tn) : 0.f;
+  stats[1] = (float)tc / (float)tn;  // accuracy_all / float(num_samples), math_functions.cpp:91
+  stats[2] = (float)tn;
 }
 
 // optimizer.cpp:22-35 — eps inside the sqrt; b1_t/b2_t are the powers BEFORE this call's post-multiply.
@@ -262,7 +270,17 @@ int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* m
 int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                              const float* losses, float* stats_d, gai_stream_t stream) {
   GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && losses && stats_d);
-  loss_acc_kernel<<<1, 1024, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, losses, stats_d);
+  size_t rows = end - begin;
+  int nparts = (int)((rows + 7) / 8);
+  const int cap = gai::sm_count() * 8;
+  if (nparts > cap) nparts = cap;
+  if (nparts < 1) nparts = 1;
+  void* ws = nullptr;
+  int rc = gai::workspace(sizeof(double) * 3 * (size_t)nparts, &ws);
+  if (rc != GAI_OK) return rc;
+  loss_acc_stage1<<<nparts, 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, losses, reinterpret_cast<double*>(ws));
+  GAI_LAUNCH_CHECK();
+  loss_acc_stage2<<<1, 32, 0, gai::S(stream)>>>(nparts, reinterpret_cast<const double*>(ws), stats_d);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

@@ -1,0 +1,160 @@
+#include "gai_graph.h"
+#include <algorithm>
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+namespace gai_host {
+static gai_stream_t g_stream = nullptr;
+gai_stream_t stream() { return g_stream; }
+void set_stream(gai_stream_t s) { g_stream = s; }
+void die_on(int status, const char* what) {
+  if (status == GAI_OK) return;
+  std::fprintf(stderr, "%s failed (status %d): %s\n", what, status, gai_last_error());
+  std::exit(EXIT_FAILURE);
+}
+}  // namespace gai_host
+using gai_host::die_on;
+
+void LearningGraph::allocateFrom(index_t nv, index_t ne) {
+  num_vertices_ = nv;
+  num_edges_ = ne;
+  rowptr_.assign((size_t)nv + 1, 0);
+  colidx_.assign(ne, 0);
+}
+
+void LearningGraph::add_selfloop() {
+  std::vector<index_t> rp((size_t)num_vertices_ + 1), ci((size_t)num_edges_ + num_vertices_);
+  die_on(gai_add_selfloop_h(num_vertices_, rowptr_.data(), colidx_.data(), rp.data(), ci.data()), "gai_add_selfloop_h");
+  rowptr_.swap(rp);
+  colidx_.swap(ci);
+  num_edges_ += num_vertices_;
+}
+
+void LearningGraph::degree_counting() {
+  max_degree = 0;
+  for (index_t v = 0; v < num_vertices_; v++) max_degree = std::max(max_degree, rowptr_[v + 1] - rowptr_[v]);
+}
+
+LearningGraph* LearningGraph::generate_masked_graph(mask_t* masks) {
+  // keep vertex ids, keep only edges whose two endpoints are in the mask (lgraph.h:231-272)
+  LearningGraph* mg = new LearningGraph(is_device);
+  std::vector<index_t> rp((size_t)num_vertices_ + 1, 0);
+  for (index_t v = 0; v < num_vertices_; v++) {
+    index_t d = 0;
+    if (masks[v] == 1)
+      for (index_t e = rowptr_[v]; e < rowptr_[v + 1]; e++) d += masks[colidx_[e]] == 1;
+    rp[v + 1] = rp[v] + d;
+  }
+  mg->allocateFrom(num_vertices_, rp[num_vertices_]);
+  for (index_t v = 0; v < num_vertices_; v++) {
+    mg->fixEndEdge(v, rp[v + 1]);
+    if (masks[v] != 1) continue;
+    index_t k = rp[v];
+    for (index_t e = rowptr_[v]; e < rowptr_[v + 1]; e++)
+      if (masks[colidx_[e]] == 1) mg->constructEdge(k++, colidx_[e]);
+  }
+  std::cout << "masked graph: num_vertices = " << mg->size() << ", num_edges = " << mg->sizeEdges() << "\n";
+  return mg;
+}
+
+void LearningGraph::alloc_on_device() {}
+void LearningGraph::alloc_on_device(index_t) {}
+
+void LearningGraph::copy_to_gpu() {
+  if (dev_) { gai_csr_destroy(dev_); dev_ = nullptr; }
+  die_on(gai_csr_create(num_vertices_, num_edges_, rowptr_.data(), colidx_.data(), gai_host::stream(), &dev_), "gai_csr_create");
+}
+
+void LearningGraph::compute_vertex_data() {
+  if (!dev_) copy_to_gpu();  // norms are produced together with the device CSR
+}
+void LearningGraph::compute_edge_data() { compute_vertex_data(); }
+
+void LearningGraph::dealloc() {
+  if (dev_) { gai_csr_destroy(dev_); dev_ = nullptr; }
+  rowptr_.clear(); rowptr_.shrink_to_fit();
+  colidx_.clear(); colidx_.shrink_to_fit();
+}
+
+// ---- Reader -------------------------------------------------------------------------------------------------------
+
+static const char* kDatasets[] = {"cora", "citeseer", "ppi", "pubmed", "flickr", "yelp", "reddit", "amazon", "tester",
+                                  "ogbn-arxiv", "ogbn-products", "ogbn-proteins", "ogbn-papers100M"};  // include/gnn/configs.h:8-11
+
+template <typename T>
+static void read_exact(const std::string& fname, T* dst, size_t count) {
+  std::ifstream in(fname.c_str(), std::ios::binary);
+  if (!in.good()) { std::cerr << "Failed to open file: " << fname << "\n"; std::exit(1); }
+  in.read(reinterpret_cast<char*>(dst), sizeof(T) * count);
+}
+
+void Reader::bin_read_graph(LearningGraph* g) {
+  const char* root = std::getenv("DATASET_PATH");
+  if (!root) { std::cerr << "DATASET_PATH is not set\n"; std::exit(1); }
+  inputfile_path = std::string(root) + dataset_str + "/";
+  std::cout << "input file path: " << inputfile_path << ", graph name: " << dataset_str << "\n";
+  std::ifstream meta((inputfile_path + "graph.meta.txt").c_str());
+  if (!meta.good()) { std::cerr << "Failed to open file: " << inputfile_path << "graph.meta.txt\n"; std::exit(1); }
+  int vid_size = 0, eid_size = 0, vlabel_size = 0, elabel_size = 0, max_degree = 0;
+  int64_t nv = 0, ne = 0;
+  meta >> nv >> ne >> vid_size >> eid_size >> vlabel_size >> elabel_size >> max_degree >> feat_len >> num_vertex_classes >> num_edge_classes;
+  meta >> train_begin >> train_end >> train_count >> val_begin >> val_end >> val_count >> test_begin >> test_end >> test_count;
+  assert(vid_size == 4 && eid_size == 8 && vlabel_size == 1);
+  assert(max_degree > 0 && max_degree < nv);
+  num_vertices_ = (index_t)nv;
+  num_edges_ = (index_t)ne;
+  g->allocateFrom(num_vertices_, num_edges_);
+  std::vector<int64_t> rows((size_t)nv + 1);
+  read_exact<int64_t>(inputfile_path + "graph.vertex.bin", rows.data(), rows.size());
+  read_exact<index_t>(inputfile_path + "graph.edge.bin", g->edge_dst_host_ptr(), num_edges_);
+  index_t* rp = g->row_start_host_ptr();
+  for (size_t i = 0; i <= (size_t)nv; i++) rp[i] = (index_t)rows[i];  // on-disk int64 -> u32 (reader.cpp:445-454)
+  g->degree_counting();
+  std::cout << "|V| " << nv << " |E| " << ne << " max_deg " << g->get_max_degree() << "\n";
+}
+
+size_t Reader::bin_read_features(std::vector<float>& feats) {
+  std::cout << "Reading features ... N x D: " << num_vertices_ << " x " << feat_len << "\n";
+  feats.resize((size_t)num_vertices_ * feat_len);
+  read_exact<float>(inputfile_path + "graph.feats.bin", feats.data(), feats.size());
+  return feat_len;
+}
+
+int Reader::bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class) {
+  assert(num_vertex_classes > 0 && num_vertex_classes < 255);
+  std::vector<vlabel_t> vl(num_vertices_);
+  std::ifstream probe((inputfile_path + "graph.vlabel.bin").c_str());
+  if (probe.good()) {
+    read_exact<vlabel_t>(inputfile_path + "graph.vlabel.bin", vl.data(), vl.size());
+  } else {
+    std::cout << "WARNING: vertex label file not exist; generating random labels\n";
+    for (auto& v : vl) v = rand() % num_vertex_classes + 1;  // reader.cpp:386-408
+  }
+  if (is_single_class) {
+    std::cout << "Using single-class (one-hot) labels\n";
+    labels.assign(vl.begin(), vl.end());
+  } else {
+    std::cout << "Using multi-class (multi-hot) labels\n";
+    labels.assign((size_t)num_vertices_ * num_vertex_classes, 0);
+    for (size_t v = 0; v < num_vertices_; v++)
+      if (vl[v] < num_vertex_classes) labels[v * num_vertex_classes + vl[v]] = 1;
+  }
+  std::cout << "maximum vertex label: " << unsigned(*std::max_element(vl.begin(), vl.end())) << "\n";
+  return num_vertex_classes;
+}
+
+size_t Reader::bin_read_masks(std::string mask_type, size_t n, size_t& begin, size_t& end, mask_t*) {
+  bool known = false;
+  for (const char* d : kDatasets) known = known || dataset_str == d;
+  if (!known) { std::cout << "Dataset currently not supported\n"; std::exit(1); }
+  size_t count;
+  if (mask_type == "train") { begin = train_begin; end = train_end; count = train_count; }
+  else if (mask_type == "val") { begin = val_begin; end = val_end; count = val_count; }
+  else { begin = test_begin; end = test_end; count = test_count; }
+  std::cout << mask_type << "_mask range: [" << begin << ", " << end << ") Number of valid samples: " << count << " ("
+            << (float)count / (float)n * 100.0f << "%)\n";
+  return count;  // the .masks.bin files are not read: ranges come from the meta file (reader.cpp:272-316)
+}

@@ -1,0 +1,99 @@
+// Host-side mirror of the reference's graph + loader API for the GNN path, over the C ABI (include/gai_b200.h).
+//
+//   LearningGraph  <- include/gnn/lgraph.h:20-273   (host CSR; the device side is one gai_csr_t handle instead of the
+//                                                     d_rowptr_/d_colidx_/d_vertex_data_/d_edge_data_ pointer set)
+//   Reader         <- include/gnn/reader.h:4-40, src/gnn/reader.cpp:248-457 (graph.meta.txt / .vertex.bin / .edge.bin /
+//                                                     .feats.bin / .vlabel.bin; DATASET_PATH; dataset whitelist)
+// Same names, argument meaning and error behaviour (exit(1) on missing files / unknown dataset, exit(EXIT_FAILURE) on
+// device errors) so that reference-side callers compile against it unchanged.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "gai_b200.h"
+
+namespace gai_host {
+void die_on(int status, const char* what);  // prints gai_last_error() and exits: the reference's CUDA_CHECK contract
+gai_stream_t stream();                      // the stream every host-class call is issued on
+void set_stream(gai_stream_t s);
+}  // namespace gai_host
+
+typedef uint32_t index_t;
+typedef uint8_t label_t;
+typedef uint8_t mask_t;
+typedef uint8_t vlabel_t;
+typedef float vdata_t;
+typedef float edata_t;
+typedef float acc_t;
+typedef std::vector<float> vec_t;
+
+class LearningGraph {
+ public:
+  typedef size_t iterator;
+  explicit LearningGraph(bool use_gpu = true) : is_device(use_gpu) {}
+
+  // construction (host)
+  void allocateFrom(index_t nv, index_t ne);
+  void fixEndEdge(index_t vid, index_t row_end) { rowptr_[vid + 1] = row_end; }
+  void constructEdge(index_t eid, index_t dst) { colidx_[eid] = dst; }
+  void add_selfloop();
+  void degree_counting();
+  LearningGraph* generate_masked_graph(mask_t* masks);
+
+  // device residency
+  void alloc_on_device();            // kept for API parity; allocation happens in copy_to_gpu
+  void alloc_on_device(index_t n);
+  void copy_to_gpu();                // uploads the CSR and builds norms / hub list / (lazily) the transpose permutation
+  void compute_vertex_data();        // 1/sqrt(deg): done on the device inside copy_to_gpu; this re-derives it if the CSR changed
+  void compute_edge_data();          // per-edge norms are never materialised (computed on the fly from vertex norms)
+  void dealloc();
+
+  size_t size() const { return num_vertices_; }
+  size_t sizeEdges() const { return num_edges_; }
+  bool on_device() const { return is_device; }
+  index_t get_max_degree() const { return max_degree; }
+  index_t get_degree(index_t v) const { return rowptr_[v + 1] - rowptr_[v]; }
+  iterator begin() const { return 0; }
+  iterator end() const { return num_vertices_; }
+
+  // host accessors (lgraph.h:116-122)
+  index_t* row_start_host_ptr() { return rowptr_.data(); }
+  index_t* edge_dst_host_ptr() { return colidx_.data(); }
+  index_t getEdgeDstHost(index_t eid) const { return colidx_[eid]; }
+  index_t edge_begin_host(index_t vid) const { return rowptr_[vid]; }
+  index_t edge_end_host(index_t vid) const { return rowptr_[vid + 1]; }
+
+  // device accessors (lgraph.h:173-181)
+  const index_t* row_start_ptr() const { return gai_csr_rowptr(dev_); }
+  const index_t* edge_dst_ptr() const { return gai_csr_colidx(dev_); }
+  const vdata_t* vertex_data_ptr() const { return gai_csr_vertex_norm(dev_); }
+  gai_csr_t device() const { return dev_; }
+
+ private:
+  bool is_device;
+  index_t num_vertices_ = 0, num_edges_ = 0, max_degree = 0;
+  std::vector<index_t> rowptr_, colidx_;
+  gai_csr_t dev_ = nullptr;
+};
+
+typedef LearningGraph Graph;
+
+class Reader {
+ public:
+  Reader() {}
+  explicit Reader(std::string dataset) : dataset_str(dataset) {}
+  void init(std::string dataset) { dataset_str = dataset; }
+
+  void bin_read_graph(LearningGraph* g);
+  size_t bin_read_features(std::vector<float>& feats);
+  int bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class = true);
+  size_t bin_read_masks(std::string mask_type, size_t n, size_t& begin, size_t& end, mask_t* masks);
+
+ private:
+  std::string dataset_str, inputfile_path;
+  index_t feat_len = 0, num_vertices_ = 0, num_edges_ = 0;
+  int num_vertex_classes = 0, num_edge_classes = 0;
+  int train_begin = 0, train_end = 0, train_count = 0;
+  int val_begin = 0, val_end = 0, val_count = 0;
+  int test_begin = 0, test_end = 0, test_count = 0;
+};

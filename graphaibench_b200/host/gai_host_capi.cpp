@@ -1,0 +1,97 @@
+// C handles over the host classes, for ctypes callers (tests, bench.py). Not part of the reference boundary: the
+// reference-facing surface is the C++ API in gai_graph.h / gai_layers.h / gai_model.h.
+#include <cstring>
+#include "gai_model.h"
+
+namespace {
+struct ModelBase {
+  virtual ~ModelBase() {}
+  virtual float train_epoch(float* loss) = 0;
+  virtual float forward(float* loss) = 0;
+  virtual void backward() = 0;
+  virtual void update() = 0;
+  virtual float evaluate(const char* which) = 0;
+  virtual void refresh(const float* feats) = 0;
+  virtual float* tensor(const char* name, int layer, size_t* n) = 0;
+};
+template <typename L>
+struct Box : ModelBase {
+  Model<L> m;
+  float train_epoch(float* loss) override { return m.train_epoch(*loss); }
+  float forward(float* loss) override { m.set_netphases(net_phase::TRAIN); return m.forward_prop(*loss); }
+  void backward() override { m.backward_prop(); }
+  void update() override { m.update_weights(m.shared_optimizer()); }
+  float evaluate(const char* which) override { return m.evaluate(which); }
+  void refresh(const float* feats) override { m.refresh_inputs_from_host(feats); }
+  float* extra(GCN_layer&, const std::string&, size_t*) { return nullptr; }
+  float* extra(SAGE_layer&, const std::string&, size_t*) { return nullptr; }
+  float* extra(GAT_layer& y, const std::string& name, size_t* n) {
+    GAT_Aggregator& a = y.aggregator_ref();
+    *n = y.get_dim_out();
+    if (name == "alpha_l") return a.d_alpha_l;
+    if (name == "alpha_r") return a.d_alpha_r;
+    if (name == "alpha_lgrad") return a.d_alpha_lgrad;
+    if (name == "alpha_rgrad") return a.d_alpha_rgrad;
+    return nullptr;
+  }
+  float* tensor(const char* name_, int l, size_t* n) override {
+    std::string name(name_);
+    if (name == "logits") { *n = m.nv() * 0; }
+    if (name == "dense_W" && m.dense()) { *n = (size_t)m.dense()->dim_in * m.dense()->dim_out; return m.dense()->d_weight; }
+    if (name == "dense_W_grad" && m.dense()) { *n = (size_t)m.dense()->dim_in * m.dense()->dim_out; return m.dense()->d_weight_grad; }
+    if (l < 0 || l >= m.num_conv_layers()) return nullptr;
+    L& y = m.conv_layer(l);
+    float* p = y.weight_ptr(name);
+    if (p) { *n = y.weight_size(name); return p; }
+    return extra(y, name, n);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+void gai_host_set_stream(void* s) { gai_host::set_stream(s); }
+
+void* gai_graph_new(uint32_t nv, uint32_t ne, const uint32_t* rowptr, const uint32_t* colidx) {
+  Graph* g = new Graph(true);
+  g->allocateFrom(nv, ne);
+  for (uint32_t v = 0; v < nv; v++) g->fixEndEdge(v, rowptr[v + 1]);
+  memcpy(g->edge_dst_host_ptr(), colidx, sizeof(uint32_t) * ne);
+  return g;
+}
+
+// arch: 0 GCN, 1 SAGE, 2 GAT. Takes ownership of the graph (self-loops are added inside, as Model::load_data does).
+void* gai_model_new(int arch, void* graph, int dim_init, int dim_hid, int num_cls, int num_layers, float lr, const float* feats_h,
+                    const uint8_t* labels_h, const int64_t* split9) {
+  Graph* g = (Graph*)graph;
+  if (arch == 0) { auto* b = new Box<GCN_layer>(); b->m.init_from_memory(gnn_arch::GCN, g, dim_init, num_cls, feats_h, labels_h, split9, dim_hid, num_layers, lr, 0, 1 << 30); b->m.construct_network(); return (ModelBase*)b; }
+  if (arch == 1) { auto* b = new Box<SAGE_layer>(); b->m.init_from_memory(gnn_arch::SAGE, g, dim_init, num_cls, feats_h, labels_h, split9, dim_hid, num_layers, lr, 0, 1 << 30); b->m.construct_network(); return (ModelBase*)b; }
+  if (arch == 2) { auto* b = new Box<GAT_layer>(); b->m.init_from_memory(gnn_arch::GAT, g, dim_init, num_cls, feats_h, labels_h, split9, dim_hid, num_layers, lr, 0, 1 << 30); b->m.construct_network(); return (ModelBase*)b; }
+  return nullptr;
+}
+float gai_model_train_epoch(void* m, float* loss) { return ((ModelBase*)m)->train_epoch(loss); }
+float gai_model_forward(void* m, float* loss) { return ((ModelBase*)m)->forward(loss); }
+void gai_model_backward(void* m) { ((ModelBase*)m)->backward(); }
+void gai_model_update(void* m) { ((ModelBase*)m)->update(); }
+float gai_model_evaluate(void* m, const char* which) { return ((ModelBase*)m)->evaluate(which); }
+void gai_model_refresh_inputs(void* m, const float* feats_h) { ((ModelBase*)m)->refresh(feats_h); }
+int64_t gai_model_tensor_size(void* m, const char* name, int layer) {
+  size_t n = 0;
+  return ((ModelBase*)m)->tensor(name, layer, &n) ? (int64_t)n : -1;
+}
+int64_t gai_model_get(void* m, const char* name, int layer, float* out_h, int64_t cap) {
+  size_t n = 0;
+  float* p = ((ModelBase*)m)->tensor(name, layer, &n);
+  if (!p || (int64_t)n > cap) return -1;
+  copy_float_to_host(n, p, out_h);
+  return (int64_t)n;
+}
+int64_t gai_model_set(void* m, const char* name, int layer, const float* in_h, int64_t n_in) {
+  size_t n = 0;
+  float* p = ((ModelBase*)m)->tensor(name, layer, &n);
+  if (!p || (int64_t)n != n_in) return -1;
+  copy_float_to_device(n, in_h, p);
+  return (int64_t)n;
+}
+void gai_model_sync() { gai_stream_sync(gai_host::stream()); }
+}

@@ -1,0 +1,326 @@
+#include "gai_layers.h"
+#include <cassert>
+#include <cmath>
+#include <cstdlib>
+#include <random>
+#include <type_traits>
+
+using gai_host::die_on;
+using gai_host::stream;
+
+// ---- helpers ------------------------------------------------------------------------------------------------------
+
+void init_glorot(size_t dim_x, size_t dim_y, vec_t& weight, unsigned seed) {
+  // Glorot & Bengio uniform(-r, r), r = sqrt(6/(fan_in+fan_out)); one draw per weight, row-major, from the C++ standard
+  // library's default engine seeded with `seed` — the generator the reference uses on the host (math_functions.cpp:11-19),
+  // so identical toolchains give identical initial weights. Never initialised on the device (cuRAND would differ).
+  const float r = (float)std::sqrt(6.0 / (double)(dim_x + dim_y));
+  std::default_random_engine engine(seed);
+  std::uniform_real_distribution<float> uniform(-r, r);
+  weight.resize(dim_x * dim_y);
+  for (size_t i = 0; i < dim_x * dim_y; i++) weight[i] = uniform(engine);
+}
+
+float* float_malloc_device_zero(size_t n) {
+  void* p = nullptr;
+  die_on(gai_malloc(&p, sizeof(float) * (n ? n : 1)), "gai_malloc");
+  die_on(gai_memset(p, 0, sizeof(float) * (n ? n : 1), stream()), "gai_memset");
+  return reinterpret_cast<float*>(p);
+}
+void copy_float_to_device(size_t n, const float* src_h, float* dst_d) {
+  die_on(gai_memcpy_h2d(dst_d, src_h, sizeof(float) * n, stream()), "gai_memcpy_h2d");
+  die_on(gai_stream_sync(stream()), "gai_stream_sync");
+}
+void copy_float_to_host(size_t n, const float* src_d, float* dst_h) {
+  die_on(gai_memcpy_d2h(dst_h, src_d, sizeof(float) * n, stream()), "gai_memcpy_d2h");
+  die_on(gai_stream_sync(stream()), "gai_stream_sync");
+}
+static float* upload_glorot(size_t dx, size_t dy, unsigned seed) {
+  vec_t w;
+  init_glorot(dx, dy, w, seed);
+  float* d = float_malloc_device_zero(dx * dy);
+  copy_float_to_device(dx * dy, w.data(), d);
+  return d;
+}
+static void mm(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, bool ta = false, bool tb = false, bool accum = false,
+               int flags = 0) {
+  die_on(gai_matmul(x, y, z, A, B, C, ta, tb, accum, flags, stream()), "gai_matmul");
+}
+
+// ---- adam ---------------------------------------------------------------------------------------------------------
+
+void adam::update_gpu(const size_t n, const float* dW, float* W) {
+  auto it = moments.find(W);
+  if (it == moments.end()) it = moments.emplace(W, std::make_pair(float_malloc_device_zero(n), float_malloc_device_zero(n))).first;
+  die_on(gai_adam_update(n, dW, W, it->second.first, it->second.second, alpha, b1, b2, b1_t, b2_t, eps, stream()), "gai_adam_update");
+  b1_t *= b1;
+  b2_t *= b2;
+}
+void adam::reset() {
+  for (auto& kv : moments) { gai_free(kv.second.first); gai_free(kv.second.second); }
+  moments.clear();
+}
+
+// ---- aggregators --------------------------------------------------------------------------------------------------
+
+void GCN_Aggregator::init(int len, int, int, float, float) { length = len; }
+void GCN_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+  die_on(gai_spmm_gcn(g.device(), len, in, len, out, len, flags, addend, stream()), "gai_spmm_gcn");
+}
+void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
+// the normalised adjacency is symmetric, so the derivative is the same product (gcn_aggregator.cpp:35-46)
+void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) { aggregate(len, g, grad_in, grad_out); }
+
+void SAGE_Aggregator::init(int len, int, int, float, float) { length = len; }
+void SAGE_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+  die_on(gai_spmm_mean(g.device(), len, in, len, out, len, 0, flags, addend, stream()), "gai_spmm_mean");
+}
+void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
+void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {
+  die_on(gai_spmm_mean(g.device(), len, grad_in, len, grad_out, len, 1, GAI_EPI_NONE, nullptr, stream()), "gai_spmm_mean(T)");
+}
+
+void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
+  length = len;
+  attn_drop = drop_rate;
+  assert(attn_drop >= 0.f && attn_drop < 1.f);
+  if (attn_drop > 0.f) { std::cerr << "attention dropout is not supported (all reference configs run 0)\n"; std::exit(1); }
+  d_alpha_l = upload_glorot(len, 1, 2);  // seeds 2 / 3: gat_aggregator.cpp:11-12
+  d_alpha_r = upload_glorot(len, 1, 3);
+  d_alpha_lgrad = float_malloc_device_zero(len);
+  d_alpha_rgrad = float_malloc_device_zero(len);
+  d_temp_scores = float_malloc_device_zero(ne);
+  d_norm_scores = float_malloc_device_zero(ne);
+  d_scores_grad = float_malloc_device_zero(ne);
+  alpha_opt = new adam(lr);
+}
+void GAT_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float*) {
+  die_on(gai_gat_forward(g.device(), len, in, d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out, flags, stream()), "gai_gat_forward");
+}
+void GAT_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
+void GAT_Aggregator::d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out) {
+  die_on(gai_gat_backward(g.device(), len, feat_in, grad_in, epsilon, d_temp_scores, d_norm_scores, d_scores_grad, d_alpha_lgrad, d_alpha_rgrad,
+                          grad_out, stream()), "gai_gat_backward");
+}
+void GAT_Aggregator::update_weights(optimizer*) {  // own optimiser, two calls (gat_aggregator.cpp:202-205)
+  alpha_opt->update_gpu(length, d_alpha_lgrad, d_alpha_l);
+  alpha_opt->update_gpu(length, d_alpha_rgrad, d_alpha_r);
+}
+
+// ---- graph_conv_layer ---------------------------------------------------------------------------------------------
+
+template <typename A>
+graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* g, bool act, bool concat, float lr, float feat_drop, float score_drop)
+    : level_(id), num_samples(nv), dim_in(din), dim_out(dout), graph(g), is_act(act), is_bias(false), use_concat(concat),
+      feat_dropout_rate(feat_drop), score_dropout_rate(score_drop) {
+  assert(feat_dropout_rate >= 0.f && feat_dropout_rate < 1.f);
+  assert(score_dropout_rate >= 0.f && score_dropout_rate < 1.f);
+  if (feat_dropout_rate > 0.f) { std::cerr << "feature dropout is not supported yet (all reference configs run 0)\n"; std::exit(1); }
+  feat_scale = 1.f / (1.f - feat_dropout_rate);
+  const size_t n = (size_t)nv;
+  d_W_neigh = upload_glorot(din, dout, 1);  // seeds: graph_conv_layer.cpp:13,18
+  d_W_neigh_grad = float_malloc_device_zero((size_t)din * dout);
+  if (concat) {
+    d_W_self = upload_glorot(din, dout, 2);
+    d_W_self_grad = float_malloc_device_zero((size_t)din * dout);
+  }
+  // temporaries: only what this layer's schedule touches (the reference allocates all of them unconditionally)
+  const bool transform_first = din > dout || std::is_same<A, GAT_Aggregator>::value;  // GAT always transforms first
+  if (transform_first) d_out_temp = float_malloc_device_zero(n * dout);
+  if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * din);
+  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * din);
+  if (id > 0) feat_in = float_malloc_device_zero(n * din);
+  grad_in = float_malloc_device_zero(n * dout);
+  optm = new adam(lr);
+}
+
+template <typename A>
+float* graph_conv_layer<A>::weight_ptr(const std::string& name) {
+  if (name == "W") return d_W_neigh;
+  if (name == "W_grad") return d_W_neigh_grad;
+  if (name == "W_self") return d_W_self;
+  if (name == "W_self_grad") return d_W_self_grad;
+  if (name == "feat_in") return feat_in;
+  if (name == "grad_in") return grad_in;
+  if (name == "out_temp") return d_out_temp;
+  if (name == "in_temp1") return d_in_temp1;
+  return nullptr;
+}
+template <typename A>
+size_t graph_conv_layer<A>::weight_size(const std::string& name) {
+  if (name == "W" || name == "W_grad") return (size_t)dim_in * dim_out;
+  if (name == "W_self" || name == "W_self_grad") return use_concat ? (size_t)dim_in * dim_out : 0;
+  if (name == "feat_in" || name == "in_temp1") return (size_t)num_samples * dim_in;
+  if (name == "grad_in" || name == "out_temp") return (size_t)num_samples * dim_out;
+  return 0;
+}
+template class graph_conv_layer<GCN_Aggregator>;
+template class graph_conv_layer<SAGE_Aggregator>;
+template class graph_conv_layer<GAT_Aggregator>;
+
+// ---- GCN ----------------------------------------------------------------------------------------------------------
+
+GCN_layer::GCN_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float fd, float sd)
+    : graph_conv_layer(id, nv, din, dout, g, act, false, lr, fd, sd) {
+  aggr.init(din < dout ? din : dout, nv);
+}
+
+void GCN_layer::forward(float* feat_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
+  if (y > z) {  // transform first: aggregate at the narrower width; ReLU rides the SpMM epilogue
+    mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
+    aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, relu, nullptr);
+  } else {      // aggregate first; ReLU rides the GEMM epilogue
+    aggr.aggregate((int)y, *graph, feat_in, d_in_temp1);
+    mm(x, z, y, d_in_temp1, d_W_neigh, feat_out, false, false, false, relu);
+  }
+}
+
+void GCN_layer::backward(float* feat_out, float* grad_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  if (y > z) {
+    aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
+    if (level_ > 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
+    mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+  } else {
+    if (level_ > 0) {
+      mm(x, y, z, grad_in, d_W_neigh, d_in_temp, false, true);
+      aggr.d_aggregate((int)y, *graph, nullptr, d_in_temp, grad_out);
+    }
+    mm(y, z, x, d_in_temp1, grad_in, d_W_neigh_grad, true, false);
+  }
+}
+
+void GCN_layer::update_weight(optimizer* opt) { opt->update_gpu((size_t)dim_in * dim_out, d_W_neigh_grad, d_W_neigh); }  // shared optimiser (gcn_layer.cpp:62-66)
+
+// ---- SAGE ---------------------------------------------------------------------------------------------------------
+
+SAGE_layer::SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float fd, float sd)
+    : graph_conv_layer(id, nv, din, dout, g, act, true, lr, fd, sd) {
+  aggr.init(din < dout ? din : dout, nv);
+}
+
+void SAGE_layer::forward(float* feat_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
+  if (y > z) {
+    // self term first, then the neighbour term is added on top inside the SpMM epilogue (+ ReLU): one pass over feat_out
+    mm(x, z, y, feat_in, d_W_self, feat_out);
+    mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
+    aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, GAI_EPI_ADD | relu, feat_out);
+  } else {
+    aggr.aggregate((int)y, *graph, feat_in, d_in_temp1);
+    mm(x, z, y, d_in_temp1, d_W_neigh, feat_out);
+    mm(x, z, y, feat_in, d_W_self, feat_out, false, false, true, relu);  // accumulate (beta = 1, sage_layer.cpp:22) + ReLU epilogue
+  }
+}
+
+void SAGE_layer::backward(float* feat_out, float* grad_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  mm(y, z, x, feat_in, grad_in, d_W_self_grad, true, false);
+  if (y > z) {
+    aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
+    if (level_ > 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
+    mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+  } else {
+    if (level_ > 0) {
+      mm(x, y, z, grad_in, d_W_neigh, d_in_temp, false, true);
+      aggr.d_aggregate((int)y, *graph, nullptr, d_in_temp, grad_out);
+    }
+    mm(y, z, x, d_in_temp1, grad_in, d_W_neigh_grad, true, false);
+  }
+  if (level_ > 0) mm(x, y, z, grad_in, d_W_self, grad_out, false, true, true);
+}
+
+void SAGE_layer::update_weight(optimizer*) {  // the layer's own optimiser, neighbour then self (sage_layer.cpp:55-59)
+  optm->update_gpu((size_t)dim_in * dim_out, d_W_neigh_grad, d_W_neigh);
+  optm->update_gpu((size_t)dim_in * dim_out, d_W_self_grad, d_W_self);
+}
+
+// ---- GAT ----------------------------------------------------------------------------------------------------------
+
+GAT_layer::GAT_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float fd, float sd)
+    : graph_conv_layer(id, nv, din, dout, g, act, false, lr, fd, sd) {
+  aggr.init(dout, nv, (int)g->sizeEdges(), lr, sd);
+}
+
+void GAT_layer::forward(float* feat_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
+  aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, is_act ? GAI_EPI_RELU : GAI_EPI_NONE, nullptr);
+}
+
+void GAT_layer::backward(float* feat_out, float* grad_out) {
+  const size_t x = num_samples, y = dim_in, z = dim_out;
+  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  aggr.d_aggregate((int)z, *graph, d_out_temp, grad_in, d_out_temp);  // dZ overwrites Z (gat_layer.cpp:33-36)
+  if (level_ != 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
+  mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+}
+
+void GAT_layer::update_weight(optimizer* opt) {
+  opt->update_gpu((size_t)dim_in * dim_out, d_W_neigh_grad, d_W_neigh);
+  aggr.update_weights(opt);
+}
+
+// ---- l2norm / dense / loss ------------------------------------------------------------------------------------------
+
+l2norm_layer::l2norm_layer(int nv, int len) : num_samples(nv), dim(len) {
+  feat_in = float_malloc_device_zero((size_t)nv * len);
+  grad_in = float_malloc_device_zero((size_t)nv * len);
+}
+void l2norm_layer::forward(float* feat_out) { die_on(gai_l2norm(num_samples, dim, feat_in, feat_out, stream()), "gai_l2norm"); }
+void l2norm_layer::backward(float* grad_out) { die_on(gai_d_l2norm(num_samples, dim, feat_in, grad_in, grad_out, stream()), "gai_d_l2norm"); }
+
+dense_layer::dense_layer(int nv, int in_len, int out_len, float lr) : dim_in(in_len), dim_out(out_len), num_samples(nv) {
+  feat_in = float_malloc_device_zero((size_t)nv * in_len);
+  grad_in = float_malloc_device_zero((size_t)nv * out_len);
+  d_weight = upload_glorot(in_len, out_len, 1);  // dense_layer.cpp:33
+  d_weight_grad = float_malloc_device_zero((size_t)in_len * out_len);
+  optm = new adam(lr);
+}
+void dense_layer::forward(float* feat_out) { mm(num_samples, dim_out, dim_in, feat_in, d_weight, feat_out); }
+void dense_layer::backward(float* grad_out) {
+  mm(dim_in, dim_out, num_samples, feat_in, grad_in, d_weight_grad, true, false);
+  mm(num_samples, dim_in, dim_out, grad_in, d_weight, grad_out, false, true);
+  optm->update_gpu((size_t)dim_in * dim_out, d_weight_grad, d_weight);
+}
+
+loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cls(ncls), labels(ptr) {
+  feat_in = float_malloc_device_zero((size_t)nv * ncls);
+  feat_out = float_malloc_device_zero((size_t)nv * ncls);
+  d_losses = float_malloc_device_zero(nv);
+  d_stats = float_malloc_device_zero(4);
+}
+
+void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
+  die_on(gai_softmax_ce_forward(num_cls, begin, end, masks, labels, feat_in, feat_out, d_losses, stream()), "gai_softmax_ce_forward");
+}
+void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
+  die_on(gai_softmax_ce_backward(num_cls, begin, end, masks, labels, feat_out, grad_out, stream()), "gai_softmax_ce_backward");
+}
+acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
+  die_on(gai_masked_loss_accuracy(num_cls, begin, end, masks, labels, feat_in, d_losses, d_stats, stream()), "gai_masked_loss_accuracy");
+  float h[3] = {0, 0, 0};
+  copy_float_to_host(3, d_stats, h);
+  (void)count;  // the reference asserts masked-row count == count; the count comes back as a float here
+  last_acc = h[1];
+  return h[0];
+}
+
+float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
+  static float* scratch = nullptr;
+  static size_t scratch_n = 0;
+  if (scratch_n < (size_t)end + 4) {
+    if (scratch) gai_free(scratch);
+    scratch_n = (size_t)end + 4;
+    scratch = float_malloc_device_zero(scratch_n);
+  }
+  die_on(gai_masked_loss_accuracy(num_classes, begin, end, masks, ground_truth, preds, scratch, scratch + end, stream()), "gai_masked_loss_accuracy");
+  float h[3];
+  copy_float_to_host(3, scratch + end, h);
+  return h[1];
+}

@@ -1,0 +1,213 @@
+// Host-side mirror of the reference's aggregator / layer / loss / optimizer classes over the C ABI.
+//
+//   optimizer, adam                      <- include/utils/optimizer.h:23-116, src/utilities/optimizer.{cpp,cu}
+//   GCN_/SAGE_/GAT_Aggregator            <- include/gnn/aggregator.h:8-88, src/gnn/gconv/*_aggregator.{cpp,cu}
+//   graph_conv_layer<A>, GCN_/SAGE_/GAT_layer <- include/layers/graph_conv_layer.h:6-106, src/gnn/gconv/*_layer.{cpp,cu}
+//   loss_layer, softmax_loss_layer       <- include/gnn/loss_layer.h:5-31, src/layers/softmax_loss_layer.{cpp,cu}
+//   dense_layer, l2norm_layer            <- include/layers/{dense,l2norm}_layer.h, src/layers/*.cpp
+//
+// All float* members and arguments are DEVICE pointers (as in the reference's GPU object set). Ownership follows the
+// reference: a layer owns grad_in, its temporaries, weights and (level > 0) feat_in; forward(feat_out) writes into a
+// buffer owned by the next layer. What differs is the schedule underneath: ReLU / "+self term" run as SpMM or GEMM
+// epilogues, no per-launch device sync, no per-call allocations.
+#pragma once
+#include <iostream>
+#include <unordered_map>
+#include "gai_graph.h"
+
+enum class net_phase { TRAIN, TEST, VAL };
+enum class gnn_arch { GCN, GAT, SAGE, GGNN };
+
+void init_glorot(size_t dim_x, size_t dim_y, vec_t& weight, unsigned seed);  // math_functions.cpp:11-19, host only
+float* float_malloc_device_zero(size_t n);                                   // float_malloc_device + init_const_gpu(0)
+void copy_float_to_device(size_t n, const float* src_h, float* dst_d);
+void copy_float_to_host(size_t n, const float* src_d, float* dst_h);
+
+// ---- optimizers ---------------------------------------------------------------------------------------------------
+struct optimizer {
+  virtual ~optimizer() {}
+  virtual void update_gpu(const size_t n, const float* dW, float* W) = 0;
+  virtual void reset() {}
+};
+
+// Adam with the reference's quirks: eps inside the sqrt, b1_t/b2_t advance once per update call on this object, first and
+// second moments keyed by the address of W (optimizer.h:47-53, optimizer.cpp:22-35).
+struct adam : public optimizer {
+  explicit adam(float lr = 0.01f) : alpha(lr), b1(0.9f), b2(0.999f), b1_t(0.9f), b2_t(0.999f), eps(1e-8f) {}
+  void update_gpu(const size_t n, const float* dW, float* W) override;
+  void reset() override;
+  float alpha, b1, b2, b1_t, b2_t;
+
+ private:
+  float eps;
+  std::unordered_map<const float*, std::pair<float*, float*>> moments;
+};
+
+// ---- aggregators --------------------------------------------------------------------------------------------------
+class aggregator {
+ public:
+  void set_vlen(int vlen) { length = vlen; }
+
+ protected:
+  int length = 0;
+};
+
+class GCN_Aggregator : public aggregator {
+ public:
+  void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
+  void aggregate(int len, Graph& g, const float* in, float* out);
+  void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
+  void aggregate_fused(int len, Graph& g, const float* in, float* out, int epilogue_flags, const float* addend);
+};
+
+class SAGE_Aggregator : public aggregator {
+ public:
+  void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
+  void aggregate(int len, Graph& g, const float* in, float* out);
+  void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
+  void aggregate_fused(int len, Graph& g, const float* in, float* out, int epilogue_flags, const float* addend);
+};
+
+class GAT_Aggregator : public aggregator {
+ public:
+  void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
+  void aggregate(int len, Graph& g, const float* in, float* out);
+  void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
+  void aggregate_fused(int len, Graph& g, const float* in, float* out, int epilogue_flags, const float* addend);
+  void update_weights(optimizer* opt);
+  float *d_alpha_l = nullptr, *d_alpha_r = nullptr, *d_alpha_lgrad = nullptr, *d_alpha_rgrad = nullptr;
+  float *d_temp_scores = nullptr, *d_norm_scores = nullptr, *d_scores_grad = nullptr;
+
+ private:
+  float epsilon = 0.2f;  // LeakyReLU slope (gat_aggregator.cpp:22)
+  float attn_drop = 0.f;
+  optimizer* alpha_opt = nullptr;
+};
+
+// ---- graph convolution layers -------------------------------------------------------------------------------------
+template <typename Aggregator>
+class graph_conv_layer {
+ public:
+  graph_conv_layer(int id, int nv, int din, int dout, Graph* g, bool act, bool concat, float lr, float feat_drop, float score_drop);
+  float* get_feat_in() { return feat_in; }
+  float* get_grad_in() { return grad_in; }
+  void set_feat_in(float* ptr) { feat_in = ptr; }
+  void set_graph_ptr(Graph* ptr) { graph = ptr; }
+  void set_netphase(net_phase phase) { phase_ = phase; }
+  void update_dim_size(size_t sz) { num_samples = (int)sz; }
+  void print_layer_info() {
+    std::cout << "GraphConv Layer " << level_ << " with " << num_samples << " samples, dims: [" << dim_in << " x " << dim_out << "]\n";
+  }
+  // weight access for parity injection / checkpointing (host <-> device copies)
+  int get_dim_in() const { return dim_in; }
+  int get_dim_out() const { return dim_out; }
+  float* weight_ptr(const std::string& name);  // "W", "W_grad", "W_self", "W_self_grad", "alpha_l", ... (device)
+  size_t weight_size(const std::string& name);
+
+ protected:
+  int level_, num_samples, dim_in, dim_out;
+  Graph* graph;
+  bool is_act, is_bias, use_concat;
+  float feat_dropout_rate, score_dropout_rate, feat_scale;
+  net_phase phase_ = net_phase::TRAIN;
+  float *feat_in = nullptr, *grad_in = nullptr;
+  float *d_in_temp = nullptr, *d_in_temp1 = nullptr, *d_out_temp = nullptr;
+  float *d_W_neigh = nullptr, *d_W_neigh_grad = nullptr, *d_W_self = nullptr, *d_W_self_grad = nullptr;
+  optimizer* optm = nullptr;
+  Aggregator aggr;
+};
+
+class GCN_layer : public graph_conv_layer<GCN_Aggregator> {
+ public:
+  GCN_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float feat_drop_rate, float score_drop_rate);
+  void forward(float* feat_out);
+  void backward(float* feat_out, float* grad_out);
+  void update_weight(optimizer* opt);
+};
+
+class SAGE_layer : public graph_conv_layer<SAGE_Aggregator> {
+ public:
+  SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float feat_drop_rate, float score_drop_rate);
+  void forward(float* feat_out);
+  void backward(float* feat_out, float* grad_out);
+  void update_weight(optimizer* opt);
+};
+
+class GAT_layer : public graph_conv_layer<GAT_Aggregator> {
+ public:
+  GAT_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float feat_drop_rate, float score_drop_rate);
+  void forward(float* feat_out);
+  void backward(float* feat_out, float* grad_out);
+  void update_weight(optimizer* opt);
+  GAT_Aggregator& aggregator_ref() { return aggr; }
+};
+
+// ---- tail layers ----------------------------------------------------------------------------------------------------
+class l2norm_layer {
+ public:
+  l2norm_layer(int nv, int len);
+  void forward(float* feat_out);
+  void backward(float* grad_out);
+  float* get_feat_in() { return feat_in; }
+  float* get_grad_in() { return grad_in; }
+  void update_dim_size(int sz) { num_samples = sz; }
+
+ private:
+  int num_samples, dim;
+  float *feat_in, *grad_in;
+};
+
+class dense_layer {
+ public:
+  dense_layer(int nv, int in_len, int out_len, float lr);
+  void forward(float* feat_out);
+  void backward(float* grad_out);  // also applies its own Adam step (dense_layer.cpp:63-69)
+  float* get_feat_in() { return feat_in; }
+  float* get_grad_in() { return grad_in; }
+  void update_dim_size(int sz) { num_samples = sz; }
+  float *d_weight, *d_weight_grad;
+  int dim_in, dim_out;
+
+ private:
+  int num_samples;
+  float *feat_in, *grad_in;
+  optimizer* optm;
+};
+
+class loss_layer {
+ public:
+  loss_layer(int nv, int ncls, label_t* ptr);
+  virtual ~loss_layer() {}
+  float* get_feat_in() { return feat_in; }
+  float* get_feat_out() { return feat_out; }
+  virtual void forward(size_t, size_t, mask_t*) {}
+  virtual void backward(size_t, size_t, mask_t*, float*) {}
+  virtual acc_t get_prediction_loss(size_t, size_t, size_t, mask_t*) { return 0; }
+  void set_labels_ptr(label_t* ptr) { labels = ptr; }
+  void set_netphase(net_phase phase) { phase_ = phase; }
+  void update_dim_size(int sz) { num_samples = sz; }
+  void print_layer_info() { std::cout << "Output Layer with " << num_samples << " samples and " << num_cls << " classes\n"; }
+
+ protected:
+  int num_samples, num_cls;
+  net_phase phase_ = net_phase::TRAIN;
+  float *feat_in, *feat_out;
+  label_t* labels;  // device
+  float* d_losses;
+  float* d_stats;   // {mean loss, accuracy, count}
+};
+
+class softmax_loss_layer : public loss_layer {
+ public:
+  softmax_loss_layer(int nv, int ncls, label_t* ptr) : loss_layer(nv, ncls, ptr) {}
+  void forward(size_t begin, size_t end, mask_t* masks) override;
+  void backward(size_t begin, size_t end, mask_t* masks, float* grad_out) override;
+  acc_t get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) override;
+  // masked_accuracy_single (math_functions.cpp:79-92) shares the reduction pass with the loss mean
+  acc_t last_accuracy() const { return last_acc; }
+
+ private:
+  acc_t last_acc = 0;
+};
+
+float masked_accuracy_single(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);

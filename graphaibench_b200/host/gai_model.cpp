@@ -1,0 +1,228 @@
+#include "gai_model.h"
+#include <cassert>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+
+using gai_host::die_on;
+using gai_host::stream;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void sync() { die_on(gai_stream_sync(stream()), "gai_stream_sync"); }
+
+template <typename T>
+static T* upload(const T* src, size_t n) {
+  void* p = nullptr;
+  die_on(gai_malloc(&p, sizeof(T) * (n ? n : 1)), "gai_malloc");
+  die_on(gai_memcpy_h2d(p, src, sizeof(T) * n, stream()), "gai_memcpy_h2d");
+  return reinterpret_cast<T*>(p);
+}
+
+template <typename L> struct arch_of;
+template <> struct arch_of<GCN_layer> { static constexpr gnn_arch value = gnn_arch::GCN; };
+template <> struct arch_of<SAGE_layer> { static constexpr gnn_arch value = gnn_arch::SAGE; };
+template <> struct arch_of<GAT_layer> { static constexpr gnn_arch value = gnn_arch::GAT; };
+
+template <typename L>
+void Model<L>::load_data(int argc, char* argv[]) {
+  // positional arguments as the reference (net.cpp:13-64)
+  dataset_name = argv[1];
+  num_epochs = atoi(argv[2]);
+  num_threads = atoi(argv[3]);  // accepted for CLI parity; the device path has no host thread fan-out
+  is_sigmoid = std::string(argv[4]) == "sigmoid";
+  arch = arch_of<L>::value;
+  if (argc >= 6) dim_hid = atoi(argv[5]);
+  if (argc >= 7) score_drop = (float)atof(argv[6]);
+  if (argc >= 8) feat_drop = (float)atof(argv[7]);
+  if (argc >= 9) lrate = (float)atof(argv[8]);
+  if (argc > 9) {
+    assert(argc == 13);
+    num_layers = atoi(argv[9]);
+    subg_size = atoi(argv[10]);
+    val_interval = atoi(argv[11]);
+    inductive = atoi(argv[12]) != 0;
+  }
+  assert(num_layers >= 2);
+  if (is_sigmoid) { std::cerr << "sigmoid (multi-label) loss is not built yet\n"; std::exit(1); }
+  if (subg_size > 0 || inductive) { std::cerr << "subgraph sampling / inductive training is out of scope of this build\n"; std::exit(1); }
+  full_graph = new Graph(true);
+  Reader reader(dataset_name);
+  reader.bin_read_graph(full_graph);
+  num_samples = (int)full_graph->size();
+  dim_init = (int)reader.bin_read_features(input_features);
+  num_cls = reader.bin_read_vlabels(labels, !is_sigmoid);
+  if (arch != gnn_arch::SAGE) full_graph->add_selfloop();  // net.cpp:96
+  std::cout << "num_threads = " << num_threads << ", num_vertices = " << num_samples << ", num_edges = " << full_graph->sizeEdges()
+            << ", num_layers = " << num_layers << ", \nnum_epochs = " << num_epochs << ", input_length = " << dim_init
+            << ", hidden_length = " << dim_hid << ", num_classes = " << num_cls << ", \nfeat_drop = " << feat_drop
+            << ", score_drop = " << score_drop << ", subg_size = " << subg_size << ", val_interval = " << val_interval
+            << ", learning_rate = " << lrate << "\n";
+  train_count = reader.bin_read_masks("train", num_samples, train_begin, train_end, nullptr);
+  val_count = reader.bin_read_masks("val", num_samples, val_begin, val_end, nullptr);
+  test_count = reader.bin_read_masks("test", num_samples, test_begin, test_end, nullptr);
+  finish_setup();
+}
+
+template <typename L>
+void Model<L>::init_from_memory(gnn_arch a, Graph* g, int dinit, int ncls, const float* feats_h, const label_t* labels_h, const int64_t* s,
+                                int dhid, int nlayers, float lr, int epochs, int vint) {
+  assert(a == arch_of<L>::value);
+  arch = a; full_graph = g; num_samples = (int)g->size(); dim_init = dinit; num_cls = ncls; dim_hid = dhid; num_layers = nlayers;
+  lrate = lr; num_epochs = epochs; val_interval = vint;
+  input_features.assign(feats_h, feats_h + (size_t)num_samples * dinit);
+  labels.assign(labels_h, labels_h + num_samples);
+  train_begin = s[0]; train_end = s[1]; train_count = s[2];
+  val_begin = s[3]; val_end = s[4]; val_count = s[5];
+  test_begin = s[6]; test_end = s[7]; test_count = s[8];
+  if (arch != gnn_arch::SAGE) full_graph->add_selfloop();
+  finish_setup();
+}
+
+template <typename L>
+void Model<L>::finish_setup() {
+  // l2norm + dense tail for GAT (net.cpp:67-71); masks from the meta ranges (net.cpp:126-142)
+  use_l2norm = (arch == gnn_arch::GAT);
+  use_dense = use_l2norm;
+  masks_train.assign(num_samples, 0); masks_val.assign(num_samples, 0); masks_test.assign(num_samples, 0);
+  for (size_t i = train_begin; i < train_end; i++) masks_train[i] = 1;
+  for (size_t i = val_begin; i < val_end; i++) masks_val[i] = 1;
+  for (size_t i = test_begin; i < test_end; i++) masks_test[i] = 1;
+  training_graph = full_graph;
+  transfer_data_to_device();
+  training_graph->alloc_on_device();
+  training_graph->copy_to_gpu();
+  training_graph->compute_edge_data();
+}
+
+template <typename L>
+void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
+  d_input_features = upload(input_features.data(), input_features.size());
+  d_labels = upload(labels.data(), labels.size());
+  d_masks_train = upload(masks_train.data(), masks_train.size());
+  d_masks_test = upload(masks_test.data(), masks_test.size());
+  d_masks_val = upload(masks_val.data(), masks_val.size());
+  sync();
+}
+
+template <typename L>
+void Model<L>::refresh_inputs_from_host(const float* feats_h) {
+  const float* src = feats_h ? feats_h : input_features.data();
+  die_on(gai_memcpy_h2d(d_input_features, src, sizeof(float) * input_features.size(), stream()), "h2d feats");
+  die_on(gai_memcpy_h2d(d_labels, labels.data(), labels.size(), stream()), "h2d labels");
+  die_on(gai_memcpy_h2d(d_masks_train, masks_train.data(), masks_train.size(), stream()), "h2d masks");
+  die_on(gai_memcpy_h2d((void*)training_graph->row_start_ptr(), training_graph->row_start_host_ptr(), sizeof(index_t) * (training_graph->size() + 1), stream()), "h2d rowptr");
+  die_on(gai_memcpy_h2d((void*)training_graph->edge_dst_ptr(), training_graph->edge_dst_host_ptr(), sizeof(index_t) * training_graph->sizeEdges(), stream()), "h2d colidx");
+}
+
+template <typename L>
+void Model<L>::construct_network() {  // net.cpp:422-453
+  std::cout << "constructing neural network...\n";
+  const int nv = num_samples;
+  layer_gconv.reserve(num_layers);
+  for (int l = 0; l < num_layers - 1; l++)
+    layer_gconv.emplace_back(l, nv, l == 0 ? dim_init : dim_hid, dim_hid, training_graph, true, lrate, feat_drop, score_drop);
+  layer_gconv.emplace_back(num_layers - 1, nv, dim_hid, use_dense ? dim_hid : num_cls, training_graph, false, lrate, feat_drop, score_drop);
+  if (use_l2norm) layer_l2norm = new l2norm_layer(nv, dim_hid);
+  if (use_dense) layer_dense = new dense_layer(nv, dim_hid, num_cls, lrate);
+  layer_gconv[0].set_feat_in(d_input_features);
+  layer_loss = new softmax_loss_layer(nv, num_cls, d_labels);
+  opt_ = new adam(lrate);  // net.cpp:362
+  sync();
+}
+
+template <typename L>
+void Model<L>::update_weights(optimizer* opt) { for (int i = 0; i < num_layers; i++) layer_gconv[i].update_weight(opt); }
+template <typename L>
+void Model<L>::set_netphases(net_phase phase) { for (auto& y : layer_gconv) y.set_netphase(phase); layer_loss->set_netphase(phase); }
+template <typename L>
+void Model<L>::print_layers_info() { for (auto& y : layer_gconv) y.print_layer_info(); layer_loss->print_layer_info(); }
+
+template <typename L>
+void Model<L>::run_forward_layers() {  // shared by forward_prop and evaluate (net.cpp:458-471, 541-554)
+  for (int l = 0; l < num_layers - 1; l++) layer_gconv[l].forward(layer_gconv[l + 1].get_feat_in());
+  if (use_dense) {
+    layer_gconv[num_layers - 1].forward(layer_l2norm->get_feat_in());
+    layer_l2norm->forward(layer_dense->get_feat_in());
+    layer_dense->forward(layer_loss->get_feat_in());
+  } else {
+    layer_gconv[num_layers - 1].forward(layer_loss->get_feat_in());
+  }
+}
+
+template <typename L>
+acc_t Model<L>::forward_prop(acc_t& loss) {
+  run_forward_layers();
+  layer_loss->forward(train_begin, train_end, d_masks_train);
+  loss = layer_loss->get_prediction_loss(train_begin, train_end, train_count, d_masks_train);
+  return static_cast<softmax_loss_layer*>(layer_loss)->last_accuracy();  // same reduction pass as the loss mean
+}
+
+template <typename L>
+acc_t Model<L>::evaluate(std::string type) {
+  set_netphases(net_phase::TEST);
+  run_forward_layers();
+  if (type == "test") return masked_accuracy_single((int)test_begin, (int)test_end, (int)test_count, num_cls, d_masks_test, layer_loss->get_feat_in(), d_labels);
+  return masked_accuracy_single((int)val_begin, (int)val_end, (int)val_count, num_cls, d_masks_val, layer_loss->get_feat_in(), d_labels);
+}
+
+template <typename L>
+void Model<L>::backward_prop() {  // net.cpp:580-615
+  if (use_dense) {
+    layer_loss->backward(train_begin, train_end, d_masks_train, layer_dense->get_grad_in());
+    layer_dense->backward(layer_l2norm->get_grad_in());
+    layer_l2norm->backward(layer_gconv[num_layers - 1].get_grad_in());
+    layer_gconv[num_layers - 1].backward(layer_l2norm->get_feat_in(), layer_gconv[num_layers - 2].get_grad_in());
+  } else {
+    layer_loss->backward(train_begin, train_end, d_masks_train, layer_gconv[num_layers - 1].get_grad_in());
+    layer_gconv[num_layers - 1].backward(layer_loss->get_feat_in(), layer_gconv[num_layers - 2].get_grad_in());
+  }
+  for (int l = num_layers - 2; l > 0; l--) layer_gconv[l].backward(layer_gconv[l + 1].get_feat_in(), layer_gconv[l - 1].get_grad_in());
+  layer_gconv[0].backward(layer_gconv[1].get_feat_in(), nullptr);
+}
+
+template <typename L>
+acc_t Model<L>::train_epoch(acc_t& loss) {
+  set_netphases(net_phase::TRAIN);
+  acc_t acc = forward_prop(loss);
+  backward_prop();
+  update_weights(opt_);
+  return acc;
+}
+
+template <typename L>
+void Model<L>::train() {  // log lines as net.cpp:364-410 so that logs diff cleanly against the reference
+  std::cout << "Start training...\n";
+  double total_train_time = 0.0;
+  for (int itr = 0; itr < num_epochs; itr++) {
+    std::cout << "Epoch " << std::setw(3) << itr << " ";
+    set_netphases(net_phase::TRAIN);
+    acc_t train_loss = 0.0;
+    const double t0 = now_s();
+    acc_t train_acc = forward_prop(train_loss);
+    const double t1 = now_s();
+    backward_prop();
+    update_weights(opt_);
+    sync();
+    const double t2 = now_s();
+    const double fw_time = t1 - t0, bw_time = t2 - t1, epoch_time = fw_time + bw_time;
+    total_train_time += epoch_time;
+    std::cout << "train_loss " << std::setprecision(3) << std::fixed << train_loss << " train_acc " << train_acc << " ";
+    if (itr % val_interval == 0 && itr != 0) {
+      const double v0 = now_s();
+      acc_t val_acc = evaluate("val");
+      const double val_time = now_s() - v0;
+      std::cout << "val_acc " << std::setprecision(3) << std::fixed << val_acc << " ";
+      std::cout << "time " << std::setprecision(3) << std::fixed << epoch_time + val_time << " s (train_time " << epoch_time << " val_time "
+                << val_time << ")\n";
+    } else {
+      std::cout << "train_time " << std::fixed << epoch_time << " s (fw " << fw_time << ", bw " << bw_time << ")\n";
+    }
+  }
+  std::cout << "Average training time per epoch: " << total_train_time / (double)num_epochs << " seconds. Throughput "
+            << (double)num_epochs / total_train_time << " epoch/s\n";
+}
+
+template class Model<GCN_layer>;
+template class Model<GAT_layer>;
+template class Model<SAGE_layer>;

@@ -1,0 +1,70 @@
+// Host-side mirror of the reference's model driver: Model<L> (include/gnn/net.h:9-83, src/gnn/net.cpp:11-620) over the
+// layer classes in gai_layers.h. Same public methods and argv contract (train.cpp:9-15); subgraph sampling is out of
+// scope (every config runs subg_size = 0) and is rejected at load time.
+#pragma once
+#include <string>
+#include <vector>
+#include "gai_layers.h"
+
+#define DEFAULT_NUM_LAYER 2
+#define DEFAULT_SIZE_HID 16
+#define DEFAULT_RATE_LEARN 0.02
+#define EVAL_INTERVAL 50
+
+template <typename gconv_layer>
+class Model {
+ public:
+  Model() {}
+  acc_t forward_prop(acc_t& loss);
+  acc_t evaluate(std::string type);
+  void backward_prop();
+  void load_data(int argc, char* argv[]);
+  void construct_network();
+  void train();
+  void update_weights(optimizer* opt);
+  void set_netphases(net_phase phase);
+  void print_layers_info();
+  void transfer_data_to_device();
+
+  // In-memory set-up: what load_data does after the Reader calls (net.cpp:88-203), for callers that already hold the
+  // arrays (tests, bench.py through gai_host_capi.cpp). `split9` = train/val/test (begin, end, count).
+  void init_from_memory(gnn_arch arch, Graph* g, int dim_init, int num_cls, const float* feats_h, const label_t* labels_h,
+                        const int64_t* split9, int dim_hid, int num_layers, float lr, int epochs, int val_interval);
+  // One training step exactly as Model::train's loop body (net.cpp:373-383); returns train accuracy.
+  acc_t train_epoch(acc_t& loss);
+  // Re-upload the epoch's inputs (features, labels, masks, CSR) from host memory: the reference's host->device boundary
+  // (net.cpp:186-187, 207-227), exposed so that an end-to-end step can include it.
+  void refresh_inputs_from_host(const float* feats_h_pinned);
+  int num_conv_layers() const { return num_layers; }
+  gconv_layer& conv_layer(int l) { return layer_gconv[l]; }
+  dense_layer* dense() { return layer_dense; }
+  loss_layer* loss() { return layer_loss; }
+  l2norm_layer* l2norm() { return layer_l2norm; }
+  optimizer* shared_optimizer() { return opt_; }
+  size_t nv() const { return num_samples; }
+
+ private:
+  int num_epochs = 0, num_layers = DEFAULT_NUM_LAYER, num_samples = 0, num_threads = 1, num_cls = 0, dim_init = 0;
+  int dim_hid = DEFAULT_SIZE_HID, subg_size = 0, val_interval = EVAL_INTERVAL;
+  float feat_drop = 0.f, score_drop = 0.f, lrate = DEFAULT_RATE_LEARN;
+  size_t train_begin = 0, train_end = 0, train_count = 0, val_begin = 0, val_end = 0, val_count = 0, test_begin = 0, test_end = 0, test_count = 0;
+  Graph* full_graph = nullptr;
+  Graph* training_graph = nullptr;
+  std::string dataset_name;
+  bool is_sigmoid = false, use_dense = false, use_l2norm = false, use_gpu = true, inductive = false;
+  gnn_arch arch = gnn_arch::GCN;
+  std::vector<gconv_layer> layer_gconv;
+  loss_layer* layer_loss = nullptr;
+  l2norm_layer* layer_l2norm = nullptr;
+  dense_layer* layer_dense = nullptr;
+  optimizer* opt_ = nullptr;
+  std::vector<float> input_features;
+  std::vector<label_t> labels;
+  std::vector<mask_t> masks_train, masks_test, masks_val;
+  float* d_input_features = nullptr;
+  label_t* d_labels = nullptr;
+  mask_t *d_masks_train = nullptr, *d_masks_test = nullptr, *d_masks_val = nullptr;
+
+  void finish_setup();
+  void run_forward_layers();
+};
