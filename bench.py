@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — the hot path measured on its headline configuration (BASELINE.json configs[1]):
+GraphSAGE-mean, 2 layers, hidden 256, full-graph training on a synthetic ogbn-products-shaped R-MAT graph
+(2.45 M vertices, ~62 M CSR edges, 100 features, 47 classes), one B200.
+
+A "step" is one training epoch exactly as the reference times it (src/gnn/net.cpp:373-383: forward_prop + backward_prop +
+update_weights, validation excluded), driven through the reference-shaped C++ API (Model<SAGE_layer>, graphaibench_b200/host).
+
+  value      whole-job throughput, CSR edges trained per second (Medges/s), inputs already resident in HBM
+  ms_per_step  the epoch time itself (BASELINE.json's "epoch ms")
+  e2e        same metric with the step's inputs (features, labels, mask, CSR) copied from pinned host memory inside the
+             timed region and the loss/accuracy read back
+  roofline   dominant kernel class of the epoch, algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline  the reference's own OpenMP implementation (oracle/_ref, built from the reference sources) on a bounded sample
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json configs[1] (SURVEY.md §8d "C2")
+C2 = dict(nv=2_449_029, nnz=62_000_000, feat=100, hid=256, ncls=47, layers=2, lr=0.01)
+SAMPLE_DIV = 16  # the CPU reference runs a 1/16-scale graph of the same shape (same generator, degree, widths)
+
+
+class quiet_stdout:
+    """The reference (and its mirror) log to C++ stdout; keep bench.py's stdout to the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.p, self.t = [], None, None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_workload(scale_div, device):
+    """ogbn-products-shaped synthetic inputs: R-MAT (0.57,0.19,0.19,0.05) seed 1, natural ids, symmetric,
+    sorted, deduplicated, no self-loops; features N(0,1) seed 2; labels U{0..46} seed 3; 50/25/25 range split."""
+    import torch
+    from graphaibench_b200 import datagen
+    nv, nnz = C2["nv"] // scale_div, C2["nnz"] // scale_div
+    rp, ci = datagen.rmat_csr_torch(nv, nnz, seed=1, device=device)
+    g = torch.Generator(device=device); g.manual_seed(2)
+    feats = torch.randn(nv, C2["feat"], generator=g, device=device, dtype=torch.float32)
+    g.manual_seed(3)
+    labels = torch.randint(0, C2["ncls"], (nv,), generator=g, device=device, dtype=torch.int64).to(torch.uint8)
+    split = datagen.split_ranges(nv)
+    return dict(nv=nv, nnz=int(ci.numel()), rowptr=rp.cpu().numpy().astype(np.uint32), colidx=ci.cpu().numpy().astype(np.uint32),
+                feats=feats.cpu().numpy(), labels=labels.cpu().numpy(), split=split)
+
+
+def config_dict(w, n_gpus, scale_div, extra=None):
+    c = {"workload": "GraphSAGE-mean 2-layer hidden 256, full-graph training, synthetic ogbn-products-shaped R-MAT graph (BASELINE.json configs[1])",
+         "vertices": w["nv"], "csr_edges": w["nnz"], "features": C2["feat"], "hidden": C2["hid"], "classes": C2["ncls"], "layers": C2["layers"],
+         "train_rows": int(w["split"][2]), "scale_div": scale_div, "parallelism": f"1d-partition x{n_gpus}" if n_gpus > 1 else "single-gpu",
+         "l2_policy": "inputs larger than L2 (features 0.98 GB, activations 2.5 GB vs 126 MB L2); no explicit flush"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_cpu_reference(w_small, threads, steps, warmup, min_seconds=0.0):
+    """The reference's own CPU implementation (oracle/_ref/libref_gnn.so: Model<SAGE_layer> from the reference sources)."""
+    import oracle
+    if not oracle.have_ref():
+        raise RuntimeError("oracle/_ref/libref_gnn.so missing (built by oracle/build_ref.sh in the build container)")
+    with quiet_stdout():
+        m = oracle.RefModel("sage", w_small["rowptr"], w_small["colidx"], w_small["feats"], w_small["labels"], w_small["split"], C2["hid"], C2["ncls"],
+                            num_layers=C2["layers"], lr=C2["lr"], threads=threads)
+    for _ in range(warmup):
+        m.train_epoch()
+    t0 = time.time()
+    done = 0
+    while done < steps or (time.time() - t0) < min_seconds:
+        m.train_epoch()
+        done += 1
+        if done >= steps and min_seconds <= 0:
+            break
+    dt = (time.time() - t0) / done
+    return dt, done
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    w = make_workload(args.scale * SAMPLE_DIV, "cpu")
+    dt, done = run_cpu_reference(w, threads, args.steps, args.warmup)
+    val = w["nnz"] / dt / 1e6
+    sample = f"1/{SAMPLE_DIV}-scale graph of the same shape ({w['nv']} vertices, {w['nnz']} CSR edges), {done} epochs, {threads} OpenMP+OpenBLAS threads"
+    from graphaibench_b200 import datagen
+    full = dict(nv=C2["nv"] // args.scale, nnz=C2["nnz"] // args.scale, split=datagen.split_ranges(C2["nv"] // args.scale))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(full, args.gpus, args.scale, {"reference_sample": sample}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+METRIC = "GraphSAGE full-graph training throughput (CSR edges trained per second; epoch ms in ms_per_step)"
+UNIT = "Medges/s"
+
+
+def roofline_from_profile(prof, peaks, n_epochs):
+    """Dominant op class by device time; achieved = algorithmic bytes (or flops) / event time for its heaviest shape."""
+    by_bucket = {}
+    for r in prof:
+        by_bucket[r["bucket"]] = by_bucket.get(r["bucket"], 0.0) + r["ms"]
+    total = sum(by_bucket.values())
+    dom = max(by_bucket, key=by_bucket.get)
+    rows = sorted([r for r in prof if r["bucket"] == dom], key=lambda r: -r["ms"])
+    top = rows[0]
+    ms = top["ms"] / top["calls"]
+    gbs = top["bytes"] / top["calls"] / (ms * 1e-3) / 1e9
+    out = {"kernel": f"{dom} {top['shape']}", "share_of_step": by_bucket[dom] / total, "launch_ms": ms, "traffic": None,
+           "peak_source": peaks["source"]}
+    tfl = top["flops"] / top["calls"] / (ms * 1e-3) / 1e12
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    if dom == "LINEAR" and tfl / tf32_peak > gbs / peaks["hbm_gbs"]:
+        out.update({"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak})
+    else:
+        out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]})
+    breakdown = {b: round(v / n_epochs, 4) for b, v in sorted(by_bucket.items(), key=lambda kv: -kv[1])}
+    per_shape = [{"op": f"{r['bucket']} {r['shape']}", "ms": round(r["ms"] / r["calls"], 4), "calls_per_step": r["calls"] / n_epochs,
+                  "GBps": round(r["bytes"] / r["calls"] / (r["ms"] / r["calls"] * 1e-3) / 1e9, 1),
+                  "TFLOPps": round(r["flops"] / r["calls"] / (r["ms"] / r["calls"] * 1e-3) / 1e12, 2)} for r in sorted(prof, key=lambda r: -r["ms"])]
+    return out, breakdown, per_shape
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from graphaibench_b200 import _abi, build, model as gmodel
+    if rank == 0:
+        with quiet_stdout():
+            build.build_all()
+    if world > 1:
+        dist.barrier()
+    L = _abi.lib()
+    peaks = load_peaks()
+
+    w = make_workload(args.scale, "cuda")  # weak scaling: every rank trains one C2-shaped shard
+    stream = torch.cuda.Stream()
+    with quiet_stdout():
+        m = gmodel.GnnModel("sage", w["rowptr"], w["colidx"], w["feats"], w["labels"], w["split"], C2["hid"], C2["ncls"], num_layers=C2["layers"],
+                            lr=C2["lr"], stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.gai_launch_count()
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, L.gai_launch_count() - l0, out, (t0, t1)
+
+    for _ in range(max(args.warmup, 3)):
+        m.train_epoch()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_step, launches, (loss, acc), span = timed(m.train_epoch, args.steps)
+
+    def e2e_step():
+        m.refresh_inputs()  # pinned host -> device: features, labels, train mask, CSR
+        return m.train_epoch()  # ends with the device -> host read of {loss, accuracy, count}
+    e2e_step()
+    ms_e2e, _, _, span2 = timed(e2e_step, args.steps)
+    clocks = sampler.stop(span[0], span2[1]) if rank == 0 else None
+
+    h2d = w["feats"].nbytes + w["labels"].nbytes + w["nv"] + w["rowptr"].nbytes + w["colidx"].nbytes
+    total_edges = w["nnz"] * world
+    value = total_edges / (ms_step * 1e-3) / 1e6
+    e2e_val = total_edges / (ms_e2e * 1e-3) / 1e6
+
+    # per-op device times (CUDA events on the launching stream) for the roofline
+    gmodel.profile_enable(True)
+    n_prof = 3
+    for _ in range(n_prof):
+        m.train_epoch()
+    prof = gmodel.profile_collect()
+    gmodel.profile_enable(False)
+    roof, breakdown, per_shape = roofline_from_profile(prof, peaks, n_prof)
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(w, world, args.scale, {"gemm_mode": {0: "auto", 1: "fp32-simt", 2: "tcgen05-3xtf32", 3: "tcgen05-1xtf32"}[L.gai_get_gemm_mode()]}),
+            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 12},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "breakdown_ms_per_step": breakdown, "ops": per_shape[:12],
+            "final": {"train_loss": loss, "train_acc": acc}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ws = make_workload(args.scale * SAMPLE_DIV, "cuda")
+        dt, done = run_cpu_reference(ws, threads, 2, 1, min_seconds=10.0)
+        line["cpu_baseline"] = {"value": ws["nnz"] / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step_sample": dt * 1e3,
+                                "sample": f"reference OpenMP build (oracle/_ref) on a 1/{SAMPLE_DIV}-scale graph of the same shape ({ws['nv']} vertices, "
+                                          f"{ws['nnz']} CSR edges), {done} epochs after 1 warm-up, {threads} threads"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("GAI_BENCH_SCALE", "1")), help="divide the workload size (development only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,11 @@ _SIGS = {
     "gai_stream_sync": (C.c_int, [c_stream]),
     "gai_host_alloc_pinned": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "gai_host_free_pinned": (C.c_int, [C.c_void_p]),
+    "gai_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "gai_event_record": (C.c_int, [C.c_void_p, c_stream]),
+    "gai_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "gai_event_destroy": (C.c_int, [C.c_void_p]),
+    "gai_launch_count": (C.c_uint64, []),
     "gai_add_selfloop_h": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gai_csr_create": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_csr_create_device": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),

@@ -22,7 +22,12 @@ int set_error(int code, const char* what, const char* detail);
     if (!(cond)) return gai::set_error(GAI_ERR_ARG, "invalid argument", #cond);   \
   } while (0)
 
-#define GAI_LAUNCH_CHECK() GAI_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;
+#define GAI_LAUNCH_CHECK()            \
+  do {                                \
+    __atomic_fetch_add(&gai::g_launches, 1ull, __ATOMIC_RELAXED); \
+    GAI_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline cudaStream_t S(gai_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

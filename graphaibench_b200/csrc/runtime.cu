@@ -8,6 +8,7 @@
 namespace gai {
 
 static thread_local std::string g_err;
+unsigned long long g_launches = 0;
 
 int set_error(int code, const char* what, const char* detail) {
   g_err = std::string(what ? what : "") + ": " + (detail ? detail : "");
@@ -56,6 +57,22 @@ extern "C" {
 
 const char* gai_last_error(void) { return gai::g_err.c_str(); }
 int gai_version(void) { return 100; }
+uint64_t gai_launch_count(void) { return __atomic_load_n(&gai::g_launches, __ATOMIC_RELAXED); }
+int gai_event_create(void** ev) {
+  GAI_CHECK_ARG(ev != nullptr);
+  cudaEvent_t e;
+  GAI_CUDA(cudaEventCreate(&e));
+  *ev = e;
+  return GAI_OK;
+}
+int gai_event_record(void* ev, gai_stream_t s) { GAI_CUDA(cudaEventRecord((cudaEvent_t)ev, gai::S(s))); return GAI_OK; }
+int gai_event_elapsed_ms(void* a, void* b, float* ms) {
+  GAI_CHECK_ARG(ms != nullptr);
+  GAI_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+  GAI_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return GAI_OK;
+}
+int gai_event_destroy(void* ev) { if (ev) GAI_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return GAI_OK; }
 
 int gai_device_count(int* n) {
   GAI_CHECK_ARG(n != nullptr);

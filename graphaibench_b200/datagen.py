@@ -75,3 +75,44 @@ def write_dataset(path, rowptr64, colidx, feats, labs, ncls, split9):
     np.asarray(colidx, np.uint32).tofile(os.path.join(path, "graph.edge.bin"))
     np.asarray(feats, np.float32).tofile(os.path.join(path, "graph.feats.bin"))
     np.asarray(labs, np.uint8).tofile(os.path.join(path, "graph.vlabel.bin"))
+
+
+def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 0.19, 0.19, 0.05), device="cuda"):
+    """Same construction as rmat_csr, vectorised with torch on `device` (input generation only; the multi-million-edge
+    bench graphs take seconds instead of minutes). Returns (rowptr int64[n+1], colidx int64[nnz]) tensors on `device`."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    scale = int(np.ceil(np.log2(max(n_vertices, 2))))
+    a, b, c, _ = abcd
+    want_pairs = target_nnz // 2
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    draw = int(want_pairs * 1.25) + 16
+    for _ in range(8):
+        src = torch.zeros(draw, dtype=torch.int64, device=device)
+        dst = torch.zeros(draw, dtype=torch.int64, device=device)
+        for _lvl in range(scale):
+            r = torch.rand(draw, generator=g, device=device)
+            sb = (r >= a + b).to(torch.int64)
+            db = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+            src = (src << 1) | sb
+            dst = (dst << 1) | db
+        ok = (src < n_vertices) & (dst < n_vertices) & (src != dst)
+        lo = torch.minimum(src[ok], dst[ok])
+        hi = torch.maximum(src[ok], dst[ok])
+        keys = torch.unique(torch.cat([keys, lo * n_vertices + hi]))
+        del src, dst, r, sb, db, ok, lo, hi
+        if keys.numel() >= want_pairs:
+            break
+        draw = int((want_pairs - keys.numel()) * 1.6) + 16
+    if keys.numel() > want_pairs:
+        sel = torch.randperm(keys.numel(), generator=g, device=device)[:want_pairs]
+        keys = keys[torch.sort(sel).values]
+    lo, hi = keys // n_vertices, keys % n_vertices
+    s = torch.cat([lo, hi])
+    d = torch.cat([hi, lo])
+    order = torch.argsort(s * n_vertices + d)
+    s, d = s[order], d[order]
+    rowptr = torch.zeros(n_vertices + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(s, minlength=n_vertices), 0)
+    return rowptr, d

@@ -15,6 +15,50 @@ void die_on(int status, const char* what) {
   std::fprintf(stderr, "%s failed (status %d): %s\n", what, status, gai_last_error());
   std::exit(EXIT_FAILURE);
 }
+
+struct Rec { std::string bucket, shape; double bytes, flops; void* e0; void* e1; };
+static bool g_prof = false;
+static std::vector<Rec> g_recs;
+void profile_enable(bool on) { g_prof = on; }
+bool profile_enabled() { return g_prof; }
+OpScope::OpScope(const char* bucket, const std::string& shape, double bytes, double flops) : idx(-1) {
+  if (!g_prof) return;
+  Rec r{bucket, shape, bytes, flops, nullptr, nullptr};
+  die_on(gai_event_create(&r.e0), "gai_event_create");
+  die_on(gai_event_create(&r.e1), "gai_event_create");
+  die_on(gai_event_record(r.e0, g_stream), "gai_event_record");
+  idx = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+OpScope::~OpScope() {
+  if (idx >= 0) die_on(gai_event_record(g_recs[idx].e1, g_stream), "gai_event_record");
+}
+std::string profile_collect_json() {
+  struct Agg { int calls = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::vector<std::pair<std::string, Agg>> aggs;
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    die_on(gai_event_elapsed_ms(r.e0, r.e1, &ms), "gai_event_elapsed_ms");
+    gai_event_destroy(r.e0); gai_event_destroy(r.e1);
+    const std::string key = r.bucket + "|" + r.shape;
+    Agg* a = nullptr;
+    for (auto& kv : aggs) if (kv.first == key) a = &kv.second;
+    if (!a) { aggs.emplace_back(key, Agg()); a = &aggs.back().second; }
+    a->calls++; a->ms += ms; a->bytes += r.bytes; a->flops += r.flops;
+  }
+  g_recs.clear();
+  std::string out = "[";
+  char buf[512];
+  for (size_t i = 0; i < aggs.size(); i++) {
+    const std::string& key = aggs[i].first;
+    const size_t bar = key.find('|');
+    std::snprintf(buf, sizeof(buf), "%s{\"bucket\":\"%s\",\"shape\":\"%s\",\"calls\":%d,\"ms\":%.6f,\"bytes\":%.0f,\"flops\":%.0f}",
+                  i ? "," : "", key.substr(0, bar).c_str(), key.substr(bar + 1).c_str(), aggs[i].second.calls, aggs[i].second.ms,
+                  aggs[i].second.bytes, aggs[i].second.flops);
+    out += buf;
+  }
+  return out + "]";
+}
 }  // namespace gai_host
 using gai_host::die_on;
 

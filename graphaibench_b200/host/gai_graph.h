@@ -16,6 +16,18 @@ namespace gai_host {
 void die_on(int status, const char* what);  // prints gai_last_error() and exits: the reference's CUDA_CHECK contract
 gai_stream_t stream();                      // the stream every host-class call is issued on
 void set_stream(gai_stream_t s);
+
+// Per-op device timing (the reference's `time_ops` buckets, include/gnn/global.h:42-54, taken with CUDA events on the
+// launching stream instead of gettimeofday around synchronous calls). Off by default; when on, every ABI call the
+// host classes make is bracketed by an event pair tagged with its algorithmic bytes / flops.
+void profile_enable(bool on);
+bool profile_enabled();
+struct OpScope {
+  OpScope(const char* bucket, const std::string& shape, double bytes, double flops);
+  ~OpScope();
+  int idx;
+};
+std::string profile_collect_json();  // synchronises, aggregates per (bucket, shape), clears the records
 }  // namespace gai_host
 
 typedef uint32_t index_t;

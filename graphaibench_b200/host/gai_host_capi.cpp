@@ -93,5 +93,12 @@ int64_t gai_model_set(void* m, const char* name, int layer, const float* in_h, i
   copy_float_to_device(n, in_h, p);
   return (int64_t)n;
 }
+void gai_host_profile_enable(int on) { gai_host::profile_enable(on != 0); }
+// Writes the aggregated per-op timings as JSON into buf (NUL-terminated, truncated to cap); returns the full length.
+int64_t gai_host_profile_json(char* buf, int64_t cap) {
+  const std::string js = gai_host::profile_collect_json();
+  if (buf && cap > 0) { const size_t n = js.size() < (size_t)cap - 1 ? js.size() : (size_t)cap - 1; memcpy(buf, js.data(), n); buf[n] = 0; }
+  return (int64_t)js.size();
+}
 void gai_model_sync() { gai_stream_sync(gai_host::stream()); }
 }

@@ -44,7 +44,14 @@ static float* upload_glorot(size_t dx, size_t dy, unsigned seed) {
 }
 static void mm(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, bool ta = false, bool tb = false, bool accum = false,
                int flags = 0) {
+  gai_host::OpScope sc("LINEAR", std::to_string(x) + "x" + std::to_string(y) + "x" + std::to_string(z) + (ta ? " TA" : "") + (tb ? " TB" : ""),
+                       4.0 * ((double)x * z + (double)z * y + (double)x * y * (accum ? 2 : 1)), 2.0 * (double)x * y * z);
   die_on(gai_matmul(x, y, z, A, B, C, ta, tb, accum, flags, stream()), "gai_matmul");
+}
+// algorithmic bytes of one aggregation call: gather model of SURVEY.md §8d
+static double spmm_bytes(Graph& g, int F, int extra_per_edge = 0) {
+  const double n = (double)g.size(), nnz = (double)g.sizeEdges();
+  return 4.0 * (nnz * F + n * F + nnz * (1 + extra_per_edge) + (n + 1) + n);
 }
 
 // ---- adam ---------------------------------------------------------------------------------------------------------
@@ -52,6 +59,7 @@ static void mm(size_t x, size_t y, size_t z, const float* A, const float* B, flo
 void adam::update_gpu(const size_t n, const float* dW, float* W) {
   auto it = moments.find(W);
   if (it == moments.end()) it = moments.emplace(W, std::make_pair(float_malloc_device_zero(n), float_malloc_device_zero(n))).first;
+  gai_host::OpScope sc("ADAM", "n=" + std::to_string(n), 28.0 * n, 0);
   die_on(gai_adam_update(n, dW, W, it->second.first, it->second.second, alpha, b1, b2, b1_t, b2_t, eps, stream()), "gai_adam_update");
   b1_t *= b1;
   b2_t *= b2;
@@ -65,6 +73,7 @@ void adam::reset() {
 
 void GCN_Aggregator::init(int len, int, int, float, float) { length = len; }
 void GCN_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+  gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
   die_on(gai_spmm_gcn(g.device(), len, in, len, out, len, flags, addend, stream()), "gai_spmm_gcn");
 }
 void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
@@ -73,10 +82,12 @@ void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* g
 
 void SAGE_Aggregator::init(int len, int, int, float, float) { length = len; }
 void SAGE_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+  gai_host::OpScope sc("AGGR", "mean F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
   die_on(gai_spmm_mean(g.device(), len, in, len, out, len, 0, flags, addend, stream()), "gai_spmm_mean");
 }
 void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
 void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {
+  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len), spmm_bytes(g, len), 2.0 * g.sizeEdges() * len);
   die_on(gai_spmm_mean(g.device(), len, grad_in, len, grad_out, len, 1, GAI_EPI_NONE, nullptr, stream()), "gai_spmm_mean(T)");
 }
 
@@ -95,10 +106,12 @@ void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
   alpha_opt = new adam(lr);
 }
 void GAT_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float*) {
+  gai_host::OpScope sc("ATTN_FWD", "gat F=" + std::to_string(len), spmm_bytes(g, len, 2) + 4.0 * g.size() * len, 2.0 * g.sizeEdges() * len);
   die_on(gai_gat_forward(g.device(), len, in, d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out, flags, stream()), "gai_gat_forward");
 }
 void GAT_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
 void GAT_Aggregator::d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out) {
+  gai_host::OpScope sc("ATTN_BWD", "gat F=" + std::to_string(len), 2.0 * spmm_bytes(g, len, 3) + 4.0 * g.size() * len, 4.0 * g.sizeEdges() * len);
   die_on(gai_gat_backward(g.device(), len, feat_in, grad_in, epsilon, d_temp_scores, d_norm_scores, d_scores_grad, d_alpha_lgrad, d_alpha_rgrad,
                           grad_out, stream()), "gai_gat_backward");
 }
@@ -179,7 +192,10 @@ void GCN_layer::forward(float* feat_out) {
 
 void GCN_layer::backward(float* feat_out, float* grad_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  if (is_act) {
+    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
+    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  }
   if (y > z) {
     aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
     if (level_ > 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
@@ -219,7 +235,10 @@ void SAGE_layer::forward(float* feat_out) {
 
 void SAGE_layer::backward(float* feat_out, float* grad_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  if (is_act) {
+    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
+    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  }
   mm(y, z, x, feat_in, grad_in, d_W_self_grad, true, false);
   if (y > z) {
     aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
@@ -255,7 +274,10 @@ void GAT_layer::forward(float* feat_out) {
 
 void GAT_layer::backward(float* feat_out, float* grad_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  if (is_act) {
+    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
+    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
+  }
   aggr.d_aggregate((int)z, *graph, d_out_temp, grad_in, d_out_temp);  // dZ overwrites Z (gat_layer.cpp:33-36)
   if (level_ != 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
   mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
@@ -272,8 +294,8 @@ l2norm_layer::l2norm_layer(int nv, int len) : num_samples(nv), dim(len) {
   feat_in = float_malloc_device_zero((size_t)nv * len);
   grad_in = float_malloc_device_zero((size_t)nv * len);
 }
-void l2norm_layer::forward(float* feat_out) { die_on(gai_l2norm(num_samples, dim, feat_in, feat_out, stream()), "gai_l2norm"); }
-void l2norm_layer::backward(float* grad_out) { die_on(gai_d_l2norm(num_samples, dim, feat_in, grad_in, grad_out, stream()), "gai_d_l2norm"); }
+void l2norm_layer::forward(float* feat_out) { gai_host::OpScope sc("NORM", "l2norm", 8.0 * num_samples * dim, 0); die_on(gai_l2norm(num_samples, dim, feat_in, feat_out, stream()), "gai_l2norm"); }
+void l2norm_layer::backward(float* grad_out) { gai_host::OpScope sc("NORM", "d_l2norm", 12.0 * num_samples * dim, 0); die_on(gai_d_l2norm(num_samples, dim, feat_in, grad_in, grad_out, stream()), "gai_d_l2norm"); }
 
 dense_layer::dense_layer(int nv, int in_len, int out_len, float lr) : dim_in(in_len), dim_out(out_len), num_samples(nv) {
   feat_in = float_malloc_device_zero((size_t)nv * in_len);
@@ -297,13 +319,18 @@ loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cl
 }
 
 void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
+  gai_host::OpScope sc("LOSS", "fwd", 8.0 * (end - begin) * num_cls, 0);
   die_on(gai_softmax_ce_forward(num_cls, begin, end, masks, labels, feat_in, feat_out, d_losses, stream()), "gai_softmax_ce_forward");
 }
 void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
+  gai_host::OpScope sc("LOSS", "bwd", 8.0 * (end - begin) * num_cls, 0);
   die_on(gai_softmax_ce_backward(num_cls, begin, end, masks, labels, feat_out, grad_out, stream()), "gai_softmax_ce_backward");
 }
 acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
-  die_on(gai_masked_loss_accuracy(num_cls, begin, end, masks, labels, feat_in, d_losses, d_stats, stream()), "gai_masked_loss_accuracy");
+  {
+    gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin) * (num_cls + 1), 0);
+    die_on(gai_masked_loss_accuracy(num_cls, begin, end, masks, labels, feat_in, d_losses, d_stats, stream()), "gai_masked_loss_accuracy");
+  }
   float h[3] = {0, 0, 0};
   copy_float_to_host(3, d_stats, h);
   (void)count;  // the reference asserts masked-row count == count; the count comes back as a float here

@@ -107,12 +107,20 @@ void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
 
 template <typename L>
 void Model<L>::refresh_inputs_from_host(const float* feats_h) {
-  const float* src = feats_h ? feats_h : input_features.data();
-  die_on(gai_memcpy_h2d(d_input_features, src, sizeof(float) * input_features.size(), stream()), "h2d feats");
-  die_on(gai_memcpy_h2d(d_labels, labels.data(), labels.size(), stream()), "h2d labels");
-  die_on(gai_memcpy_h2d(d_masks_train, masks_train.data(), masks_train.size(), stream()), "h2d masks");
-  die_on(gai_memcpy_h2d((void*)training_graph->row_start_ptr(), training_graph->row_start_host_ptr(), sizeof(index_t) * (training_graph->size() + 1), stream()), "h2d rowptr");
-  die_on(gai_memcpy_h2d((void*)training_graph->edge_dst_ptr(), training_graph->edge_dst_host_ptr(), sizeof(index_t) * training_graph->sizeEdges(), stream()), "h2d colidx");
+  // All five inputs are staged once in page-locked host memory so that the per-step copies are true async DMA.
+  static void* pin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const size_t bytes[5] = {sizeof(float) * input_features.size(), labels.size(), masks_train.size(),
+                           sizeof(index_t) * (training_graph->size() + 1), sizeof(index_t) * training_graph->sizeEdges()};
+  const void* srcs[5] = {feats_h ? (const void*)feats_h : (const void*)input_features.data(), labels.data(), masks_train.data(),
+                         training_graph->row_start_host_ptr(), training_graph->edge_dst_host_ptr()};
+  void* dsts[5] = {d_input_features, d_labels, d_masks_train, (void*)training_graph->row_start_ptr(), (void*)training_graph->edge_dst_ptr()};
+  for (int i = 0; i < 5; i++) {
+    if (!pin[i]) {
+      die_on(gai_host_alloc_pinned(&pin[i], bytes[i]), "gai_host_alloc_pinned");
+      memcpy(pin[i], srcs[i], bytes[i]);
+    }
+    die_on(gai_memcpy_h2d(dsts[i], pin[i], bytes[i], stream()), "gai_memcpy_h2d");
+  }
 }
 
 template <typename L>

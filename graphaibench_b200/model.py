@@ -40,8 +40,24 @@ def hostlib():
         L.gai_model_get.restype = C.c_int64
         L.gai_model_set.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]
         L.gai_model_set.restype = C.c_int64
+        L.gai_host_profile_enable.argtypes = [C.c_int]
+        L.gai_host_profile_json.argtypes = [C.c_char_p, C.c_int64]
+        L.gai_host_profile_json.restype = C.c_int64
+        L.gai_model_sync.argtypes = []
         _h = L
     return _h
+
+
+def profile_enable(on: bool):
+    hostlib().gai_host_profile_enable(int(on))
+
+
+def profile_collect():
+    """Per-(bucket, shape) device timings recorded since profile_enable(True): list of dicts (calls, ms, bytes, flops)."""
+    import json
+    buf = C.create_string_buffer(1 << 20)
+    hostlib().gai_host_profile_json(buf, len(buf))
+    return json.loads(buf.value.decode())
 
 
 class GnnModel:

@@ -53,6 +53,14 @@ int gai_stream_sync(gai_stream_t stream);
 int gai_host_alloc_pinned(void** p_h, size_t bytes);
 int gai_host_free_pinned(void* p_h);
 
+/* ---- events + launch accounting (measurement; the reference times with gettimeofday around synchronous ops,
+ *      include/timer.h:6-32; here device time is taken with CUDA events on the launching stream) ---------- */
+int gai_event_create(void** ev);
+int gai_event_record(void* ev, gai_stream_t stream);
+int gai_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
+int gai_event_destroy(void* ev);
+uint64_t gai_launch_count(void); /* kernels launched by this library since load (all streams) */
+
 /* ---- host-side graph construction (integer work, bit-exact) ---------------------------------------- */
 /* LearningGraph::add_selfloop (include/gnn/lgraph.h:185-218). colidx_out_h has nnz+nv entries. */
 int gai_add_selfloop_h(uint32_t nv, const uint32_t* rowptr_h, const uint32_t* colidx_h, uint32_t* rowptr_out_h, uint32_t* colidx_out_h);
