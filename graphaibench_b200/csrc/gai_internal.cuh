@@ -35,7 +35,8 @@ static inline cudaStream_t S(gai_stream_t s) { return reinterpret_cast<cudaStrea
 int sm_count();
 
 // Library-owned scratch (split-K partials, reductions). Grown on demand, never shrunk; one per device.
-int workspace(size_t bytes, void** out);
+int workspace(size_t bytes, void** out);          // slot 0: split-K partials, GAT per-vertex scratch, reductions
+int workspace_slot(int slot, size_t bytes, void** out);  // slot 1: SpMM padded-input staging
 
 constexpr uint32_t HUB_DEGREE = 1024;  // rows longer than this go to the CTA-per-row kernel
 

@@ -30,13 +30,15 @@ int sm_count() {
 
 struct Ws { void* p = nullptr; size_t bytes = 0; };
 static std::mutex g_ws_mu;
-static std::map<int, Ws> g_ws;
+static std::map<std::pair<int, int>, Ws> g_ws;
 
-int workspace(size_t bytes, void** out) {
+int workspace(size_t bytes, void** out) { return workspace_slot(0, bytes, out); }
+
+int workspace_slot(int slot, size_t bytes, void** out) {
   int dev = 0;
   GAI_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_ws_mu);
-  Ws& w = g_ws[dev];
+  Ws& w = g_ws[std::make_pair(dev, slot)];
   if (w.bytes < bytes) {
     if (w.p) {
       GAI_CUDA(cudaDeviceSynchronize());

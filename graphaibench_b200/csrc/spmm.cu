@@ -4,18 +4,20 @@
 // Replaces update_all_gcn / update_all_sage / reduce_warp+reduce_cta (include/gnn/graph_operations.h:8-178) and the
 // CPU loops they mirror (src/gnn/gconv/gcn_aggregator.cpp:48-77, sage_aggregator.cpp:7-54, gat_aggregator.cpp:26-45).
 //
-// Design (B200: HBM/L2-latency bound gather; no tensor-core shape here):
-//   * row-split by degree bucket. Rows with deg <= HUB_DEGREE: a group of G lanes (G = 4..32, chosen from the
-//     feature width so that one 128-bit load per lane covers the row) owns one output row and keeps it in
-//     registers; the group loads G column indices + edge weights with one coalesced request, broadcasts them by
-//     shuffle, and issues U=4 independent 128-bit neighbour-row loads (ld.global.nc) before consuming them.
-//   * hub rows (deg > HUB_DEGREE): one CTA per row. All 8 warps gather and scale neighbour rows into a shared-memory
-//     tile in parallel; then one thread per column adds the tile's entries IN EDGE ORDER.
-//   * numerics: acc = fadd_rn(acc, fmul_rn(w, x)) per edge, sequential per column — exactly the reference CPU
-//     path's scale()+vadd() (math_functions.cpp:266,336), so results are bit-identical for every row length,
-//     including hub rows (the parallel part is only the gather).
-//   * fused: zero-init (no memset pass), optional "+ addend" and ReLU epilogue, leading dimensions (so the output can
-//     land inside a wider buffer), row ranges (1D partition: interior vs boundary rows).
+// Design (B200: an HBM/L2 gather; no tensor-core shape here):
+//   * every input row is read with 128-bit loads: if F % 4 != 0 or the layout is misaligned, the input is first copied
+//     into a zero-padded workspace with ld = ceil4(F) (one N x F pass, ~1% of the gather traffic).
+//   * row-split by degree bucket.
+//       light rows (deg <= HUB_DEGREE): a group of G lanes (G = 4..32, from the feature width) owns one output row in
+//         registers; the group loads G column indices + edge weights with one coalesced request, broadcasts them by
+//         shuffle, and keeps U independent 128-bit neighbour-row loads in flight per lane.
+//       hub rows (deg > HUB_DEGREE): one warp-specialised CTA per row. 12 producer warps gather + scale neighbour rows
+//         into a 4-stage shared-memory ring (mbarrier full/empty pairs); 4 consumer warps (one thread per 4 columns)
+//         add the staged products IN EDGE ORDER. The gather runs at SM bandwidth while the add chain stays sequential.
+//   * numerics: acc = fadd_rn(acc, fmul_rn(w, x)) per edge, sequential per column — exactly the reference CPU path's
+//     scale()+vadd() (math_functions.cpp:266,336): results are bit-identical for every row length, hub rows included.
+//   * fused: zero-init (no memset pass), optional "+ addend" and ReLU epilogue, leading dimensions, row ranges
+//     (1D partition: interior vs boundary rows).
 #include "gai_internal.cuh"
 
 namespace {
@@ -28,32 +30,17 @@ struct SpmmArgs {
   const float* norm;
   const float* vals;
   const uint32_t* perm;
-  const float* in;
+  const float* in;   // rows 16-byte aligned, ld_in % 4 == 0
   float* out;
   const float* addend;
-  int F, ld_in, ld_out;
+  int F;             // logical width (columns written)
+  int nchunks;       // ceil(F / 4): float4 chunks read per neighbour row
+  int ld_in, ld_out;
   uint32_t row_begin, row_end;
   int mode, flags;
+  int out_vec;       // 1: out/addend rows are 16-byte aligned and F % 4 == 0 -> float4 epilogue
   uint32_t hub_threshold;
 };
-
-template <int VEC> struct VecT;
-template <> struct VecT<4> { using T = float4; };
-template <> struct VecT<2> { using T = float2; };
-template <> struct VecT<1> { using T = float; };
-
-template <int VEC>
-__device__ __forceinline__ void ldv(const float* p, float (&r)[VEC]) {
-  if constexpr (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
-  else if constexpr (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); r[0] = t.x; r[1] = t.y; }
-  else { r[0] = __ldg(p); }
-}
-template <int VEC>
-__device__ __forceinline__ void stv(float* p, const float (&r)[VEC]) {
-  if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
-  else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
-  else *p = r[0];
-}
 
 __device__ __forceinline__ float edge_weight(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
   switch (a.mode) {
@@ -65,11 +52,36 @@ __device__ __forceinline__ float edge_weight(const SpmmArgs& a, float wrow, uint
   }
 }
 
-constexpr int U = 4;  // independent neighbour rows in flight per lane
+// out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
+__device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int chunk, float4 r) {
+  const size_t o = (size_t)row * a.ld_out + (size_t)chunk * 4;
+  if (a.out_vec) {
+    if (a.flags & GAI_EPI_ADD) {
+      const float4 ad = *reinterpret_cast<const float4*>(a.addend + o);
+      r.x = __fadd_rn(r.x, ad.x); r.y = __fadd_rn(r.y, ad.y); r.z = __fadd_rn(r.z, ad.z); r.w = __fadd_rn(r.w, ad.w);
+    }
+    if (a.flags & GAI_EPI_RELU) { r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f; r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f; }
+    *reinterpret_cast<float4*>(a.out + o) = r;
+  } else {
+    const float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (chunk * 4 + k < a.F) {
+        float t = v[k];
+        if (a.flags & GAI_EPI_ADD) t = __fadd_rn(t, a.addend[o + k]);
+        if (a.flags & GAI_EPI_RELU) t = t > 0.f ? t : 0.f;
+        a.out[o + k] = t;
+      }
+    }
+  }
+}
 
-template <int VEC, int G, int K>
+// ---- light rows -----------------------------------------------------------------------------------------------------
+template <int G, int K>
 __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   constexpr int ROWS_PER_WARP = 32 / G;
+  constexpr int UMAX = (K == 1) ? 8 : (K == 2 ? 4 : 2);
+  constexpr int U = G < UMAX ? G : UMAX;  // independent neighbour rows in flight per lane (up to 8 float4)
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;
   const int grp = lane / G;
@@ -80,17 +92,17 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   const uint32_t row = (uint32_t)row64;
   const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
   if (e - s > a.hub_threshold) return;
-  const int nchunks = a.F / VEC;
   const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
+  const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const size_t ld4 = (size_t)a.ld_in >> 2;
 
-  for (int cb = 0; cb < nchunks; cb += G * K) {
-    float acc[K][VEC];
+  for (int cb = 0; cb < a.nchunks; cb += G * K) {
+    float4 acc[K];
     bool act[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      act[k] = (cb + gl + G * k) < nchunks;
-#pragma unroll
-      for (int v = 0; v < VEC; v++) acc[k][v] = 0.0f;
+      act[k] = (cb + gl + G * k) < a.nchunks;
+      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (uint32_t base = s; base < e; base += G) {
       const uint32_t idx = base + gl;
@@ -104,163 +116,193 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
 #pragma unroll
       for (int j = 0; j < G; j += U) {
         if (j >= cnt) break;
-        float x[U][K][VEC];
+        float4 x[U][K];
         float ww[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const int jj = j + u;
           const uint32_t cc = __shfl_sync(gmask, c, jj, G);
           ww[u] = __shfl_sync(gmask, w, jj, G);
-          const float* src = a.in + (size_t)cc * a.ld_in + (size_t)(cb + gl) * VEC;
+          const float4* src = in4 + (size_t)cc * ld4 + (cb + gl);
 #pragma unroll
           for (int k = 0; k < K; k++) {
-            if (jj < cnt && act[k]) ldv<VEC>(src + (size_t)G * k * VEC, x[u][k]);
-            else {
-#pragma unroll
-              for (int v = 0; v < VEC; v++) x[u][k][v] = 0.0f;
-            }
+            if (jj < cnt && act[k]) x[u][k] = __ldg(src + G * k);
+            else x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (jj >= cnt) ww[u] = 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
-          for (int k = 0; k < K; k++)
-#pragma unroll
-            for (int v = 0; v < VEC; v++) acc[k][v] = __fadd_rn(acc[k][v], __fmul_rn(ww[u], x[u][k][v]));
+          for (int k = 0; k < K; k++) {
+            acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(ww[u], x[u][k].x));
+            acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(ww[u], x[u][k].y));
+            acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(ww[u], x[u][k].z));
+            acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(ww[u], x[u][k].w));
+          }
       }
     }
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      if (!act[k]) continue;
-      const size_t col = (size_t)(cb + gl + G * k) * VEC;
-      float r[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; v++) r[v] = acc[k][v];
-      if (a.flags & GAI_EPI_ADD) {
-        float ad[VEC];
-        ldv<VEC>(a.addend + (size_t)row * a.ld_out + col, ad);
-#pragma unroll
-        for (int v = 0; v < VEC; v++) r[v] = __fadd_rn(r[v], ad[v]);
-      }
-      if (a.flags & GAI_EPI_RELU) {
-#pragma unroll
-        for (int v = 0; v < VEC; v++) r[v] = r[v] > 0.0f ? r[v] : 0.0f;
-      }
-      stv<VEC>(a.out + (size_t)row * a.ld_out + col, r);
-    }
+    for (int k = 0; k < K; k++)
+      if (act[k]) store_chunk(a, row, cb + gl + G * k, acc[k]);
   }
 }
 
-// Hub rows: one CTA per row; parallel gather into shared memory, then an in-order add per column.
-constexpr int HUB_THREADS = 256;
-constexpr int HUB_KMAX = 4;  // columns per thread per column block (block = 1024 columns)
+// ---- hub rows: warp-specialised CTA, mbarrier ring ------------------------------------------------------------------
+constexpr int HUB_CONS_THREADS = 128;  // warps 0..3: one thread per float4 column chunk
+constexpr int HUB_PROD_WARPS = 12;     // warps 4..15: gather + scale
+constexpr int HUB_THREADS = HUB_CONS_THREADS + HUB_PROD_WARPS * 32;
+constexpr int HUB_STAGES = 4;
+constexpr int HUB_MAX_CHUNKS = 128;    // column block = 512 floats
 
-template <int VEC>
-__global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows, int chunk_edges) {
-  extern __shared__ float tile[];  // [chunk_edges][Fb]
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// EW = edges per producer warp per stage (stage = 12*EW edges). Dynamic smem: HUB_STAGES * 12*EW * nch_blk float4.
+template <int EW>
+__global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
+  extern __shared__ float4 ring[];
+  __shared__ uint64_t full_bar[HUB_STAGES], empty_bar[HUB_STAGES];
+  constexpr int E = HUB_PROD_WARPS * EW;
   const uint32_t row = hub_rows[blockIdx.x];
-  if (row < a.row_begin || row >= a.row_end) return;
+  if (row < a.row_begin || row >= a.row_end) return;  // uniform for the CTA
   const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-  for (int cb = 0; cb < a.F; cb += HUB_THREADS * HUB_KMAX) {
-    const int Fb = (a.F - cb) < HUB_THREADS * HUB_KMAX ? (a.F - cb) : HUB_THREADS * HUB_KMAX;
-    const int nch = Fb / VEC;
-    float acc[HUB_KMAX];
+  const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const size_t ld4 = (size_t)a.ld_in >> 2;
+  uint32_t it = 0;  // global stage counter, carried across column blocks so that barrier phases keep alternating
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HUB_STAGES; i++) { mbar_init(&full_bar[i], HUB_PROD_WARPS); mbar_init(&empty_bar[i], HUB_CONS_THREADS / 32); }
+  }
+  __syncthreads();
+
+  for (int cb = 0; cb < a.nchunks; cb += HUB_MAX_CHUNKS) {
+    const int nch = (a.nchunks - cb) < HUB_MAX_CHUNKS ? (a.nchunks - cb) : HUB_MAX_CHUNKS;
+    if (warp >= HUB_CONS_THREADS / 32) {
+      // ---------------- producers ----------------
+      const int pw = warp - HUB_CONS_THREADS / 32;
+      const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
+      uint32_t my_it = it;
+      for (uint32_t base = s; base < e; base += E, my_it++) {
+        const int stage = my_it % HUB_STAGES;
+        mbar_wait(&empty_bar[stage], ((my_it / HUB_STAGES) & 1) ^ 1);
+        float4* tile = ring + (size_t)stage * E * nch;
+        uint32_t c[EW];
+        float w[EW];
 #pragma unroll
-    for (int k = 0; k < HUB_KMAX; k++) acc[k] = 0.0f;
-    for (uint32_t base = s; base < e; base += chunk_edges) {
-      const int cnt = (e - base) < (uint32_t)chunk_edges ? (int)(e - base) : chunk_edges;
-      for (int j0 = warp * 2; j0 < cnt; j0 += (HUB_THREADS / 32) * 2) {
-        uint32_t c[2];
-        float w[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const int j = j0 + u;
+        for (int u = 0; u < EW; u++) {
+          const uint32_t idx = base + pw * EW + u;
           c[u] = 0; w[u] = 0.0f;
-          if (j < cnt) {
-            c[u] = __ldg(a.colidx + base + j);
-            w[u] = edge_weight(a, wrow, base + j, c[u]);
-          }
+          if (idx < e) { c[u] = __ldg(a.colidx + idx); w[u] = edge_weight(a, wrow, idx, c[u]); }
         }
         for (int ch = lane; ch < nch; ch += 32) {
-          float x[2][VEC];
+          float4 x[EW];
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (j0 + u < cnt) ldv<VEC>(a.in + (size_t)c[u] * a.ld_in + cb + (size_t)ch * VEC, x[u]);
-          }
+          for (int u = 0; u < EW; u++)
+            if (base + pw * EW + u < e) x[u] = __ldg(in4 + (size_t)c[u] * ld4 + cb + ch);
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (j0 + u < cnt) {
-#pragma unroll
-              for (int v = 0; v < VEC; v++) tile[(size_t)(j0 + u) * Fb + ch * VEC + v] = __fmul_rn(w[u], x[u][v]);
+          for (int u = 0; u < EW; u++) {
+            if (base + pw * EW + u < e) {
+              float4 p;
+              p.x = __fmul_rn(w[u], x[u].x); p.y = __fmul_rn(w[u], x[u].y); p.z = __fmul_rn(w[u], x[u].z); p.w = __fmul_rn(w[u], x[u].w);
+              tile[(size_t)(pw * EW + u) * nch + ch] = p;
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
       }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < HUB_KMAX; k++) {
-        const int col = threadIdx.x + k * HUB_THREADS;
-        if (col < Fb) {
-          float r = acc[k];
-          for (int j = 0; j < cnt; j++) r = __fadd_rn(r, tile[(size_t)j * Fb + col]);
-          acc[k] = r;
+    } else {
+      // ---------------- consumers: in-order add, one float4 chunk per thread ----------------
+      const int t = threadIdx.x;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t my_it = it;
+      for (uint32_t base = s; base < e; base += E, my_it++) {
+        const int stage = my_it % HUB_STAGES;
+        const int cnt = (e - base) < (uint32_t)E ? (int)(e - base) : E;
+        mbar_wait(&full_bar[stage], (my_it / HUB_STAGES) & 1);
+        if (t < nch) {
+          const float4* tile = ring + (size_t)stage * E * nch + t;
+#pragma unroll 4
+          for (int j = 0; j < cnt; j++) {
+            const float4 p = tile[(size_t)j * nch];
+            acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+          }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
       }
-      __syncthreads();
+      if (t < nch) store_chunk(a, row, cb + t, acc);
     }
-#pragma unroll
-    for (int k = 0; k < HUB_KMAX; k++) {
-      const int col = threadIdx.x + k * HUB_THREADS;
-      if (col < Fb) {
-        float r = acc[k];
-        const size_t o = (size_t)row * a.ld_out + cb + col;
-        if (a.flags & GAI_EPI_ADD) r = __fadd_rn(r, __ldg(a.addend + o));
-        if (a.flags & GAI_EPI_RELU) r = r > 0.0f ? r : 0.0f;
-        a.out[o] = r;
-      }
-    }
+    it += (e - s + E - 1) / E;
   }
 }
 
-inline bool aligned(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+// in [n x F] (ld_in) -> padded [n x 4*nchunks], zero-filled tail columns
+__global__ void pad_rows_kernel(size_t n_rows, int F, int Fp, const float* __restrict__ in, int ld_in, float* __restrict__ out) {
+  const size_t total = n_rows * (size_t)Fp;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / Fp;
+    const int c = (int)(i % Fp);
+    out[i] = c < F ? __ldg(in + r * ld_in + c) : 0.0f;
+  }
+}
 
-template <int VEC>
+inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
+
 int launch_rows(const SpmmArgs& a, cudaStream_t st) {
-  const int nchunks = a.F / VEC;
   const uint64_t rows = (uint64_t)a.row_end - a.row_begin;
   int G = 4;
-  while (G < 32 && G < nchunks) G <<= 1;
+  while (G < 32 && G < a.nchunks) G <<= 1;
   int K = 1;
-  if (G == 32) { K = (nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
+  if (G == 32) { K = (a.nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
   const uint64_t rows_per_cta = (uint64_t)8 * (32 / G);
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
   if (grid == 0) return GAI_OK;
-#define GAI_SPMM_CASE(g_, k_) spmm_rows_kernel<VEC, g_, k_><<<grid, 256, 0, st>>>(a)
-  if (G == 4) GAI_SPMM_CASE(4, 1);
-  else if (G == 8) GAI_SPMM_CASE(8, 1);
-  else if (G == 16) GAI_SPMM_CASE(16, 1);
-  else if (K == 1) GAI_SPMM_CASE(32, 1);
-  else if (K == 2) GAI_SPMM_CASE(32, 2);
-  else GAI_SPMM_CASE(32, 4);
-#undef GAI_SPMM_CASE
+  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(a);
+  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(a);
+  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(a);
+  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(a);
+  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(a);
+  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(a);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
 
-template <int VEC>
-int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
-  if (g->n_hub == 0) return GAI_OK;
-  const int Fb = a.F < HUB_THREADS * HUB_KMAX ? a.F : HUB_THREADS * HUB_KMAX;
-  int chunk = (int)((48 * 1024) / (sizeof(float) * (size_t)Fb));
-  if (chunk > 64) chunk = 64;
-  if (chunk < 1) chunk = 1;
-  const size_t smem = sizeof(float) * (size_t)chunk * Fb;
-  spmm_hub_kernel<VEC><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows, chunk);
+template <int EW>
+int launch_hub_ew(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  spmm_hub_kernel<EW><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
+}
+
+int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+  if (g->n_hub == 0) return GAI_OK;
+  const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
+  // largest EW in {4,2,1} whose 4-stage ring fits 96 KB (two CTAs per SM)
+  auto bytes = [&](int ew) { return (size_t)HUB_STAGES * HUB_PROD_WARPS * ew * nch * sizeof(float4); };
+  if (bytes(4) <= 96 * 1024) return launch_hub_ew<4>(a, g, bytes(4), st);
+  if (bytes(2) <= 96 * 1024) return launch_hub_ew<2>(a, g, bytes(2), st);
+  return launch_hub_ew<1>(a, g, bytes(1), st);
 }
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
@@ -273,20 +315,33 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   GAI_CHECK_ARG(!(flags & GAI_EPI_ADD) || addend != nullptr);
   GAI_CHECK_ARG(mode < M_EDGE || vals != nullptr);
   GAI_CHECK_ARG(in != out);
+  cudaStream_t st = gai::S(stream);
   SpmmArgs a;
   a.rowptr = g->rowptr; a.colidx = g->colidx;
   a.norm = (mode == M_GCN) ? g->norm_gcn : g->norm_mean;
-  a.vals = vals; a.perm = perm; a.in = in; a.out = out; a.addend = addend;
-  a.F = F; a.ld_in = ld_in; a.ld_out = ld_out; a.row_begin = rb; a.row_end = re;
+  a.vals = vals; a.perm = perm; a.out = out; a.addend = addend;
+  a.F = F; a.nchunks = (F + 3) / 4; a.ld_out = ld_out; a.row_begin = rb; a.row_end = re;
   a.mode = mode; a.flags = flags;
   a.hub_threshold = g->n_hub ? gai::HUB_DEGREE : 0xffffffffu;
-  cudaStream_t st = gai::S(stream);
-  const bool v4 = (F % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && aligned(in, 16) && aligned(out, 16) && aligned(addend, 16);
-  const bool v2 = (F % 2 == 0) && (ld_in % 2 == 0) && (ld_out % 2 == 0) && aligned(in, 8) && aligned(out, 8) && aligned(addend, 8);
-  int rc;
-  if (v4) { rc = launch_rows<4>(a, st); if (rc == GAI_OK) rc = launch_hub<4>(a, g, st); }
-  else if (v2) { rc = launch_rows<2>(a, st); if (rc == GAI_OK) rc = launch_hub<2>(a, g, st); }
-  else { rc = launch_rows<1>(a, st); if (rc == GAI_OK) rc = launch_hub<1>(a, g, st); }
+  a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
+  if ((F % 4 == 0) && (ld_in % 4 == 0) && aligned16(in)) {
+    a.in = in; a.ld_in = ld_in;
+  } else {
+    // gather source must be 128-bit loadable: stage a zero-padded copy (all nv rows can be neighbours)
+    const int Fp = a.nchunks * 4;
+    void* ws = nullptr;
+    int rc = gai::workspace_slot(1, sizeof(float) * (size_t)g->nv * Fp, &ws);
+    if (rc != GAI_OK) return rc;
+    const size_t total = (size_t)g->nv * Fp;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)gai::sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    pad_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(g->nv, F, Fp, in, ld_in, reinterpret_cast<float*>(ws));
+    GAI_LAUNCH_CHECK();
+    a.in = reinterpret_cast<const float*>(ws); a.ld_in = Fp;
+  }
+  int rc = launch_rows(a, st);
+  if (rc == GAI_OK) rc = launch_hub(a, g, st);
   return rc;
 }
 
