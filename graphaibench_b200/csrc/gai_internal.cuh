@@ -38,7 +38,9 @@ int sm_count();
 int workspace(size_t bytes, void** out);          // slot 0: split-K partials, GAT per-vertex scratch, reductions
 int workspace_slot(int slot, size_t bytes, void** out);  // slot 1: SpMM padded-input staging
 
-constexpr uint32_t HUB_DEGREE = 1024;  // rows longer than this go to the CTA-per-row kernel
+// Hub threshold: rows longer than a warp's fair share of the edges (nnz / resident warp slots), clamped to [1024, 8192],
+// go to the CTA-per-row kernels; everything else is one lane-group per row.
+uint32_t hub_degree_for(uint64_t nnz);
 
 }  // namespace gai
 
@@ -53,6 +55,7 @@ struct gai_csr {
   float* norm_mean = nullptr;  // 1/deg
   uint32_t* hub_rows = nullptr;
   uint32_t n_hub = 0;
+  uint32_t hub_degree = 1024;
   uint32_t* tperm = nullptr;  // e -> e^T
   bool owns_csr = false;
 };

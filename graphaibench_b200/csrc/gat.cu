@@ -237,7 +237,7 @@ __global__ void alpha_grad_stage2(int F, int nparts, const float* __restrict__ p
 RowSel make_sel(gai_csr_t g) {
   RowSel r;
   r.rowptr = g->rowptr; r.hub_rows = g->hub_rows; r.nv = g->nv; r.n_hub = g->n_hub;
-  r.hub_threshold = g->n_hub ? gai::HUB_DEGREE : 0xffffffffu;
+  r.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   return r;
 }
 inline unsigned warp_grid(uint32_t nv) { return (unsigned)(((uint64_t)nv * 32 + 255) / 256); }

@@ -11,7 +11,7 @@ namespace {
 //   sage_aggregator.cpp:17  b = float(1.0 / double(float(deg)))        (inf for deg == 0, never used by a row of its own)
 __global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, float* __restrict__ norm_gcn,
                              float* __restrict__ norm_mean, uint32_t* __restrict__ hub_rows, uint32_t* __restrict__ hub_count,
-                             uint32_t hub_cap) {
+                             uint32_t hub_cap, uint32_t hub_degree) {
   uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   uint32_t deg = rowptr[v + 1] - rowptr[v];
@@ -19,7 +19,7 @@ __global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, f
   float t = __fsqrt_rn(fdeg);
   norm_gcn[v] = (t == 0.0f) ? 0.0f : __double2float_rn(__ddiv_rn(1.0, (double)t));
   norm_mean[v] = __double2float_rn(__ddiv_rn(1.0, (double)fdeg));
-  if (deg > gai::HUB_DEGREE) {
+  if (deg > hub_degree) {
     uint32_t slot = atomicAdd(hub_count, 1u);
     if (slot < hub_cap) hub_rows[slot] = v;
   }
@@ -52,12 +52,13 @@ __global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ 
 int finish_create(gai_csr* g, cudaStream_t st) {
   GAI_CUDA(cudaMalloc(&g->norm_gcn, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
   GAI_CUDA(cudaMalloc(&g->norm_mean, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
-  uint32_t hub_cap = (uint32_t)(g->nnz / gai::HUB_DEGREE) + 1;
+  g->hub_degree = gai::hub_degree_for(g->nnz);
+  uint32_t hub_cap = (uint32_t)(g->nnz / g->hub_degree) + 1;
   GAI_CUDA(cudaMalloc(&g->hub_rows, sizeof(uint32_t) * (size_t)(hub_cap + 1)));
   uint32_t* d_count = g->hub_rows + hub_cap;
   GAI_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
   if (g->nv) {
-    norms_kernel<<<(g->nv + 255) / 256, 256, 0, st>>>(g->nv, g->rowptr, g->norm_gcn, g->norm_mean, g->hub_rows, d_count, hub_cap);
+    norms_kernel<<<(g->nv + 255) / 256, 256, 0, st>>>(g->nv, g->rowptr, g->norm_gcn, g->norm_mean, g->hub_rows, d_count, hub_cap, g->hub_degree);
     GAI_LAUNCH_CHECK();
   }
   uint32_t n_hub = 0;

@@ -7,12 +7,21 @@
 
 namespace gai {
 
+int sm_count();
 static thread_local std::string g_err;
 unsigned long long g_launches = 0;
 
 int set_error(int code, const char* what, const char* detail) {
   g_err = std::string(what ? what : "") + ": " + (detail ? detail : "");
   return code;
+}
+
+uint32_t hub_degree_for(uint64_t nnz) {
+  const uint64_t slots = (uint64_t)sm_count() * 32;
+  uint64_t t = nnz / (slots ? slots : 1);
+  if (t < 1024) t = 1024;
+  if (t > 8192) t = 8192;
+  return (uint32_t)t;
 }
 
 int sm_count() {

@@ -8,12 +8,13 @@
 //   * every input row is read with 128-bit loads: if F % 4 != 0 or the layout is misaligned, the input is first copied
 //     into a zero-padded workspace with ld = ceil4(F) (one N x F pass, ~1% of the gather traffic).
 //   * row-split by degree bucket.
-//       light rows (deg <= HUB_DEGREE): a group of G lanes (G = 4..32, from the feature width) owns one output row in
+//       light rows (deg <= hub_degree): a group of G lanes (G = 4..32, from the feature width) owns one output row in
 //         registers; the group loads G column indices + edge weights with one coalesced request, broadcasts them by
 //         shuffle, and keeps U independent 128-bit neighbour-row loads in flight per lane.
-//       hub rows (deg > HUB_DEGREE): one warp-specialised CTA per row. 12 producer warps gather + scale neighbour rows
-//         into a 4-stage shared-memory ring (mbarrier full/empty pairs); 4 consumer warps (one thread per 4 columns)
-//         add the staged products IN EDGE ORDER. The gather runs at SM bandwidth while the add chain stays sequential.
+//       hub rows (deg > hub_degree, a per-graph threshold = a warp's fair share of the edges): one warp-specialised CTA
+//         per row. 16 producer warps gather + scale neighbour rows into a shared-memory ring (one slot per producer,
+//         mbarrier full/empty pairs); 4 consumer warps (one thread per 4 columns) add the staged products IN EDGE
+//         ORDER. The gather runs at SM bandwidth while the add chain stays sequential.
 //   * numerics: acc = fadd_rn(acc, fmul_rn(w, x)) per edge, sequential per column — exactly the reference CPU path's
 //     scale()+vadd() (math_functions.cpp:266,336): results are bit-identical for every row length, hub rows included.
 //   * fused: zero-init (no memset pass), optional "+ addend" and ReLU epilogue, leading dimensions, row ranges
@@ -149,11 +150,17 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
 }
 
 // ---- hub rows: warp-specialised CTA, mbarrier ring ------------------------------------------------------------------
-constexpr int HUB_CONS_THREADS = 128;  // warps 0..3: one thread per float4 column chunk
-constexpr int HUB_PROD_WARPS = 12;     // warps 4..15: gather + scale
+// 16 producer warps + 4 consumer warps. Producer warp w owns ring slot w and fills it for stages w, w+16, w+32, ...
+// (stage k = edges [s + k*ES, s + (k+1)*ES) of the row): it loads the stage's column indices / weights with one
+// coalesced request (prefetched one stage ahead), gathers the ES neighbour rows with up to 8 independent 128-bit loads in
+// flight per lane, scales them and stores the PRODUCTS into its slot. The consumers (one thread per float4 column
+// chunk) wait for the slots in stage order and add the products in edge order, so the fp32 result is the sequential
+// sum the reference computes, while 16 stages are being gathered concurrently.
+constexpr int HUB_CONS_WARPS = 4;
+constexpr int HUB_CONS_THREADS = HUB_CONS_WARPS * 32;
+constexpr int HUB_PROD_WARPS = 16;
 constexpr int HUB_THREADS = HUB_CONS_THREADS + HUB_PROD_WARPS * 32;
-constexpr int HUB_STAGES = 4;
-constexpr int HUB_MAX_CHUNKS = 128;    // column block = 512 floats
+constexpr int HUB_MAX_CHUNKS = 128;  // column block = 512 floats
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -170,84 +177,110 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-// EW = edges per producer warp per stage (stage = 12*EW edges). Dynamic smem: HUB_STAGES * 12*EW * nch_blk float4.
-template <int EW>
+// ES = edges per stage (16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(nchunks,128) float4.
+template <int ES>
 __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
   extern __shared__ float4 ring[];
-  __shared__ uint64_t full_bar[HUB_STAGES], empty_bar[HUB_STAGES];
-  constexpr int E = HUB_PROD_WARPS * EW;
+  __shared__ uint64_t full_bar[HUB_PROD_WARPS], empty_bar[HUB_PROD_WARPS];
   const uint32_t row = hub_rows[blockIdx.x];
   if (row < a.row_begin || row >= a.row_end) return;  // uniform for the CTA
   const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+  const uint32_t nstages = (e - s + ES - 1) / ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
   const size_t ld4 = (size_t)a.ld_in >> 2;
-  uint32_t it = 0;  // global stage counter, carried across column blocks so that barrier phases keep alternating
+  const int nch_max = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
+  const size_t slot_stride = (size_t)ES * nch_max;
+  uint32_t blk = 0;  // column-block index; slot p has been used blk * uses(p) times before this block (mbarrier phase bookkeeping)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < HUB_STAGES; i++) { mbar_init(&full_bar[i], HUB_PROD_WARPS); mbar_init(&empty_bar[i], HUB_CONS_THREADS / 32); }
+    for (int i = 0; i < HUB_PROD_WARPS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], HUB_CONS_WARPS); }
   }
   __syncthreads();
 
   for (int cb = 0; cb < a.nchunks; cb += HUB_MAX_CHUNKS) {
     const int nch = (a.nchunks - cb) < HUB_MAX_CHUNKS ? (a.nchunks - cb) : HUB_MAX_CHUNKS;
-    if (warp >= HUB_CONS_THREADS / 32) {
+    if (warp >= HUB_CONS_WARPS) {
       // ---------------- producers ----------------
-      const int pw = warp - HUB_CONS_THREADS / 32;
+      const int pw = warp - HUB_CONS_WARPS;
       const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-      uint32_t my_it = it;
-      for (uint32_t base = s; base < e; base += E, my_it++) {
-        const int stage = my_it % HUB_STAGES;
-        mbar_wait(&empty_bar[stage], ((my_it / HUB_STAGES) & 1) ^ 1);
-        float4* tile = ring + (size_t)stage * E * nch;
-        uint32_t c[EW];
-        float w[EW];
-#pragma unroll
-        for (int u = 0; u < EW; u++) {
-          const uint32_t idx = base + pw * EW + u;
-          c[u] = 0; w[u] = 0.0f;
-          if (idx < e) { c[u] = __ldg(a.colidx + idx); w[u] = edge_weight(a, wrow, idx, c[u]); }
+      float4* slot = ring + (size_t)pw * slot_stride;
+      const uint32_t round0 = blk * ((nstages + HUB_PROD_WARPS - 1 - pw) / HUB_PROD_WARPS);
+      // prefetch the first stage's indices / weights (lane l < ES holds edge l of the stage)
+      uint32_t c = 0; float w = 0.0f;
+      {
+        const uint32_t idx = s + (uint32_t)pw * ES + lane;
+        if (lane < ES && idx < e) { c = __ldg(a.colidx + idx); w = edge_weight(a, wrow, idx, c); }
+      }
+      for (uint32_t k = pw, r = 0; k < nstages; k += HUB_PROD_WARPS, r++) {
+        const uint32_t base = s + k * ES;
+        const int cnt = (e - base) < (uint32_t)ES ? (int)(e - base) : ES;
+        const uint32_t cur_c = c; const float cur_w = w;
+        // prefetch the next stage this warp owns
+        c = 0; w = 0.0f;
+        {
+          const uint64_t nidx = (uint64_t)base + (uint64_t)HUB_PROD_WARPS * ES + lane;
+          if (lane < ES && nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight(a, wrow, (uint32_t)nidx, c); }
         }
-        for (int ch = lane; ch < nch; ch += 32) {
-          float4 x[EW];
+        mbar_wait(&empty_bar[pw], ((round0 + r) & 1) ^ 1);
+        for (int ch0 = 0; ch0 < nch; ch0 += 32) {
+          const int ch = ch0 + lane;
+          const bool chv = ch < nch;
+          constexpr int UB = ES < 8 ? ES : 8;
 #pragma unroll
-          for (int u = 0; u < EW; u++)
-            if (base + pw * EW + u < e) x[u] = __ldg(in4 + (size_t)c[u] * ld4 + cb + ch);
+          for (int j0 = 0; j0 < ES; j0 += UB) {
+            float4 x[UB]; float ww[UB];
 #pragma unroll
-          for (int u = 0; u < EW; u++) {
-            if (base + pw * EW + u < e) {
-              float4 p;
-              p.x = __fmul_rn(w[u], x[u].x); p.y = __fmul_rn(w[u], x[u].y); p.z = __fmul_rn(w[u], x[u].z); p.w = __fmul_rn(w[u], x[u].w);
-              tile[(size_t)(pw * EW + u) * nch + ch] = p;
+            for (int u = 0; u < UB; u++) {
+              const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j0 + u);
+              ww[u] = __shfl_sync(0xffffffffu, cur_w, j0 + u);
+              if (chv && j0 + u < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + ch);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+              if (chv && j0 + u < cnt) {
+                float4 p;
+                p.x = __fmul_rn(ww[u], x[u].x); p.y = __fmul_rn(ww[u], x[u].y); p.z = __fmul_rn(ww[u], x[u].z); p.w = __fmul_rn(ww[u], x[u].w);
+                slot[(size_t)(j0 + u) * nch + ch] = p;
+              }
             }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (lane == 0) mbar_arrive(&full_bar[pw]);
       }
     } else {
       // ---------------- consumers: in-order add, one float4 chunk per thread ----------------
       const int t = threadIdx.x;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t my_it = it;
-      for (uint32_t base = s; base < e; base += E, my_it++) {
-        const int stage = my_it % HUB_STAGES;
-        const int cnt = (e - base) < (uint32_t)E ? (int)(e - base) : E;
-        mbar_wait(&full_bar[stage], (my_it / HUB_STAGES) & 1);
+      for (uint32_t k = 0; k < nstages; k++) {
+        const int pw = k % HUB_PROD_WARPS;
+        const uint32_t r = k / HUB_PROD_WARPS;
+        const uint32_t round0 = blk * ((nstages + HUB_PROD_WARPS - 1 - pw) / HUB_PROD_WARPS);
+        const uint32_t base = s + k * ES;
+        const int cnt = (e - base) < (uint32_t)ES ? (int)(e - base) : ES;
+        mbar_wait(&full_bar[pw], (round0 + r) & 1);
         if (t < nch) {
-          const float4* tile = ring + (size_t)stage * E * nch + t;
-#pragma unroll 4
-          for (int j = 0; j < cnt; j++) {
-            const float4 p = tile[(size_t)j * nch];
-            acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+          const float4* tile = ring + (size_t)pw * slot_stride + t;
+          if (cnt == ES) {
+#pragma unroll
+            for (int j = 0; j < ES; j++) {
+              const float4 p = tile[(size_t)j * nch];
+              acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+            }
+          } else {
+            for (int j = 0; j < cnt; j++) {
+              const float4 p = tile[(size_t)j * nch];
+              acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+            }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (lane == 0) mbar_arrive(&empty_bar[pw]);
       }
       if (t < nch) store_chunk(a, row, cb + t, acc);
     }
-    it += (e - s + E - 1) / E;
+    blk++;
   }
 }
 
@@ -283,14 +316,14 @@ int launch_rows(const SpmmArgs& a, cudaStream_t st) {
   return GAI_OK;
 }
 
-template <int EW>
-int launch_hub_ew(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
+template <int ES>
+int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  spmm_hub_kernel<EW><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
+  spmm_hub_kernel<ES><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -298,11 +331,11 @@ int launch_hub_ew(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t
 int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   if (g->n_hub == 0) return GAI_OK;
   const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
-  // largest EW in {4,2,1} whose 4-stage ring fits 96 KB (two CTAs per SM)
-  auto bytes = [&](int ew) { return (size_t)HUB_STAGES * HUB_PROD_WARPS * ew * nch * sizeof(float4); };
-  if (bytes(4) <= 96 * 1024) return launch_hub_ew<4>(a, g, bytes(4), st);
-  if (bytes(2) <= 96 * 1024) return launch_hub_ew<2>(a, g, bytes(2), st);
-  return launch_hub_ew<1>(a, g, bytes(1), st);
+  // largest stage size in {16, 8, 4} edges whose 16-slot ring fits 192 KB of shared memory
+  auto bytes = [&](int es) { return (size_t)HUB_PROD_WARPS * es * nch * sizeof(float4); };
+  if (bytes(16) <= 192 * 1024) return launch_hub_es<16>(a, g, bytes(16), st);
+  if (bytes(8) <= 192 * 1024) return launch_hub_es<8>(a, g, bytes(8), st);
+  return launch_hub_es<4>(a, g, bytes(4), st);
 }
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
@@ -322,7 +355,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.vals = vals; a.perm = perm; a.out = out; a.addend = addend;
   a.F = F; a.nchunks = (F + 3) / 4; a.ld_out = ld_out; a.row_begin = rb; a.row_end = re;
   a.mode = mode; a.flags = flags;
-  a.hub_threshold = g->n_hub ? gai::HUB_DEGREE : 0xffffffffu;
+  a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
   if ((F % 4 == 0) && (ld_in % 4 == 0) && aligned16(in)) {
     a.in = in; a.ld_in = ld_in;
