@@ -56,6 +56,10 @@ struct gai_csr {
   uint32_t* hub_rows = nullptr;
   uint32_t n_hub = 0;
   uint32_t hub_degree = 1024;
+  unsigned long long* row_counters = nullptr;  // 16 rotating work counters for the persistent light-row kernel
+  unsigned counter_seq = 0;
+  cudaStream_t aux_stream = nullptr;  // hub-row kernels run here, concurrently with the light-row kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* tperm = nullptr;  // e -> e^T
   bool owns_csr = false;
 };

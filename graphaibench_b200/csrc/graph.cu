@@ -1,6 +1,7 @@
 // Device CSR for the GNN path: upload, degree normalisers, hub-row list, transpose permutation.
 // Replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data (src/gnn/lgraph.cu:51-105) and the
 // per-backward cusparseCsr2cscEx2 call (src/utilities/math_functions.cu:345-358, src/gnn/gconv/gat_aggregator.cu:86-89).
+#include <algorithm>
 #include <vector>
 #include "gai_internal.cuh"
 
@@ -21,7 +22,7 @@ __global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, f
   norm_mean[v] = __double2float_rn(__ddiv_rn(1.0, (double)fdeg));
   if (deg > hub_degree) {
     uint32_t slot = atomicAdd(hub_count, 1u);
-    if (slot < hub_cap) hub_rows[slot] = v;
+    if (slot < hub_cap) { hub_rows[slot] = v; hub_rows[hub_cap + 1 + slot] = deg; }
   }
 }
 
@@ -52,9 +53,10 @@ __global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ 
 int finish_create(gai_csr* g, cudaStream_t st) {
   GAI_CUDA(cudaMalloc(&g->norm_gcn, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
   GAI_CUDA(cudaMalloc(&g->norm_mean, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
+  GAI_CUDA(cudaMalloc(&g->row_counters, sizeof(unsigned long long) * 16));
   g->hub_degree = gai::hub_degree_for(g->nnz);
   uint32_t hub_cap = (uint32_t)(g->nnz / g->hub_degree) + 1;
-  GAI_CUDA(cudaMalloc(&g->hub_rows, sizeof(uint32_t) * (size_t)(hub_cap + 1)));
+  GAI_CUDA(cudaMalloc(&g->hub_rows, sizeof(uint32_t) * (size_t)(2 * hub_cap + 1)));  // [rows | count | degrees]
   uint32_t* d_count = g->hub_rows + hub_cap;
   GAI_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
   if (g->nv) {
@@ -65,6 +67,17 @@ int finish_create(gai_csr* g, cudaStream_t st) {
   GAI_CUDA(cudaMemcpyAsync(&n_hub, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GAI_CUDA(cudaStreamSynchronize(st));
   g->n_hub = n_hub < hub_cap ? n_hub : hub_cap;
+  if (g->n_hub > 1) {
+    // longest rows first: the hub kernel's CTAs are scheduled in list order and the longest row is the critical path
+    std::vector<uint32_t> rows(g->n_hub), degs(g->n_hub), order(g->n_hub);
+    GAI_CUDA(cudaMemcpy(rows.data(), g->hub_rows, sizeof(uint32_t) * g->n_hub, cudaMemcpyDeviceToHost));
+    GAI_CUDA(cudaMemcpy(degs.data(), g->hub_rows + hub_cap + 1, sizeof(uint32_t) * g->n_hub, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < g->n_hub; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return degs[x] != degs[y] ? degs[x] > degs[y] : rows[x] < rows[y]; });
+    std::vector<uint32_t> sorted(g->n_hub);
+    for (uint32_t i = 0; i < g->n_hub; i++) sorted[i] = rows[order[i]];
+    GAI_CUDA(cudaMemcpy(g->hub_rows, sorted.data(), sizeof(uint32_t) * g->n_hub, cudaMemcpyHostToDevice));
+  }
   return GAI_OK;
 }
 
@@ -133,7 +146,8 @@ int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, c
 int gai_csr_destroy(gai_csr_t g) {
   if (!g) return GAI_OK;
   if (g->owns_csr) { cudaFree(g->rowptr); cudaFree(g->colidx); }
-  cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->hub_rows); cudaFree(g->tperm);
+  cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->hub_rows); cudaFree(g->tperm); cudaFree(g->row_counters);
+  if (g->aux_stream) { cudaStreamDestroy(g->aux_stream); cudaEventDestroy(g->ev_fork); cudaEventDestroy(g->ev_join); }
   delete g;
   return GAI_OK;
 }

@@ -78,19 +78,11 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int
 }
 
 // ---- light rows -----------------------------------------------------------------------------------------------------
+// One output row per group of G lanes, kept in registers.
 template <int G, int K>
-__global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
-  constexpr int ROWS_PER_WARP = 32 / G;
+__device__ __forceinline__ void spmm_one_row(const SpmmArgs& a, uint32_t row, int gl, unsigned gmask) {
   constexpr int UMAX = (K == 1) ? 8 : (K == 2 ? 4 : 2);
   constexpr int U = G < UMAX ? G : UMAX;  // independent neighbour rows in flight per lane (up to 8 float4)
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G;
-  const int grp = lane / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-  const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const uint64_t row64 = (uint64_t)a.row_begin + warp_global * ROWS_PER_WARP + grp;
-  if (row64 >= a.row_end) return;
-  const uint32_t row = (uint32_t)row64;
   const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
   if (e - s > a.hub_threshold) return;
   const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
@@ -146,6 +138,32 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
 #pragma unroll
     for (int k = 0; k < K; k++)
       if (act[k]) store_chunk(a, row, cb + gl + G * k, acc[k]);
+  }
+}
+
+// Persistent warps (grid = 4 CTAs per SM): each warp claims ROW_CHUNK consecutive row-groups at a time from a global
+// counter, so a warp that drew a long row does not hold idle siblings resident (power-law graphs: 40% of the rows of the
+// bench graph are empty while others are 8 K edges long).
+constexpr int ROW_CHUNK = 8;
+
+template <int G, int K>
+__global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, unsigned long long* __restrict__ counter) {
+  constexpr int ROWS_PER_WARP = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int grp = lane / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+  const unsigned long long nrows = (unsigned long long)a.row_end - a.row_begin;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)(ROW_CHUNK * ROWS_PER_WARP));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= nrows) break;
+#pragma unroll 1
+    for (int i = 0; i < ROW_CHUNK; i++) {
+      const unsigned long long r = base + (unsigned long long)i * ROWS_PER_WARP + grp;
+      if (r < nrows) spmm_one_row<G, K>(a, (uint32_t)(a.row_begin + r), gl, gmask);
+    }
   }
 }
 
@@ -263,10 +281,12 @@ __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a,
         if (t < nch) {
           const float4* tile = ring + (size_t)pw * slot_stride + t;
           if (cnt == ES) {
+            float4 p[ES];  // all loads first (independent), then the dependent add chain
+#pragma unroll
+            for (int j = 0; j < ES; j++) p[j] = tile[(size_t)j * nch];
 #pragma unroll
             for (int j = 0; j < ES; j++) {
-              const float4 p = tile[(size_t)j * nch];
-              acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
+              acc.x = __fadd_rn(acc.x, p[j].x); acc.y = __fadd_rn(acc.y, p[j].y); acc.z = __fadd_rn(acc.z, p[j].z); acc.w = __fadd_rn(acc.w, p[j].w);
             }
           } else {
             for (int j = 0; j < cnt; j++) {
@@ -297,21 +317,29 @@ __global__ void pad_rows_kernel(size_t n_rows, int F, int Fp, const float* __res
 
 inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
 
-int launch_rows(const SpmmArgs& a, cudaStream_t st) {
+int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   const uint64_t rows = (uint64_t)a.row_end - a.row_begin;
   int G = 4;
   while (G < 32 && G < a.nchunks) G <<= 1;
   int K = 1;
   if (G == 32) { K = (a.nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
-  const uint64_t rows_per_cta = (uint64_t)8 * (32 / G);
-  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-  if (grid == 0) return GAI_OK;
-  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(a);
-  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(a);
-  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(a);
-  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(a);
-  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(a);
-  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(a);
+  const uint64_t rows_per_fetch = (uint64_t)ROW_CHUNK * (32 / G);
+  const uint64_t fetches = (rows + rows_per_fetch - 1) / rows_per_fetch;
+  uint64_t ctas = (fetches + 7) / 8;
+  const uint64_t persistent = (uint64_t)gai::sm_count() * 4;
+  if (ctas > persistent) ctas = persistent;
+  if (ctas == 0) return GAI_OK;
+  const unsigned grid = (unsigned)ctas;
+  // rotating work counters: launches on one stream are ordered; the rotation keeps up to 16 launches that overlap on
+  // different streams (interior / boundary rows of the 1D partition) from sharing a counter
+  unsigned long long* ctr = g->row_counters + (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 16u);
+  GAI_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(a, ctr);
+  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(a, ctr);
+  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(a, ctr);
+  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(a, ctr);
+  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(a, ctr);
+  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(a, ctr);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -373,8 +401,25 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
     GAI_LAUNCH_CHECK();
     a.in = reinterpret_cast<const float*>(ws); a.ld_in = Fp;
   }
-  int rc = launch_rows(a, st);
-  if (rc == GAI_OK) rc = launch_hub(a, g, st);
+  // Hub rows go first, on a high-priority side stream (fork/join with events): their CTAs are the long poles (one
+  // 94 K-edge row is ~0.3 ms of in-order adds), the persistent light-row warps on `st` fill the other SMs meanwhile.
+  int rc = GAI_OK;
+  if (g->n_hub) {
+    if (!g->aux_stream) {
+      int lo = 0, hi = 0;
+      GAI_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      GAI_CUDA(cudaStreamCreateWithPriority(&g->aux_stream, cudaStreamNonBlocking, hi));
+      GAI_CUDA(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+      GAI_CUDA(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+    }
+    GAI_CUDA(cudaEventRecord(g->ev_fork, st));
+    GAI_CUDA(cudaStreamWaitEvent(g->aux_stream, g->ev_fork, 0));
+    rc = launch_hub(a, g, g->aux_stream);
+    if (rc != GAI_OK) return rc;
+    GAI_CUDA(cudaEventRecord(g->ev_join, g->aux_stream));
+  }
+  rc = launch_rows(a, g, st);
+  if (g->n_hub) GAI_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
   return rc;
 }
 
