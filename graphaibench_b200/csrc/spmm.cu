@@ -41,6 +41,7 @@ struct SpmmArgs {
   int mode, flags;
   int out_vec;       // 1: out/addend rows are 16-byte aligned and F % 4 == 0 -> float4 epilogue
   uint32_t hub_threshold;
+  unsigned long long scramble;  // odd multiplier coprime to the row count (1 = natural order)
 };
 
 __device__ __forceinline__ float edge_weight(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
@@ -161,8 +162,10 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, uns
     if (base >= nrows) break;
 #pragma unroll 1
     for (int i = 0; i < ROW_CHUNK; i++) {
-      const unsigned long long r = base + (unsigned long long)i * ROWS_PER_WARP + grp;
-      if (r < nrows) spmm_one_row<G, K>(a, (uint32_t)(a.row_begin + r), gl, gmask);
+      const unsigned long long q = base + (unsigned long long)i * ROWS_PER_WARP + grp;
+      // multiplicative permutation of the work order (scramble is coprime to nrows): long rows that sit next to each
+      // other in id space (R-MAT, BFS orderings) land in different chunks; every row is still produced exactly once
+      if (q < nrows) spmm_one_row<G, K>(a, (uint32_t)(a.row_begin + (q * a.scramble) % nrows), gl, gmask);
     }
   }
 }
@@ -195,7 +198,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-// ES = edges per stage (16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(nchunks,128) float4.
+// ES = edges per stage (32, 16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(nchunks,128) float4.
 template <int ES>
 __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
   extern __shared__ float4 ring[];
@@ -281,12 +284,23 @@ __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a,
         if (t < nch) {
           const float4* tile = ring + (size_t)pw * slot_stride + t;
           if (cnt == ES) {
-            float4 p[ES];  // all loads first (independent), then the dependent add chain
+            // software pipeline in sub-blocks of SB edges: the shared-memory loads of sub-block i+1 are issued before the
+            // dependent add chain of sub-block i, so only the first load latency of a stage is exposed
+            constexpr int SB = ES < 8 ? ES : 8;
+            float4 p[2][SB];
 #pragma unroll
-            for (int j = 0; j < ES; j++) p[j] = tile[(size_t)j * nch];
+            for (int j = 0; j < SB; j++) p[0][j] = tile[(size_t)j * nch];
 #pragma unroll
-            for (int j = 0; j < ES; j++) {
-              acc.x = __fadd_rn(acc.x, p[j].x); acc.y = __fadd_rn(acc.y, p[j].y); acc.z = __fadd_rn(acc.z, p[j].z); acc.w = __fadd_rn(acc.w, p[j].w);
+            for (int b = 0; b < ES / SB; b++) {
+              if (b + 1 < ES / SB) {
+#pragma unroll
+                for (int j = 0; j < SB; j++) p[(b + 1) & 1][j] = tile[(size_t)((b + 1) * SB + j) * nch];
+              }
+#pragma unroll
+              for (int j = 0; j < SB; j++) {
+                const float4 q = p[b & 1][j];
+                acc.x = __fadd_rn(acc.x, q.x); acc.y = __fadd_rn(acc.y, q.y); acc.z = __fadd_rn(acc.z, q.z); acc.w = __fadd_rn(acc.w, q.w);
+              }
             }
           } else {
             for (int j = 0; j < cnt; j++) {
@@ -330,16 +344,26 @@ int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   if (ctas > persistent) ctas = persistent;
   if (ctas == 0) return GAI_OK;
   const unsigned grid = (unsigned)ctas;
+  SpmmArgs b = a;
+  b.scramble = 1;
+  if (rows > 64) {
+    static const unsigned long long primes[] = {1000003ull, 998244353ull, 2654435761ull, 40503ull, 7919ull};
+    for (unsigned long long pr : primes) {
+      unsigned long long x = pr % rows, y = rows;
+      while (y) { const unsigned long long t = x % y; x = y; y = t; }  // gcd(pr mod rows, rows)
+      if (x == 1 && (pr % rows) > 1) { b.scramble = pr % rows; break; }
+    }
+  }
   // rotating work counters: launches on one stream are ordered; the rotation keeps up to 16 launches that overlap on
   // different streams (interior / boundary rows of the 1D partition) from sharing a counter
   unsigned long long* ctr = g->row_counters + (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 16u);
   GAI_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
-  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(a, ctr);
-  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(a, ctr);
-  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(a, ctr);
-  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(a, ctr);
-  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(a, ctr);
-  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(a, ctr);
+  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(b, ctr);
+  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(b, ctr);
+  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(b, ctr);
+  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(b, ctr);
+  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(b, ctr);
+  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(b, ctr);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -348,7 +372,7 @@ template <int ES>
 int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     configured = true;
   }
   spmm_hub_kernel<ES><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
@@ -359,8 +383,10 @@ int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t
 int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   if (g->n_hub == 0) return GAI_OK;
   const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
-  // largest stage size in {16, 8, 4} edges whose 16-slot ring fits 192 KB of shared memory
+  // largest stage size in {32, 16, 8, 4} edges whose 16-slot ring fits 200 KB of shared memory (longer stages amortise the
+  // consumer's per-stage barrier round trip over more in-order adds)
   auto bytes = [&](int es) { return (size_t)HUB_PROD_WARPS * es * nch * sizeof(float4); };
+  if (bytes(32) <= 200 * 1024) return launch_hub_es<32>(a, g, bytes(32), st);
   if (bytes(16) <= 192 * 1024) return launch_hub_es<16>(a, g, bytes(16), st);
   if (bytes(8) <= 192 * 1024) return launch_hub_es<8>(a, g, bytes(8), st);
   return launch_hub_es<4>(a, g, bytes(4), st);
