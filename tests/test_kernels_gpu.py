@@ -241,3 +241,36 @@ def test_gather_rows(T, ops):
     ids = rng.integers(0, 1000, 333).astype(np.int32)
     out = ops.gather_rows(dev(T, ids), dev(T, src)).cpu().numpy()
     assert np.array_equal(out, src[ids])
+
+
+@pytest.mark.parametrize("shape", [(5000, 256, 100, 0), (8192, 47, 256, 0), (6000, 256, 47, 1), (4096, 16, 1433, 0), (20000, 100, 256, 1),
+                                   (4500, 7, 16, 0), (33000, 172, 128, 0)])
+def test_matmul_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape):
+    """tcgen05/TMEM path (mode 2 = forced, 3xTF32): fp32-level accuracy (norm-wise 1e-5) on aligned and unaligned widths,
+    ragged row counts, transposed weights, accumulate and ReLU epilogues. Mode 3 (single TF32 pass) is ~1e-3 by design."""
+    from graphaibench_b200._abi import lib
+    x, y, z, tb = shape
+    rng = np.random.default_rng(x + 3 * y + z)
+    A = rng.standard_normal((x, z), dtype=np.float32)
+    B = rng.standard_normal((y, z) if tb else (z, y), dtype=np.float32)
+    C0 = rng.standard_normal((x, y), dtype=np.float32)
+    ref = np.zeros((x, y), np.float32)
+    liborc.orc_gemm(x, y, z, A.reshape(-1), B.reshape(-1), ref.reshape(-1), 0, tb, 0)
+    try:
+        lib().gai_set_gemm_mode(2)
+        out = ops.matmul(dev(T, A), dev(T, B), transB=bool(tb))
+        close(out.cpu().numpy(), ref)
+        out = ops.matmul(dev(T, A), dev(T, B), transB=bool(tb), flags=ops.EPI_RELU)
+        close(out.cpu().numpy(), np.maximum(ref, 0))
+        acc = dev(T, C0.copy())
+        ops.matmul(dev(T, A), dev(T, B), out=acc, transB=bool(tb), accum=True)
+        ref2 = C0.copy()
+        liborc.orc_gemm(x, y, z, A.reshape(-1), B.reshape(-1), ref2.reshape(-1), 0, tb, 1)
+        close(acc.cpu().numpy(), ref2)
+        lib().gai_set_gemm_mode(3)
+        out = ops.matmul(dev(T, A), dev(T, B), transB=bool(tb))
+        close(out.cpu().numpy(), ref, 3e-3)
+        err1 = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err1 > 1e-6, "single-pass TF32 should be visibly less accurate than 3xTF32 (is the tensor-core path running?)"
+    finally:
+        lib().gai_set_gemm_mode(0)
