@@ -12,15 +12,14 @@
 // Kernel (persistent, one CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: per k-block (32 fp32 = one 128-byte swizzle row) loads the A tile [128 x 32] and the
 //               pre-split weight tiles B_hi/B_lo [N x 32] into a multi-stage shared-memory ring (mbarrier expect_tx).
-//   warps 8-11  splitter: rewrites the landed A tile in place as A_hi = A & 0xffffe000 and writes A_lo = (A - A_hi) &
-//               0xffffe000 next to it (same swizzled offsets), then fence.proxy.async + arrive.
+//   warps 8-11  splitter: rewrites the landed A tile in place as A_hi = rn_tf32(A) and writes A_lo = rn_tf32(A - A_hi)
+//               next to it (same swizzled offsets), then fence.proxy.async + arrive.
 //   warp 1      MMA issuer: one thread issues 3 x 4 tcgen05.mma (M128 x N x K8) per k-block into one of two TMEM
 //               accumulators; tcgen05.commit releases the smem stage / publishes the accumulator.
 //   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns per warp, optional "+C" and ReLU, 128-byte row stores.
 // The weight is prepared once per call by a tiny kernel (transpose to K-major if needed, zero-pad to [Npad x Kpad],
 // split into tf32 hi/lo) so that both operands are K-major and TMA-addressable whatever the caller's layout.
-#include <cuda.h>
-#include "gai_internal.cuh"
+#include "tc_common.cuh"
 
 namespace gai {
 
@@ -29,61 +28,8 @@ namespace {
 constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 32;           // fp32 per k-block = 128 bytes = one SWIZZLE_128B row
 constexpr int THREADS = 384;
-constexpr uint32_t TF32_MASK = 0xffffe000u;
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
-// leading byte offset (unused for swizzled K-major, set to 1) in [16,30), stride byte offset = 1024 B (8 rows x 128 B)
-// >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
+using namespace tc;
 
 struct TcArgs {
   float* C;
@@ -191,11 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int idx = t + i * 128;
             uint4 v = hi[idx];
             uint4 h, l;
-            h.x = v.x & TF32_MASK; h.y = v.y & TF32_MASK; h.z = v.z & TF32_MASK; h.w = v.w & TF32_MASK;
-            l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(h.x))) & TF32_MASK;
-            l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(h.y))) & TF32_MASK;
-            l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(h.z))) & TF32_MASK;
-            l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(h.w))) & TF32_MASK;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
             hi[idx] = h;
             lo[idx] = l;
           }
@@ -264,9 +206,10 @@ __global__ void prep_b_kernel(const float* __restrict__ B, size_t ldb, int tb, s
     const size_t n = i / k_pad, k = i % k_pad;
     float v = 0.f;
     if (n < N && k < K) v = tb ? B[n * ldb + k] : B[k * ldb + n];
-    const uint32_t h = __float_as_uint(v) & TF32_MASK;
+    uint32_t h, l;
+    split_tf32(__float_as_uint(v), h, l);
     hi[i] = __uint_as_float(h);
-    lo[i] = __uint_as_float(__float_as_uint(__fsub_rn(v, __uint_as_float(h))) & TF32_MASK);
+    lo[i] = __uint_as_float(l);
   }
 }
 
@@ -276,34 +219,6 @@ __global__ void pad_a_kernel(size_t M, size_t K, size_t Kp, const float* __restr
     const size_t r = i / Kp, c = i % Kp;
     out[i] = c < K ? __ldg(A + r * lda + c) : 0.f;
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D fp32 row-major [rows x cols] (row stride ld floats), box = [box_rows x 32 floats], SWIZZLE_128B, zero OOB fill.
-bool make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, bool stream_once) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, stream_once ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -346,8 +261,8 @@ int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const floa
     a_src = apad; a_ld = kp4;
   }
   CUtensorMap map_a, map_bhi, map_blo;
-  if (!make_map(&map_a, a_src, M, a_ok ? K : kp4, a_ld, BM, true) || !make_map(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false) ||
-      !make_map(&map_blo, blo, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false))
+  if (!make_map_f32(&map_a, a_src, M, a_ok ? K : kp4, a_ld, BM, true) || !make_map_f32(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false) ||
+      !make_map_f32(&map_blo, blo, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false))
     return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed");
 
   TcArgs g;

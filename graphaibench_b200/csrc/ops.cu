@@ -8,6 +8,8 @@ int gemm_simt(size_t M, size_t N, size_t K, const float* A, size_t lda, const fl
               int accum, int flags, cudaStream_t st);
 int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int ta, int tb,
             int accum, int flags, int passes, cudaStream_t st);  // returns GAI_ERR_UNSUPPORTED when the shape is not taken
+int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int accum,
+                  int flags, int passes, cudaStream_t st);
 static int g_gemm_mode = 0;
 }  // namespace gai
 
@@ -319,7 +321,9 @@ int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, cons
   cudaStream_t st = gai::S(stream);
   const int mode = gai::g_gemm_mode;
   if (mode != 1) {
-    int rc = gai::gemm_tc(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, mode == 3 ? 1 : 3, st);
+    // op(A) = A^T with a long reduction over the stored rows (dW = X^T·G): the MN-major split-over-rows kernel
+    int rc = (transA && !transB) ? gai::gemm_tc_wgrad(x, y, z, A, lda, B, ldb, C, ldc, accum, flags, mode == 3 ? 1 : 3, st)
+                                 : gai::gemm_tc(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, mode == 3 ? 1 : 3, st);
     if (rc != GAI_ERR_UNSUPPORTED) return rc;
     if (mode >= 2) return rc;  // an explicit tensor-core request must not silently degrade
   }

@@ -274,3 +274,33 @@ def test_matmul_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape):
         assert err1 > 1e-6, "single-pass TF32 should be visibly less accurate than 3xTF32 (is the tensor-core path running?)"
     finally:
         lib().gai_set_gemm_mode(0)
+
+
+@pytest.mark.parametrize("shape", [(100, 256, 50000), (256, 47, 30011), (47, 256, 9000), (256, 256, 20000), (16, 7, 4100), (128, 172, 33333),
+                                   (200, 130, 12345)])
+def test_wgrad_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape):
+    """dW = X^T·G on the tcgen05 MN-major split-over-rows kernel (mode 2 forced): every output tile shape (1 and 2 M tiles,
+    unaligned widths -> padded staging, ragged row counts), accumulate; against the oracle GEMM and an fp64 product."""
+    from graphaibench_b200._abi import lib
+    kx, my, n = shape
+    rng = np.random.default_rng(kx + 3 * my + n)
+    X = rng.standard_normal((n, kx), dtype=np.float32)
+    G = rng.standard_normal((n, my), dtype=np.float32)
+    C0 = rng.standard_normal((kx, my), dtype=np.float32)
+    ref = np.zeros((kx, my), np.float32)
+    liborc.orc_gemm(kx, my, n, X.reshape(-1), G.reshape(-1), ref.reshape(-1), 1, 0, 0)
+    ref64 = X.astype(np.float64).T @ G.astype(np.float64)
+    try:
+        lib().gai_set_gemm_mode(2)
+        out = ops.matmul(dev(T, X), dev(T, G), transA=True).cpu().numpy()
+        close(out, ref)
+        close(out, ref64, 5e-6)
+        acc = dev(T, C0.copy())
+        ops.matmul(dev(T, X), dev(T, G), out=acc, transA=True, accum=True)
+        close(acc.cpu().numpy(), ref64 + C0, 5e-6)
+        lib().gai_set_gemm_mode(3)
+        out1 = ops.matmul(dev(T, X), dev(T, G), transA=True).cpu().numpy()
+        close(out1, ref64, 3e-3)
+        assert np.abs(out1 - ref64).max() / np.abs(ref64).max() > 1e-6, "single-pass TF32 should be visibly less accurate"
+    finally:
+        lib().gai_set_gemm_mode(0)
