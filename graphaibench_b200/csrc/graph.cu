@@ -10,9 +10,7 @@ namespace {
 // One thread per vertex. Both normalisers reproduce the reference's mixed float/double expressions exactly:
 //   lgraph.cpp:29-32        temp = sqrtf(float(deg)); v = temp == 0 ? 0 : float(1.0 / double(temp))
 //   sage_aggregator.cpp:17  b = float(1.0 / double(float(deg)))        (inf for deg == 0, never used by a row of its own)
-__global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, float* __restrict__ norm_gcn,
-                             float* __restrict__ norm_mean, uint32_t* __restrict__ hub_rows, uint32_t* __restrict__ hub_count,
-                             uint32_t hub_cap, uint32_t hub_degree) {
+__global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, float* __restrict__ norm_gcn, float* __restrict__ norm_mean) {
   uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   uint32_t deg = rowptr[v + 1] - rowptr[v];
@@ -20,10 +18,6 @@ __global__ void norms_kernel(uint32_t nv, const uint32_t* __restrict__ rowptr, f
   float t = __fsqrt_rn(fdeg);
   norm_gcn[v] = (t == 0.0f) ? 0.0f : __double2float_rn(__ddiv_rn(1.0, (double)t));
   norm_mean[v] = __double2float_rn(__ddiv_rn(1.0, (double)fdeg));
-  if (deg > hub_degree) {
-    uint32_t slot = atomicAdd(hub_count, 1u);
-    if (slot < hub_cap) { hub_rows[slot] = v; hub_rows[hub_cap + 1 + slot] = deg; }
-  }
 }
 
 // One warp per row; each lane binary-searches its edges' mirror position. Pattern must be symmetric
@@ -50,35 +44,66 @@ __global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ 
   }
 }
 
-int finish_create(gai_csr* g, cudaStream_t st) {
+// Work lists for the aggregation kernels (integer work on the host, once per graph):
+//   row_order  all rows, longest first, ascending id among equal degrees (counting sort, O(nv + max degree));
+//              its first n_hub entries (degree > hub_degree) are the hub rows, served one CTA each;
+//   claim_ptr  the remaining (light) rows cut into claims of at most 32 rows and at most CLAIM_EDGES edges: the unit a
+//              warp takes from the shared work counter. Long rows travel alone and first, short rows in groups of 32.
+constexpr uint64_t CLAIM_EDGES = 2048;
+
+int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
+  const uint32_t nv = g->nv;
+  g->n_hub = 0; g->n_claims = 0;
+  if (nv == 0) return GAI_OK;
+  std::vector<uint32_t> host_rp;
+  if (!rowptr_h) {  // CSR supplied in device memory: bring the row pointers back once
+    host_rp.resize((size_t)nv + 1);
+    GAI_CUDA(cudaMemcpyAsync(host_rp.data(), g->rowptr, sizeof(uint32_t) * ((size_t)nv + 1), cudaMemcpyDeviceToHost, st));
+    GAI_CUDA(cudaStreamSynchronize(st));
+    rowptr_h = host_rp.data();
+  }
+  auto deg = [&](uint32_t v) { return rowptr_h[v + 1] - rowptr_h[v]; };
+  uint32_t maxdeg = 0;
+  for (uint32_t v = 0; v < nv; v++) maxdeg = std::max(maxdeg, deg(v));
+  std::vector<uint64_t> start((size_t)maxdeg + 2, 0);
+  for (uint32_t v = 0; v < nv; v++) start[(size_t)maxdeg - deg(v) + 1]++;  // bucket 0 = longest
+  for (size_t d = 1; d < start.size(); d++) start[d] += start[d - 1];
+  std::vector<uint32_t> order(nv);
+  for (uint32_t v = 0; v < nv; v++) order[start[(size_t)maxdeg - deg(v)]++] = v;
+  uint32_t n_hub = 0;
+  while (n_hub < nv && deg(order[n_hub]) > g->hub_degree) n_hub++;
+  std::vector<uint32_t> claims;
+  claims.reserve((nv - n_hub) / 16 + 2);
+  claims.push_back(0);
+  uint64_t edges = 0;
+  uint32_t rows = 0;
+  for (uint32_t i = n_hub; i < nv; i++) {
+    const uint32_t d = deg(order[i]);
+    if (rows > 0 && (rows == 32 || edges + d > CLAIM_EDGES)) { claims.push_back(i - n_hub); rows = 0; edges = 0; }
+    rows++; edges += d;
+  }
+  claims.push_back(nv - n_hub);
+  g->n_hub = n_hub;
+  g->n_claims = (uint32_t)claims.size() - 1;
+  GAI_CUDA(cudaMalloc(&g->row_order, sizeof(uint32_t) * (size_t)nv));
+  GAI_CUDA(cudaMalloc(&g->claim_ptr, sizeof(uint32_t) * claims.size()));
+  GAI_CUDA(cudaMemcpyAsync(g->row_order, order.data(), sizeof(uint32_t) * (size_t)nv, cudaMemcpyHostToDevice, st));
+  GAI_CUDA(cudaMemcpyAsync(g->claim_ptr, claims.data(), sizeof(uint32_t) * claims.size(), cudaMemcpyHostToDevice, st));
+  GAI_CUDA(cudaStreamSynchronize(st));  // the staging vectors are pageable and go out of scope
+  g->hub_rows = g->row_order;
+  return GAI_OK;
+}
+
+int finish_create(gai_csr* g, cudaStream_t st, const uint32_t* rowptr_h) {
   GAI_CUDA(cudaMalloc(&g->norm_gcn, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
   GAI_CUDA(cudaMalloc(&g->norm_mean, sizeof(float) * (size_t)(g->nv ? g->nv : 1)));
   GAI_CUDA(cudaMalloc(&g->row_counters, sizeof(unsigned long long) * 16));
   g->hub_degree = gai::hub_degree_for(g->nnz);
-  uint32_t hub_cap = (uint32_t)(g->nnz / g->hub_degree) + 1;
-  GAI_CUDA(cudaMalloc(&g->hub_rows, sizeof(uint32_t) * (size_t)(2 * hub_cap + 1)));  // [rows | count | degrees]
-  uint32_t* d_count = g->hub_rows + hub_cap;
-  GAI_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
   if (g->nv) {
-    norms_kernel<<<(g->nv + 255) / 256, 256, 0, st>>>(g->nv, g->rowptr, g->norm_gcn, g->norm_mean, g->hub_rows, d_count, hub_cap, g->hub_degree);
+    norms_kernel<<<(g->nv + 255) / 256, 256, 0, st>>>(g->nv, g->rowptr, g->norm_gcn, g->norm_mean);
     GAI_LAUNCH_CHECK();
   }
-  uint32_t n_hub = 0;
-  GAI_CUDA(cudaMemcpyAsync(&n_hub, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  GAI_CUDA(cudaStreamSynchronize(st));
-  g->n_hub = n_hub < hub_cap ? n_hub : hub_cap;
-  if (g->n_hub > 1) {
-    // longest rows first: the hub kernel's CTAs are scheduled in list order and the longest row is the critical path
-    std::vector<uint32_t> rows(g->n_hub), degs(g->n_hub), order(g->n_hub);
-    GAI_CUDA(cudaMemcpy(rows.data(), g->hub_rows, sizeof(uint32_t) * g->n_hub, cudaMemcpyDeviceToHost));
-    GAI_CUDA(cudaMemcpy(degs.data(), g->hub_rows + hub_cap + 1, sizeof(uint32_t) * g->n_hub, cudaMemcpyDeviceToHost));
-    for (uint32_t i = 0; i < g->n_hub; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return degs[x] != degs[y] ? degs[x] > degs[y] : rows[x] < rows[y]; });
-    std::vector<uint32_t> sorted(g->n_hub);
-    for (uint32_t i = 0; i < g->n_hub; i++) sorted[i] = rows[order[i]];
-    GAI_CUDA(cudaMemcpy(g->hub_rows, sorted.data(), sizeof(uint32_t) * g->n_hub, cudaMemcpyHostToDevice));
-  }
-  return GAI_OK;
+  return build_work_lists(g, rowptr_h, st);
 }
 
 }  // namespace
@@ -123,7 +148,7 @@ int gai_csr_create(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_h, const ui
       rc = gai::set_error(GAI_ERR_CUDA, "gai_csr_create upload", cudaGetErrorString(cudaGetLastError()));
       break;
     }
-    rc = finish_create(g, st);
+    rc = finish_create(g, st, rowptr_h);
   } while (0);
   if (rc != GAI_OK) { gai_csr_destroy(g); return rc; }
   *out = g;
@@ -137,7 +162,7 @@ int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, c
   g->nv = nv; g->nnz = nnz; g->owns_csr = false;
   g->rowptr = const_cast<uint32_t*>(rowptr_d);
   g->colidx = const_cast<uint32_t*>(colidx_d);
-  int rc = finish_create(g, gai::S(stream));
+  int rc = finish_create(g, gai::S(stream), nullptr);
   if (rc != GAI_OK) { gai_csr_destroy(g); return rc; }
   *out = g;
   return GAI_OK;
@@ -146,7 +171,7 @@ int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, c
 int gai_csr_destroy(gai_csr_t g) {
   if (!g) return GAI_OK;
   if (g->owns_csr) { cudaFree(g->rowptr); cudaFree(g->colidx); }
-  cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->hub_rows); cudaFree(g->tperm); cudaFree(g->row_counters);
+  cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->tperm); cudaFree(g->row_counters); cudaFree(g->row_order); cudaFree(g->claim_ptr);
   if (g->aux_stream) { cudaStreamDestroy(g->aux_stream); cudaEventDestroy(g->ev_fork); cudaEventDestroy(g->ev_join); }
   delete g;
   return GAI_OK;

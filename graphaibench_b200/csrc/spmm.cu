@@ -41,7 +41,6 @@ struct SpmmArgs {
   int mode, flags;
   int out_vec;       // 1: out/addend rows are 16-byte aligned and F % 4 == 0 -> float4 epilogue
   uint32_t hub_threshold;
-  unsigned long long scramble;  // odd multiplier coprime to the row count (1 = natural order)
 };
 
 __device__ __forceinline__ float edge_weight(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
@@ -79,93 +78,165 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int
 }
 
 // ---- light rows -----------------------------------------------------------------------------------------------------
-// One output row per group of G lanes, kept in registers.
-template <int G, int K>
-__device__ __forceinline__ void spmm_one_row(const SpmmArgs& a, uint32_t row, int gl, unsigned gmask) {
-  constexpr int UMAX = (K == 1) ? 8 : (K == 2 ? 4 : 2);
-  constexpr int U = G < UMAX ? G : UMAX;  // independent neighbour rows in flight per lane (up to 8 float4)
-  const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
-  if (e - s > a.hub_threshold) return;
-  const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-  const float4* in4 = reinterpret_cast<const float4*>(a.in);
-  const size_t ld4 = (size_t)a.ld_in >> 2;
-
-  for (int cb = 0; cb < a.nchunks; cb += G * K) {
-    float4 acc[K];
-    bool act[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      act[k] = (cb + gl + G * k) < a.nchunks;
-      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (uint32_t base = s; base < e; base += G) {
-      const uint32_t idx = base + gl;
-      uint32_t c = 0;
-      float w = 0.0f;
-      if (idx < e) {
-        c = __ldg(a.colidx + idx);
-        w = edge_weight(a, wrow, idx, c);
-      }
-      const int cnt = (e - base) < (uint32_t)G ? (int)(e - base) : G;
-#pragma unroll
-      for (int j = 0; j < G; j += U) {
-        if (j >= cnt) break;
-        float4 x[U][K];
-        float ww[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int jj = j + u;
-          const uint32_t cc = __shfl_sync(gmask, c, jj, G);
-          ww[u] = __shfl_sync(gmask, w, jj, G);
-          const float4* src = in4 + (size_t)cc * ld4 + (cb + gl);
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            if (jj < cnt && act[k]) x[u][k] = __ldg(src + G * k);
-            else x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (jj >= cnt) ww[u] = 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(ww[u], x[u][k].x));
-            acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(ww[u], x[u][k].y));
-            acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(ww[u], x[u][k].z));
-            acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(ww[u], x[u][k].w));
-          }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++)
-      if (act[k]) store_chunk(a, row, cb + gl + G * k, acc[k]);
-  }
+// One output row per group of G lanes, kept in registers; a warp owns 32/G rows at a time.
+//
+// Work list: rows in DEGREE order (g->row_order, longest first, built once per graph), hub rows excluded. The rows a
+// warp processes together therefore have (nearly) equal lengths — no lane group idles while its sibling finishes a long
+// row — the longest rows start first, and the empty rows (40% of an R-MAT graph) end up in all-empty warps.
+// A warp claims 32 consecutive list entries with one atomic, loads their row ids and row bounds with one coalesced
+// request each into shared memory, and then walks them with a two-deep index pipeline:
+//     column indices of the NEXT row's first batch and of the NEXT batch of this row are requested before the current
+//     batch's neighbour rows are gathered, so a row costs one exposed memory latency (the gather) instead of three
+//     (rowptr -> colidx -> gather).
+// Arithmetic per edge and column: p = mul.rn(w, x); acc = add.rn(acc, p) — the reference's scale()+vadd(). The multiply
+// is issued as FMUL2 (two columns per instruction); the add stays scalar: ptxas contracts a packed mul + packed add
+// pair into FFMA2 even with .rn on both (12.9), which would break bit-exactness.
+__device__ __forceinline__ void mul_w_f4(float w, const float4& x, float4& p) {
+  unsigned long long w2, lo, hi;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(w2) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(lo) : "f"(x.x), "f"(x.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(hi) : "f"(x.z), "f"(x.w));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(lo) : "l"(w2), "l"(lo));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hi) : "l"(w2), "l"(hi));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(p.x), "=f"(p.y) : "l"(lo));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(p.z), "=f"(p.w) : "l"(hi));
+}
+__device__ __forceinline__ void acc_add(float4& acc, const float4& p) {
+  acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
 }
 
-// Persistent warps (grid = 4 CTAs per SM): each warp claims ROW_CHUNK consecutive row-groups at a time from a global
-// counter, so a warp that drew a long row does not hold idle siblings resident (power-law graphs: 40% of the rows of the
-// bench graph are empty while others are 8 K edges long).
-constexpr int ROW_CHUNK = 8;
+template <int MODE>
+__device__ __forceinline__ float edge_weight_t(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
+  if (MODE == M_GCN) return __fmul_rn(wrow, __ldg(a.norm + c));  // b = a_i * a_j (gcn_aggregator.cpp:66)
+  if (MODE == M_MEAN) return wrow;                               // 1/deg_i (sage_aggregator.cpp:17)
+  if (MODE == M_MEAN_T) return __ldg(a.norm + c);                // 1/deg_j (sage_aggregator.cpp:41)
+  if (MODE == M_EDGE) return __ldg(a.vals + idx);
+  return __ldg(a.vals + __ldg(a.perm + idx));
+}
 
-template <int G, int K>
-__global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, unsigned long long* __restrict__ counter) {
-  constexpr int ROWS_PER_WARP = 32 / G;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % G;
-  const int grp = lane / G;
+constexpr int SLOTS = 32;  // work-list entries per claim
+
+template <int MODE, int G, int K>
+__global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, const uint32_t* __restrict__ order, const uint32_t* __restrict__ claim_ptr,
+                                                         unsigned long long n_claims, unsigned long long* __restrict__ counter) {
+  constexpr int RPW = 32 / G;                                  // rows in flight per warp
+  constexpr int UMAX = (K == 1) ? 8 : (K == 2 ? 4 : 2);
+  constexpr int U = G < UMAX ? G : UMAX;                       // independent neighbour rows in flight per lane
+  __shared__ uint32_t sm_row[8][SLOTS], sm_s[8][SLOTS], sm_e[8][SLOTS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gl = lane % G, grp = lane / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-  const unsigned long long nrows = (unsigned long long)a.row_end - a.row_begin;
+  const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const size_t ld4 = (size_t)a.ld_in >> 2;
+  // lanes whose chunk lies past the row width re-read chunk 0 (same sectors as lane 0) and store nothing
+  int chunk[K];
+  bool act[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { act[k] = (gl + G * k) < a.nchunks; chunk[k] = act[k] ? gl + G * k : 0; }
+
   for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(counter, (unsigned long long)(ROW_CHUNK * ROWS_PER_WARP));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= nrows) break;
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(counter, 1ull);
+    claim = __shfl_sync(0xffffffffu, claim, 0);
+    if (claim >= n_claims) break;
+    {
+      // ordered list: claim boundaries come from claim_ptr; natural order (row ranges): 32 consecutive rows per claim
+      unsigned long long base, end;
+      if (order) { base = __ldg(claim_ptr + claim); end = __ldg(claim_ptr + claim + 1); }
+      else { base = claim * SLOTS; end = base + SLOTS; const unsigned long long n = (unsigned long long)a.row_end - a.row_begin; if (end > n) end = n; }
+      uint32_t r = 0xffffffffu, s = 0, e = 0;
+      if (base + lane < end) {
+        r = order ? __ldg(order + base + lane) : (uint32_t)(a.row_begin + base + lane);
+        if (r >= a.row_begin && r < a.row_end) { s = __ldg(a.rowptr + r); e = __ldg(a.rowptr + r + 1); } else r = 0xffffffffu;
+        if (e - s > a.hub_threshold) r = 0xffffffffu;  // hub rows belong to the CTA-per-row kernel
+      }
+      __syncwarp();
+      sm_row[warp][lane] = r; sm_s[warp][lane] = s; sm_e[warp][lane] = e;
+      __syncwarp();
+    }
+    // first batch of the first row of this group
+    uint32_t c_first = 0;
+    {
+      const uint32_t s0 = sm_s[warp][grp], e0 = sm_e[warp][grp];
+      if (sm_row[warp][grp] != 0xffffffffu && s0 + gl < e0) c_first = __ldg(a.colidx + s0 + gl);
+    }
 #pragma unroll 1
-    for (int i = 0; i < ROW_CHUNK; i++) {
-      const unsigned long long q = base + (unsigned long long)i * ROWS_PER_WARP + grp;
-      // multiplicative permutation of the work order (scramble is coprime to nrows): long rows that sit next to each
-      // other in id space (R-MAT, BFS orderings) land in different chunks; every row is still produced exactly once
-      if (q < nrows) spmm_one_row<G, K>(a, (uint32_t)(a.row_begin + (q * a.scramble) % nrows), gl, gmask);
+    for (int it = 0; it < SLOTS / RPW; it++) {
+      const int slot = it * RPW + grp;
+      const uint32_t row = sm_row[warp][slot];
+      const uint32_t s = sm_s[warp][slot], e = sm_e[warp][slot];
+      // request the first batch of the next row this group will process
+      uint32_t c_nextrow = 0;
+      if (it + 1 < SLOTS / RPW) {
+        const uint32_t ns = sm_s[warp][slot + RPW], ne = sm_e[warp][slot + RPW];
+        if (sm_row[warp][slot + RPW] != 0xffffffffu && ns + gl < ne) c_nextrow = __ldg(a.colidx + ns + gl);
+      }
+      if (row != 0xffffffffu) {
+        const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
+        for (int cb = 0; cb < a.nchunks; cb += G * K) {  // one pass unless F > 128*K
+          float4 acc[K];
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          int ch[K];
+          bool av[K];
+#pragma unroll
+          for (int k = 0; k < K; k++) { av[k] = cb == 0 ? act[k] : (cb + gl + G * k) < a.nchunks; ch[k] = cb == 0 ? chunk[k] : (av[k] ? cb + gl + G * k : 0); }
+          uint32_t c_cur = c_first;
+          if (cb != 0 && s + gl < e) c_cur = __ldg(a.colidx + s + gl);
+          for (uint32_t b = s; b < e; b += G) {
+            const uint32_t idx = b + gl;
+            uint32_t c_nb = 0;
+            if (idx + G < e) c_nb = __ldg(a.colidx + idx + G);  // next batch of this row
+            const float w = idx < e ? edge_weight_t<MODE>(a, wrow, idx, c_cur) : 0.0f;
+            const int cnt = (e - b) < (uint32_t)G ? (int)(e - b) : G;
+            if (cnt == G) {
+#pragma unroll
+              for (int j = 0; j < G; j += U) {
+                float4 x[U][K];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                  const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
+                  const float4* src = in4 + (size_t)cc * ld4;
+#pragma unroll
+                  for (int k = 0; k < K; k++) x[u][k] = __ldg(src + ch[k]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                  const float ww = __shfl_sync(gmask, w, j + u, G);
+#pragma unroll
+                  for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < G; j += U) {
+                if (j >= cnt) break;
+                float4 x[U][K];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                  const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
+                  const float4* src = in4 + (size_t)cc * ld4;
+#pragma unroll
+                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? __ldg(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                  const float ww = __shfl_sync(gmask, w, j + u, G);
+                  if (j + u < cnt) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }
+                  }
+                }
+              }
+            }
+            c_cur = c_nb;
+          }
+#pragma unroll
+          for (int k = 0; k < K; k++)
+            if (av[k]) store_chunk(a, row, cb + gl + G * k, acc[k]);
+        }
+      }
+      c_first = c_nextrow;
     }
   }
 }
@@ -331,41 +402,46 @@ __global__ void pad_rows_kernel(size_t n_rows, int F, int Fp, const float* __res
 
 inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
 
-int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
-  const uint64_t rows = (uint64_t)a.row_end - a.row_begin;
+template <int MODE>
+int launch_rows_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+  // full-graph calls walk the degree-ordered list (hub rows sit at its head and are skipped by offset); row-range calls
+  // (1D partition: interior / boundary rows) walk the range in natural order
+  const bool full = a.row_begin == 0 && a.row_end == g->nv && g->row_order != nullptr;
+  const uint32_t* order = full ? g->row_order + g->n_hub : nullptr;
+  const unsigned long long n_rows = full ? (unsigned long long)g->nv - g->n_hub : (unsigned long long)a.row_end - a.row_begin;
+  if (n_rows == 0) return GAI_OK;
+  const unsigned long long claims = full ? g->n_claims : (n_rows + SLOTS - 1) / SLOTS;
+  const uint32_t* claim_ptr = g->claim_ptr;
   int G = 4;
   while (G < 32 && G < a.nchunks) G <<= 1;
   int K = 1;
   if (G == 32) { K = (a.nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
-  const uint64_t rows_per_fetch = (uint64_t)ROW_CHUNK * (32 / G);
-  const uint64_t fetches = (rows + rows_per_fetch - 1) / rows_per_fetch;
-  uint64_t ctas = (fetches + 7) / 8;
-  const uint64_t persistent = (uint64_t)gai::sm_count() * 4;
+  unsigned long long ctas = (claims + 7) / 8;
+  const unsigned long long persistent = (unsigned long long)gai::sm_count() * 4;
   if (ctas > persistent) ctas = persistent;
-  if (ctas == 0) return GAI_OK;
   const unsigned grid = (unsigned)ctas;
-  SpmmArgs b = a;
-  b.scramble = 1;
-  if (rows > 64) {
-    static const unsigned long long primes[] = {1000003ull, 998244353ull, 2654435761ull, 40503ull, 7919ull};
-    for (unsigned long long pr : primes) {
-      unsigned long long x = pr % rows, y = rows;
-      while (y) { const unsigned long long t = x % y; x = y; y = t; }  // gcd(pr mod rows, rows)
-      if (x == 1 && (pr % rows) > 1) { b.scramble = pr % rows; break; }
-    }
-  }
   // rotating work counters: launches on one stream are ordered; the rotation keeps up to 16 launches that overlap on
   // different streams (interior / boundary rows of the 1D partition) from sharing a counter
   unsigned long long* ctr = g->row_counters + (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 16u);
   GAI_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
-  if (G == 4) spmm_rows_kernel<4, 1><<<grid, 256, 0, st>>>(b, ctr);
-  else if (G == 8) spmm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(b, ctr);
-  else if (G == 16) spmm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(b, ctr);
-  else if (K == 1) spmm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(b, ctr);
-  else if (K == 2) spmm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(b, ctr);
-  else spmm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(b, ctr);
+  if (G == 4) spmm_rows_kernel<MODE, 4, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  else if (G == 8) spmm_rows_kernel<MODE, 8, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  else if (G == 16) spmm_rows_kernel<MODE, 16, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  else if (K == 1) spmm_rows_kernel<MODE, 32, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  else if (K == 2) spmm_rows_kernel<MODE, 32, 2><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  else spmm_rows_kernel<MODE, 32, 4><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
+}
+
+int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+  switch (a.mode) {
+    case M_GCN: return launch_rows_mode<M_GCN>(a, g, st);
+    case M_MEAN: return launch_rows_mode<M_MEAN>(a, g, st);
+    case M_MEAN_T: return launch_rows_mode<M_MEAN_T>(a, g, st);
+    case M_EDGE: return launch_rows_mode<M_EDGE>(a, g, st);
+    default: return launch_rows_mode<M_EDGE_PERM>(a, g, st);
+  }
 }
 
 template <int ES>
