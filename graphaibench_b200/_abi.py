@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libgai_b200.so")
+LIB_PATH = os.environ.get("GAI_B200_LIB", os.path.join(PKG, "libgai_b200.so"))  # override: A/B builds of the same ABI
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 c_u32p = C.c_void_p

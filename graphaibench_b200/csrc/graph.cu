@@ -2,6 +2,7 @@
 // Replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data (src/gnn/lgraph.cu:51-105) and the
 // per-backward cusparseCsr2cscEx2 call (src/utilities/math_functions.cu:345-358, src/gnn/gconv/gat_aggregator.cu:86-89).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "gai_internal.cuh"
 
@@ -47,8 +48,8 @@ __global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ 
 // Work lists for the aggregation kernels (integer work on the host, once per graph):
 //   row_order  all rows, longest first, ascending id among equal degrees (counting sort, O(nv + max degree));
 //              its first n_hub entries (degree > hub_degree) are the hub rows, served one CTA each;
-//   claim_ptr  the remaining (light) rows cut into claims of at most 32 rows and at most CLAIM_EDGES edges: the unit a
-//              warp takes from the shared work counter. Long rows travel alone and first, short rows in groups of 32.
+//   claim_ptr  the remaining (light) rows cut into claims of at most 32 rows and at most CLAIM_EDGES edges, stored as
+//              (begin, end) pairs in execution order: the unit a warp takes from the shared work counter.
 constexpr uint64_t CLAIM_EDGES = 2048;
 
 int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
@@ -72,19 +73,43 @@ int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
   for (uint32_t v = 0; v < nv; v++) order[start[(size_t)maxdeg - deg(v)]++] = v;
   uint32_t n_hub = 0;
   while (n_hub < nv && deg(order[n_hub]) > g->hub_degree) n_hub++;
-  std::vector<uint32_t> claims;
-  claims.reserve((nv - n_hub) / 16 + 2);
-  claims.push_back(0);
+  // claims as (begin, end) pairs into the light part of the list, in EXECUTION order
+  std::vector<uint32_t> cuts;
+  cuts.reserve((nv - n_hub) / 16 + 2);
+  cuts.push_back(0);
   uint64_t edges = 0;
-  uint32_t rows = 0;
+  uint32_t rows = 0, n_big = 0;
   for (uint32_t i = n_hub; i < nv; i++) {
     const uint32_t d = deg(order[i]);
-    if (rows > 0 && (rows == 32 || edges + d > CLAIM_EDGES)) { claims.push_back(i - n_hub); rows = 0; edges = 0; }
+    if (rows > 0 && (rows == 32 || edges + d > CLAIM_EDGES)) { cuts.push_back(i - n_hub); rows = 0; edges = 0; }
+    if (d > CLAIM_EDGES) n_big++;  // rows longer than the budget travel alone
     rows++; edges += d;
   }
-  claims.push_back(nv - n_hub);
+  cuts.push_back(nv - n_hub);
+  const uint32_t n_claims = (uint32_t)cuts.size() - 1;
+  // Execution order: the over-budget single-row claims first (longest-processing-time first keeps the tail short), then
+  // the rest interleaved by a stride permutation so that, at any moment, the machine works on a mix of long-row claims
+  // (bandwidth-bound) and short-row claims (latency-bound) instead of one degree class at a time.
+  std::vector<uint32_t> claims((size_t)2 * n_claims);
+  const char* env = getenv("GAI_CLAIM_ORDER");
+  const int mode = env ? atoi(env) : 1;
+  const uint32_t rest = n_claims - n_big;
+  uint64_t stride = 1;
+  if (mode == 1 && rest > 64) {
+    static const uint64_t primes[] = {1000003ull, 998244353ull, 2654435761ull, 40503ull, 7919ull};
+    for (uint64_t pr : primes) {
+      uint64_t x = pr % rest, y = rest;
+      while (y) { const uint64_t t = x % y; x = y; y = t; }
+      if (x == 1 && (pr % rest) > 1) { stride = pr % rest; break; }
+    }
+  }
+  for (uint32_t i = 0; i < n_claims; i++) {
+    const uint32_t src = i < n_big ? i : n_big + (uint32_t)(((uint64_t)(i - n_big) * stride) % rest);
+    claims[2 * (size_t)i] = cuts[src];
+    claims[2 * (size_t)i + 1] = cuts[src + 1];
+  }
   g->n_hub = n_hub;
-  g->n_claims = (uint32_t)claims.size() - 1;
+  g->n_claims = n_claims;
   GAI_CUDA(cudaMalloc(&g->row_order, sizeof(uint32_t) * (size_t)nv));
   GAI_CUDA(cudaMalloc(&g->claim_ptr, sizeof(uint32_t) * claims.size()));
   GAI_CUDA(cudaMemcpyAsync(g->row_order, order.data(), sizeof(uint32_t) * (size_t)nv, cudaMemcpyHostToDevice, st));

@@ -43,16 +43,6 @@ struct SpmmArgs {
   uint32_t hub_threshold;
 };
 
-__device__ __forceinline__ float edge_weight(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
-  switch (a.mode) {
-    case M_GCN: return __fmul_rn(wrow, __ldg(a.norm + c));  // b = a_i * a_j (gcn_aggregator.cpp:66)
-    case M_MEAN: return wrow;                               // 1/deg_i (sage_aggregator.cpp:17)
-    case M_MEAN_T: return __ldg(a.norm + c);                // 1/deg_j (sage_aggregator.cpp:41)
-    case M_EDGE: return __ldg(a.vals + idx);
-    default: return __ldg(a.vals + __ldg(a.perm + idx));
-  }
-}
-
 // out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
 __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int chunk, float4 r) {
   const size_t o = (size_t)row * a.ld_out + (size_t)chunk * 4;
@@ -142,7 +132,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
     {
       // ordered list: claim boundaries come from claim_ptr; natural order (row ranges): 32 consecutive rows per claim
       unsigned long long base, end;
-      if (order) { base = __ldg(claim_ptr + claim); end = __ldg(claim_ptr + claim + 1); }
+      if (order) { base = __ldg(claim_ptr + 2 * claim); end = __ldg(claim_ptr + 2 * claim + 1); }
       else { base = claim * SLOTS; end = base + SLOTS; const unsigned long long n = (unsigned long long)a.row_end - a.row_begin; if (end > n) end = n; }
       uint32_t r = 0xffffffffu, s = 0, e = 0;
       if (base + lane < end) {
@@ -253,6 +243,11 @@ constexpr int HUB_CONS_THREADS = HUB_CONS_WARPS * 32;
 constexpr int HUB_PROD_WARPS = 16;
 constexpr int HUB_THREADS = HUB_CONS_THREADS + HUB_PROD_WARPS * 32;
 constexpr int HUB_MAX_CHUNKS = 128;  // column block = 512 floats
+#ifndef GAI_HUB_MIN_CTAS
+#define GAI_HUB_MIN_CTAS 1
+#endif
+constexpr int HUB_MIN_CTAS = GAI_HUB_MIN_CTAS;
+constexpr size_t HUB_RING_CAP = (HUB_MIN_CTAS == 1 ? 200 : 100) * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -270,8 +265,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ES = edges per stage (32, 16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(nchunks,128) float4.
-template <int ES>
-__global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
+template <int MODE, int ES>
+__global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
   extern __shared__ float4 ring[];
   __shared__ uint64_t full_bar[HUB_PROD_WARPS], empty_bar[HUB_PROD_WARPS];
   const uint32_t row = hub_rows[blockIdx.x];
@@ -295,14 +290,14 @@ __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a,
     if (warp >= HUB_CONS_WARPS) {
       // ---------------- producers ----------------
       const int pw = warp - HUB_CONS_WARPS;
-      const float wrow = (a.mode == M_GCN || a.mode == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
+      const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
       float4* slot = ring + (size_t)pw * slot_stride;
       const uint32_t round0 = blk * ((nstages + HUB_PROD_WARPS - 1 - pw) / HUB_PROD_WARPS);
       // prefetch the first stage's indices / weights (lane l < ES holds edge l of the stage)
       uint32_t c = 0; float w = 0.0f;
       {
         const uint32_t idx = s + (uint32_t)pw * ES + lane;
-        if (lane < ES && idx < e) { c = __ldg(a.colidx + idx); w = edge_weight(a, wrow, idx, c); }
+        if (lane < ES && idx < e) { c = __ldg(a.colidx + idx); w = edge_weight_t<MODE>(a, wrow, idx, c); }
       }
       for (uint32_t k = pw, r = 0; k < nstages; k += HUB_PROD_WARPS, r++) {
         const uint32_t base = s + k * ES;
@@ -312,7 +307,7 @@ __global__ void __launch_bounds__(HUB_THREADS) spmm_hub_kernel(const SpmmArgs a,
         c = 0; w = 0.0f;
         {
           const uint64_t nidx = (uint64_t)base + (uint64_t)HUB_PROD_WARPS * ES + lane;
-          if (lane < ES && nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight(a, wrow, (uint32_t)nidx, c); }
+          if (lane < ES && nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight_t<MODE>(a, wrow, (uint32_t)nidx, c); }
         }
         mbar_wait(&empty_bar[pw], ((round0 + r) & 1) ^ 1);
         for (int ch0 = 0; ch0 < nch; ch0 += 32) {
@@ -444,28 +439,39 @@ int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   }
 }
 
-template <int ES>
+template <int MODE, int ES>
 int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<MODE, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     configured = true;
   }
-  spmm_hub_kernel<ES><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
+  spmm_hub_kernel<MODE, ES><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
 
-int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
-  if (g->n_hub == 0) return GAI_OK;
+template <int MODE>
+int launch_hub_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
   // largest stage size in {32, 16, 8, 4} edges whose 16-slot ring fits 200 KB of shared memory (longer stages amortise the
   // consumer's per-stage barrier round trip over more in-order adds)
   auto bytes = [&](int es) { return (size_t)HUB_PROD_WARPS * es * nch * sizeof(float4); };
-  if (bytes(32) <= 200 * 1024) return launch_hub_es<32>(a, g, bytes(32), st);
-  if (bytes(16) <= 192 * 1024) return launch_hub_es<16>(a, g, bytes(16), st);
-  if (bytes(8) <= 192 * 1024) return launch_hub_es<8>(a, g, bytes(8), st);
-  return launch_hub_es<4>(a, g, bytes(4), st);
+  if (bytes(32) <= HUB_RING_CAP) return launch_hub_es<MODE, 32>(a, g, bytes(32), st);
+  if (bytes(16) <= HUB_RING_CAP) return launch_hub_es<MODE, 16>(a, g, bytes(16), st);
+  if (bytes(8) <= HUB_RING_CAP) return launch_hub_es<MODE, 8>(a, g, bytes(8), st);
+  return launch_hub_es<MODE, 4>(a, g, bytes(4), st);
+}
+
+int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+  if (g->n_hub == 0) return GAI_OK;
+  switch (a.mode) {
+    case M_GCN: return launch_hub_mode<M_GCN>(a, g, st);
+    case M_MEAN: return launch_hub_mode<M_MEAN>(a, g, st);
+    case M_MEAN_T: return launch_hub_mode<M_MEAN_T>(a, g, st);
+    case M_EDGE: return launch_hub_mode<M_EDGE>(a, g, st);
+    default: return launch_hub_mode<M_EDGE_PERM>(a, g, st);
+  }
 }
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Standalone SpMM aggregation sweep (BASELINE.json configs[4], SURVEY.md §8d "C5"): R-MAT power-law graphs, GCN-normalised and
+mean aggregation at several feature widths, timed with CUDA events; prints one JSON line per point with the three
+bandwidth figures of §8d (gather model B_spmm/t, compulsory bound/t) against the measured HBM peak.
+
+  python tools/spmm_sweep.py [--nv 1000000,4000000] [--deg 16,64] [--feat 16,32,64,128,256,512] [--reps 5] [--modes gcn,mean]
+"""
+import argparse, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nv", default="1000000")
+    ap.add_argument("--deg", default="16,64")
+    ap.add_argument("--feat", default="16,32,64,128,256,512")
+    ap.add_argument("--modes", default="gcn,mean")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--max-gb", type=float, default=150.0)
+    args = ap.parse_args()
+    import torch
+    from graphaibench_b200 import datagen, ops
+    peak = 6650.0
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+    for nv in [int(x) for x in args.nv.split(",")]:
+        for deg in [int(x) for x in args.deg.split(",")]:
+            rp, ci = datagen.rmat_csr_torch(nv, nv * deg, seed=1, device="cuda")
+            rp32 = rp.to(torch.int32); ci32 = ci.to(torch.int32)
+            nnz = int(ci32.numel())
+            g = ops.DeviceGraph(rp32, ci32, device_arrays=True)
+            for F in [int(x) for x in args.feat.split(",")]:
+                if 4.0 * (2 * nv * F + nnz) / 1e9 > args.max_gb:
+                    continue
+                x = torch.randn(nv, F, device="cuda")
+                out = torch.empty_like(x)
+                for mode in args.modes.split(","):
+                    fn = (lambda: ops.spmm_gcn(g, x, out=out)) if mode == "gcn" else (lambda: ops.spmm_mean(g, x, out=out, transposed=(mode == "meanT")))
+                    for _ in range(3):
+                        fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(args.reps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / args.reps
+                    b_gather = 4.0 * (nnz * F + nv * F + nnz + (nv + 1) + nv)
+                    b_comp = 4.0 * (2 * nv * F + nnz + 2 * nv + 1)
+                    print(json.dumps({"nv": nv, "nnz": nnz, "avg_deg": round(nnz / nv, 1), "F": F, "mode": mode, "ms": round(ms, 4), "n_hub": g.n_hub,
+                                      "gather_GBps": round(b_gather / ms / 1e6, 1), "compulsory_GBps": round(b_comp / ms / 1e6, 1),
+                                      "edges_x_feats_per_s": round(nnz * F / ms * 1e3, 0), "frac_of_hbm_peak": round(b_gather / ms / 1e6 / peak, 3),
+                                      "hbm_peak_GBps": peak}), flush=True)
+                del x, out
+            del g, rp, ci, rp32, ci32
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
