@@ -10,7 +10,7 @@
  * (x86-64 SSE2 → IEEE binary32 arithmetic, no FMA contraction, no reassociation).
  *
  * Pinning: validated against the reference itself (oracle/_ref/libref_gnn.so, built from the reference's own
- * sources by oracle/build_ref.sh) in tests/test_oracle_vs_ref.py, and against golden vectors generated from
+ * sources by oracle/build_ref.sh) in tests/test_oracle.py (test_restatement_against_live_reference), and against golden vectors generated from
  * that build and committed under tests/golden/ (tests/golden/make_golden.py). The one routine that is NOT
  * pinned bit-for-bit is orc_gemm: the reference calls cblas_sgemm from an unpinned third-party BLAS
  * (math_functions.cpp:148); orc_gemm accumulates in double and rounds once, which is at least as close to
