@@ -120,6 +120,23 @@ def make_workload(scale_div, device):
                 feats=feats.cpu().numpy(), labels=labels.cpu().numpy(), split=split)
 
 
+def make_shard(scale_div, world, rank, device):
+    """N > 1, weak scaling: ONE graph of world x the C2 shape (world x 2.45 M vertices, world x 62 M CSR edges, same R-MAT
+    generator and seed), vertex ids randomly relabelled so that the reference's contiguous 1D ownership rule gives every rank
+    an equal share of the edges; each rank keeps the rows of its own range. Features / labels are per-rank streams."""
+    import torch
+    from graphaibench_b200 import datagen, dist as gdist
+    nv = (C2["nv"] // scale_div) * world
+    nnz = (C2["nnz"] // scale_div) * world
+    _, first, last = gdist.owner_range(nv, world, rank)
+    rp, ci = datagen.rmat_csr_torch(nv, nnz, seed=1, device=device, permute=True, rows=(first, last))
+    g = torch.Generator(device=device); g.manual_seed(2 + 1000 * rank)
+    feats = torch.randn(last - first, C2["feat"], generator=g, device=device, dtype=torch.float32)
+    g.manual_seed(3 + 1000 * rank)
+    labels = torch.randint(0, C2["ncls"], (last - first,), generator=g, device=device, dtype=torch.int64).to(torch.uint8)
+    return dict(nv=nv, first=first, last=last, rowptr=rp, colidx=ci, feats=feats, labels=labels, split=datagen.split_ranges(nv))
+
+
 def config_dict(w, n_gpus, scale_div, extra=None):
     c = {"workload": "GraphSAGE-mean 2-layer hidden 256, full-graph training, synthetic ogbn-products-shaped R-MAT graph (BASELINE.json configs[1])",
          "vertices": w["nv"], "csr_edges": w["nnz"], "features": C2["feat"], "hidden": C2["hid"], "classes": C2["ncls"], "layers": C2["layers"],
@@ -210,7 +227,9 @@ def ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with quiet_stdout():  # NCCL announces its version on stdout at communicator creation
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     from graphaibench_b200 import _abi, build, model as gmodel
     if rank == 0:
         with quiet_stdout():
@@ -220,7 +239,9 @@ def ours(args):
     L = _abi.lib()
     peaks = load_peaks()
 
-    w = make_workload(args.scale, "cuda")  # weak scaling: every rank trains one C2-shaped shard
+    if world > 1:
+        return ours_partitioned(args, world, rank, local, L, peaks)
+    w = make_workload(args.scale, "cuda")
     stream = torch.cuda.Stream()
     with quiet_stdout():
         m = gmodel.GnnModel("sage", w["rowptr"], w["colidx"], w["feats"], w["labels"], w["split"], C2["hid"], C2["ncls"], num_layers=C2["layers"],
@@ -294,6 +315,118 @@ def ours(args):
         line["cpu_baseline"] = {"value": ws["nnz"] / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step_sample": dt * 1e3,
                                 "sample": f"reference OpenMP build (oracle/_ref) on a 1/{SAMPLE_DIV}-scale graph of the same shape ({ws['nv']} vertices, "
                                           f"{ws['nnz']} CSR edges), {done} epochs after 1 warm-up, {threads} threads"}
+    print(json.dumps(line), flush=True)
+
+
+def ours_partitioned(args, world, rank, local, L, peaks):
+    """N > 1: the same model on a 1D-partitioned graph (graphaibench_b200/dist.py): halo exchange per aggregation over NCCL,
+    interior rows overlapped with the exchange, dW all-reduce. Weak scaling (per-GPU rows and edges fixed)."""
+    import torch
+    import torch.distributed as dist
+    from graphaibench_b200 import dist as gdist
+    sh = make_shard(args.scale, world, rank, "cuda")
+    comm = gdist.TorchComm()
+    plan = gdist.HaloPlan(comm, sh["nv"], sh["rowptr"], sh["colidx"])
+    gids = plan.master_gids
+    split = sh["split"]
+    mask = ((gids >= int(split[0])) & (gids < int(split[1]))).to(torch.uint8)
+    loc = (gids - sh["first"])
+    dims = [C2["feat"]] + [C2["hid"]] * (C2["layers"] - 1) + [C2["ncls"]]
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        m = gdist.DistGnn("sage", plan, sh["feats"][loc], sh["labels"][loc], mask, int(split[1] - split[0]), dims, lr=C2["lr"])
+        # pinned host copies of this rank's inputs for the end-to-end step
+        host = {k: v.cpu().pin_memory() for k, v in dict(feats=sh["feats"][loc], labels=m.labels, mask=m.mask, rowptr=plan.rowptr, colidx=plan.colidx).items()}
+        dev_scratch = {k: torch.empty_like(v, device="cuda") for k, v in host.items() if k != "feats"}
+    del sh
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.gai_launch_count()
+        t0 = time.time()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                out = fn()
+            e1.record(stream)
+        barrier()
+        t1 = time.time()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, L.gai_launch_count() - l0, out, (t0, t1)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            m.train_epoch_async()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ex0 = (m.exchanges, m.exchange_bytes)
+    ms_step, launches, tot, span = timed(m.train_epoch_async, args.steps)
+    ex_per_step = (m.exchanges - ex0[0]) / args.steps
+    exb_per_step = (m.exchange_bytes - ex0[1]) / args.steps
+
+    n = plan.n_loc
+
+    def e2e_step():
+        # pinned host -> device: this rank's features, labels, train mask and local CSR; the static input halo is re-fetched from
+        # the owners; the step ends with the device -> host read of {loss sum, correct, count}
+        m.feat_in[0][:n, : dims[0]].copy_(host["feats"], non_blocking=True)
+        for k, v in dev_scratch.items():
+            v.copy_(host[k], non_blocking=True)
+        m._exchange(m.feat_in[0])
+        return m.train_epoch_async().cpu()
+    with torch.cuda.stream(stream):
+        e2e_step()
+    ms_e2e, _, tot, span2 = timed(e2e_step, args.steps)
+    clocks = sampler.stop(span[0], span2[1]) if rank == 0 else None
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d_t = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(h2d_t)
+
+    # per-op device times (events on the launching stream; the interior/halo overlap is serialised while timing)
+    m.timer = gdist.OpTimer()
+    n_prof = 3
+    with torch.cuda.stream(stream):
+        for _ in range(n_prof):
+            m.train_epoch_async()
+    prof = m.timer.collect()
+    m.timer = None
+    roof, breakdown, per_shape = roofline_from_profile([r for r in prof if r["bucket"] not in ("HALO", "ALLREDUCE")], peaks, n_prof)
+    halo_ms = sum(r["ms"] for r in prof if r["bucket"] == "HALO") / n_prof
+    breakdown["HALO"] = round(halo_ms, 4)
+    breakdown["ALLREDUCE"] = round(sum(r["ms"] for r in prof if r["bucket"] == "ALLREDUCE") / n_prof, 4)
+
+    sizes = torch.tensor([plan.n_loc, plan.n_int, plan.n_halo, plan.nnz, plan.n_send], device="cuda", dtype=torch.float64)
+    gathered = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(gathered, sizes)
+    if rank != 0:
+        return
+    per_rank = [dict(masters=int(t[0]), interior=int(t[1]), halo=int(t[2]), edges=int(t[3]), rows_sent=int(t[4])) for t in gathered]
+    total_edges = sum(r["edges"] for r in per_rank)
+    w = dict(nv=plan.nv, nnz=total_edges, split=split)
+    value = total_edges / (ms_step * 1e-3) / 1e6
+    cnt = float(tot[2])
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(w, world, args.scale, {
+                "graph": f"one R-MAT graph of {world} x the configs[1] shape, vertex ids randomly relabelled (balanced contiguous 1D ownership)",
+                "halo": "layer-0 input features of halo vertices replicated at setup; one all-to-all-v (NCCL) per later aggregation at min(F_in, F_out) "
+                        "width, interior rows aggregated on a side stream meanwhile",
+                "per_rank": per_rank, "gemm_mode": "auto"}),
+            "e2e": {"value": total_edges / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_t.item()),
+                    "d2h_bytes_per_step": 24 * world},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "breakdown_ms_per_step": breakdown, "ops": per_shape[:12],
+            "halo_exchange": {"exchanges_per_step": ex_per_step, "recv_bytes_per_step_rank0": exb_per_step, "ms_per_step_rank0": halo_ms,
+                              "GBps_rank0": exb_per_step / max(halo_ms, 1e-9) / 1e6, "nvlink_peak_GBps_per_dir": 900.0},
+            "final": {"train_loss": float(tot[0]) / cnt if cnt else None, "train_acc": float(tot[1]) / cnt if cnt else None}}
     print(json.dumps(line), flush=True)
 
 

@@ -48,6 +48,7 @@ _SIGS = {
     "gai_csr_vertex_norm": (C.c_void_p, [C.c_void_p]),
     "gai_csr_set_norms": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_stream]),
     "gai_csr_num_hub_rows": (C.c_uint32, [C.c_void_p]),
+    "gai_csr_set_row_segments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_stream]),
     "gai_csr_build_transpose": (C.c_int, [C.c_void_p, c_stream]),
     "gai_csr_transpose_perm": (C.c_void_p, [C.c_void_p]),
     "gai_spmm_gcn": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
@@ -69,6 +70,7 @@ _SIGS = {
     "gai_d_l2norm": (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_forward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_backward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_stream]),
+    "gai_softmax_ce_backward_scaled": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, C.c_int, C.c_uint64, c_stream]),
     "gai_masked_loss_accuracy": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
     "gai_adam_update": (C.c_int, [C.c_size_t, c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, c_stream]),

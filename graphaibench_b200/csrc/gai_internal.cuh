@@ -44,6 +44,16 @@ uint32_t hub_degree_for(uint64_t nnz);
 
 }  // namespace gai
 
+// Degree-ordered work list of the aggregation kernels over one row range [rb, re) (the whole graph, or one registered segment:
+// interior / boundary rows of a 1D partition).
+struct gai_worklist {
+  uint32_t rb = 0, re = 0;
+  uint32_t* row_order = nullptr;  // rows of the range, longest first (ties: ascending id); the first n_hub entries are the hub rows
+  uint32_t* claim_ptr = nullptr;  // light rows (row_order + n_hub) cut into claims of <= 32 rows / <= 2048 edges: (begin, end) pairs in execution order
+  uint32_t n_hub = 0, n_claims = 0;
+};
+constexpr int GAI_MAX_SEGMENTS = 8;
+
 // Device graph. Plain struct of device pointers, passed by value into kernels (as the reference passes its
 // LearningGraph, include/gnn/graph_operations.h:85).
 struct gai_csr {
@@ -63,6 +73,8 @@ struct gai_csr {
   unsigned counter_seq = 0;
   cudaStream_t aux_stream = nullptr;  // hub-row kernels run here, concurrently with the light-row kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  gai_worklist seg[GAI_MAX_SEGMENTS];  // work lists of registered row segments (gai_csr_set_row_segments)
+  int n_seg = 0;
   uint32_t* tperm = nullptr;  // e -> e^T
   bool owns_csr = false;
 };

@@ -52,40 +52,34 @@ __global__ void transpose_perm_kernel(uint32_t nv, const uint32_t* __restrict__ 
 //              (begin, end) pairs in execution order: the unit a warp takes from the shared work counter.
 constexpr uint64_t CLAIM_EDGES = 2048;
 
-int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
-  const uint32_t nv = g->nv;
-  g->n_hub = 0; g->n_claims = 0;
-  if (nv == 0) return GAI_OK;
-  std::vector<uint32_t> host_rp;
-  if (!rowptr_h) {  // CSR supplied in device memory: bring the row pointers back once
-    host_rp.resize((size_t)nv + 1);
-    GAI_CUDA(cudaMemcpyAsync(host_rp.data(), g->rowptr, sizeof(uint32_t) * ((size_t)nv + 1), cudaMemcpyDeviceToHost, st));
-    GAI_CUDA(cudaStreamSynchronize(st));
-    rowptr_h = host_rp.data();
-  }
+// Builds the list of rows [rb, re) into `out` (device arrays owned by `out`).
+int build_list(const gai_csr* g, const uint32_t* rowptr_h, uint32_t rb, uint32_t re, gai_worklist* out, cudaStream_t st) {
+  out->rb = rb; out->re = re; out->n_hub = 0; out->n_claims = 0;
+  const uint32_t n = re - rb;
+  if (n == 0) return GAI_OK;
   auto deg = [&](uint32_t v) { return rowptr_h[v + 1] - rowptr_h[v]; };
   uint32_t maxdeg = 0;
-  for (uint32_t v = 0; v < nv; v++) maxdeg = std::max(maxdeg, deg(v));
+  for (uint32_t v = rb; v < re; v++) maxdeg = std::max(maxdeg, deg(v));
   std::vector<uint64_t> start((size_t)maxdeg + 2, 0);
-  for (uint32_t v = 0; v < nv; v++) start[(size_t)maxdeg - deg(v) + 1]++;  // bucket 0 = longest
+  for (uint32_t v = rb; v < re; v++) start[(size_t)maxdeg - deg(v) + 1]++;  // bucket 0 = longest
   for (size_t d = 1; d < start.size(); d++) start[d] += start[d - 1];
-  std::vector<uint32_t> order(nv);
-  for (uint32_t v = 0; v < nv; v++) order[start[(size_t)maxdeg - deg(v)]++] = v;
+  std::vector<uint32_t> order(n);
+  for (uint32_t v = rb; v < re; v++) order[start[(size_t)maxdeg - deg(v)]++] = v;
   uint32_t n_hub = 0;
-  while (n_hub < nv && deg(order[n_hub]) > g->hub_degree) n_hub++;
+  while (n_hub < n && deg(order[n_hub]) > g->hub_degree) n_hub++;
   // claims as (begin, end) pairs into the light part of the list, in EXECUTION order
   std::vector<uint32_t> cuts;
-  cuts.reserve((nv - n_hub) / 16 + 2);
+  cuts.reserve((n - n_hub) / 16 + 2);
   cuts.push_back(0);
   uint64_t edges = 0;
   uint32_t rows = 0, n_big = 0;
-  for (uint32_t i = n_hub; i < nv; i++) {
+  for (uint32_t i = n_hub; i < n; i++) {
     const uint32_t d = deg(order[i]);
     if (rows > 0 && (rows == 32 || edges + d > CLAIM_EDGES)) { cuts.push_back(i - n_hub); rows = 0; edges = 0; }
     if (d > CLAIM_EDGES) n_big++;  // rows longer than the budget travel alone
     rows++; edges += d;
   }
-  cuts.push_back(nv - n_hub);
+  cuts.push_back(n - n_hub);
   const uint32_t n_claims = (uint32_t)cuts.size() - 1;
   // Execution order: the over-budget single-row claims first (longest-processing-time first keeps the tail short), then
   // the rest interleaved by a stride permutation so that, at any moment, the machine works on a mix of long-row claims
@@ -108,13 +102,36 @@ int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
     claims[2 * (size_t)i] = cuts[src];
     claims[2 * (size_t)i + 1] = cuts[src + 1];
   }
-  g->n_hub = n_hub;
-  g->n_claims = n_claims;
-  GAI_CUDA(cudaMalloc(&g->row_order, sizeof(uint32_t) * (size_t)nv));
-  GAI_CUDA(cudaMalloc(&g->claim_ptr, sizeof(uint32_t) * claims.size()));
-  GAI_CUDA(cudaMemcpyAsync(g->row_order, order.data(), sizeof(uint32_t) * (size_t)nv, cudaMemcpyHostToDevice, st));
-  GAI_CUDA(cudaMemcpyAsync(g->claim_ptr, claims.data(), sizeof(uint32_t) * claims.size(), cudaMemcpyHostToDevice, st));
+  out->n_hub = n_hub;
+  out->n_claims = n_claims;
+  GAI_CUDA(cudaMalloc(&out->row_order, sizeof(uint32_t) * (size_t)n));
+  GAI_CUDA(cudaMalloc(&out->claim_ptr, sizeof(uint32_t) * claims.size()));
+  GAI_CUDA(cudaMemcpyAsync(out->row_order, order.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  GAI_CUDA(cudaMemcpyAsync(out->claim_ptr, claims.data(), sizeof(uint32_t) * claims.size(), cudaMemcpyHostToDevice, st));
   GAI_CUDA(cudaStreamSynchronize(st));  // the staging vectors are pageable and go out of scope
+  return GAI_OK;
+}
+
+// rowptr_h == NULL: CSR supplied in device memory, bring the row pointers back once
+int host_rowptr(const gai_csr* g, const uint32_t*& rowptr_h, std::vector<uint32_t>& keep, cudaStream_t st) {
+  if (rowptr_h) return GAI_OK;
+  keep.resize((size_t)g->nv + 1);
+  GAI_CUDA(cudaMemcpyAsync(keep.data(), g->rowptr, sizeof(uint32_t) * ((size_t)g->nv + 1), cudaMemcpyDeviceToHost, st));
+  GAI_CUDA(cudaStreamSynchronize(st));
+  rowptr_h = keep.data();
+  return GAI_OK;
+}
+
+int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
+  g->n_hub = 0; g->n_claims = 0;
+  if (g->nv == 0) return GAI_OK;
+  std::vector<uint32_t> keep;
+  int rc = host_rowptr(g, rowptr_h, keep, st);
+  if (rc != GAI_OK) return rc;
+  gai_worklist full;
+  rc = build_list(g, rowptr_h, 0, g->nv, &full, st);
+  if (rc != GAI_OK) return rc;
+  g->row_order = full.row_order; g->claim_ptr = full.claim_ptr; g->n_hub = full.n_hub; g->n_claims = full.n_claims;
   g->hub_rows = g->row_order;
   return GAI_OK;
 }
@@ -196,6 +213,7 @@ int gai_csr_create_device(uint32_t nv, uint64_t nnz, const uint32_t* rowptr_d, c
 int gai_csr_destroy(gai_csr_t g) {
   if (!g) return GAI_OK;
   if (g->owns_csr) { cudaFree(g->rowptr); cudaFree(g->colidx); }
+  for (int i = 0; i < g->n_seg; i++) { cudaFree(g->seg[i].row_order); cudaFree(g->seg[i].claim_ptr); }
   cudaFree(g->norm_gcn); cudaFree(g->norm_mean); cudaFree(g->tperm); cudaFree(g->row_counters); cudaFree(g->row_order); cudaFree(g->claim_ptr);
   if (g->aux_stream) { cudaStreamDestroy(g->aux_stream); cudaEventDestroy(g->ev_fork); cudaEventDestroy(g->ev_join); }
   delete g;
@@ -213,6 +231,25 @@ int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_me
   GAI_CHECK_ARG(g != nullptr);
   if (norm_gcn_d) GAI_CUDA(cudaMemcpyAsync(g->norm_gcn, norm_gcn_d, sizeof(float) * (size_t)g->nv, cudaMemcpyDeviceToDevice, gai::S(stream)));
   if (norm_mean_d) GAI_CUDA(cudaMemcpyAsync(g->norm_mean, norm_mean_d, sizeof(float) * (size_t)g->nv, cudaMemcpyDeviceToDevice, gai::S(stream)));
+  return GAI_OK;
+}
+
+int gai_csr_set_row_segments(gai_csr_t g, int n_segments, const uint32_t* bounds_h, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr && n_segments >= 0 && n_segments <= GAI_MAX_SEGMENTS && (bounds_h || n_segments == 0));
+  for (int i = 0; i < n_segments; i++) GAI_CHECK_ARG(bounds_h[2 * i] <= bounds_h[2 * i + 1] && bounds_h[2 * i + 1] <= g->nv);
+  cudaStream_t st = gai::S(stream);
+  for (int i = 0; i < g->n_seg; i++) { cudaFree(g->seg[i].row_order); cudaFree(g->seg[i].claim_ptr); g->seg[i] = gai_worklist(); }
+  g->n_seg = 0;
+  if (n_segments == 0 || g->nv == 0) return GAI_OK;
+  const uint32_t* rowptr_h = nullptr;
+  std::vector<uint32_t> keep;
+  int rc = host_rowptr(g, rowptr_h, keep, st);
+  if (rc != GAI_OK) return rc;
+  for (int i = 0; i < n_segments; i++) {
+    rc = build_list(g, rowptr_h, bounds_h[2 * i], bounds_h[2 * i + 1], &g->seg[i], st);
+    if (rc != GAI_OK) return rc;
+    g->n_seg = i + 1;
+  }
   return GAI_OK;
 }
 

@@ -126,16 +126,16 @@ __global__ void softmax_ce_fwd_kernel(int ncls, size_t begin, size_t end, const 
 }
 
 __global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
-                                      const float* __restrict__ probs, float* __restrict__ grad) {
+                                      const float* __restrict__ probs, float* __restrict__ grad, double denom, size_t ld_grad) {
   const size_t n = (end - begin) * ncls;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const double inv_range = (double)(end - begin);
+  const double inv_range = denom;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     const size_t row = begin + k / ncls;
     const int j = (int)(k % ncls);
     if (masks && masks[row] != 1) continue;
     // softmax_loss_layer.cpp:31: (pred - onehot) / (end - begin), evaluated in double then rounded
-    grad[row * ncls + j] = (float)(((double)probs[row * ncls + j] - (labels[row] == j ? 1.0 : 0.0)) / inv_range);
+    grad[row * ld_grad + j] = (float)(((double)probs[row * ncls + j] - (labels[row] == j ? 1.0 : 0.0)) / inv_range);
   }
 }
 
@@ -265,7 +265,17 @@ int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* m
                             gai_stream_t stream) {
   GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out);
   if (begin == end) return GAI_OK;
-  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out);
+  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out,
+                                                                                         (double)(end - begin), (size_t)ncls);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_softmax_ce_backward_scaled(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
+                                   float* grad_out, int ld_grad, uint64_t denom, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out && denom > 0 && ld_grad >= ncls);
+  if (begin == end) return GAI_OK;
+  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out,
+                                                                                         (double)denom, (size_t)ld_grad);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

@@ -397,16 +397,28 @@ __global__ void pad_rows_kernel(size_t n_rows, int F, int Fp, const float* __res
 
 inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16) == 0; }
 
+// Work list serving a call: the whole-graph list, the list of a registered segment (gai_csr_set_row_segments) whose bounds
+// equal the requested range, or none (natural order, 32 consecutive rows per claim).
+struct ListSel { const uint32_t* order; const uint32_t* claim_ptr; const uint32_t* hub_rows; uint32_t n_hub; unsigned long long n_claims; bool listed; };
+ListSel select_list(const SpmmArgs& a, const gai_csr* g) {
+  if (a.row_begin == 0 && a.row_end == g->nv && g->row_order != nullptr)
+    return {g->row_order + g->n_hub, g->claim_ptr, g->hub_rows, g->n_hub, g->n_claims, true};
+  for (int i = 0; i < g->n_seg; i++)
+    if (g->seg[i].rb == a.row_begin && g->seg[i].re == a.row_end && g->seg[i].row_order != nullptr)
+      return {g->seg[i].row_order + g->seg[i].n_hub, g->seg[i].claim_ptr, g->seg[i].row_order, g->seg[i].n_hub, g->seg[i].n_claims, true};
+  const unsigned long long n_rows = (unsigned long long)a.row_end - a.row_begin;
+  return {nullptr, nullptr, g->hub_rows, g->n_hub, (n_rows + SLOTS - 1) / SLOTS, false};
+}
+
 template <int MODE>
 int launch_rows_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
-  // full-graph calls walk the degree-ordered list (hub rows sit at its head and are skipped by offset); row-range calls
-  // (1D partition: interior / boundary rows) walk the range in natural order
-  const bool full = a.row_begin == 0 && a.row_end == g->nv && g->row_order != nullptr;
-  const uint32_t* order = full ? g->row_order + g->n_hub : nullptr;
-  const unsigned long long n_rows = full ? (unsigned long long)g->nv - g->n_hub : (unsigned long long)a.row_end - a.row_begin;
-  if (n_rows == 0) return GAI_OK;
-  const unsigned long long claims = full ? g->n_claims : (n_rows + SLOTS - 1) / SLOTS;
-  const uint32_t* claim_ptr = g->claim_ptr;
+  // listed calls walk a degree-ordered list (hub rows sit at its head and are skipped by offset); other row-range calls walk
+  // the range in natural order
+  const ListSel sel = select_list(a, g);
+  const uint32_t* order = sel.order;
+  const unsigned long long claims = sel.n_claims;
+  if (claims == 0) return GAI_OK;
+  const uint32_t* claim_ptr = sel.claim_ptr;
   int G = 4;
   while (G < 32 && G < a.nchunks) G <<= 1;
   int K = 1;
@@ -446,7 +458,8 @@ int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t
     GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<MODE, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     configured = true;
   }
-  spmm_hub_kernel<MODE, ES><<<g->n_hub, HUB_THREADS, smem, st>>>(a, g->hub_rows);
+  const ListSel sel = select_list(a, g);
+  spmm_hub_kernel<MODE, ES><<<sel.n_hub, HUB_THREADS, smem, st>>>(a, sel.hub_rows);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -464,7 +477,7 @@ int launch_hub_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
 }
 
 int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
-  if (g->n_hub == 0) return GAI_OK;
+  if (select_list(a, g).n_hub == 0) return GAI_OK;
   switch (a.mode) {
     case M_GCN: return launch_hub_mode<M_GCN>(a, g, st);
     case M_MEAN: return launch_hub_mode<M_MEAN>(a, g, st);
@@ -493,7 +506,9 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.mode = mode; a.flags = flags;
   a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
-  if ((F % 4 == 0) && (ld_in % 4 == 0) && aligned16(in)) {
+  if ((ld_in % 4 == 0) && aligned16(in) && ld_in >= a.nchunks * 4) {
+    // rows are 128-bit loadable as stored; when F % 4 != 0 the tail chunk also reads the (ld_in - F) padding columns of
+    // the row: they land in accumulator lanes that are never stored (store_chunk masks columns >= F)
     a.in = in; a.ld_in = ld_in;
   } else {
     // gather source must be 128-bit loadable: stage a zero-padded copy (all nv rows can be neighbours)
@@ -512,7 +527,8 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   // Hub rows go first, on a high-priority side stream (fork/join with events): their CTAs are the long poles (one
   // 94 K-edge row is ~0.3 ms of in-order adds), the persistent light-row warps on `st` fill the other SMs meanwhile.
   int rc = GAI_OK;
-  if (g->n_hub) {
+  const bool has_hub = select_list(a, g).n_hub != 0;
+  if (has_hub) {
     if (!g->aux_stream) {
       int lo = 0, hi = 0;
       GAI_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -527,7 +543,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
     GAI_CUDA(cudaEventRecord(g->ev_join, g->aux_stream));
   }
   rc = launch_rows(a, g, st);
-  if (g->n_hub) GAI_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
+  if (has_hub) GAI_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
   return rc;
 }
 

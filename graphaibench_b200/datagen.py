@@ -77,9 +77,8 @@ def write_dataset(path, rowptr64, colidx, feats, labs, ncls, split9):
     np.asarray(labs, np.uint8).tofile(os.path.join(path, "graph.vlabel.bin"))
 
 
-def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 0.19, 0.19, 0.05), device="cuda"):
-    """Same construction as rmat_csr, vectorised with torch on `device` (input generation only; the multi-million-edge
-    bench graphs take seconds instead of minutes). Returns (rowptr int64[n+1], colidx int64[nnz]) tensors on `device`."""
+def _rmat_pairs_torch(n_vertices, target_nnz, seed, abcd, device):
+    """Unique undirected R-MAT pairs (lo < hi) as int64 keys lo * n + hi; ~target_nnz / 2 of them."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -87,7 +86,8 @@ def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 
     a, b, c, _ = abcd
     want_pairs = target_nnz // 2
     keys = torch.empty(0, dtype=torch.int64, device=device)
-    draw = int(want_pairs * 1.25) + 16
+    keep = (n_vertices / float(1 << scale)) ** 2   # share of draws whose two ends are both < n_vertices
+    draw = int(want_pairs * 1.25 / max(keep, 0.05)) + 16
     for _ in range(8):
         src = torch.zeros(draw, dtype=torch.int64, device=device)
         dst = torch.zeros(draw, dtype=torch.int64, device=device)
@@ -104,15 +104,35 @@ def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 
         del src, dst, r, sb, db, ok, lo, hi
         if keys.numel() >= want_pairs:
             break
-        draw = int((want_pairs - keys.numel()) * 1.6) + 16
+        draw = int((want_pairs - keys.numel()) * 1.6 / max(keep, 0.05)) + 16
     if keys.numel() > want_pairs:
         sel = torch.randperm(keys.numel(), generator=g, device=device)[:want_pairs]
         keys = keys[torch.sort(sel).values]
+    return keys, g
+
+
+def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 0.19, 0.19, 0.05), device="cuda", permute=False, rows=None):
+    """Same construction as rmat_csr, vectorised with torch on `device` (input generation only; the multi-million-edge
+    bench graphs take seconds instead of minutes). Returns (rowptr int64, colidx int64) tensors on `device`.
+    permute: relabel the vertices with a seeded random permutation (balances a contiguous 1D partition: natural R-MAT ids
+    put most edges into the low id ranges). rows=(first, last): return only those rows (rowptr rebased to 0, global column ids)
+    — what one rank of a 1D partition loads."""
+    import torch
+    keys, g = _rmat_pairs_torch(n_vertices, target_nnz, seed, abcd, device)
     lo, hi = keys // n_vertices, keys % n_vertices
+    del keys
+    if permute:
+        perm = torch.randperm(n_vertices, generator=g, device=device)
+        lo, hi = perm[lo], perm[hi]
     s = torch.cat([lo, hi])
     d = torch.cat([hi, lo])
+    del lo, hi
+    first, last = (0, n_vertices) if rows is None else rows
+    if rows is not None:
+        sel = (s >= first) & (s < last)
+        s, d = s[sel], d[sel]
     order = torch.argsort(s * n_vertices + d)
     s, d = s[order], d[order]
-    rowptr = torch.zeros(n_vertices + 1, dtype=torch.int64, device=device)
-    rowptr[1:] = torch.cumsum(torch.bincount(s, minlength=n_vertices), 0)
+    rowptr = torch.zeros(last - first + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(s - first, minlength=last - first), 0)
     return rowptr, d

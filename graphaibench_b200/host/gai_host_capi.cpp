@@ -52,6 +52,14 @@ extern "C" {
 
 void gai_host_set_stream(void* s) { gai_host::set_stream(s); }
 
+// Glorot initial weights exactly as the layers draw them (init_glorot, gai_layers.cpp): used by the 1D-partitioned trainer,
+// whose replicated weights must start from the reference's values.
+void gai_host_glorot(uint64_t dim_x, uint64_t dim_y, unsigned seed, float* out_h) {
+  vec_t w;
+  init_glorot(dim_x, dim_y, w, seed);
+  memcpy(out_h, w.data(), sizeof(float) * w.size());
+}
+
 void* gai_graph_new(uint32_t nv, uint32_t ne, const uint32_t* rowptr, const uint32_t* colidx) {
   Graph* g = new Graph(true);
   g->allocateFrom(nv, ne);

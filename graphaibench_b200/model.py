@@ -44,8 +44,16 @@ def hostlib():
         L.gai_host_profile_json.argtypes = [C.c_char_p, C.c_int64]
         L.gai_host_profile_json.restype = C.c_int64
         L.gai_model_sync.argtypes = []
+        L.gai_host_glorot.argtypes = [C.c_uint64, C.c_uint64, C.c_uint, C.c_void_p]
         _h = L
     return _h
+
+
+def glorot(dim_x, dim_y, seed):
+    """Reference-exact Glorot-uniform initial weights (init_glorot, math_functions.cpp:11-19), [dim_x, dim_y] fp32 on the host."""
+    out = np.empty((dim_x, dim_y), np.float32)
+    hostlib().gai_host_glorot(dim_x, dim_y, seed, out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def profile_enable(on: bool):

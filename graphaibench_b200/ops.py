@@ -81,6 +81,11 @@ class DeviceGraph:
         check(lib().gai_memcpy_d2d(_p(out), lib().gai_csr_transpose_perm(self._h), 4 * self.nnz, _stream()))
         return out[: self.nnz]
 
+    def set_row_segments(self, segments):
+        """segments: list of (row_begin, row_end); the *_rows calls with exactly these bounds use a degree-ordered work list."""
+        b = np.ascontiguousarray(np.asarray(segments, np.uint32).reshape(-1, 2))
+        check(lib().gai_csr_set_row_segments(self._h, len(b), b.ctypes.data_as(C.c_void_p), _stream()), "gai_csr_set_row_segments")
+
     def set_norms(self, norm_gcn=None, norm_mean=None):
         check(lib().gai_csr_set_norms(self._h, _f32(norm_gcn) if norm_gcn is not None else None,
                                       _f32(norm_mean) if norm_mean is not None else None, _stream()))
@@ -180,6 +185,12 @@ def softmax_ce_forward(logits, labels, masks, begin, end, probs, losses):
 def softmax_ce_backward(probs, labels, masks, begin, end, grad):
     check(lib().gai_softmax_ce_backward(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), _f32(grad), _stream()),
           "gai_softmax_ce_backward")
+
+
+def softmax_ce_backward_scaled(probs, labels, masks, begin, end, grad, denom):
+    """grad rows may be wider than ncls (grad.stride(0) is the leading dimension); scaled by 1/denom (the global range length)."""
+    check(lib().gai_softmax_ce_backward_scaled(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), _f32(grad), grad.stride(0), denom,
+                                               _stream()), "gai_softmax_ce_backward_scaled")
 
 
 def masked_loss_accuracy(logits, labels, masks, begin, end, losses, stats=None):

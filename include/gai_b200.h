@@ -84,6 +84,11 @@ const float* gai_csr_vertex_norm(gai_csr_t g); /* LearningGraph::vertex_data_ptr
 /* Override the per-vertex normalisers with values computed elsewhere (1D partition: norms come from GLOBAL degrees). */
 int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream);
 uint32_t gai_csr_num_hub_rows(gai_csr_t g);
+/* Register up to 8 row segments [bounds_h[2i], bounds_h[2i+1]) (1D partition: interior rows, boundary rows, all masters; they
+ * may overlap). Each gets its own
+ * degree-ordered, edge-budgeted work list, used by the *_rows entry points when called with exactly those bounds; any other
+ * row range is walked in natural order. Replaces the previous registration. */
+int gai_csr_set_row_segments(gai_csr_t g, int n_segments, const uint32_t* bounds_h, gai_stream_t stream);
 /* e -> e^T permutation on a structurally symmetric pattern (binary search per edge, as
  * symmetric_csr_transpose, src/utilities/math_functions.cpp:46-74); built once, cached in the handle. */
 int gai_csr_build_transpose(gai_csr_t g, gai_stream_t stream);
@@ -146,6 +151,11 @@ int gai_softmax_ce_forward(int ncls, size_t begin, size_t end, const uint8_t* ma
                            float* probs, float* losses, gai_stream_t stream);
 int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
                             float* grad_out, gai_stream_t stream);
+/* Same backward with an explicit denominator and gradient leading dimension: a 1D-partitioned rank owns only part of the
+ * reference's [begin,end) range but must scale by the GLOBAL range length (softmax_loss_layer.cpp:31); ld_grad >= ncls lets the
+ * gradient land in a 16-byte-aligned row layout the aggregation can gather without a staging copy. */
+int gai_softmax_ce_backward_scaled(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
+                                   float* grad_out, int ld_grad, uint64_t denom, gai_stream_t stream);
 int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                              const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
 
