@@ -61,6 +61,15 @@ _SIGS = {
     "gai_matmul": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "gai_matmul_ld": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t,
                                 C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "gai_matmul_kcat": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t,
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, C.c_int, c_f32p, C.c_size_t, c_stream]),
+    "gai_matmul_ncat": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+    "gai_wgrad_two_a": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+    "gai_wgrad_two_b": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+    "gai_d_relu_ld": (C.c_int, [C.c_size_t, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
     "gai_set_gemm_mode": (C.c_int, [C.c_int]),
     "gai_get_gemm_mode": (C.c_int, []),
     "gai_relu": (C.c_int, [C.c_size_t, c_f32p, c_f32p, c_stream]),

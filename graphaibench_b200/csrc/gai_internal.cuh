@@ -42,6 +42,35 @@ int workspace_slot(int slot, size_t bytes, void** out);  // slot 1: SpMM padded-
 // go to the CTA-per-row kernels; everything else is one lane-group per row.
 uint32_t hub_degree_for(uint64_t nnz);
 
+// Concatenated dense transforms (gemm_tc.cu): C_j[M x N_j] (+)= sum_p A_p[M x K_p] · op(B_pj), p < nk (K-concatenation: two tall
+// operands, one accumulator), j < nn (N-concatenation: one pass over A, two outputs). B_pj is stored [K_p x N_j], or [N_j x K_p] if tb.
+struct GemmCat {
+  size_t M = 0;
+  int nk = 1, nn = 1, tb = 0;
+  const float* A[2] = {nullptr, nullptr};
+  size_t lda[2] = {0, 0}, K[2] = {0, 0};
+  const float* B[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t ldb[2][2] = {{0, 0}, {0, 0}};
+  size_t N[2] = {0, 0};
+  float* C[2] = {nullptr, nullptr};
+  size_t ldc[2] = {0, 0};
+  int accum = 0, flags = 0;
+  const float* mask = nullptr;  // GAI_EPI_MASK: C = mask > 0 ? C : 0 (nn == 1)
+  size_t ldmask = 0;
+};
+// Concatenated weight gradients (gemm_tc_wgrad.cu): C_i = A_i^T · B_i over nrows rows; dual = 1: two A parts (<= 128 columns
+// each) against B_0; dual = 2: A_0 against two B parts; dual = 0: the plain product.
+struct WgradCat {
+  size_t nrows = 0;
+  int dual = 0, accum = 0;
+  const float* A[2] = {nullptr, nullptr};
+  size_t lda[2] = {0, 0}, Kx[2] = {0, 0};
+  const float* B[2] = {nullptr, nullptr};
+  size_t ldb[2] = {0, 0}, My[2] = {0, 0};
+  float* C[2] = {nullptr, nullptr};
+  size_t ldc[2] = {0, 0};
+};
+
 }  // namespace gai
 
 // Degree-ordered work list of the aggregation kernels over one row range [rb, re) (the whole graph, or one registered segment:

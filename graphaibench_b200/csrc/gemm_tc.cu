@@ -6,8 +6,12 @@
 // Shapes served (row-major, the tall operand is the N x K activation / gradient matrix, the weight is tiny):
 //   C[M x N] = A[M x K] · B[K x N]          (forward transforms X·W)           transB = 0
 //   C[M x N] = A[M x K] · B[N x K]^T        (input gradients G·W^T)            transB = 1
-// with N <= 256 (one MMA tile covers the full output width) and any M. The reduction-over-rows product X^T·G (weight
-// gradient) and anything else is declined (GAI_ERR_UNSUPPORTED) and served by gemm_simt.cu.
+// with N <= 256 (one MMA tile covers the full output width) and any M, and their concatenated forms (GemmCat):
+//   K-concatenation   C = A_0·op(B_0) + A_1·op(B_1)   two tall operands streamed by two TMA maps into ONE accumulator
+//                     (SAGE: [ÂX | X]·[W_neigh; W_self], sage_layer.cpp:20-23, and dH = dY·W_n^T + dZ·W_s^T, :44-52)
+//   N-concatenation   C_0 = A·B_0, C_1 = A·B_1        one pass over A, two outputs (SAGE transform-first: H·[W_n | W_s])
+// The reduction-over-rows product X^T·G (weight gradient) and anything else is declined (GAI_ERR_UNSUPPORTED) and
+// served by gemm_tc_wgrad.cu / gemm_simt.cu.
 //
 // Kernel (persistent, one CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: per k-block (32 fp32 = one 128-byte swizzle row) loads the A tile [128 x 32] and the
@@ -16,7 +20,9 @@
 //               next to it (same swizzled offsets), then fence.proxy.async + arrive.
 //   warp 1      MMA issuer: one thread issues 3 x 4 tcgen05.mma (M128 x N x K8) per k-block into one of two TMEM
 //               accumulators; tcgen05.commit releases the smem stage / publishes the accumulator.
-//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns per warp, optional "+C" and ReLU, 128-byte row stores.
+//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns per warp, transposed through a padded shared-memory tile so
+//               that every global access is a full 128-byte row segment (4 rows per instruction); optional "+C",
+//               ReLU, and d_ReLU by a mask matrix (grad = mask > 0 ? grad : 0, math_functions.cpp:453-463).
 // The weight is prepared once per call by a tiny kernel (transpose to K-major if needed, zero-pad to [Npad x Kpad],
 // split into tf32 hi/lo) so that both operands are K-major and TMA-addressable whatever the caller's layout.
 #include "tc_common.cuh"
@@ -31,11 +37,21 @@ constexpr int THREADS = 384;
 
 using namespace tc;
 
+constexpr int EPI_PITCH = 36;    // floats per staged row: 32 + 4 keeps 128-bit shared accesses conflict-free both ways
+constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_PITCH * 4;  // four epilogue warps
+
 struct TcArgs {
-  float* C;
-  size_t M, N, ldc;
-  int n_mma;       // N rounded up to a multiple of 16 (UMMA N)
-  int num_kb;      // k-blocks of 32
+  float* C[2];
+  size_t ldc[2];
+  int N[2];        // columns of each output; output 1 starts at tile column noff1 (a multiple of 32)
+  int noff1, nouts;
+  const float* mask;
+  size_t ldmask;
+  size_t M;
+  int n_mma;       // tile width rounded up to a multiple of 16 (UMMA N)
+  int nkb0;        // k-blocks of the first K part
+  int num_kb;      // k-blocks of 32, both parts
+  int last_steps[2];  // k-steps (of 8) the last k-block of each part needs
   int stages;
   int passes;      // 3 = 3xTF32, 1 = single TF32 pass
   int accum, flags;
@@ -43,8 +59,8 @@ struct TcArgs {
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-               const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], conv_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -78,7 +94,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
           uint8_t* st = smem + (size_t)s * g.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], A_BYTES + (g.passes == 3 ? 2 : 1) * g.b_tile_bytes);
-          tma_load_2d(st, &map_a, kb * BK, (int)(tile * BM), &full_bar[s]);
+          if (kb < g.nkb0) tma_load_2d(st, &map_a0, kb * BK, (int)(tile * BM), &full_bar[s]);
+          else             tma_load_2d(st, &map_a1, (kb - g.nkb0) * BK, (int)(tile * BM), &full_bar[s]);
           tma_load_2d(st + 2 * A_BYTES, &map_bhi, kb * BK, 0, &full_bar[s]);
           if (g.passes == 3) tma_load_2d(st + 2 * A_BYTES + g.b_tile_bytes, &map_blo, kb * BK, 0, &full_bar[s]);
         }
@@ -104,8 +121,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t a_lo = a_hi + A_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_BYTES;
           const uint32_t b_lo = b_hi + g.b_tile_bytes;
-#pragma unroll
-          for (int k = 0; k < BK / 8; k++) {
+          // the last k-block of a part holds K mod 32 live columns: the all-zero k-steps behind them are not issued
+          const int steps = kb == g.nkb0 - 1 ? g.last_steps[0] : (kb == g.num_kb - 1 ? g.last_steps[1] : BK / 8);
+          for (int k = 0; k < steps; k++) {
             const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along the swizzled 128-byte row
             const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
             if (g.passes == 3) {
@@ -148,41 +166,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- epilogue: TMEM -> registers -> padded smem tile -> full-line global accesses ----------------
     const int q = warp - 4;  // TMEM lane quarter == warp index within the warpgroup
+    float* stg = reinterpret_cast<float*>(smem + (size_t)g.stages * g.stage_bytes) + q * (32 * EPI_PITCH);
+    const int rsub = lane >> 3, csub = (lane & 7) * 4;  // read-back: 8 lanes cover one 128-byte row segment, 4 rows per pass
+    const bool relu = (g.flags & GAI_EPI_RELU) != 0;
+    const bool mask_ok = g.mask == nullptr || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
     uint32_t tcount = 0;
     for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
       const int acc = tcount & 1;
       mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1);
       tcgen05_fence_after();
-      const size_t row = tile * BM + (size_t)q * 32 + lane;
-      const bool row_ok = row < g.M;
-      float* crow = g.C + row * g.ldc;
-      const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+      const size_t row0 = tile * BM + (size_t)q * 32;
       for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
+        const int j = (g.nouts > 1 && c0 >= g.noff1) ? 1 : 0;
+        const int cbase = c0 - (j ? g.noff1 : 0);
+        int ncol = (j ? g.N[1] : g.N[0]) - cbase;  // live columns of this 32-column chunk (warp-uniform)
+        if (ncol <= 0) continue;
+        if (ncol > 32) ncol = 32;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)c0, r);
-        if (row_ok) {
-          if (vec_ok && c0 + 32 <= (int)g.N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-              if (g.accum) { const float4 o = *reinterpret_cast<const float4*>(crow + c0 + j); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              if (g.flags & GAI_EPI_RELU) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
-              *reinterpret_cast<float4*>(crow + c0 + j) = v;
-            }
-          } else {
+        for (int jj = 0; jj < 32; jj += 4)
+          *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + jj) = make_uint4(r[jj], r[jj + 1], r[jj + 2], r[jj + 3]);
+        __syncwarp();
+        float* Cj = j ? g.C[1] : g.C[0];
+        const size_t ld = j ? g.ldc[1] : g.ldc[0];
+        const bool vec_ok = mask_ok && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cj) & 15) == 0);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              if (c0 + j < (int)g.N) {
-                float v = __uint_as_float(r[j]);
-                if (g.accum) v += crow[c0 + j];
-                if (g.flags & GAI_EPI_RELU) v = v > 0.f ? v : 0.f;
-                crow[c0 + j] = v;
+        for (int i = 0; i < 8; i++) {
+          const int rl = i * 4 + rsub;
+          const size_t row = row0 + rl;
+          if (row < g.M && csub < ncol) {
+            float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + csub);
+            float* cp = Cj + row * ld + cbase + csub;
+            if (vec_ok && csub + 4 <= ncol) {
+              if (g.accum) { const float4 o = *reinterpret_cast<const float4*>(cp); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              if (g.mask) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(g.mask + row * g.ldmask + cbase + csub));
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+              }
+              if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+              *reinterpret_cast<float4*>(cp) = v;
+            } else {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (csub + k < ncol) {
+                  float x = e[k];
+                  if (g.accum) x += cp[k];
+                  if (g.mask) x = g.mask[row * g.ldmask + cbase + csub + k] > 0.f ? x : 0.f;
+                  if (relu) x = x > 0.f ? x : 0.f;
+                  cp[k] = x;
+                }
               }
             }
           }
         }
+        __syncwarp();  // the staged tile is rewritten by the next chunk
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -198,14 +239,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// Weight preparation: Bt[n][k] = op(B)[k][n] zero-padded to [n_pad x k_pad], split into tf32 hi / lo (both K-major).
-__global__ void prep_b_kernel(const float* __restrict__ B, size_t ldb, int tb, size_t K, size_t N, int k_pad, int n_pad,
-                              float* __restrict__ hi, float* __restrict__ lo) {
+// Weight preparation: Bt[n][k] = op(B_pj)[k][n] laid out as the tile sees it — K parts back to back (each padded to a
+// multiple of 32), output 1's columns from tile column noff1 — zero elsewhere, split into tf32 hi / lo (both K-major).
+struct PrepArgs {
+  const float* B[2][2];
+  size_t ldb[2][2];
+  size_t K[2], N[2];
+  int tb, nk, nn, noff1, kpad0;
+};
+__global__ void prep_b_kernel(const PrepArgs a, int k_pad, int n_pad, float* __restrict__ hi, float* __restrict__ lo) {
   const size_t total = (size_t)k_pad * n_pad;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t n = i / k_pad, k = i % k_pad;
+    size_t n = i / k_pad, k = i % k_pad;
+    const int j = (a.nn > 1 && n >= (size_t)a.noff1) ? 1 : 0;
+    const int p = (a.nk > 1 && k >= (size_t)a.kpad0) ? 1 : 0;
+    if (j) n -= a.noff1;
+    if (p) k -= a.kpad0;
     float v = 0.f;
-    if (n < N && k < K) v = tb ? B[n * ldb + k] : B[k * ldb + n];
+    if (n < a.N[j] && k < a.K[p]) v = a.tb ? a.B[p][j][n * a.ldb[p][j] + k] : a.B[p][j][k * a.ldb[p][j] + n];
     uint32_t h, l;
     split_tf32(__float_as_uint(v), h, l);
     hi[i] = __uint_as_float(h);
@@ -223,52 +274,88 @@ __global__ void pad_a_kernel(size_t M, size_t K, size_t Kp, const float* __restr
 
 }  // namespace
 
-int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int ta, int tb,
-            int accum, int flags, int passes, cudaStream_t st) {
+int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   // shapes this kernel takes: tall A (not transposed), narrow output, enough rows to fill the machine
-  if (ta || N > 256 || N < 1 || K < 1 || M < 4096) return GAI_ERR_UNSUPPORTED;
+  const size_t M = q.M;
+  if (q.nk < 1 || q.nk > 2 || q.nn < 1 || q.nn > 2 || M < 4096) return GAI_ERR_UNSUPPORTED;
+  if (q.mask && (q.nn != 1)) return GAI_ERR_UNSUPPORTED;
+  for (int p = 0; p < q.nk; p++) if (q.K[p] < 1) return GAI_ERR_UNSUPPORTED;
+  for (int j = 0; j < q.nn; j++) if (q.N[j] < 1) return GAI_ERR_UNSUPPORTED;
+  const int noff1 = q.nn > 1 ? (int)((q.N[0] + 31) / 32 * 32) : 0;
+  const size_t n_tile = q.nn > 1 ? (size_t)noff1 + q.N[1] : q.N[0];
+  if (n_tile > 256) return GAI_ERR_UNSUPPORTED;
   if (!encode_fn()) return GAI_ERR_UNSUPPORTED;
-  const int n_mma = (int)((N + 15) / 16 * 16);
-  const int k_pad = (int)((K + BK - 1) / BK * BK);
-  const int num_kb = k_pad / BK;
+  const int n_mma = (int)((n_tile + 15) / 16 * 16);
+  int nkb[2] = {0, 0}, last_steps[2] = {BK / 8, BK / 8};
+  for (int p = 0; p < q.nk; p++) {
+    nkb[p] = (int)((q.K[p] + BK - 1) / BK);
+    last_steps[p] = (int)((q.K[p] - (size_t)(nkb[p] - 1) * BK + 7) / 8);
+  }
+  if (q.nk == 1) last_steps[1] = last_steps[0];  // num_kb - 1 == nkb0 - 1: both tests name the same block
+  const int num_kb = nkb[0] + nkb[1];
+  const int k_pad = num_kb * BK;
   const uint32_t b_tile_bytes = (uint32_t)n_mma * BK * 4;
   const uint32_t stage_bytes = 2 * BM * BK * 4 + 2 * b_tile_bytes;  // A_hi | A_lo | B_hi | B_lo   (all multiples of 1024)
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  int stages = (int)((204u * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return GAI_ERR_UNSUPPORTED;
 
-  // workspace (slot 2): [B_hi | B_lo | padded A (only if A is not TMA-addressable)]
-  const bool a_ok = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
-  const size_t kp4 = (K + 3) / 4 * 4;
-  const size_t b_elems = (size_t)n_mma * k_pad;
-  const size_t ws_bytes = sizeof(float) * (2 * b_elems + (a_ok ? 0 : M * kp4)) + 256;
+  // workspace (slot 2): [B_hi | B_lo | padded copies of the A parts TMA cannot address]
+  bool a_ok[2] = {true, true};
+  size_t kp4[2] = {0, 0}, pad_elems = 0;
+  for (int p = 0; p < q.nk; p++) {
+    a_ok[p] = (q.lda[p] % 4 == 0) && (reinterpret_cast<uintptr_t>(q.A[p]) % 16 == 0);
+    kp4[p] = (q.K[p] + 3) / 4 * 4;
+    if (!a_ok[p]) pad_elems += (M * kp4[p] + 63) / 64 * 64;
+  }
+  const size_t b_elems = ((size_t)n_mma * k_pad + 63) / 64 * 64;
   void* ws = nullptr;
-  int rc = workspace_slot(2, ws_bytes, &ws);
+  int rc = workspace_slot(2, sizeof(float) * (2 * b_elems + pad_elems) + 256, &ws);
   if (rc != GAI_OK) return rc;
   float* bhi = reinterpret_cast<float*>(ws);
   float* blo = bhi + b_elems;
-  prep_b_kernel<<<(unsigned)((b_elems + 255) / 256), 256, 0, st>>>(B, ldb, tb, K, N, k_pad, n_mma, bhi, blo);
-  GAI_LAUNCH_CHECK();
-  const float* a_src = A;
-  size_t a_ld = lda;
-  if (!a_ok) {
-    float* apad = blo + b_elems + ((64 - ((2 * b_elems) % 64)) % 64);  // keep 256-byte alignment
-    size_t blocks = (M * kp4 + 255) / 256;
-    const size_t cap = (size_t)sm_count() * 32;
-    if (blocks > cap) blocks = cap;
-    pad_a_kernel<<<(unsigned)blocks, 256, 0, st>>>(M, K, kp4, A, lda, apad);
-    GAI_LAUNCH_CHECK();
-    a_src = apad; a_ld = kp4;
+  PrepArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  for (int p = 0; p < q.nk; p++) {
+    pa.K[p] = q.K[p];
+    for (int j = 0; j < q.nn; j++) { pa.B[p][j] = q.B[p][j]; pa.ldb[p][j] = q.ldb[p][j]; }
   }
-  CUtensorMap map_a, map_bhi, map_blo;
-  if (!make_map_f32(&map_a, a_src, M, a_ok ? K : kp4, a_ld, BM, true) || !make_map_f32(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false) ||
+  for (int j = 0; j < q.nn; j++) pa.N[j] = q.N[j];
+  pa.tb = q.tb; pa.nk = q.nk; pa.nn = q.nn; pa.noff1 = noff1; pa.kpad0 = nkb[0] * BK;
+  prep_b_kernel<<<(unsigned)(((size_t)n_mma * k_pad + 255) / 256), 256, 0, st>>>(pa, k_pad, n_mma, bhi, blo);
+  GAI_LAUNCH_CHECK();
+  CUtensorMap map_a[2], map_bhi, map_blo;
+  float* apad = blo + b_elems;
+  for (int p = 0; p < 2; p++) {
+    const int s = p < q.nk ? p : 0;  // an unused second map mirrors the first (never dereferenced)
+    const float* a_src = q.A[s];
+    size_t a_ld = q.lda[s], a_cols = q.K[s];
+    if (p < q.nk && !a_ok[p]) {
+      size_t blocks = (M * kp4[p] + 255) / 256;
+      const size_t cap = (size_t)sm_count() * 32;
+      if (blocks > cap) blocks = cap;
+      pad_a_kernel<<<(unsigned)blocks, 256, 0, st>>>(M, q.K[p], kp4[p], q.A[p], q.lda[p], apad);
+      GAI_LAUNCH_CHECK();
+      a_src = apad; a_ld = kp4[p]; a_cols = kp4[p];
+      apad += (M * kp4[p] + 63) / 64 * 64;
+    } else if (p >= q.nk) {
+      map_a[1] = map_a[0];
+      continue;
+    }
+    if (!make_map_f32(&map_a[p], a_src, M, a_cols, a_ld, BM, true)) return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed (A)");
+  }
+  if (!make_map_f32(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false) ||
       !make_map_f32(&map_blo, blo, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false))
-    return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed");
+    return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed (B)");
 
   TcArgs g;
-  g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.n_mma = n_mma; g.num_kb = num_kb; g.stages = stages; g.passes = passes;
-  g.accum = accum; g.flags = flags; g.stage_bytes = stage_bytes; g.b_tile_bytes = b_tile_bytes;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  memset(&g, 0, sizeof(g));
+  for (int j = 0; j < q.nn; j++) { g.C[j] = q.C[j]; g.ldc[j] = q.ldc[j]; g.N[j] = (int)q.N[j]; }
+  g.noff1 = noff1; g.nouts = q.nn; g.mask = (q.flags & GAI_EPI_MASK) ? q.mask : nullptr; g.ldmask = q.ldmask;
+  g.M = M; g.n_mma = n_mma; g.nkb0 = nkb[0]; g.num_kb = num_kb; g.last_steps[0] = last_steps[0]; g.last_steps[1] = last_steps[1];
+  g.stages = stages; g.passes = passes; g.accum = q.accum; g.flags = q.flags; g.stage_bytes = stage_bytes; g.b_tile_bytes = b_tile_bytes;
+  if ((q.flags & GAI_EPI_MASK) && !q.mask) return set_error(GAI_ERR_ARG, "gemm_tc", "GAI_EPI_MASK without a mask matrix");
+  const size_t smem = (size_t)stages * stage_bytes + EPI_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
     GAI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
@@ -276,9 +363,18 @@ int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const floa
   }
   const size_t tiles = (M + BM - 1) / BM;
   const unsigned grid = (unsigned)(tiles < (size_t)sm_count() ? tiles : (size_t)sm_count());
-  gemm_tc_kernel<<<grid, THREADS, smem, st>>>(map_a, map_bhi, map_blo, g);
+  gemm_tc_kernel<<<grid, THREADS, smem, st>>>(map_a[0], map_a[1], map_bhi, map_blo, g);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
+}
+
+int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int ta, int tb,
+            int accum, int flags, int passes, cudaStream_t st) {
+  if (ta || N > 256 || N < 1 || K < 1) return GAI_ERR_UNSUPPORTED;
+  GemmCat q;
+  q.M = M; q.A[0] = A; q.lda[0] = lda; q.K[0] = K; q.B[0][0] = B; q.ldb[0][0] = ldb; q.tb = tb;
+  q.N[0] = N; q.C[0] = C; q.ldc[0] = ldc; q.accum = accum; q.flags = flags;
+  return gemm_tc_cat(q, passes, st);
 }
 
 }  // namespace gai

@@ -11,6 +11,10 @@
 //   * split over the rows: a persistent grid of one CTA per SM, each CTA reduces a contiguous range of rows into its own
 //     TMEM accumulators (1 or 2 M tiles x up to 256 columns = up to all 512 TMEM columns), writes one fp32 partial, and a
 //     second kernel adds the partials in CTA order (deterministic, no atomics).
+//   * concatenated forms (WgradCat), one pass over the shared operand instead of two:
+//       two A, shared B   [dWn; dWs] = [ÂX | X]^T · dH   each A part fills one 128-column M tile (own TMA map)
+//       shared A, two B   [dWn | dWs] = H^T · [dY | dZ]   the B parts sit side by side in the N dimension (own TMA maps)
+//     (SAGE keeps W_neigh and W_self apart, sage_layer.cpp:37-47; the reference runs two sgemm calls.)
 // HBM-bound by design: bytes = 4·n·(Kx + My), tensor work = 3 · 2·n·128·ceil(Kx/128)·My.
 #include "tc_common.cuh"
 
@@ -26,13 +30,17 @@ constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 
 constexpr int WG_SPLIT_WARPS = 8;
 
 struct WgArgs {
-  float* partial;  // [grid][Kx][My]
+  float* partial;  // [grid][Kx_total][My_total], parts concatenated
   size_t nrows;
   size_t blocks_per_cta;  // k-blocks per CTA
-  int Kx, My;
-  int mt;      // 128-column tiles of A (1 or 2)
-  int n_mma;   // My rounded up to a multiple of 32
-  int nbox_a, nbox_b;
+  int Kx, My;      // totals over the parts
+  int mt;          // 128-column tiles of A (1 or 2)
+  int n_mma;       // tile width (multiple of 32)
+  int dual_a;      // 1: M tile t streams from map_a[t]; 0: both tiles are column ranges of map_a[0]
+  int nbox_at[2];  // live 32-column boxes of each M tile
+  int rows_t[2];   // live accumulator rows of each M tile
+  int nbox_b, nbox_b0;  // B boxes; the first nbox_b0 stream from map_b[0], the rest from map_b[1]
+  int my0;         // live columns of the first B part (the second starts at tile column 32*nbox_b0)
   int stages, passes;
   uint32_t a_bytes, b_bytes, stage_bytes;
 };
@@ -46,7 +54,8 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const WgArgs g) {
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                     const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const WgArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], conv_bar[8], empty_bar[8], done_bar;
   __shared__ uint32_t tmem_base_slot;
@@ -80,10 +89,13 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
         uint8_t* st = smem + (size_t)s * g.stage_bytes;
         const int row = (int)((kb0 + it) * WG_BK);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(g.nbox_a + g.nbox_b) * WG_BOX);
-        for (int c = 0; c < g.nbox_a; c++) tma_load_2d(st + (size_t)c * WG_BOX, &map_a, c * 32, row, &full_bar[s]);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(g.nbox_at[0] + g.nbox_at[1] + g.nbox_b) * WG_BOX);
+        for (int c = 0; c < g.nbox_at[0]; c++) tma_load_2d(st + (size_t)c * WG_BOX, &map_a0, c * 32, row, &full_bar[s]);
+        for (int c = 0; c < g.nbox_at[1]; c++)
+          tma_load_2d(st + (size_t)(4 + c) * WG_BOX, g.dual_a ? &map_a1 : &map_a0, (g.dual_a ? c : 4 + c) * 32, row, &full_bar[s]);
         uint8_t* sb = st + 2 * g.a_bytes;
-        for (int c = 0; c < g.nbox_b; c++) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b, c * 32, row, &full_bar[s]);
+        for (int c = 0; c < g.nbox_b0; c++) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b0, c * 32, row, &full_bar[s]);
+        for (int c = g.nbox_b0; c < g.nbox_b; c++) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b1, (c - g.nbox_b0) * 32, row, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -123,12 +135,15 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ---------------- splitters: x -> (rn_tf32(x) in place, rn_tf32(x - hi)) for the A and B boxes ----------------
     const int t = threadIdx.x - 128;  // 0..255
     const uint32_t a_u4 = g.a_bytes / 16, b_u4 = g.b_bytes / 16;
-    // zero the A boxes TMA never fills (columns >= 32*nbox_a of the last M tile), once per stage buffer
-    if (g.nbox_a < g.mt * 4) {
+    // zero the A boxes TMA never fills (the tail boxes of each M tile), once per stage buffer
+    constexpr uint32_t BOX_U4 = WG_BOX / 16;
+    if (g.nbox_at[0] < 4 || (g.mt > 1 && g.nbox_at[1] < 4)) {
       for (int s = 0; s < g.stages; s++) {
         uint4* base = reinterpret_cast<uint4*>(smem + (size_t)s * g.stage_bytes);
-        const uint32_t z0 = (uint32_t)g.nbox_a * (WG_BOX / 16);
-        for (uint32_t i = z0 + t; i < a_u4; i += WG_SPLIT_WARPS * 32) { base[i] = make_uint4(0, 0, 0, 0); base[a_u4 + i] = make_uint4(0, 0, 0, 0); }
+        for (int tl = 0; tl < g.mt; tl++) {
+          const uint32_t z0 = (uint32_t)(tl * 4 + g.nbox_at[tl]) * BOX_U4, z1 = (uint32_t)(tl * 4 + 4) * BOX_U4;
+          for (uint32_t i = z0 + t; i < z1; i += WG_SPLIT_WARPS * 32) { base[i] = make_uint4(0, 0, 0, 0); base[a_u4 + i] = make_uint4(0, 0, 0, 0); }
+        }
       }
       fence_proxy_async();
     }
@@ -138,9 +153,11 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (g.passes == 3) {
         uint4* ahi = reinterpret_cast<uint4*>(smem + (size_t)s * g.stage_bytes);
         uint4* bhi = ahi + 2 * a_u4;
-        const uint32_t a_live = (uint32_t)g.nbox_a * (WG_BOX / 16);
+        const uint32_t a_live0 = (uint32_t)g.nbox_at[0] * BOX_U4;
+        const uint32_t a_live = a_live0 + (uint32_t)g.nbox_at[1] * BOX_U4;
         for (uint32_t i = t; i < a_live + b_u4; i += WG_SPLIT_WARPS * 32) {
-          uint4* hi = i < a_live ? ahi + i : bhi + (i - a_live);
+          // live A boxes: [0, nbox_at[0]) of tile 0, then [4, 4 + nbox_at[1]) of tile 1
+          uint4* hi = i < a_live0 ? ahi + i : (i < a_live ? ahi + (i - a_live0) + 4 * BOX_U4 : bhi + (i - a_live));
           uint4* lo = i < a_live ? hi + a_u4 : hi + b_u4;
           const uint4 v = *hi;
           uint4 h, l;
@@ -159,15 +176,21 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (tile < g.mt) {
       mbar_wait(&done_bar, 0);
       tcgen05_fence_after();
-      const int kx = tile * 128 + q * 32 + lane;
-      float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (kx < g.Kx ? kx : 0)) * g.My;
+      const int kl = q * 32 + lane;  // accumulator row within the tile
+      const bool live = kl < g.rows_t[tile];
+      const int kx = (tile ? g.rows_t[0] : 0) + kl;  // row of the concatenated partial
+      float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (live ? kx : 0)) * g.My;
       for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
-        if (kx < g.Kx) {
+        // tile columns -> concatenated partial columns: part 0 at [0, my0), part 1 from tile column 32*nbox_b0
+        const int part1 = c0 >= 32 * g.nbox_b0;
+        const int pc0 = part1 ? g.my0 + c0 - 32 * g.nbox_b0 : c0;
+        const int lim = part1 ? g.My : g.my0;
+        if (live) {
 #pragma unroll
           for (int j = 0; j < 32; j++)
-            if (c0 + j < g.My) prow[c0 + j] = __uint_as_float(r[j]);
+            if (pc0 + j < lim) prow[pc0 + j] = __uint_as_float(r[j]);
         }
       }
     }
@@ -181,15 +204,21 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
-// C = (accum ? C : 0) + sum_p partial[p], p ascending (deterministic).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int Kx, int My, size_t ldc, int parts, int accum) {
+// C = (accum ? C : 0) + sum_p partial[p], p ascending (deterministic). The concatenated partial [Kx x My] is cut back into
+// its destinations: rows >= kx0 belong to C1 (two-A form), columns >= my0 belong to C1 (two-B form).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C0, size_t ldc0, float* __restrict__ C1, size_t ldc1,
+                                    int Kx, int My, int kx0, int my0, int parts, int accum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Kx * My) return;
-  const int m = i / My, n = i % My;
-  float r = accum ? C[(size_t)m * ldc + n] : 0.0f;
+  int m = i / My, n = i % My;
+  float* dst;
+  if (m >= kx0) dst = C1 + (size_t)(m - kx0) * ldc1 + n;
+  else if (n >= my0) dst = C1 + (size_t)m * ldc1 + (n - my0);
+  else dst = C0 + (size_t)m * ldc0 + n;
+  float r = accum ? *dst : 0.0f;
   const size_t stride = (size_t)Kx * My;
   for (int p = 0; p < parts; p++) r += partial[(size_t)p * stride + i];
-  C[(size_t)m * ldc + n] = r;
+  *dst = r;
 }
 
 // [n x F] (ld) -> [n x Fp], zero-filled tail columns (operands whose row pitch is not a multiple of 16 bytes)
@@ -205,17 +234,36 @@ inline bool tma_ok(const float* p, size_t ld) { return (ld % 4 == 0) && (reinter
 
 }  // namespace
 
-// C[Kx x My] (+)= A^T · B,  A [nrows x Kx] (lda), B [nrows x My] (ldb).
-int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int accum,
-                  int flags, int passes, cudaStream_t st) {
-  if (Kx < 1 || Kx > 256 || My < 1 || My > 256 || nrows < 4096 || flags != 0) return GAI_ERR_UNSUPPORTED;
+// C_0 = A_0^T·B_0 (and C_1 = A_1^T·B_1 with one operand shared), A_i [nrows x Kx_i] (lda), B_i [nrows x My_i] (ldb).
+int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
+  const size_t nrows = q.nrows;
+  if (nrows < 4096 || q.dual < 0 || q.dual > 2) return GAI_ERR_UNSUPPORTED;
+  const int na = q.dual == 1 ? 2 : 1, nb = q.dual == 2 ? 2 : 1;
+  for (int i = 0; i < na; i++) if (q.Kx[i] < 1 || q.Kx[i] > (na == 2 ? 128u : 256u)) return GAI_ERR_UNSUPPORTED;
+  for (int i = 0; i < nb; i++) if (q.My[i] < 1 || q.My[i] > 256) return GAI_ERR_UNSUPPORTED;
   if (!encode_fn()) return GAI_ERR_UNSUPPORTED;
   WgArgs g;
-  g.Kx = (int)Kx; g.My = (int)My; g.nrows = nrows; g.passes = passes;
-  g.mt = Kx > 128 ? 2 : 1;
-  g.n_mma = (int)((My + 31) / 32 * 32);
-  g.nbox_a = (int)((Kx + 31) / 32);
-  g.nbox_b = g.n_mma / 32;
+  memset(&g, 0, sizeof(g));
+  g.nrows = nrows; g.passes = passes;
+  g.dual_a = na == 2;
+  if (na == 2) {
+    g.mt = 2;
+    for (int i = 0; i < 2; i++) { g.rows_t[i] = (int)q.Kx[i]; g.nbox_at[i] = (int)((q.Kx[i] + 31) / 32); }
+    g.Kx = (int)(q.Kx[0] + q.Kx[1]);
+  } else {
+    g.Kx = (int)q.Kx[0];
+    g.mt = g.Kx > 128 ? 2 : 1;
+    g.rows_t[0] = g.Kx > 128 ? 128 : g.Kx;
+    g.rows_t[1] = g.Kx > 128 ? g.Kx - 128 : 0;
+    g.nbox_at[0] = (g.rows_t[0] + 31) / 32;
+    g.nbox_at[1] = (g.rows_t[1] + 31) / 32;
+  }
+  g.nbox_b0 = (int)((q.My[0] + 31) / 32);
+  g.nbox_b = g.nbox_b0 + (nb == 2 ? (int)((q.My[1] + 31) / 32) : 0);
+  if (g.nbox_b > 8) return GAI_ERR_UNSUPPORTED;
+  g.my0 = (int)q.My[0];
+  g.My = (int)(q.My[0] + (nb == 2 ? q.My[1] : 0));
+  g.n_mma = g.nbox_b * 32;
   g.a_bytes = (uint32_t)g.mt * 4u * WG_BOX;
   g.b_bytes = (uint32_t)g.nbox_b * WG_BOX;
   g.stage_bytes = 2 * (g.a_bytes + g.b_bytes);
@@ -230,34 +278,38 @@ int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
-  int rc = workspace(sizeof(float) * grid * Kx * My, &ws);
+  int rc = workspace(sizeof(float) * grid * g.Kx * g.My, &ws);
   if (rc != GAI_OK) return rc;
   g.partial = reinterpret_cast<float*>(ws);
-  const bool a_ok = tma_ok(A, lda), b_ok = tma_ok(B, ldb);
-  const size_t kxp = (Kx + 3) / 4 * 4, myp = (My + 3) / 4 * 4;
-  if (!a_ok || !b_ok) {
+  const float* src[4] = {q.A[0], na == 2 ? q.A[1] : q.A[0], q.B[0], nb == 2 ? q.B[1] : q.B[0]};
+  size_t ld[4] = {q.lda[0], na == 2 ? q.lda[1] : q.lda[0], q.ldb[0], nb == 2 ? q.ldb[1] : q.ldb[0]};
+  size_t cols[4] = {q.Kx[0], na == 2 ? q.Kx[1] : q.Kx[0], q.My[0], nb == 2 ? q.My[1] : q.My[0]};
+  const bool used[4] = {true, na == 2, true, nb == 2};
+  size_t pad_elems = 0;
+  for (int i = 0; i < 4; i++)
+    if (used[i] && !tma_ok(src[i], ld[i])) pad_elems += (nrows * ((cols[i] + 3) / 4 * 4) + 63) / 64 * 64;
+  if (pad_elems) {
     void* ws2 = nullptr;
-    rc = workspace_slot(2, sizeof(float) * nrows * ((a_ok ? 0 : kxp) + (b_ok ? 0 : myp)) + 512, &ws2);
+    rc = workspace_slot(2, sizeof(float) * pad_elems + 512, &ws2);
     if (rc != GAI_OK) return rc;
     float* p = reinterpret_cast<float*>(ws2);
     const size_t cap = (size_t)sm_count() * 32;
-    if (!a_ok) {
-      size_t blocks = (nrows * kxp + 255) / 256;
-      wgrad_pad_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(nrows, Kx, kxp, A, lda, p);
+    for (int i = 0; i < 4; i++) {
+      if (!used[i] || tma_ok(src[i], ld[i])) continue;
+      const size_t cp = (cols[i] + 3) / 4 * 4;
+      const size_t blocks = (nrows * cp + 255) / 256;
+      wgrad_pad_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(nrows, cols[i], cp, src[i], ld[i], p);
       GAI_LAUNCH_CHECK();
-      A = p; lda = kxp;
-      p += (nrows * kxp + 63) / 64 * 64;
-    }
-    if (!b_ok) {
-      size_t blocks = (nrows * myp + 255) / 256;
-      wgrad_pad_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(nrows, My, myp, B, ldb, p);
-      GAI_LAUNCH_CHECK();
-      B = p; ldb = myp;
+      src[i] = p; ld[i] = cp; cols[i] = cp;
+      p += (nrows * cp + 63) / 64 * 64;
     }
   }
-  CUtensorMap map_a, map_b;
-  if (!make_map_f32(&map_a, A, nrows, a_ok ? Kx : kxp, lda, WG_BK, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) || !make_map_f32(&map_b, B, nrows, b_ok ? My : myp, ldb, WG_BK, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-    return set_error(GAI_ERR_CUDA, "gemm_tc_wgrad", "cuTensorMapEncodeTiled failed");
+  CUtensorMap maps[4];
+  for (int i = 0; i < 4; i++) {
+    if (!used[i]) { maps[i] = maps[i - 1]; continue; }
+    if (!make_map_f32(&maps[i], src[i], nrows, cols[i], ld[i], WG_BK, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return set_error(GAI_ERR_CUDA, "gemm_tc_wgrad", "cuTensorMapEncodeTiled failed");
+  }
 
   const size_t smem = (size_t)g.stages * g.stage_bytes + 1024;
   static bool configured = false;
@@ -265,12 +317,25 @@ int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda
     GAI_CUDA(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     configured = true;
   }
-  gemm_tc_wgrad_kernel<<<(unsigned)grid, WG_THREADS, smem, st>>>(map_a, map_b, g);
+  gemm_tc_wgrad_kernel<<<(unsigned)grid, WG_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], g);
   GAI_LAUNCH_CHECK();
-  const int n = (int)(Kx * My);
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(g.partial, C, (int)Kx, (int)My, ldc, (int)grid, accum);
+  const int n = g.Kx * g.My;
+  const int kx0 = na == 2 ? (int)q.Kx[0] : g.Kx, my0 = nb == 2 ? (int)q.My[0] : g.My;
+  float* C1 = q.dual ? q.C[1] : q.C[0];
+  const size_t ldc1 = q.dual ? q.ldc[1] : q.ldc[0];
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, kx0, my0, (int)grid, q.accum);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
+}
+
+// C[Kx x My] (+)= A^T · B,  A [nrows x Kx] (lda), B [nrows x My] (ldb).
+int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int accum,
+                  int flags, int passes, cudaStream_t st) {
+  if (Kx < 1 || Kx > 256 || My < 1 || My > 256 || flags != 0) return GAI_ERR_UNSUPPORTED;
+  WgradCat q;
+  q.nrows = nrows; q.dual = 0;
+  q.A[0] = A; q.lda[0] = lda; q.Kx[0] = Kx; q.B[0] = B; q.ldb[0] = ldb; q.My[0] = My; q.C[0] = C; q.ldc[0] = ldc; q.accum = accum;
+  return gemm_tc_wgrad_cat(q, passes, st);
 }
 
 }  // namespace gai

@@ -10,6 +10,8 @@ int gemm_tc(size_t M, size_t N, size_t K, const float* A, size_t lda, const floa
             int accum, int flags, int passes, cudaStream_t st);  // returns GAI_ERR_UNSUPPORTED when the shape is not taken
 int gemm_tc_wgrad(size_t Kx, size_t My, size_t nrows, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int accum,
                   int flags, int passes, cudaStream_t st);
+int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st);
+int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st);
 static int g_gemm_mode = 0;
 }  // namespace gai
 
@@ -54,6 +56,15 @@ __global__ void d_relu_kernel(size_t n, const float* __restrict__ grad, const fl
     for (size_t k = n4 * 4 + i; k < n; k += stride) out[k] = data[k] > 0.f ? grad[k] : 0.f;
   } else {
     for (size_t k = i; k < n; k += stride) out[k] = data[k] > 0.f ? grad[k] : 0.f;
+  }
+}
+
+__global__ void d_relu_ld_kernel(size_t rows, int F, const float* __restrict__ grad, size_t ldg, const float* __restrict__ data, size_t ldd,
+                                 float* __restrict__ out, size_t ldo) {
+  const size_t total = rows * (size_t)F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / F, c = i % F;
+    out[r * ldo + c] = data[r * ldd + c] > 0.f ? grad[r * ldg + c] : 0.f;
   }
 }
 
@@ -231,6 +242,15 @@ int gai_d_relu(size_t n, const float* grad, const float* data, float* out, gai_s
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
+int gai_d_relu_ld(size_t rows, int F, const float* grad, size_t ld_grad, const float* data, size_t ld_data, float* out, size_t ld_out,
+                  gai_stream_t stream) {
+  if (rows == 0 || F <= 0) return GAI_OK;
+  GAI_CHECK_ARG(grad && data && out && ld_grad >= (size_t)F && ld_data >= (size_t)F && ld_out >= (size_t)F);
+  if (ld_grad == (size_t)F && ld_data == (size_t)F && ld_out == (size_t)F) return gai_d_relu(rows * F, grad, data, out, stream);
+  d_relu_ld_kernel<<<grid_for(rows * F, 256), 256, 0, gai::S(stream)>>>(rows, F, grad, ld_grad, data, ld_data, out, ld_out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
 int gai_fill(size_t n, float value, float* out, gai_stream_t stream) {
   if (n == 0) return GAI_OK;
   GAI_CHECK_ARG(out != nullptr);
@@ -338,6 +358,97 @@ int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, cons
     if (mode >= 2) return rc;  // an explicit tensor-core request must not silently degrade
   }
   return gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, st);
+}
+
+int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t ldb1, size_t z2, const float* A2,
+                    size_t lda2, const float* B2, size_t ldb2, float* C, size_t ldc, int transB, int flags, const float* mask, size_t ldmask,
+                    gai_stream_t stream) {
+  if (x == 0 || y == 0) return GAI_OK;
+  GAI_CHECK_ARG(A1 && B1 && A2 && B2 && C && z1 > 0 && z2 > 0);
+  GAI_CHECK_ARG(lda1 >= z1 && lda2 >= z2 && ldc >= y && ldb1 >= (transB ? z1 : y) && ldb2 >= (transB ? z2 : y));
+  GAI_CHECK_ARG((flags & ~(GAI_EPI_RELU | GAI_EPI_MASK)) == 0);
+  GAI_CHECK_ARG(!(flags & GAI_EPI_MASK) || (mask && ldmask >= y && !(flags & GAI_EPI_RELU)));
+  cudaStream_t st = gai::S(stream);
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    gai::GemmCat q;
+    q.M = x; q.nk = 2; q.tb = transB;
+    q.A[0] = A1; q.lda[0] = lda1; q.K[0] = z1; q.B[0][0] = B1; q.ldb[0][0] = ldb1;
+    q.A[1] = A2; q.lda[1] = lda2; q.K[1] = z2; q.B[1][0] = B2; q.ldb[1][0] = ldb2;
+    q.N[0] = y; q.C[0] = C; q.ldc[0] = ldc; q.flags = flags; q.mask = mask; q.ldmask = ldmask;
+    int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+  }
+  // shapes the tensor-core kernel declines (few rows, wide outputs): the same sum as two SIMT products + the mask pass
+  const int relu = (flags & GAI_EPI_MASK) ? 0 : (flags & GAI_EPI_RELU);
+  int rc = gai::gemm_simt(x, y, z1, A1, lda1, B1, ldb1, C, ldc, 0, transB, 0, 0, st);
+  if (rc != GAI_OK) return rc;
+  rc = gai::gemm_simt(x, y, z2, A2, lda2, B2, ldb2, C, ldc, 0, transB, 1, relu, st);
+  if (rc != GAI_OK) return rc;
+  if (flags & GAI_EPI_MASK) {
+    rc = gai_d_relu_ld(x, (int)y, C, ldc, mask, ldmask, C, ldc, stream);
+    if (rc != GAI_OK) return rc;
+  }
+  return GAI_OK;
+}
+
+int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream) {
+  if (x == 0) return GAI_OK;
+  GAI_CHECK_ARG(A && B1 && B2 && C1 && C2 && z > 0 && y1 > 0 && y2 > 0);
+  GAI_CHECK_ARG(lda >= z && ldb1 >= y1 && ldb2 >= y2 && ldc1 >= y1 && ldc2 >= y2);
+  cudaStream_t st = gai::S(stream);
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    gai::GemmCat q;
+    q.M = x; q.nn = 2;
+    q.A[0] = A; q.lda[0] = lda; q.K[0] = z;
+    q.B[0][0] = B1; q.ldb[0][0] = ldb1; q.N[0] = y1; q.C[0] = C1; q.ldc[0] = ldc1;
+    q.B[0][1] = B2; q.ldb[0][1] = ldb2; q.N[1] = y2; q.C[1] = C2; q.ldc[1] = ldc2;
+    int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+  }
+  int rc = gai::gemm_simt(x, y1, z, A, lda, B1, ldb1, C1, ldc1, 0, 0, 0, 0, st);
+  if (rc != GAI_OK) return rc;
+  return gai::gemm_simt(x, y2, z, A, lda, B2, ldb2, C2, ldc2, 0, 0, 0, 0, st);
+}
+
+static int wgrad_cat_or_simt(const gai::WgradCat& q, cudaStream_t st) {
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    int rc = gai::gemm_tc_wgrad_cat(q, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+  }
+  for (int i = 0; i < 2; i++) {
+    const int a = q.dual == 1 ? i : 0, b = q.dual == 2 ? i : 0;
+    int rc = gai::gemm_simt(q.Kx[a], q.My[b], q.nrows, q.A[a], q.lda[a], q.B[b], q.ldb[b], q.C[i], q.ldc[i], 1, 0, 0, 0, st);
+    if (rc != GAI_OK) return rc;
+  }
+  return GAI_OK;
+}
+
+int gai_wgrad_two_a(size_t z, size_t y, const float* B, size_t ldb, size_t x1, const float* A1, size_t lda1, float* C1, size_t ldc1, size_t x2,
+                    const float* A2, size_t lda2, float* C2, size_t ldc2, gai_stream_t stream) {
+  GAI_CHECK_ARG(B && A1 && A2 && C1 && C2 && z > 0 && y > 0 && x1 > 0 && x2 > 0);
+  GAI_CHECK_ARG(ldb >= y && lda1 >= x1 && lda2 >= x2 && ldc1 >= y && ldc2 >= y);
+  gai::WgradCat q;
+  q.nrows = z; q.dual = 1;
+  q.A[0] = A1; q.lda[0] = lda1; q.Kx[0] = x1; q.A[1] = A2; q.lda[1] = lda2; q.Kx[1] = x2;
+  q.B[0] = B; q.ldb[0] = ldb; q.My[0] = y;
+  q.C[0] = C1; q.ldc[0] = ldc1; q.C[1] = C2; q.ldc[1] = ldc2;
+  return wgrad_cat_or_simt(q, gai::S(stream));
+}
+
+int gai_wgrad_two_b(size_t z, size_t x, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream) {
+  GAI_CHECK_ARG(A && B1 && B2 && C1 && C2 && z > 0 && x > 0 && y1 > 0 && y2 > 0);
+  GAI_CHECK_ARG(lda >= x && ldb1 >= y1 && ldb2 >= y2 && ldc1 >= y1 && ldc2 >= y2);
+  gai::WgradCat q;
+  q.nrows = z; q.dual = 2;
+  q.A[0] = A; q.lda[0] = lda; q.Kx[0] = x;
+  q.B[0] = B1; q.ldb[0] = ldb1; q.My[0] = y1; q.B[1] = B2; q.ldb[1] = ldb2; q.My[1] = y2;
+  q.C[0] = C1; q.ldc[0] = ldc1; q.C[1] = C2; q.ldc[1] = ldc2;
+  return wgrad_cat_or_simt(q, gai::S(stream));
 }
 
 int gai_matmul(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, int transA, int transB, int accum, int flags,

@@ -9,7 +9,7 @@ import torch
 
 from ._abi import check, lib
 
-EPI_NONE, EPI_RELU, EPI_ADD = 0, 1, 2
+EPI_NONE, EPI_RELU, EPI_ADD, EPI_MASK = 0, 1, 2, 4
 
 
 def _stream():
@@ -151,6 +151,48 @@ def matmul(A, B, out=None, transA=False, transB=False, accum=False, flags=0):
     check(lib().gai_matmul_ld(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), int(transA), int(transB),
                               int(accum), flags, _stream()), "gai_matmul_ld")
     return out
+
+
+def matmul_kcat(A1, B1, A2, B2, out=None, transB=False, flags=0, mask=None):
+    """C = A1·op(B1) + A2·op(B2) in one pass (gai_matmul_kcat); flags: EPI_RELU, or EPI_MASK with `mask` (d_relu by the activation)."""
+    x, z1, z2 = A1.shape[0], A1.shape[1], A2.shape[1]
+    y = B1.shape[0] if transB else B1.shape[1]
+    if out is None:
+        out = torch.empty(x, y, dtype=torch.float32, device=A1.device)
+    check(lib().gai_matmul_kcat(x, y, z1, _f32(A1), A1.stride(0), _f32(B1), B1.stride(0), z2, _f32(A2), A2.stride(0), _f32(B2), B2.stride(0),
+                                _f32(out), out.stride(0), int(transB), flags, _f32(mask) if mask is not None else None,
+                                mask.stride(0) if mask is not None else 0, _stream()), "gai_matmul_kcat")
+    return out
+
+
+def matmul_ncat(A, B1, B2, out1=None, out2=None):
+    """C1 = A·B1, C2 = A·B2 with A read once (gai_matmul_ncat)."""
+    x, z = A.shape
+    out1 = torch.empty(x, B1.shape[1], dtype=torch.float32, device=A.device) if out1 is None else out1
+    out2 = torch.empty(x, B2.shape[1], dtype=torch.float32, device=A.device) if out2 is None else out2
+    check(lib().gai_matmul_ncat(x, z, _f32(A), A.stride(0), B1.shape[1], _f32(B1), B1.stride(0), _f32(out1), out1.stride(0), B2.shape[1],
+                                _f32(B2), B2.stride(0), _f32(out2), out2.stride(0), _stream()), "gai_matmul_ncat")
+    return out1, out2
+
+
+def wgrad_two_a(A1, A2, B):
+    """C1 = A1^T·B, C2 = A2^T·B with B read once (gai_wgrad_two_a)."""
+    z, y = B.shape
+    c1 = torch.empty(A1.shape[1], y, dtype=torch.float32, device=B.device)
+    c2 = torch.empty(A2.shape[1], y, dtype=torch.float32, device=B.device)
+    check(lib().gai_wgrad_two_a(z, y, _f32(B), B.stride(0), A1.shape[1], _f32(A1), A1.stride(0), _f32(c1), y, A2.shape[1], _f32(A2),
+                                A2.stride(0), _f32(c2), y, _stream()), "gai_wgrad_two_a")
+    return c1, c2
+
+
+def wgrad_two_b(A, B1, B2):
+    """C1 = A^T·B1, C2 = A^T·B2 with A read once (gai_wgrad_two_b)."""
+    z, x = A.shape
+    c1 = torch.empty(x, B1.shape[1], dtype=torch.float32, device=A.device)
+    c2 = torch.empty(x, B2.shape[1], dtype=torch.float32, device=A.device)
+    check(lib().gai_wgrad_two_b(z, x, _f32(A), A.stride(0), B1.shape[1], _f32(B1), B1.stride(0), _f32(c1), B1.shape[1], B2.shape[1],
+                                _f32(B2), B2.stride(0), _f32(c2), B2.shape[1], _stream()), "gai_wgrad_two_b")
+    return c1, c2
 
 
 def relu(x, out=None):

@@ -97,7 +97,7 @@ const uint32_t* gai_csr_transpose_perm(gai_csr_t g);
 /* ---- neighbour aggregation (SpMM) -------------------------------------------------------------------
  * out[i, 0:F] = epilogue( sum_{e in row i} w_e * in[col_e, 0:F] ), i in [row_begin, row_end).
  * flags: GAI_EPI_ADD  -> add `addend[i, :]` (ld = ld_out) after the sum;  GAI_EPI_RELU -> max(.,0) last. */
-enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2 };
+enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2, GAI_EPI_MASK = 4 /* dense transforms only: see gai_matmul_kcat */ };
 /* GCN_Aggregator::aggregate == d_aggregate (src/gnn/gconv/gcn_aggregator.cpp:23-77): w_e = norm_i * norm_j. */
 int gai_spmm_gcn(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
 /* SAGE_Aggregator::aggregate (transposed=0, w_e = 1/deg_i) / d_aggregate (transposed=1, w_e = 1/deg_j)
@@ -129,6 +129,28 @@ int gai_matmul(size_t x, size_t y, size_t z, const float* A, const float* B, flo
 /* Same with explicit leading dimensions (lda/ldb are those of the STORED matrices). */
 int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc,
                   int transA, int transB, int accum, int flags, gai_stream_t stream);
+/* K-concatenated transform: C[x×y] = A1[x×z1]·op(B1) + A2[x×z2]·op(B2) in ONE pass (one accumulator, C written once),
+ * op(B) = B[z×y] or, if transB, B[y×z]^T.  Replaces the reference's sgemm pair with beta = 1 on the second call:
+ * SAGE forward  ÂX·W_neigh + X·W_self (src/gnn/gconv/sage_layer.cpp:20-23) and SAGE input gradient
+ * dY·W_neigh^T + dZ·W_self^T (sage_layer.cpp:44-52).  flags: GAI_EPI_RELU, and GAI_EPI_MASK = zero C where
+ * mask[i,j] <= 0 (d_relu by the forward activation, math_functions.cpp:453-463, applied before C is ever written). */
+int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t ldb1, size_t z2, const float* A2,
+                    size_t lda2, const float* B2, size_t ldb2, float* C, size_t ldc, int transB, int flags, const float* mask, size_t ldmask,
+                    gai_stream_t stream);
+/* N-concatenated transform: C1[x×y1] = A[x×z]·B1[z×y1], C2[x×y2] = A·B2[z×y2] with A read once (SAGE transform-first
+ * forward: H·W_neigh for the aggregation and H·W_self for the self term, sage_layer.cpp:26-30). */
+int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream);
+/* Concatenated weight gradients over the same z rows (sage_layer.cpp:37-47, two sgemm(transA) calls in the reference):
+ *   gai_wgrad_two_a:  C1[x1×y] = A1[z×x1]^T·B,  C2[x2×y] = A2[z×x2]^T·B    (B read once;  x1, x2 <= 128 on the tensor path)
+ *   gai_wgrad_two_b:  C1[x×y1] = A[z×x]^T·B1,   C2[x×y2] = A^T·B2          (A read once) */
+int gai_wgrad_two_a(size_t z, size_t y, const float* B, size_t ldb, size_t x1, const float* A1, size_t lda1, float* C1, size_t ldc1, size_t x2,
+                    const float* A2, size_t lda2, float* C2, size_t ldc2, gai_stream_t stream);
+int gai_wgrad_two_b(size_t z, size_t x, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream);
+/* out[i, 0:F] = data[i, 0:F] > 0 ? grad[i, 0:F] : 0 with leading dimensions (d_relu on padded row layouts). */
+int gai_d_relu_ld(size_t rows, int F, const float* grad, size_t ld_grad, const float* data, size_t ld_data, float* out, size_t ld_out,
+                  gai_stream_t stream);
 /* Select the dense path: 0 = auto, 1 = fp32 SIMT FFMA, 2 = tcgen05 3xTF32, 3 = tcgen05 1xTF32 (fast, ~1e-3). */
 int gai_set_gemm_mode(int mode);
 int gai_get_gemm_mode(void);

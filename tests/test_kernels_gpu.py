@@ -304,3 +304,83 @@ def test_wgrad_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape):
         assert np.abs(out1 - ref64).max() / np.abs(ref64).max() > 1e-6, "single-pass TF32 should be visibly less accurate"
     finally:
         lib().gai_set_gemm_mode(0)
+
+
+@pytest.mark.parametrize("shape", [(20000, 256, 100, 100, 0), (9000, 256, 47, 47, 1), (4100, 64, 33, 8, 0), (12345, 172, 128, 40, 1),
+                                   (2000, 16, 30, 20, 0)])
+@pytest.mark.parametrize("padded", [False, True])
+def test_matmul_kcat_vs_oracle(T, ops, liborc, shape, padded):
+    """C = A1·op(B1) + A2·op(B2) in one pass (SAGE neighbour + self transforms, sage_layer.cpp:20-23,44-52): tensor-core path
+    for x >= 4096 (two TMA maps, one TMEM accumulator), SIMT composition below; ReLU and d_ReLU-mask epilogues; operands in
+    16-byte-padded row layouts (ld = width rounded up to 4) and in the reference's dense layout."""
+    x, y, z1, z2, tb = shape
+    rng = np.random.default_rng(x + y + z1 + z2)
+    pad = (lambda w: (w + 3) // 4 * 4) if padded else (lambda w: w)
+
+    def mat(r, c):
+        full = np.zeros((r, pad(c)), np.float32)
+        full[:, :c] = rng.standard_normal((r, c), dtype=np.float32)
+        return full
+    A1, A2 = mat(x, z1), mat(x, z2)
+    B1 = rng.standard_normal((y, z1) if tb else (z1, y), dtype=np.float32)
+    B2 = rng.standard_normal((y, z2) if tb else (z2, y), dtype=np.float32)
+    M = mat(x, y)
+    ref = np.zeros((x, y), np.float32)
+    a1c, a2c = np.ascontiguousarray(A1[:, :z1]), np.ascontiguousarray(A2[:, :z2])
+    liborc.orc_gemm(x, y, z1, a1c.reshape(-1), B1.reshape(-1), ref.reshape(-1), 0, tb, 0)
+    liborc.orc_gemm(x, y, z2, a2c.reshape(-1), B2.reshape(-1), ref.reshape(-1), 0, tb, 1)
+    dA1, dA2, dM = dev(T, A1)[:, :z1], dev(T, A2)[:, :z2], dev(T, M)[:, :y]
+    out = T.zeros(x, pad(y), device="cuda")[:, :y]
+    ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=out, transB=bool(tb))
+    close(out.cpu().numpy(), ref)
+    ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=out, transB=bool(tb), flags=ops.EPI_RELU)
+    close(out.cpu().numpy(), np.maximum(ref, 0))
+    ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=out, transB=bool(tb), flags=ops.EPI_MASK, mask=dM)
+    close(out.cpu().numpy(), np.where(M[:, :y] > 0, ref, 0))
+
+
+@pytest.mark.parametrize("shape", [(20000, 256, 47, 47), (5000, 100, 64, 33), (4096, 128, 128, 100), (3000, 50, 7, 9)])
+def test_matmul_ncat_vs_oracle(T, ops, liborc, shape):
+    """C1 = A·B1, C2 = A·B2 with A streamed once (SAGE transform-first forward): two outputs with different row pitches."""
+    x, z, y1, y2 = shape
+    rng = np.random.default_rng(x + z + y1)
+    A = rng.standard_normal((x, z), dtype=np.float32)
+    B1 = rng.standard_normal((z, y1), dtype=np.float32)
+    B2 = rng.standard_normal((z, y2), dtype=np.float32)
+    r1, r2 = np.zeros((x, y1), np.float32), np.zeros((x, y2), np.float32)
+    liborc.orc_gemm(x, y1, z, A.reshape(-1), B1.reshape(-1), r1.reshape(-1), 0, 0, 0)
+    liborc.orc_gemm(x, y2, z, A.reshape(-1), B2.reshape(-1), r2.reshape(-1), 0, 0, 0)
+    o1 = T.full((x, (y1 + 3) // 4 * 4), 7.0, device="cuda")
+    o2 = T.empty(x, y2, device="cuda")
+    ops.matmul_ncat(dev(T, A), dev(T, B1), dev(T, B2), out1=o1[:, :y1], out2=o2)
+    close(o1[:, :y1].cpu().numpy(), r1)
+    close(o2.cpu().numpy(), r2)
+    assert bool((o1[:, y1:] == 7.0).all()), "padding columns of the first output must not be written"
+
+
+@pytest.mark.parametrize("shape", [(50000, 100, 100, 256), (30011, 47, 128, 64), (4100, 16, 7, 33), (3000, 20, 30, 16)])
+def test_wgrad_two_a_vs_fp64(T, ops, shape):
+    """[dW_neigh; dW_self] = [ÂX | X]^T·dH with dH streamed once (sage_layer.cpp:37-47)."""
+    n, x1, x2, y = shape
+    rng = np.random.default_rng(n + x1)
+    A1 = rng.standard_normal((n, x1), dtype=np.float32)
+    A2 = rng.standard_normal((n, x2), dtype=np.float32)
+    B = rng.standard_normal((n, y), dtype=np.float32)
+    c1, c2 = ops.wgrad_two_a(dev(T, A1), dev(T, A2), dev(T, B))
+    close(c1.cpu().numpy(), A1.astype(np.float64).T @ B.astype(np.float64), 5e-6)
+    close(c2.cpu().numpy(), A2.astype(np.float64).T @ B.astype(np.float64), 5e-6)
+
+
+@pytest.mark.parametrize("shape", [(50000, 256, 47, 47), (30011, 100, 64, 33), (4100, 200, 100, 128), (3000, 20, 30, 16)])
+@pytest.mark.parametrize("padded", [False, True])
+def test_wgrad_two_b_vs_fp64(T, ops, shape, padded):
+    """[dW_neigh | dW_self] = H^T·[dY | dZ] with H streamed once; gradient operands in dense and 16-byte-padded row layouts."""
+    n, x, y1, y2 = shape
+    rng = np.random.default_rng(n + x + y1)
+    A = rng.standard_normal((n, x), dtype=np.float32)
+    pad = (lambda w: (w + 3) // 4 * 4) if padded else (lambda w: w)
+    B1 = np.zeros((n, pad(y1)), np.float32); B1[:, :y1] = rng.standard_normal((n, y1), dtype=np.float32)
+    B2 = np.zeros((n, pad(y2)), np.float32); B2[:, :y2] = rng.standard_normal((n, y2), dtype=np.float32)
+    c1, c2 = ops.wgrad_two_b(dev(T, A), dev(T, B1)[:, :y1], dev(T, B2)[:, :y2])
+    close(c1.cpu().numpy(), A.astype(np.float64).T @ B1[:, :y1].astype(np.float64), 5e-6)
+    close(c2.cpu().numpy(), A.astype(np.float64).T @ B2[:, :y2].astype(np.float64), 5e-6)
