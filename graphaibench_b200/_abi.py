@@ -29,6 +29,7 @@ _SIGS = {
     "gai_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "gai_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "gai_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "gai_memcpy2d": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, c_stream]),
     "gai_stream_sync": (C.c_int, [c_stream]),
     "gai_host_alloc_pinned": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "gai_host_free_pinned": (C.c_int, [C.c_void_p]),
@@ -63,8 +64,10 @@ _SIGS = {
                                 C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "gai_matmul_kcat": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t,
                                   c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, C.c_int, c_f32p, C.c_size_t, c_stream]),
+    "gai_matmul_mask": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int,
+                                  c_f32p, C.c_size_t, C.c_int, c_stream]),
     "gai_matmul_ncat": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
-                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, c_stream]),
     "gai_wgrad_two_a": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
                                   c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
     "gai_wgrad_two_b": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
@@ -77,6 +80,11 @@ _SIGS = {
     "gai_fill": (C.c_int, [C.c_size_t, C.c_float, c_f32p, c_stream]),
     "gai_l2norm": (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_stream]),
     "gai_d_l2norm": (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
+    "gai_l2norm_ld": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+    "gai_d_l2norm_ld": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
+    "gai_softmax_ce_forward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, c_stream]),
+    "gai_softmax_ce_backward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_uint64, c_stream]),
+    "gai_masked_loss_accuracy_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_forward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_backward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_backward_scaled": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, C.c_int, C.c_uint64, c_stream]),

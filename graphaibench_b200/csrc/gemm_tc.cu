@@ -25,6 +25,7 @@
 //               ReLU, and d_ReLU by a mask matrix (grad = mask > 0 ? grad : 0, math_functions.cpp:453-463).
 // The weight is prepared once per call by a tiny kernel (transpose to K-major if needed, zero-pad to [Npad x Kpad],
 // split into tf32 hi/lo) so that both operands are K-major and TMA-addressable whatever the caller's layout.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace gai {
@@ -56,6 +57,8 @@ struct TcArgs {
   int passes;      // 3 = 3xTF32, 1 = single TF32 pass
   int accum, flags;
   uint32_t stage_bytes, b_tile_bytes;
+  int debug;       // GAI_TC_DEBUG (timing experiments only, results are wrong): 1 = weights loaded once per stage slot, 2 = no global stores,
+                   // 4 = no hi/lo split, 8 = no MMA issue
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -93,11 +96,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int s = it % g.stages;
           mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
           uint8_t* st = smem + (size_t)s * g.stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], A_BYTES + (g.passes == 3 ? 2 : 1) * g.b_tile_bytes);
+          const bool load_b = !(g.debug & 1) || it < (uint32_t)g.stages;
+          mbar_arrive_expect_tx(&full_bar[s], A_BYTES + (load_b ? (g.passes == 3 ? 2 : 1) * g.b_tile_bytes : 0u));
           if (kb < g.nkb0) tma_load_2d(st, &map_a0, kb * BK, (int)(tile * BM), &full_bar[s]);
           else             tma_load_2d(st, &map_a1, (kb - g.nkb0) * BK, (int)(tile * BM), &full_bar[s]);
-          tma_load_2d(st + 2 * A_BYTES, &map_bhi, kb * BK, 0, &full_bar[s]);
-          if (g.passes == 3) tma_load_2d(st + 2 * A_BYTES + g.b_tile_bytes, &map_blo, kb * BK, 0, &full_bar[s]);
+          if (load_b) {
+            tma_load_2d(st + 2 * A_BYTES, &map_bhi, kb * BK, 0, &full_bar[s]);
+            if (g.passes == 3) tma_load_2d(st + 2 * A_BYTES + g.b_tile_bytes, &map_blo, kb * BK, 0, &full_bar[s]);
+          }
         }
       }
     }
@@ -123,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t b_lo = b_hi + g.b_tile_bytes;
           // the last k-block of a part holds K mod 32 live columns: the all-zero k-steps behind them are not issued
           const int steps = kb == g.nkb0 - 1 ? g.last_steps[0] : (kb == g.num_kb - 1 ? g.last_steps[1] : BK / 8);
-          for (int k = 0; k < steps; k++) {
+          for (int k = 0; k < ((g.debug & 8) ? 0 : steps); k++) {
             const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along the swizzled 128-byte row
             const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
             if (g.passes == 3) {
@@ -147,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int kb = 0; kb < g.num_kb; kb++, it++) {
         const int s = it % g.stages;
         mbar_wait(&full_bar[s], (it / g.stages) & 1);
-        if (g.passes == 3) {
+        if (g.passes == 3 && !(g.debug & 4)) {
           uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * g.stage_bytes);
           uint4* lo = reinterpret_cast<uint4*>(smem + (size_t)s * g.stage_bytes + A_BYTES);
 #pragma unroll
@@ -178,47 +184,107 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1);
       tcgen05_fence_after();
       const size_t row0 = tile * BM + (size_t)q * 32;
+      const bool tile_full = tile * BM + BM <= g.M;
+      const int nrows = tile_full ? 32 : (g.M > row0 ? (int)(g.M - row0 < 32 ? g.M - row0 : 32) : 0);  // live rows of this warp's quarter
       for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
         const int j = (g.nouts > 1 && c0 >= g.noff1) ? 1 : 0;
         const int cbase = c0 - (j ? g.noff1 : 0);
         int ncol = (j ? g.N[1] : g.N[0]) - cbase;  // live columns of this 32-column chunk (warp-uniform)
         if (ncol <= 0) continue;
         if (ncol > 32) ncol = 32;
+        float* Cj = j ? g.C[1] : g.C[0];
+        const size_t ld = j ? g.ldc[1] : g.ldc[0];
+        const bool vec_ok = mask_ok && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cj) & 15) == 0);
+        // columns written with 128-bit stores: all of them when the chunk is a whole number of float4 groups, or when the caller
+        // declared its rows padded to 4 floats (GAI_EPI_PADDED: the tail group then also covers up to 3 padding columns, which
+        // receive the accumulator's zero columns)
+        int ncol4 = ncol & ~3;
+        if ((g.flags & GAI_EPI_PADDED) && (size_t)(cbase + ((ncol + 3) & ~3)) <= ld) ncol4 = (ncol + 3) & ~3;
+        const bool lean = vec_ok && ncol4 >= ncol && !(g.accum && g.mask != nullptr);
         uint32_t r[32];
+        if (lean) {
+          // ---- lean path: one address per lane, 8 row segments of 16 bytes each, nothing but the epilogue ops in the loop ----
+          const bool on = csub < ncol4 && !(g.debug & 2);
+          float* cp = Cj + (row0 + rsub) * ld + cbase + csub;
+          const size_t step = 4 * ld;
+          float4 x[8];  // "+C" or mask operands, requested before the accumulator is read back (their latency overlaps the transpose)
+          if (g.accum) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (on && i * 4 + rsub < nrows) x[i] = *reinterpret_cast<const float4*>(cp + i * step);
+          } else if (g.mask != nullptr) {
+            const float* mp = g.mask + (row0 + rsub) * g.ldmask + cbase + csub;
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (on && i * 4 + rsub < nrows) x[i] = __ldg(reinterpret_cast<const float4*>(mp + i * 4 * g.ldmask));
+          }
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)c0, r);
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + jj) = make_uint4(r[jj], r[jj + 1], r[jj + 2], r[jj + 3]);
+          __syncwarp();
+          const float* sp = stg + rsub * EPI_PITCH + csub;
+          if (g.accum) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (on && i * 4 + rsub < nrows) {
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+                v.x += x[i].x; v.y += x[i].y; v.z += x[i].z; v.w += x[i].w;
+                if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+                *reinterpret_cast<float4*>(cp + i * step) = v;
+              }
+            }
+          } else if (g.mask != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (on && i * 4 + rsub < nrows) {
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+                v.x = x[i].x > 0.f ? v.x : 0.f; v.y = x[i].y > 0.f ? v.y : 0.f; v.z = x[i].z > 0.f ? v.z : 0.f; v.w = x[i].w > 0.f ? v.w : 0.f;
+                *reinterpret_cast<float4*>(cp + i * step) = v;
+              }
+            }
+          } else if (tile_full) {
+            if (on) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+                if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+                *reinterpret_cast<float4*>(cp + i * step) = v;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (on && i * 4 + rsub < nrows) {
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+                if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+                *reinterpret_cast<float4*>(cp + i * step) = v;
+              }
+            }
+          }
+          __syncwarp();  // the staged tile is rewritten by the next chunk
+          continue;
+        }
+        // ---- general path: ragged column tails, unaligned rows, "+C" together with a mask ----
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)c0, r);
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4)
           *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + jj) = make_uint4(r[jj], r[jj + 1], r[jj + 2], r[jj + 3]);
         __syncwarp();
-        float* Cj = j ? g.C[1] : g.C[0];
-        const size_t ld = j ? g.ldc[1] : g.ldc[0];
-        const bool vec_ok = mask_ok && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cj) & 15) == 0);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 8; i++) {
           const int rl = i * 4 + rsub;
           const size_t row = row0 + rl;
-          if (row < g.M && csub < ncol) {
-            float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + csub);
+          if (row < g.M && csub < ncol && !(g.debug & 2)) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + csub);
             float* cp = Cj + row * ld + cbase + csub;
-            if (vec_ok && csub + 4 <= ncol) {
-              if (g.accum) { const float4 o = *reinterpret_cast<const float4*>(cp); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              if (g.mask) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(g.mask + row * g.ldmask + cbase + csub));
-                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-              }
-              if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
-              *reinterpret_cast<float4*>(cp) = v;
-            } else {
-              const float e[4] = {v.x, v.y, v.z, v.w};
+            const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                if (csub + k < ncol) {
-                  float x = e[k];
-                  if (g.accum) x += cp[k];
-                  if (g.mask) x = g.mask[row * g.ldmask + cbase + csub + k] > 0.f ? x : 0.f;
-                  if (relu) x = x > 0.f ? x : 0.f;
-                  cp[k] = x;
-                }
+            for (int k = 0; k < 4; k++) {
+              if (csub + k < ncol) {
+                float x = e[k];
+                if (g.accum) x += cp[k];
+                if (g.mask) x = g.mask[row * g.ldmask + cbase + csub + k] > 0.f ? x : 0.f;
+                if (relu) x = x > 0.f ? x : 0.f;
+                cp[k] = x;
               }
             }
           }
@@ -353,6 +419,8 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   for (int j = 0; j < q.nn; j++) { g.C[j] = q.C[j]; g.ldc[j] = q.ldc[j]; g.N[j] = (int)q.N[j]; }
   g.noff1 = noff1; g.nouts = q.nn; g.mask = (q.flags & GAI_EPI_MASK) ? q.mask : nullptr; g.ldmask = q.ldmask;
   g.M = M; g.n_mma = n_mma; g.nkb0 = nkb[0]; g.num_kb = num_kb; g.last_steps[0] = last_steps[0]; g.last_steps[1] = last_steps[1];
+  static const int debug_knobs = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+  g.debug = debug_knobs;
   g.stages = stages; g.passes = passes; g.accum = q.accum; g.flags = q.flags; g.stage_bytes = stage_bytes; g.b_tile_bytes = b_tile_bytes;
   if ((q.flags & GAI_EPI_MASK) && !q.mask) return set_error(GAI_ERR_ARG, "gemm_tc", "GAI_EPI_MASK without a mask matrix");
   const size_t smem = (size_t)stages * stage_bytes + EPI_BYTES + 1024;

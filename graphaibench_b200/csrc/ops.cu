@@ -85,43 +85,45 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // One warp per row (the reference GPU kernel is thread-per-row with strided, uncoalesced access: math_functions.cu:158-205).
-__global__ void l2norm_kernel(int n, int dim, const float* __restrict__ in, float* __restrict__ out) {
+__global__ void l2norm_kernel(int n, int dim, const float* __restrict__ in, size_t ld_in, float* __restrict__ out, size_t ld_out) {
   const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const float* x = in + (size_t)row * dim;
+  const float* x = in + (size_t)row * ld_in;
   float s = 0.f;
   for (int j = lane; j < dim; j += 32) s += x[j] * x[j];
   s = warp_sum(s);
   s = s < 1.0e-12f ? 1.0e-12f : s;  // l2norm_layer.cpp:29
   s = sqrtf(s);
-  for (int j = lane; j < dim; j += 32) out[(size_t)row * dim + j] = x[j] / s;
+  for (int j = lane; j < dim; j += 32) out[(size_t)row * ld_out + j] = x[j] / s;
 }
 
 // l2norm_layer.cpp:45-62: grad_out = x*coef0*coef1 + g*sum_x2*coef1, coef0 = -<x,g>, coef1 = sum_x2^-1.5
-__global__ void d_l2norm_kernel(int n, int dim, const float* __restrict__ feat_in, const float* __restrict__ grad_in, float* __restrict__ grad_out) {
+__global__ void d_l2norm_kernel(int n, int dim, const float* __restrict__ feat_in, size_t ld_x, const float* __restrict__ grad_in, size_t ld_g,
+                                float* __restrict__ grad_out, size_t ld_o) {
   const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const float* x = feat_in + (size_t)row * dim;
-  const float* g = grad_in + (size_t)row * dim;
+  const float* x = feat_in + (size_t)row * ld_x;
+  const float* g = grad_in + (size_t)row * ld_g;
   float sx = 0.f, c0 = 0.f;
   for (int j = lane; j < dim; j += 32) { sx += x[j] * x[j]; c0 -= x[j] * g[j]; }
   sx = warp_sum(sx);
   c0 = warp_sum(c0);
   sx = sx < 1.0e-12f ? 1.0e-12f : sx;
   const float c1 = powf(sx, -1.5f);
-  for (int j = lane; j < dim; j += 32) grad_out[(size_t)row * dim + j] = x[j] * c0 * c1 + g[j] * sx * c1;
+  for (int j = lane; j < dim; j += 32) grad_out[(size_t)row * ld_o + j] = x[j] * c0 * c1 + g[j] * sx * c1;
 }
 
 // Masked softmax + cross entropy, one warp per row in [begin, end).
 __global__ void softmax_ce_fwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
-                                      const float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ losses) {
+                                      const float* __restrict__ logits, size_t ld_logits, float* __restrict__ probs, size_t ld_probs,
+                                      float* __restrict__ losses) {
   const size_t row = begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= end) return;
   if (masks && masks[row] != 1) return;
-  const float* x = logits + row * ncls;
+  const float* x = logits + row * ld_logits;
   float mx = -INFINITY;
   for (int j = lane; j < ncls; j += 32) mx = fmaxf(mx, x[j]);
   mx = warp_max(mx);
@@ -131,13 +133,13 @@ __global__ void softmax_ce_fwd_kernel(int ncls, size_t begin, size_t end, const 
   const int lab = labels[row];
   for (int j = lane; j < ncls; j += 32) {
     const float p = expf(x[j] - mx) / s;
-    probs[row * ncls + j] = p;
+    probs[row * ld_probs + j] = p;
     if (j == lab) losses[row] = -((p == 0.f) ? logf(1e-10f) : logf(p));  // math_functions.cpp:531-542
   }
 }
 
 __global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
-                                      const float* __restrict__ probs, float* __restrict__ grad, double denom, size_t ld_grad) {
+                                      const float* __restrict__ probs, size_t ld_probs, float* __restrict__ grad, double denom, size_t ld_grad) {
   const size_t n = (end - begin) * ncls;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const double inv_range = denom;
@@ -146,7 +148,7 @@ __global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const 
     const int j = (int)(k % ncls);
     if (masks && masks[row] != 1) continue;
     // softmax_loss_layer.cpp:31: (pred - onehot) / (end - begin), evaluated in double then rounded
-    grad[row * ld_grad + j] = (float)(((double)probs[row * ncls + j] - (labels[row] == j ? 1.0 : 0.0)) / inv_range);
+    grad[row * ld_grad + j] = (float)(((double)probs[row * ld_probs + j] - (labels[row] == j ? 1.0 : 0.0)) / inv_range);
   }
 }
 
@@ -154,7 +156,7 @@ __global__ void softmax_ce_bwd_kernel(int ncls, size_t begin, size_t end, const 
 // reference's tie-break (first maximum, math_functions.cpp:129-139); each CTA folds its rows into one partial
 // {loss sum, correct, count}. Stage 2: one CTA adds the partials in index order. stats = {mean loss, accuracy, count}.
 __global__ void loss_acc_stage1(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
-                                const float* __restrict__ logits, const float* __restrict__ losses, double* __restrict__ partial) {
+                                const float* __restrict__ logits, size_t ld_logits, const float* __restrict__ losses, double* __restrict__ partial) {
   __shared__ double s_l[8];
   __shared__ unsigned s_c[8], s_n[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,7 +164,7 @@ __global__ void loss_acc_stage1(int ncls, size_t begin, size_t end, const uint8_
   double l = 0.0; unsigned c = 0, n = 0;
   for (size_t row = begin + (size_t)blockIdx.x * 8 + warp; row < end; row += nwarps) {
     if (masks && masks[row] != 1) continue;
-    const float* x = logits + row * ncls;
+    const float* x = logits + row * ld_logits;
     float mx = -INFINITY; int am = 0x7fffffff;
     for (int j = lane; j < ncls; j += 32) { const float v = x[j]; if (v > mx) { mx = v; am = j; } }
 #pragma unroll
@@ -258,50 +260,62 @@ int gai_fill(size_t n, float value, float* out, gai_stream_t stream) {
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
-int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream) {
+int gai_l2norm_ld(int n, int dim, const float* in, size_t ld_in, float* out, size_t ld_out, gai_stream_t stream) {
   if (n <= 0) return GAI_OK;
-  GAI_CHECK_ARG(in && out && dim > 0);
-  l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, in, out);
+  GAI_CHECK_ARG(in && out && dim > 0 && ld_in >= (size_t)dim && ld_out >= (size_t)dim);
+  l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, in, ld_in, out, ld_out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream) { return gai_l2norm_ld(n, dim, in, (size_t)dim, out, (size_t)dim, stream); }
+int gai_d_l2norm_ld(int n, int dim, const float* feat_in, size_t ld_feat, const float* grad_in, size_t ld_grad_in, float* grad_out,
+                    size_t ld_grad_out, gai_stream_t stream) {
+  if (n <= 0) return GAI_OK;
+  GAI_CHECK_ARG(feat_in && grad_in && grad_out && dim > 0 && ld_feat >= (size_t)dim && ld_grad_in >= (size_t)dim && ld_grad_out >= (size_t)dim);
+  d_l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, feat_in, ld_feat, grad_in, ld_grad_in, grad_out,
+                                                                                         ld_grad_out);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
 int gai_d_l2norm(int n, int dim, const float* feat_in, const float* grad_in, float* grad_out, gai_stream_t stream) {
-  if (n <= 0) return GAI_OK;
-  GAI_CHECK_ARG(feat_in && grad_in && grad_out && dim > 0);
-  d_l2norm_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(n, dim, feat_in, grad_in, grad_out);
+  return gai_d_l2norm_ld(n, dim, feat_in, (size_t)dim, grad_in, (size_t)dim, grad_out, (size_t)dim, stream);
+}
+
+int gai_softmax_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                              size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && probs && losses && ld_logits >= (size_t)ncls && ld_probs >= (size_t)ncls);
+  if (begin == end) return GAI_OK;
+  softmax_ce_fwd_kernel<<<(unsigned)(((end - begin) * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits,
+                                                                                                    ld_logits, probs, ld_probs, losses);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
-
 int gai_softmax_ce_forward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits, float* probs,
                            float* losses, gai_stream_t stream) {
-  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && probs && losses);
+  return gai_softmax_ce_forward_ld(ncls, begin, end, masks, labels, logits, (size_t)ncls, probs, (size_t)ncls, losses, stream);
+}
+int gai_softmax_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
+                               size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out && denom > 0 && ld_grad >= (size_t)ncls && ld_probs >= (size_t)ncls);
   if (begin == end) return GAI_OK;
-  softmax_ce_fwd_kernel<<<(unsigned)(((end - begin) * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, probs, losses);
+  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, ld_probs,
+                                                                                         grad_out, (double)denom, ld_grad);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
 int gai_softmax_ce_backward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs, float* grad_out,
                             gai_stream_t stream) {
-  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out);
   if (begin == end) return GAI_OK;
-  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out,
-                                                                                         (double)(end - begin), (size_t)ncls);
-  GAI_LAUNCH_CHECK();
-  return GAI_OK;
+  return gai_softmax_ce_backward_ld(ncls, begin, end, masks, labels, probs, (size_t)ncls, grad_out, (size_t)ncls, (uint64_t)(end - begin), stream);
 }
 int gai_softmax_ce_backward_scaled(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
                                    float* grad_out, int ld_grad, uint64_t denom, gai_stream_t stream) {
-  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out && denom > 0 && ld_grad >= ncls);
-  if (begin == end) return GAI_OK;
-  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, grad_out,
-                                                                                         (double)denom, (size_t)ld_grad);
-  GAI_LAUNCH_CHECK();
-  return GAI_OK;
+  GAI_CHECK_ARG(ld_grad >= ncls);
+  return gai_softmax_ce_backward_ld(ncls, begin, end, masks, labels, probs, (size_t)ncls, grad_out, (size_t)ld_grad, denom, stream);
 }
-int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
-                             const float* losses, float* stats_d, gai_stream_t stream) {
-  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && losses && stats_d);
+int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                                size_t ld_logits, const float* losses, float* stats_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && losses && stats_d && ld_logits >= (size_t)ncls);
   size_t rows = end - begin;
   int nparts = (int)((rows + 7) / 8);
   const int cap = gai::sm_count() * 8;
@@ -310,11 +324,15 @@ int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* 
   void* ws = nullptr;
   int rc = gai::workspace(sizeof(double) * 3 * (size_t)nparts, &ws);
   if (rc != GAI_OK) return rc;
-  loss_acc_stage1<<<nparts, 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, losses, reinterpret_cast<double*>(ws));
+  loss_acc_stage1<<<nparts, 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, ld_logits, losses, reinterpret_cast<double*>(ws));
   GAI_LAUNCH_CHECK();
   loss_acc_stage2<<<1, 32, 0, gai::S(stream)>>>(nparts, reinterpret_cast<const double*>(ws), stats_d);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
+}
+int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                             const float* losses, float* stats_d, gai_stream_t stream) {
+  return gai_masked_loss_accuracy_ld(ncls, begin, end, masks, labels, logits, (size_t)ncls, losses, stats_d, stream);
 }
 
 int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, float lr, float b1, float b2, float b1_t, float b2_t, float eps,
@@ -366,7 +384,7 @@ int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1,
   if (x == 0 || y == 0) return GAI_OK;
   GAI_CHECK_ARG(A1 && B1 && A2 && B2 && C && z1 > 0 && z2 > 0);
   GAI_CHECK_ARG(lda1 >= z1 && lda2 >= z2 && ldc >= y && ldb1 >= (transB ? z1 : y) && ldb2 >= (transB ? z2 : y));
-  GAI_CHECK_ARG((flags & ~(GAI_EPI_RELU | GAI_EPI_MASK)) == 0);
+  GAI_CHECK_ARG((flags & ~(GAI_EPI_RELU | GAI_EPI_MASK | GAI_EPI_PADDED)) == 0);
   GAI_CHECK_ARG(!(flags & GAI_EPI_MASK) || (mask && ldmask >= y && !(flags & GAI_EPI_RELU)));
   cudaStream_t st = gai::S(stream);
   const int mode = gai::g_gemm_mode;
@@ -392,10 +410,29 @@ int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1,
   return GAI_OK;
 }
 
+int gai_matmul_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int transB,
+                    const float* mask, size_t ldmask, int flags, gai_stream_t stream) {
+  if (x == 0 || y == 0) return GAI_OK;
+  GAI_CHECK_ARG(A && B && C && mask && z > 0 && lda >= z && ldc >= y && ldmask >= y && ldb >= (transB ? z : y) && (flags & ~GAI_EPI_PADDED) == 0);
+  cudaStream_t st = gai::S(stream);
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    gai::GemmCat q;
+    q.M = x; q.tb = transB;
+    q.A[0] = A; q.lda[0] = lda; q.K[0] = z; q.B[0][0] = B; q.ldb[0][0] = ldb;
+    q.N[0] = y; q.C[0] = C; q.ldc[0] = ldc; q.flags = GAI_EPI_MASK | flags; q.mask = mask; q.ldmask = ldmask;
+    int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+  }
+  int rc = gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, 0, transB, 0, 0, st);
+  if (rc != GAI_OK) return rc;
+  return gai_d_relu_ld(x, (int)y, C, ldc, mask, ldmask, C, ldc, stream);
+}
+
 int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
-                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream) {
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, int flags, gai_stream_t stream) {
   if (x == 0) return GAI_OK;
-  GAI_CHECK_ARG(A && B1 && B2 && C1 && C2 && z > 0 && y1 > 0 && y2 > 0);
+  GAI_CHECK_ARG(A && B1 && B2 && C1 && C2 && z > 0 && y1 > 0 && y2 > 0 && (flags & ~GAI_EPI_PADDED) == 0);
   GAI_CHECK_ARG(lda >= z && ldb1 >= y1 && ldb2 >= y2 && ldc1 >= y1 && ldc2 >= y2);
   cudaStream_t st = gai::S(stream);
   const int mode = gai::g_gemm_mode;
@@ -404,7 +441,7 @@ int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, c
     q.M = x; q.nn = 2;
     q.A[0] = A; q.lda[0] = lda; q.K[0] = z;
     q.B[0][0] = B1; q.ldb[0][0] = ldb1; q.N[0] = y1; q.C[0] = C1; q.ldc[0] = ldc1;
-    q.B[0][1] = B2; q.ldb[0][1] = ldb2; q.N[1] = y2; q.C[1] = C2; q.ldc[1] = ldc2;
+    q.B[0][1] = B2; q.ldb[0][1] = ldb2; q.N[1] = y2; q.C[1] = C2; q.ldc[1] = ldc2; q.flags = flags;
     int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
     if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
   }

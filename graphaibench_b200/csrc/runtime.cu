@@ -105,6 +105,10 @@ int gai_free(void* p) { if (p) GAI_CUDA(cudaFree(p)); return GAI_OK; }
 int gai_memset(void* p, int value, size_t bytes, gai_stream_t s) { if (bytes) GAI_CUDA(cudaMemsetAsync(p, value, bytes, gai::S(s))); return GAI_OK; }
 int gai_memcpy_h2d(void* dst, const void* src, size_t bytes, gai_stream_t s) { if (bytes) GAI_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, gai::S(s))); return GAI_OK; }
 int gai_memcpy_d2h(void* dst, const void* src, size_t bytes, gai_stream_t s) { if (bytes) GAI_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, gai::S(s))); return GAI_OK; }
+int gai_memcpy2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, gai_stream_t s) {
+  if (width_bytes && rows) GAI_CUDA(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDefault, gai::S(s)));
+  return GAI_OK;
+}
 int gai_memcpy_d2d(void* dst, const void* src, size_t bytes, gai_stream_t s) { if (bytes) GAI_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, gai::S(s))); return GAI_OK; }
 int gai_stream_sync(gai_stream_t s) { GAI_CUDA(cudaStreamSynchronize(gai::S(s))); return GAI_OK; }
 int gai_host_alloc_pinned(void** p, size_t bytes) { GAI_CHECK_ARG(p != nullptr); GAI_CUDA(cudaMallocHost(p, bytes ? bytes : 1)); return GAI_OK; }

@@ -387,8 +387,8 @@ class DistGnn:
             self.Tm.append(buf(m, din) if (not tf and l > 0) else None)  # G·Wᵀ before the transposed aggregation
             self.D.append(buf(n, dout) if tf else None)            # Âᵀ·G
         ncls = dims[-1]
-        self.logits = torch.zeros(max(n, 1), ncls, dtype=torch.float32, device=dev)     # ld = ncls (loss kernels)
-        self.probs = torch.zeros_like(self.logits)
+        self.logits = buf(n, ncls)[:, :ncls]     # rows padded to 4 floats like every tall buffer; the loss kernels take the pitch
+        self.probs = buf(n, ncls)[:, :ncls]
         self.losses = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
         self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self.sendbuf = torch.empty(max(p.n_send, 1), _ceil4(max(dims)), dtype=torch.float32, device=dev)
@@ -458,15 +458,37 @@ class DistGnn:
             self._exchange(B)
             self._spmm(B, F, out, transposed, flags, addend, (0, p.n_loc))
 
-    def _mm(self, A, B, out, transA=False, transB=False, accum=False, flags=0):
+    def _mm(self, A, B, out, transA=False, transB=False, accum=False, flags=0, mask=None):
         x, z = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
         y = out.shape[1]
-        with self._scope("LINEAR", f"{x}x{y}x{z}" + (" TA" if transA else "") + (" TB" if transB else ""),
-                         4.0 * (x * z + z * y + x * y * (2 if accum else 1)), 2.0 * x * y * z):
-            self.ops.matmul(A, B, out=out, transA=transA, transB=transB, accum=accum, flags=flags)
+        with self._scope("LINEAR", f"{x}x{y}x{z}" + (" TA" if transA else "") + (" TB" if transB else "") + (" mask" if mask is not None else ""),
+                         4.0 * (x * z + z * y + x * y * (2 if accum or mask is not None else 1)), 2.0 * x * y * z):
+            if mask is not None:
+                self.ops.matmul_mask(A, B, mask, out=out, transB=transB, flags=self._pad(out))
+            else:
+                self.ops.matmul(A, B, out=out, transA=transA, transB=transB, accum=accum, flags=flags | (0 if transA else self._pad(out)))
+
+    def _pad(self, out):
+        # every tall buffer of this class has rows padded to 4 floats (buf()): the transforms may use 128-bit stores throughout
+        return self.ops.EPI_PADDED if out.stride(0) % 4 == 0 and out.stride(0) >= _ceil4(out.shape[1]) else 0
+
+    def _mm_kcat(self, A1, B1, A2, B2, out, transB=False, flags=0, mask=None):
+        x, z1, z2, y = A1.shape[0], A1.shape[1], A2.shape[1], out.shape[1]
+        with self._scope("LINEAR", f"{x}x{y}x{z1}+{z2}" + (" TB" if transB else "") + " kcat" + (" mask" if mask is not None else ""),
+                         4.0 * (x * (z1 + z2) + (z1 + z2) * y + x * y * (2 if mask is not None else 1)), 2.0 * x * y * (z1 + z2)):
+            self.ops.matmul_kcat(A1, B1, A2, B2, out=out, transB=transB, flags=flags | self._pad(out) | (self.ops.EPI_MASK if mask is not None else 0),
+                                 mask=mask)
 
     def _out_buffer(self, l):
         return self.logits if l == self.L - 1 else self.feat_in[l + 1]
+
+    def _transform_first(self, l):
+        return self.dims[l] > self.dims[l + 1]
+
+    def _premasked(self, l):
+        """grad_in[l] arrives already multiplied by d_relu: layer l+1 ends its backward with a dense transform whose epilogue
+        applies the mask (host/gai_layers.cpp: can_mask_grad_out)."""
+        return l < self.L - 1 and self._transform_first(l + 1)
 
     # -- layers (schedules of GCN_layer / SAGE_layer in host/gai_layers.cpp; reference gcn_layer.cpp:5-60, sage_layer.cpp:5-53) --
     def _forward_layer(self, l):
@@ -478,19 +500,19 @@ class DistGnn:
         if din > dout:
             T = self.T[l]
             if self.arch == "sage":
-                self._mm(X[:n, :din], self.Ws[l], out)
-            self._mm(X[:n, :din], self.W[l], T[:n, :dout])
-            if self.arch == "sage":
+                with self._scope("LINEAR", f"{n}x{dout}x{din} ncat2", 4.0 * (n * din + 2 * din * dout + 2 * n * dout), 4.0 * n * dout * din):
+                    ops.matmul_ncat(X[:n, :din], self.W[l], self.Ws[l], out1=T[:n, :dout], out2=out,
+                                    flags=self._pad(T[:n, :dout]) & self._pad(out))
                 self._aggregate(T, dout, out, flags=ops.EPI_ADD | relu, addend=out)
             else:
+                self._mm(X[:n, :din], self.W[l], T[:n, :dout])
                 self._aggregate(T, dout, out, flags=relu)
         else:
             A = self.A[l]
             static = l == 0 and self.static_input_halo
             self._aggregate(X, din, A[:n], exchange=not static)
             if self.arch == "sage":
-                self._mm(A[:n, :din], self.W[l], out)
-                self._mm(X[:n, :din], self.Ws[l], out, accum=True, flags=relu)
+                self._mm_kcat(A[:n, :din], self.W[l], X[:n, :din], self.Ws[l], out, flags=relu)
             else:
                 self._mm(A[:n, :din], self.W[l], out, flags=relu)
 
@@ -499,28 +521,42 @@ class DistGnn:
         din, dout = self.dims[l], self.dims[l + 1]
         X = self.feat_in[l]
         G = self.grad_in[l]
-        if l < self.L - 1:
+        if l < self.L - 1 and not self._premasked(l):
             Y = self.feat_in[l + 1]
             assert Y.shape[1] == G.shape[1]
             with self._scope("RELU", f"d_relu n={n * G.shape[1]}", 12.0 * n * G.shape[1]):
                 ops.d_relu(G[:n], Y[:n], out=G[:n])
         gout = self.grad_in[l - 1][:n, :din] if l > 0 else None
-        if self.arch == "sage":
-            self._mm(X[:n, :din], G[:n, :dout], self.dWs[l], transA=True)
+        sage = self.arch == "sage"
         if din > dout:
             D = self.D[l]
             self._aggregate(G, dout, D[:n], transposed=True)
+            if sage:
+                with self._scope("LINEAR", f"{din}x{dout}x{n} TA two_b", 4.0 * (n * (din + 2 * dout) + 2 * din * dout), 4.0 * n * dout * din):
+                    ops.wgrad_two_b(X[:n, :din], G[:n, :dout], D[:n, :dout], out1=self.dWs[l], out2=self.dW[l])
+            else:
+                self._mm(X[:n, :din], D[:n, :dout], self.dW[l], transA=True)
             if l > 0:
-                self._mm(D[:n, :dout], self.W[l], gout, transB=True)
-            self._mm(X[:n, :din], D[:n, :dout], self.dW[l], transA=True)
+                mask = X[:n, :din] if self._premasked(l - 1) else None   # X = output of layer l-1 (post-ReLU)
+                if sage:
+                    self._mm_kcat(D[:n, :dout], self.W[l], G[:n, :dout], self.Ws[l], gout, transB=True, mask=mask)
+                else:
+                    self._mm(D[:n, :dout], self.W[l], gout, transB=True, mask=mask)
         else:
+            A = self.A[l]
+            if sage:
+                with self._scope("LINEAR", f"{din}x{dout}x{n} TA two_a", 4.0 * (n * (2 * din + dout) + 2 * din * dout), 4.0 * n * dout * din):
+                    ops.wgrad_two_a(A[:n, :din], X[:n, :din], G[:n, :dout], out1=self.dW[l], out2=self.dWs[l])
+            else:
+                self._mm(A[:n, :din], G[:n, :dout], self.dW[l], transA=True)
             if l > 0:
                 Tm = self.Tm[l]
                 self._mm(G[:n, :dout], self.W[l], Tm[:n, :din], transB=True)
-                self._aggregate(Tm, din, gout, transposed=True)
-            self._mm(self.A[l][:n, :din], G[:n, :dout], self.dW[l], transA=True)
-        if self.arch == "sage" and l > 0:
-            self._mm(G[:n, :dout], self.Ws[l], gout, transB=True, accum=True)
+                if sage:   # self term first, the neighbour term is added on top by the aggregation epilogue
+                    self._mm(G[:n, :dout], self.Ws[l], gout, transB=True)
+                    self._aggregate(Tm, din, gout, transposed=True, flags=ops.EPI_ADD, addend=gout)
+                else:
+                    self._aggregate(Tm, din, gout, transposed=True)
 
     def forward(self):
         """forward_prop (net.cpp:458-476): returns (mean train loss, train accuracy) over the GLOBAL train range."""

@@ -12,7 +12,8 @@ struct ModelBase {
   virtual void update() = 0;
   virtual float evaluate(const char* which) = 0;
   virtual void refresh(const float* feats) = 0;
-  virtual float* tensor(const char* name, int layer, size_t* n) = 0;
+  // device pointer + logical element count; cols/ld != 0 for per-vertex tensors stored with a row pitch
+  virtual float* tensor(const char* name, int layer, size_t* n, size_t* cols, size_t* ld) = 0;
 };
 template <typename L>
 struct Box : ModelBase {
@@ -34,15 +35,15 @@ struct Box : ModelBase {
     if (name == "alpha_rgrad") return a.d_alpha_rgrad;
     return nullptr;
   }
-  float* tensor(const char* name_, int l, size_t* n) override {
+  float* tensor(const char* name_, int l, size_t* n, size_t* cols, size_t* ld) override {
     std::string name(name_);
-    if (name == "logits") { *n = m.nv() * 0; }
+    *cols = 0; *ld = 0;
     if (name == "dense_W" && m.dense()) { *n = (size_t)m.dense()->dim_in * m.dense()->dim_out; return m.dense()->d_weight; }
     if (name == "dense_W_grad" && m.dense()) { *n = (size_t)m.dense()->dim_in * m.dense()->dim_out; return m.dense()->d_weight_grad; }
     if (l < 0 || l >= m.num_conv_layers()) return nullptr;
     L& y = m.conv_layer(l);
     float* p = y.weight_ptr(name);
-    if (p) { *n = y.weight_size(name); return p; }
+    if (p) { *n = y.weight_size(name); y.tensor_layout(name, cols, ld); return p; }
     return extra(y, name, n);
   }
 };
@@ -84,21 +85,32 @@ void gai_model_update(void* m) { ((ModelBase*)m)->update(); }
 float gai_model_evaluate(void* m, const char* which) { return ((ModelBase*)m)->evaluate(which); }
 void gai_model_refresh_inputs(void* m, const float* feats_h) { ((ModelBase*)m)->refresh(feats_h); }
 int64_t gai_model_tensor_size(void* m, const char* name, int layer) {
-  size_t n = 0;
-  return ((ModelBase*)m)->tensor(name, layer, &n) ? (int64_t)n : -1;
+  size_t n = 0, cols = 0, ld = 0;
+  return ((ModelBase*)m)->tensor(name, layer, &n, &cols, &ld) ? (int64_t)n : -1;
 }
+// Dense host copies of a named tensor; pitched per-vertex tensors are packed / unpacked row by row.
 int64_t gai_model_get(void* m, const char* name, int layer, float* out_h, int64_t cap) {
-  size_t n = 0;
-  float* p = ((ModelBase*)m)->tensor(name, layer, &n);
+  size_t n = 0, cols = 0, ld = 0;
+  float* p = ((ModelBase*)m)->tensor(name, layer, &n, &cols, &ld);
   if (!p || (int64_t)n > cap) return -1;
-  copy_float_to_host(n, p, out_h);
+  if (cols && ld != cols) {
+    gai_host::die_on(gai_memcpy2d(out_h, cols * sizeof(float), p, ld * sizeof(float), cols * sizeof(float), n / cols, gai_host::stream()), "gai_memcpy2d");
+    gai_host::die_on(gai_stream_sync(gai_host::stream()), "gai_stream_sync");
+  } else {
+    copy_float_to_host(n, p, out_h);
+  }
   return (int64_t)n;
 }
 int64_t gai_model_set(void* m, const char* name, int layer, const float* in_h, int64_t n_in) {
-  size_t n = 0;
-  float* p = ((ModelBase*)m)->tensor(name, layer, &n);
+  size_t n = 0, cols = 0, ld = 0;
+  float* p = ((ModelBase*)m)->tensor(name, layer, &n, &cols, &ld);
   if (!p || (int64_t)n != n_in) return -1;
-  copy_float_to_device(n, in_h, p);
+  if (cols && ld != cols) {
+    gai_host::die_on(gai_memcpy2d(p, ld * sizeof(float), in_h, cols * sizeof(float), cols * sizeof(float), n / cols, gai_host::stream()), "gai_memcpy2d");
+    gai_host::die_on(gai_stream_sync(gai_host::stream()), "gai_stream_sync");
+  } else {
+    copy_float_to_device(n, in_h, p);
+  }
   return (int64_t)n;
 }
 void gai_host_profile_enable(int on) { gai_host::profile_enable(on != 0); }

@@ -42,11 +42,56 @@ static float* upload_glorot(size_t dx, size_t dy, unsigned seed) {
   copy_float_to_device(dx * dy, w.data(), d);
   return d;
 }
-static void mm(size_t x, size_t y, size_t z, const float* A, const float* B, float* C, bool ta = false, bool tb = false, bool accum = false,
-               int flags = 0) {
-  gai_host::OpScope sc("LINEAR", std::to_string(x) + "x" + std::to_string(y) + "x" + std::to_string(z) + (ta ? " TA" : "") + (tb ? " TB" : ""),
+static std::string shape(size_t x, size_t y, size_t z) { return std::to_string(x) + "x" + std::to_string(y) + "x" + std::to_string(z); }
+// matmul(x,y,z,A,B,C,transA,transB,accum) of the reference (math_functions.cpp:142-171) with explicit row pitches
+static void mm(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, bool ta = false,
+               bool tb = false, bool accum = false, int flags = 0) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z) + (ta ? " TA" : "") + (tb ? " TB" : ""),
                        4.0 * ((double)x * z + (double)z * y + (double)x * y * (accum ? 2 : 1)), 2.0 * (double)x * y * z);
-  die_on(gai_matmul(x, y, z, A, B, C, ta, tb, accum, flags, stream()), "gai_matmul");
+  // tall outputs live in layer-owned buffers whose rows are padded to 4 floats: every epilogue store can be 128-bit
+  const int padded = (!ta && ldc % 4 == 0 && ldc >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  die_on(gai_matmul_ld(x, y, z, A, lda, B, ldb, C, ldc, ta, tb, accum, flags | padded, stream()), "gai_matmul_ld");
+}
+// C = A1·op(B1) + A2·op(B2) in one pass; mask != NULL folds the d_relu of the layer below into the epilogue
+static void mm_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t z2, const float* A2, size_t lda2,
+                    const float* B2, float* C, size_t ldc, bool tb, int flags, const float* mask, size_t ldmask) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z1) + "+" + std::to_string(z2) + (tb ? " TB" : "") + " kcat" + (mask ? " mask" : ""),
+                       4.0 * ((double)x * (z1 + z2) + (double)(z1 + z2) * y + (double)x * y * (mask ? 2 : 1)), 2.0 * (double)x * y * (z1 + z2));
+  const size_t ldb1 = tb ? z1 : y, ldb2 = tb ? z2 : y;
+  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && (!mask || (ldmask % 4 == 0 && ldmask >= pitch4(y)))) ? GAI_EPI_PADDED : 0;
+  die_on(gai_matmul_kcat(x, y, z1, A1, lda1, B1, ldb1, z2, A2, lda2, B2, ldb2, C, ldc, tb, flags | padded | (mask ? GAI_EPI_MASK : 0), mask, ldmask,
+                         stream()), "gai_matmul_kcat");
+}
+static void mm_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, float* C, size_t ldc, bool tb, const float* mask,
+                    size_t ldmask) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z) + (tb ? " TB" : "") + " mask", 4.0 * ((double)x * z + (double)z * y + 2.0 * (double)x * y),
+                       2.0 * (double)x * y * z);
+  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && ldmask % 4 == 0 && ldmask >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  die_on(gai_matmul_mask(x, y, z, A, lda, B, tb ? z : y, C, ldc, tb, mask, ldmask, padded, stream()), "gai_matmul_mask");
+}
+// C1 = A·B1, C2 = A·B2, A read once
+static void mm_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y, const float* B1, float* C1, size_t ldc1, const float* B2, float* C2,
+                    size_t ldc2) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z) + " ncat2", 4.0 * ((double)x * z + 2.0 * (double)z * y + 2.0 * (double)x * y), 4.0 * (double)x * y * z);
+  const int padded = (ldc1 % 4 == 0 && ldc1 >= pitch4(y) && ldc2 % 4 == 0 && ldc2 >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  die_on(gai_matmul_ncat(x, z, A, lda, y, B1, y, C1, ldc1, y, B2, y, C2, ldc2, padded, stream()), "gai_matmul_ncat");
+}
+// weight gradients of one layer in one pass over the shared operand: dW1 = A1^T·B, dW2 = A2^T·B (two_a) / dW1 = A^T·B1, dW2 = A^T·B2 (two_b)
+static void wgrad_two_a(size_t n, size_t y, const float* B, size_t ldb, size_t x, const float* A1, size_t lda1, float* C1, const float* A2, size_t lda2,
+                        float* C2) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, n) + " TA two_a", 4.0 * ((double)n * (2 * x + y) + 2.0 * (double)x * y), 4.0 * (double)x * y * n);
+  die_on(gai_wgrad_two_a(n, y, B, ldb, x, A1, lda1, C1, y, x, A2, lda2, C2, y, stream()), "gai_wgrad_two_a");
+}
+static void wgrad_two_b(size_t n, size_t x, const float* A, size_t lda, size_t y, const float* B1, size_t ldb1, float* C1, const float* B2, size_t ldb2,
+                        float* C2) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, n) + " TA two_b", 4.0 * ((double)n * (x + 2 * y) + 2.0 * (double)x * y), 4.0 * (double)x * y * n);
+  die_on(gai_wgrad_two_b(n, x, A, lda, y, B1, ldb1, C1, y, y, B2, ldb2, C2, y, stream()), "gai_wgrad_two_b");
+}
+static void d_relu_rows(size_t rows, int F, float* grad, size_t ldg, const float* data, size_t ldd) {
+  gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(rows * (size_t)F), 12.0 * rows * F, 0);
+  // pitched rows carry zero padding on both sides, so the flat kernel over rows*pitch elements is the same op
+  if (ldg == ldd) die_on(gai_d_relu(rows * ldg, grad, data, grad, stream()), "gai_d_relu");
+  else die_on(gai_d_relu_ld(rows, F, grad, ldg, data, ldd, grad, ldg, stream()), "gai_d_relu_ld");
 }
 // algorithmic bytes of one aggregation call: gather model of SURVEY.md §8d
 static double spmm_bytes(Graph& g, int F, int extra_per_edge = 0) {
@@ -72,23 +117,29 @@ void adam::reset() {
 // ---- aggregators --------------------------------------------------------------------------------------------------
 
 void GCN_Aggregator::init(int len, int, int, float, float) { length = len; }
-void GCN_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+void GCN_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend) {
   gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_gcn(g.device(), len, in, len, out, len, flags, addend, stream()), "gai_spmm_gcn");
+  die_on(gai_spmm_gcn(g.device(), len, in, (int)ld_in, out, (int)ld_out, flags, addend, stream()), "gai_spmm_gcn");
 }
-void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
 // the normalised adjacency is symmetric, so the derivative is the same product (gcn_aggregator.cpp:35-46)
+void GCN_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend) {
+  aggregate_ld(len, g, grad_in, ld_in, grad_out, ld_out, flags, addend);
+}
+void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) { aggregate(len, g, grad_in, grad_out); }
 
 void SAGE_Aggregator::init(int len, int, int, float, float) { length = len; }
-void SAGE_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float* addend) {
+void SAGE_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend) {
   gai_host::OpScope sc("AGGR", "mean F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_mean(g.device(), len, in, len, out, len, 0, flags, addend, stream()), "gai_spmm_mean");
+  die_on(gai_spmm_mean(g.device(), len, in, (int)ld_in, out, (int)ld_out, 0, flags, addend, stream()), "gai_spmm_mean");
 }
-void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
+void SAGE_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend) {
+  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
+  die_on(gai_spmm_mean(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, stream()), "gai_spmm_mean(T)");
+}
+void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {
-  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len), spmm_bytes(g, len), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_mean(g.device(), len, grad_in, len, grad_out, len, 1, GAI_EPI_NONE, nullptr, stream()), "gai_spmm_mean(T)");
+  d_aggregate_ld(len, g, grad_in, len, grad_out, len, GAI_EPI_NONE, nullptr);
 }
 
 void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
@@ -137,14 +188,28 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
     d_W_self = upload_glorot(din, dout, 2);
     d_W_self_grad = float_malloc_device_zero((size_t)din * dout);
   }
+  // row pitches: layer 0 reads the caller's dense feature matrix; everything the layers own is padded to 4 floats
+  ld_in = id == 0 ? (size_t)din : pitch4(din);
+  ld_out = pitch4(dout);
+  if (std::is_same<A, GAT_Aggregator>::value && (ld_out != (size_t)dout || ld_in != (size_t)din)) {
+    std::cerr << "GAT layers need widths that are multiples of 4 (dense attention buffers)\n";
+    std::exit(1);
+  }
   // temporaries: only what this layer's schedule touches (the reference allocates all of them unconditionally)
   const bool transform_first = din > dout || std::is_same<A, GAT_Aggregator>::value;  // GAT always transforms first
-  if (transform_first) d_out_temp = float_malloc_device_zero(n * dout);
-  if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * din);
-  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * din);
-  if (id > 0) feat_in = float_malloc_device_zero(n * din);
-  grad_in = float_malloc_device_zero(n * dout);
+  if (transform_first) d_out_temp = float_malloc_device_zero(n * ld_out);
+  if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * pitch4(din));
+  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * pitch4(din));
+  if (id > 0) feat_in = float_malloc_device_zero(n * ld_in);
+  grad_in = float_malloc_device_zero(n * ld_out);
   optm = new adam(lr);
+}
+
+template <typename A>
+bool graph_conv_layer<A>::can_mask_grad_out() const {
+  // transform-first layers end their backward with grad_out = (...)·W^T, a dense transform whose epilogue can apply the mask;
+  // aggregate-first layers end with an aggregation (plus, for SAGE, an accumulating transform)
+  return level_ > 0 && (dim_in > dim_out || std::is_same<A, GAT_Aggregator>::value);
 }
 
 template <typename A>
@@ -167,6 +232,13 @@ size_t graph_conv_layer<A>::weight_size(const std::string& name) {
   if (name == "grad_in" || name == "out_temp") return (size_t)num_samples * dim_out;
   return 0;
 }
+template <typename A>
+void graph_conv_layer<A>::tensor_layout(const std::string& name, size_t* cols, size_t* ld) {
+  *cols = 0; *ld = 0;
+  if (name == "feat_in") { *cols = dim_in; *ld = ld_in; }
+  else if (name == "in_temp1") { *cols = dim_in; *ld = pitch4(dim_in); }
+  else if (name == "grad_in" || name == "out_temp") { *cols = dim_out; *ld = ld_out; }
+}
 template class graph_conv_layer<GCN_Aggregator>;
 template class graph_conv_layer<SAGE_Aggregator>;
 template class graph_conv_layer<GAT_Aggregator>;
@@ -179,39 +251,44 @@ GCN_layer::GCN_layer(int id, int nv, int din, int dout, Graph* g, bool act, floa
 }
 
 void GCN_layer::forward(float* feat_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out;
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
   if (y > z) {  // transform first: aggregate at the narrower width; ReLU rides the SpMM epilogue
-    mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
-    aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, relu, nullptr);
+    mm(x, z, y, feat_in, ld_in, d_W_neigh, z, d_out_temp, ld_out);
+    aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, relu, nullptr);
   } else {      // aggregate first; ReLU rides the GEMM epilogue
-    aggr.aggregate((int)y, *graph, feat_in, d_in_temp1);
-    mm(x, z, y, d_in_temp1, d_W_neigh, feat_out, false, false, false, relu);
+    aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    mm(x, z, y, d_in_temp1, ldt, d_W_neigh, z, feat_out, ld_out, false, false, false, relu);
   }
 }
 
 void GCN_layer::backward(float* feat_out, float* grad_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) {
-    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
-    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
-  }
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   if (y > z) {
-    aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
-    if (level_ > 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
-    mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+    aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
+    if (level_ > 0) {
+      if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in);
+      else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
+    }
+    mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);
   } else {
     if (level_ > 0) {
-      mm(x, y, z, grad_in, d_W_neigh, d_in_temp, false, true);
-      aggr.d_aggregate((int)y, *graph, nullptr, d_in_temp, grad_out);
+      mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
+      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_NONE, nullptr);
     }
-    mm(y, z, x, d_in_temp1, grad_in, d_W_neigh_grad, true, false);
+    mm(y, z, x, d_in_temp1, ldt, grad_in, ld_out, d_W_neigh_grad, z, true, false);
   }
 }
 
 void GCN_layer::update_weight(optimizer* opt) { opt->update_gpu((size_t)dim_in * dim_out, d_W_neigh_grad, d_W_neigh); }  // shared optimiser (gcn_layer.cpp:62-66)
 
 // ---- SAGE ---------------------------------------------------------------------------------------------------------
+// Same sums as sage_layer.cpp:5-53, regrouped so that every tall matrix is streamed once:
+//   forward, aggregate first   out = ReLU([ÂX | X]·[W_n; W_s])                 one K-concatenated transform (reference: 2 sgemm, beta = 1)
+//   forward, transform first   [T | S] = X·[W_n | W_s]; out = ReLU(ÂT + S)     one N-concatenated transform, self term added in the SpMM epilogue
+//   backward, transform first  dT = Âᵀ·dOut;  [dW_s | dW_n] = Xᵀ·[dOut | dT];  dX = mask(dT·W_nᵀ + dOut·W_sᵀ)
+//   backward, aggregate first  [dW_n; dW_s] = [ÂX | X]ᵀ·dOut;  dX = Âᵀ(dOut·W_nᵀ) + dOut·W_sᵀ  (self term first, neighbour term added by the SpMM)
 
 SAGE_layer::SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, float lr, float fd, float sd)
     : graph_conv_layer(id, nv, din, dout, g, act, true, lr, fd, sd) {
@@ -219,39 +296,33 @@ SAGE_layer::SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, fl
 }
 
 void SAGE_layer::forward(float* feat_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out;
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
   if (y > z) {
-    // self term first, then the neighbour term is added on top inside the SpMM epilogue (+ ReLU): one pass over feat_out
-    mm(x, z, y, feat_in, d_W_self, feat_out);
-    mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
-    aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, GAI_EPI_ADD | relu, feat_out);
+    mm_ncat(x, y, feat_in, ld_in, z, d_W_neigh, d_out_temp, ld_out, d_W_self, feat_out, ld_out);
+    aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, GAI_EPI_ADD | relu, feat_out);
   } else {
-    aggr.aggregate((int)y, *graph, feat_in, d_in_temp1);
-    mm(x, z, y, d_in_temp1, d_W_neigh, feat_out);
-    mm(x, z, y, feat_in, d_W_self, feat_out, false, false, true, relu);  // accumulate (beta = 1, sage_layer.cpp:22) + ReLU epilogue
+    aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, feat_in, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0);
   }
 }
 
 void SAGE_layer::backward(float* feat_out, float* grad_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) {
-    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
-    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
-  }
-  mm(y, z, x, feat_in, grad_in, d_W_self_grad, true, false);
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   if (y > z) {
-    aggr.d_aggregate((int)z, *graph, nullptr, grad_in, d_out_temp);
-    if (level_ > 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
-    mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+    aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
+    wgrad_two_b(x, y, feat_in, ld_in, z, grad_in, ld_out, d_W_self_grad, d_out_temp, ld_out, d_W_neigh_grad);
+    if (level_ > 0)
+      mm_kcat(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_in, ld_out, d_W_self, grad_out, ld_in, true, 0, mask_grad_out ? feat_in : nullptr, ld_in);
   } else {
+    wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad, feat_in, ld_in, d_W_self_grad);
     if (level_ > 0) {
-      mm(x, y, z, grad_in, d_W_neigh, d_in_temp, false, true);
-      aggr.d_aggregate((int)y, *graph, nullptr, d_in_temp, grad_out);
+      mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
+      mm(x, y, z, grad_in, ld_out, d_W_self, z, grad_out, ld_in, false, true);
+      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_ADD, grad_out);
     }
-    mm(y, z, x, d_in_temp1, grad_in, d_W_neigh_grad, true, false);
   }
-  if (level_ > 0) mm(x, y, z, grad_in, d_W_self, grad_out, false, true, true);
 }
 
 void SAGE_layer::update_weight(optimizer*) {  // the layer's own optimiser, neighbour then self (sage_layer.cpp:55-59)
@@ -268,19 +339,19 @@ GAT_layer::GAT_layer(int id, int nv, int din, int dout, Graph* g, bool act, floa
 
 void GAT_layer::forward(float* feat_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  mm(x, z, y, feat_in, d_W_neigh, d_out_temp);
+  mm(x, z, y, feat_in, ld_in, d_W_neigh, z, d_out_temp, ld_out);
   aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, is_act ? GAI_EPI_RELU : GAI_EPI_NONE, nullptr);
 }
 
 void GAT_layer::backward(float* feat_out, float* grad_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  if (is_act) {
-    gai_host::OpScope sc("RELU", "d_relu n=" + std::to_string(x * z), 12.0 * x * z, 0);
-    die_on(gai_d_relu(x * z, grad_in, feat_out, grad_in, stream()), "gai_d_relu");
-  }
+  if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   aggr.d_aggregate((int)z, *graph, d_out_temp, grad_in, d_out_temp);  // dZ overwrites Z (gat_layer.cpp:33-36)
-  if (level_ != 0) mm(x, y, z, d_out_temp, d_W_neigh, grad_out, false, true);
-  mm(y, z, x, feat_in, d_out_temp, d_W_neigh_grad, true, false);
+  if (level_ != 0) {
+    if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in);
+    else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
+  }
+  mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);
 }
 
 void GAT_layer::update_weight(optimizer* opt) {
@@ -291,45 +362,55 @@ void GAT_layer::update_weight(optimizer* opt) {
 // ---- l2norm / dense / loss ------------------------------------------------------------------------------------------
 
 l2norm_layer::l2norm_layer(int nv, int len) : num_samples(nv), dim(len) {
-  feat_in = float_malloc_device_zero((size_t)nv * len);
-  grad_in = float_malloc_device_zero((size_t)nv * len);
+  feat_in = float_malloc_device_zero((size_t)nv * pitch4(len));
+  grad_in = float_malloc_device_zero((size_t)nv * pitch4(len));
 }
-void l2norm_layer::forward(float* feat_out) { gai_host::OpScope sc("NORM", "l2norm", 8.0 * num_samples * dim, 0); die_on(gai_l2norm(num_samples, dim, feat_in, feat_out, stream()), "gai_l2norm"); }
-void l2norm_layer::backward(float* grad_out) { gai_host::OpScope sc("NORM", "d_l2norm", 12.0 * num_samples * dim, 0); die_on(gai_d_l2norm(num_samples, dim, feat_in, grad_in, grad_out, stream()), "gai_d_l2norm"); }
+void l2norm_layer::forward(float* feat_out) {
+  gai_host::OpScope sc("NORM", "l2norm", 8.0 * num_samples * dim, 0);
+  die_on(gai_l2norm_ld(num_samples, dim, feat_in, pitch4(dim), feat_out, pitch4(dim), stream()), "gai_l2norm");
+}
+void l2norm_layer::backward(float* grad_out) {
+  gai_host::OpScope sc("NORM", "d_l2norm", 12.0 * num_samples * dim, 0);
+  die_on(gai_d_l2norm_ld(num_samples, dim, feat_in, pitch4(dim), grad_in, pitch4(dim), grad_out, pitch4(dim), stream()), "gai_d_l2norm");
+}
 
 dense_layer::dense_layer(int nv, int in_len, int out_len, float lr) : dim_in(in_len), dim_out(out_len), num_samples(nv) {
-  feat_in = float_malloc_device_zero((size_t)nv * in_len);
-  grad_in = float_malloc_device_zero((size_t)nv * out_len);
+  feat_in = float_malloc_device_zero((size_t)nv * pitch4(in_len));
+  grad_in = float_malloc_device_zero((size_t)nv * pitch4(out_len));
   d_weight = upload_glorot(in_len, out_len, 1);  // dense_layer.cpp:33
   d_weight_grad = float_malloc_device_zero((size_t)in_len * out_len);
   optm = new adam(lr);
 }
-void dense_layer::forward(float* feat_out) { mm(num_samples, dim_out, dim_in, feat_in, d_weight, feat_out); }
+void dense_layer::forward(float* feat_out) { mm(num_samples, dim_out, dim_in, feat_in, pitch4(dim_in), d_weight, dim_out, feat_out, pitch4(dim_out)); }
 void dense_layer::backward(float* grad_out) {
-  mm(dim_in, dim_out, num_samples, feat_in, grad_in, d_weight_grad, true, false);
-  mm(num_samples, dim_in, dim_out, grad_in, d_weight, grad_out, false, true);
+  mm(dim_in, dim_out, num_samples, feat_in, pitch4(dim_in), grad_in, pitch4(dim_out), d_weight_grad, dim_out, true, false);
+  mm(num_samples, dim_in, dim_out, grad_in, pitch4(dim_out), d_weight, dim_out, grad_out, pitch4(dim_in), false, true);
   optm->update_gpu((size_t)dim_in * dim_out, d_weight_grad, d_weight);
 }
 
 loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cls(ncls), labels(ptr) {
-  feat_in = float_malloc_device_zero((size_t)nv * ncls);
-  feat_out = float_malloc_device_zero((size_t)nv * ncls);
+  feat_in = float_malloc_device_zero((size_t)nv * pitch4(ncls));
+  feat_out = float_malloc_device_zero((size_t)nv * pitch4(ncls));
   d_losses = float_malloc_device_zero(nv);
   d_stats = float_malloc_device_zero(4);
 }
 
 void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
   gai_host::OpScope sc("LOSS", "fwd", 8.0 * (end - begin) * num_cls, 0);
-  die_on(gai_softmax_ce_forward(num_cls, begin, end, masks, labels, feat_in, feat_out, d_losses, stream()), "gai_softmax_ce_forward");
+  die_on(gai_softmax_ce_forward_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, stream()),
+         "gai_softmax_ce_forward");
 }
 void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
   gai_host::OpScope sc("LOSS", "bwd", 8.0 * (end - begin) * num_cls, 0);
-  die_on(gai_softmax_ce_backward(num_cls, begin, end, masks, labels, feat_out, grad_out, stream()), "gai_softmax_ce_backward");
+  if (begin == end) return;
+  die_on(gai_softmax_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, pitch4(num_cls), grad_out, pitch4(num_cls), (uint64_t)(end - begin),
+                                    stream()), "gai_softmax_ce_backward");
 }
 acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
   {
     gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin) * (num_cls + 1), 0);
-    die_on(gai_masked_loss_accuracy(num_cls, begin, end, masks, labels, feat_in, d_losses, d_stats, stream()), "gai_masked_loss_accuracy");
+    die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), d_losses, d_stats, stream()),
+           "gai_masked_loss_accuracy");
   }
   float h[3] = {0, 0, 0};
   copy_float_to_host(3, d_stats, h);
@@ -338,6 +419,7 @@ acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t c
   return h[0];
 }
 
+// preds: the loss layer's feat_in (rows pitched to 4 floats, as every layer-owned buffer)
 float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
   static float* scratch = nullptr;
   static size_t scratch_n = 0;
@@ -346,7 +428,8 @@ float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* m
     scratch_n = (size_t)end + 4;
     scratch = float_malloc_device_zero(scratch_n);
   }
-  die_on(gai_masked_loss_accuracy(num_classes, begin, end, masks, ground_truth, preds, scratch, scratch + end, stream()), "gai_masked_loss_accuracy");
+  die_on(gai_masked_loss_accuracy_ld(num_classes, begin, end, masks, ground_truth, preds, pitch4(num_classes), scratch, scratch + end, stream()),
+         "gai_masked_loss_accuracy");
   float h[3];
   copy_float_to_host(3, scratch + end, h);
   return h[1];

@@ -43,7 +43,12 @@ struct adam : public optimizer {
   std::unordered_map<const float*, std::pair<float*, float*>> moments;
 };
 
+// Row pitch of every per-vertex activation / gradient buffer the layer classes own (floats).
+inline size_t pitch4(size_t dim) { return (dim + 3) / 4 * 4; }
+
 // ---- aggregators --------------------------------------------------------------------------------------------------
+// aggregate / d_aggregate keep the reference signatures (dense rows, aggregator.h:21-88); the *_ld forms take row pitches
+// and epilogue flags (GAI_EPI_ADD with an addend of pitch ld_out, GAI_EPI_RELU) and are what the layers call.
 class aggregator {
  public:
   void set_vlen(int vlen) { length = vlen; }
@@ -57,7 +62,8 @@ class GCN_Aggregator : public aggregator {
   void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
-  void aggregate_fused(int len, Graph& g, const float* in, float* out, int epilogue_flags, const float* addend);
+  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
+  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend);
 };
 
 class SAGE_Aggregator : public aggregator {
@@ -65,7 +71,8 @@ class SAGE_Aggregator : public aggregator {
   void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
-  void aggregate_fused(int len, Graph& g, const float* in, float* out, int epilogue_flags, const float* addend);
+  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
+  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend);
 };
 
 class GAT_Aggregator : public aggregator {
@@ -102,7 +109,20 @@ class graph_conv_layer {
   int get_dim_in() const { return dim_in; }
   int get_dim_out() const { return dim_out; }
   float* weight_ptr(const std::string& name);  // "W", "W_grad", "W_self", "W_self_grad", "alpha_l", ... (device)
-  size_t weight_size(const std::string& name);
+  size_t weight_size(const std::string& name);   // logical element count (rows x cols, dense)
+  // Row layout of a named per-vertex tensor: logical columns and the pitch it is stored with (0/0 for weights: dense).
+  void tensor_layout(const std::string& name, size_t* cols, size_t* ld);
+  // Row pitches. Per-vertex activation / gradient buffers owned by the layer classes are stored with their rows padded to
+  // a multiple of 4 floats (pitch4), so that every aggregation gather, TMA box and epilogue store is 16-byte aligned for
+  // any width (47 classes -> pitch 48); layer 0's feat_in is the caller's dense input matrix.
+  size_t ld_feat_in() const { return ld_in; }
+  size_t ld_grad_in() const { return ld_out; }
+  // d_relu fusion across the layer boundary: the layer above writes this layer's grad_in already masked by this layer's
+  // activation (the GEMM epilogue reads its own feat_in = this layer's output), so backward() skips the separate pass.
+  bool can_mask_grad_out() const;                 // this layer's last backward op on grad_out is a dense transform
+  void set_mask_grad_out(bool on) { mask_grad_out = on; }
+  void set_grad_premasked(bool on) { grad_premasked = on; }
+  bool has_activation() const { return is_act; }
 
  protected:
   int level_, num_samples, dim_in, dim_out;
@@ -110,6 +130,8 @@ class graph_conv_layer {
   bool is_act, is_bias, use_concat;
   float feat_dropout_rate, score_dropout_rate, feat_scale;
   net_phase phase_ = net_phase::TRAIN;
+  size_t ld_in = 0, ld_out = 0;  // row pitches of feat_in / (grad_in, out_temp, the feat_out this layer writes)
+  bool mask_grad_out = false, grad_premasked = false;
   float *feat_in = nullptr, *grad_in = nullptr;
   float *d_in_temp = nullptr, *d_in_temp1 = nullptr, *d_out_temp = nullptr;
   float *d_W_neigh = nullptr, *d_W_neigh_grad = nullptr, *d_W_self = nullptr, *d_W_self_grad = nullptr;

@@ -134,6 +134,13 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   if (use_l2norm) layer_l2norm = new l2norm_layer(nv, dim_hid);
   if (use_dense) layer_dense = new dense_layer(nv, dim_hid, num_cls, lrate);
   layer_gconv[0].set_feat_in(d_input_features);
+  // d_relu of layer l-1 (gcn_layer.cpp:38-40) rides the epilogue of the transform that produces its grad_in in layer l
+  for (int l = 1; l < num_layers; l++) {
+    if (layer_gconv[l - 1].has_activation() && layer_gconv[l].can_mask_grad_out()) {
+      layer_gconv[l].set_mask_grad_out(true);
+      layer_gconv[l - 1].set_grad_premasked(true);
+    }
+  }
   layer_loss = new softmax_loss_layer(nv, num_cls, d_labels);
   opt_ = new adam(lrate);  // net.cpp:362
   sync();

@@ -9,7 +9,7 @@ import torch
 
 from ._abi import check, lib
 
-EPI_NONE, EPI_RELU, EPI_ADD, EPI_MASK = 0, 1, 2, 4
+EPI_NONE, EPI_RELU, EPI_ADD, EPI_MASK, EPI_PADDED = 0, 1, 2, 4, 8
 
 
 def _stream():
@@ -165,31 +165,42 @@ def matmul_kcat(A1, B1, A2, B2, out=None, transB=False, flags=0, mask=None):
     return out
 
 
-def matmul_ncat(A, B1, B2, out1=None, out2=None):
-    """C1 = A·B1, C2 = A·B2 with A read once (gai_matmul_ncat)."""
+def matmul_mask(A, B, mask, out=None, transB=False, flags=0):
+    """C = mask > 0 ? A·op(B) : 0 (gai_matmul_mask: the input gradient with the d_relu of the layer below folded in)."""
+    x, z = A.shape
+    y = B.shape[0] if transB else B.shape[1]
+    if out is None:
+        out = torch.empty(x, y, dtype=torch.float32, device=A.device)
+    check(lib().gai_matmul_mask(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), int(transB), _f32(mask),
+                                mask.stride(0), flags, _stream()), "gai_matmul_mask")
+    return out
+
+
+def matmul_ncat(A, B1, B2, out1=None, out2=None, flags=0):
+    """C1 = A·B1, C2 = A·B2 with A read once (gai_matmul_ncat); flags: EPI_PADDED."""
     x, z = A.shape
     out1 = torch.empty(x, B1.shape[1], dtype=torch.float32, device=A.device) if out1 is None else out1
     out2 = torch.empty(x, B2.shape[1], dtype=torch.float32, device=A.device) if out2 is None else out2
     check(lib().gai_matmul_ncat(x, z, _f32(A), A.stride(0), B1.shape[1], _f32(B1), B1.stride(0), _f32(out1), out1.stride(0), B2.shape[1],
-                                _f32(B2), B2.stride(0), _f32(out2), out2.stride(0), _stream()), "gai_matmul_ncat")
+                                _f32(B2), B2.stride(0), _f32(out2), out2.stride(0), flags, _stream()), "gai_matmul_ncat")
     return out1, out2
 
 
-def wgrad_two_a(A1, A2, B):
+def wgrad_two_a(A1, A2, B, out1=None, out2=None):
     """C1 = A1^T·B, C2 = A2^T·B with B read once (gai_wgrad_two_a)."""
     z, y = B.shape
-    c1 = torch.empty(A1.shape[1], y, dtype=torch.float32, device=B.device)
-    c2 = torch.empty(A2.shape[1], y, dtype=torch.float32, device=B.device)
+    c1 = torch.empty(A1.shape[1], y, dtype=torch.float32, device=B.device) if out1 is None else out1
+    c2 = torch.empty(A2.shape[1], y, dtype=torch.float32, device=B.device) if out2 is None else out2
     check(lib().gai_wgrad_two_a(z, y, _f32(B), B.stride(0), A1.shape[1], _f32(A1), A1.stride(0), _f32(c1), y, A2.shape[1], _f32(A2),
                                 A2.stride(0), _f32(c2), y, _stream()), "gai_wgrad_two_a")
     return c1, c2
 
 
-def wgrad_two_b(A, B1, B2):
+def wgrad_two_b(A, B1, B2, out1=None, out2=None):
     """C1 = A^T·B1, C2 = A^T·B2 with A read once (gai_wgrad_two_b)."""
     z, x = A.shape
-    c1 = torch.empty(x, B1.shape[1], dtype=torch.float32, device=A.device)
-    c2 = torch.empty(x, B2.shape[1], dtype=torch.float32, device=A.device)
+    c1 = torch.empty(x, B1.shape[1], dtype=torch.float32, device=A.device) if out1 is None else out1
+    c2 = torch.empty(x, B2.shape[1], dtype=torch.float32, device=A.device) if out2 is None else out2
     check(lib().gai_wgrad_two_b(z, x, _f32(A), A.stride(0), B1.shape[1], _f32(B1), B1.stride(0), _f32(c1), B1.shape[1], B2.shape[1],
                                 _f32(B2), B2.stride(0), _f32(c2), B2.shape[1], _stream()), "gai_wgrad_two_b")
     return c1, c2
@@ -220,25 +231,28 @@ def d_l2norm(feat_in, grad_in, out=None):
 
 
 def softmax_ce_forward(logits, labels, masks, begin, end, probs, losses):
-    check(lib().gai_softmax_ce_forward(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), _f32(probs), _f32(losses), _stream()),
-          "gai_softmax_ce_forward")
+    """logits / probs may be column views of row-padded buffers (their stride(0) is the row pitch)."""
+    check(lib().gai_softmax_ce_forward_ld(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), logits.stride(0), _f32(probs),
+                                          probs.stride(0), _f32(losses), _stream()), "gai_softmax_ce_forward_ld")
 
 
 def softmax_ce_backward(probs, labels, masks, begin, end, grad):
-    check(lib().gai_softmax_ce_backward(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), _f32(grad), _stream()),
-          "gai_softmax_ce_backward")
+    if begin == end:
+        return
+    check(lib().gai_softmax_ce_backward_ld(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), probs.stride(0), _f32(grad),
+                                           grad.stride(0), end - begin, _stream()), "gai_softmax_ce_backward_ld")
 
 
 def softmax_ce_backward_scaled(probs, labels, masks, begin, end, grad, denom):
     """grad rows may be wider than ncls (grad.stride(0) is the leading dimension); scaled by 1/denom (the global range length)."""
-    check(lib().gai_softmax_ce_backward_scaled(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), _f32(grad), grad.stride(0), denom,
-                                               _stream()), "gai_softmax_ce_backward_scaled")
+    check(lib().gai_softmax_ce_backward_ld(probs.shape[1], begin, end, _p(masks), _p(labels), _f32(probs), probs.stride(0), _f32(grad),
+                                           grad.stride(0), denom, _stream()), "gai_softmax_ce_backward_ld")
 
 
 def masked_loss_accuracy(logits, labels, masks, begin, end, losses, stats=None):
     stats = torch.empty(3, dtype=torch.float32, device=logits.device) if stats is None else stats
-    check(lib().gai_masked_loss_accuracy(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), _f32(losses), _f32(stats), _stream()),
-          "gai_masked_loss_accuracy")
+    check(lib().gai_masked_loss_accuracy_ld(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), logits.stride(0), _f32(losses),
+                                            _f32(stats), _stream()), "gai_masked_loss_accuracy_ld")
     return stats
 
 

@@ -49,6 +49,8 @@ int gai_memset(void* p, int value, size_t bytes, gai_stream_t stream);
 int gai_memcpy_h2d(void* dst, const void* src_h, size_t bytes, gai_stream_t stream);
 int gai_memcpy_d2h(void* dst_h, const void* src, size_t bytes, gai_stream_t stream);
 int gai_memcpy_d2d(void* dst, const void* src, size_t bytes, gai_stream_t stream);
+/* Pitched copy in either direction (host or device pointers, cudaMemcpyDefault): `rows` rows of width_bytes. */
+int gai_memcpy2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, gai_stream_t stream);
 int gai_stream_sync(gai_stream_t stream);
 int gai_host_alloc_pinned(void** p_h, size_t bytes);
 int gai_host_free_pinned(void* p_h);
@@ -97,7 +99,9 @@ const uint32_t* gai_csr_transpose_perm(gai_csr_t g);
 /* ---- neighbour aggregation (SpMM) -------------------------------------------------------------------
  * out[i, 0:F] = epilogue( sum_{e in row i} w_e * in[col_e, 0:F] ), i in [row_begin, row_end).
  * flags: GAI_EPI_ADD  -> add `addend[i, :]` (ld = ld_out) after the sum;  GAI_EPI_RELU -> max(.,0) last. */
-enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2, GAI_EPI_MASK = 4 /* dense transforms only: see gai_matmul_kcat */ };
+enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2, GAI_EPI_MASK = 4 /* dense transforms only: see gai_matmul_kcat */,
+       GAI_EPI_PADDED = 8 /* dense transforms only: the rows of C (and of the mask) are padded to a multiple of 4 floats (ldc % 4 == 0,
+                             ldc >= round_up(y, 4)); the transform may overwrite the padding columns with zeros (all stores 128-bit) */ };
 /* GCN_Aggregator::aggregate == d_aggregate (src/gnn/gconv/gcn_aggregator.cpp:23-77): w_e = norm_i * norm_j. */
 int gai_spmm_gcn(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
 /* SAGE_Aggregator::aggregate (transposed=0, w_e = 1/deg_i) / d_aggregate (transposed=1, w_e = 1/deg_j)
@@ -137,10 +141,14 @@ int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, cons
 int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t ldb1, size_t z2, const float* A2,
                     size_t lda2, const float* B2, size_t ldb2, float* C, size_t ldc, int transB, int flags, const float* mask, size_t ldmask,
                     gai_stream_t stream);
+/* Input gradient with the previous layer's d_relu folded into the epilogue: C[x×y] = mask > 0 ? A[x×z]·op(B) : 0
+ * (gcn_layer.cpp:51-54 followed by the d_relu of the layer below, gcn_layer.cpp:38-40 / math_functions.cpp:453-463). */
+int gai_matmul_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int transB,
+                    const float* mask, size_t ldmask, int flags /* 0 or GAI_EPI_PADDED */, gai_stream_t stream);
 /* N-concatenated transform: C1[x×y1] = A[x×z]·B1[z×y1], C2[x×y2] = A·B2[z×y2] with A read once (SAGE transform-first
  * forward: H·W_neigh for the aggregation and H·W_self for the self term, sage_layer.cpp:26-30). */
 int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,
-                    const float* B2, size_t ldb2, float* C2, size_t ldc2, gai_stream_t stream);
+                    const float* B2, size_t ldb2, float* C2, size_t ldc2, int flags /* 0 or GAI_EPI_PADDED */, gai_stream_t stream);
 /* Concatenated weight gradients over the same z rows (sage_layer.cpp:37-47, two sgemm(transA) calls in the reference):
  *   gai_wgrad_two_a:  C1[x1×y] = A1[z×x1]^T·B,  C2[x2×y] = A2[z×x2]^T·B    (B read once;  x1, x2 <= 128 on the tensor path)
  *   gai_wgrad_two_b:  C1[x×y1] = A[z×x]^T·B1,   C2[x×y2] = A^T·B2          (A read once) */
@@ -163,6 +171,10 @@ int gai_fill(size_t n, float value, float* out, gai_stream_t stream); /* init_co
 /* ---- l2norm_layer (src/layers/l2norm_layer.cpp:19-64; l2norm/d_l2norm math_functions.cu:158-205) ---- */
 int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream);
 int gai_d_l2norm(int n, int dim, const float* feat_in, const float* grad_in, float* grad_out, gai_stream_t stream);
+/* Same with explicit row pitches (activation buffers of the layer classes are pitched to a multiple of 4 floats). */
+int gai_l2norm_ld(int n, int dim, const float* in, size_t ld_in, float* out, size_t ld_out, gai_stream_t stream);
+int gai_d_l2norm_ld(int n, int dim, const float* feat_in, size_t ld_feat, const float* grad_in, size_t ld_grad_in, float* grad_out,
+                    size_t ld_grad_out, gai_stream_t stream);
 
 /* ---- softmax_loss_layer (src/layers/softmax_loss_layer.cpp:4-55) + masked_accuracy_single (math_functions.cpp:79-92)
  * forward : rows i in [begin,end) with masks[i]==1 (masks NULL = all): probs_i = softmax(logits_i);
@@ -180,6 +192,13 @@ int gai_softmax_ce_backward_scaled(int ncls, size_t begin, size_t end, const uin
                                    float* grad_out, int ld_grad, uint64_t denom, gai_stream_t stream);
 int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                              const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
+/* The three loss entry points with explicit row pitches for logits / probs / grad (denom = the reference's end - begin). */
+int gai_softmax_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                              size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream);
+int gai_softmax_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
+                               size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream);
+int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                                size_t ld_logits, const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
 
 /* ---- adam::update (src/utilities/optimizer.cpp:22-35; GPU twin optimizer.cu:5-36).  The caller owns m, v and
  *      the running powers b1_t/b2_t (they advance once per update() call on the reference's optimiser object). */

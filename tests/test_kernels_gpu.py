@@ -337,6 +337,23 @@ def test_matmul_kcat_vs_oracle(T, ops, liborc, shape, padded):
     close(out.cpu().numpy(), np.maximum(ref, 0))
     ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=out, transB=bool(tb), flags=ops.EPI_MASK, mask=dM)
     close(out.cpu().numpy(), np.where(M[:, :y] > 0, ref, 0))
+    if padded:
+        # GAI_EPI_PADDED: the caller owns rows padded to 4 floats; the padding columns may be overwritten, but only with zeros
+        full = T.full((x, pad(y)), 7.0, device="cuda")
+        ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), flags=ops.EPI_RELU | ops.EPI_PADDED)
+        close(full[:, :y].cpu().numpy(), np.maximum(ref, 0))
+        tail = full[:, y:]
+        assert bool(((tail == 7.0) | (tail == 0.0)).all())
+        ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), flags=ops.EPI_MASK | ops.EPI_PADDED, mask=dM)
+        close(full[:, :y].cpu().numpy(), np.where(M[:, :y] > 0, ref, 0))
+        # single-operand masked input gradient (GCN / GAT layers) and the accumulating form on the same shapes
+        ops.matmul_mask(dA1, dev(T, B1), dM, out=full[:, :y], transB=bool(tb), flags=ops.EPI_PADDED)
+        ref1 = np.zeros((x, y), np.float32)
+        liborc.orc_gemm(x, y, z1, a1c.reshape(-1), B1.reshape(-1), ref1.reshape(-1), 0, tb, 0)
+        close(full[:, :y].cpu().numpy(), np.where(M[:, :y] > 0, ref1, 0))
+        ops.matmul(dA1, dev(T, B1), out=full[:, :y], transB=bool(tb), flags=ops.EPI_PADDED)
+        ops.matmul(dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), accum=True, flags=ops.EPI_RELU | ops.EPI_PADDED)
+        close(full[:, :y].cpu().numpy(), np.maximum(ref, 0))
 
 
 @pytest.mark.parametrize("shape", [(20000, 256, 47, 47), (5000, 100, 64, 33), (4096, 128, 128, 100), (3000, 50, 7, 9)])
@@ -356,6 +373,9 @@ def test_matmul_ncat_vs_oracle(T, ops, liborc, shape):
     close(o1[:, :y1].cpu().numpy(), r1)
     close(o2.cpu().numpy(), r2)
     assert bool((o1[:, y1:] == 7.0).all()), "padding columns of the first output must not be written"
+    ops.matmul_ncat(dev(T, A), dev(T, B1), dev(T, B2), out1=o1[:, :y1], out2=o2, flags=ops.EPI_PADDED if y2 % 4 == 0 else 0)
+    close(o1[:, :y1].cpu().numpy(), r1)
+    close(o2.cpu().numpy(), r2)
 
 
 @pytest.mark.parametrize("shape", [(50000, 100, 100, 256), (30011, 47, 128, 64), (4100, 16, 7, 33), (3000, 20, 30, 16)])
