@@ -83,6 +83,8 @@ _SIGS = {
     "gai_l2norm_ld": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
     "gai_d_l2norm_ld": (C.c_int, [C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_stream]),
     "gai_softmax_ce_forward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, c_stream]),
+    "gai_softmax_ce_forward_stats_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p,
+                                                  c_f32p, c_stream]),
     "gai_softmax_ce_backward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_uint64, c_stream]),
     "gai_masked_loss_accuracy_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_forward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),

@@ -185,13 +185,120 @@ __global__ void loss_acc_stage1(int ncls, size_t begin, size_t end, const uint8_
     partial[(size_t)blockIdx.x * 3 + 2] = (double)tn;
   }
 }
-__global__ void loss_acc_stage2(int nparts, const double* __restrict__ partial, float* __restrict__ stats) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// ---- vectorised loss kernels: a group of G lanes owns one row (G = 4..32 by class count), 128-bit accesses on row-padded layouts ----
+// Forward: probs = softmax(logits), losses[row] = -log(probs[label]) (math_functions.cpp:46-74,531-542), and — when `partial` is given —
+// the masked_avg_loss / masked_accuracy_single statistics of the same rows (argmax of the LOGITS with the reference's first-maximum
+// tie-break, math_functions.cpp:79-92,129-139) folded into one {loss sum, correct, count} partial per CTA, in a fixed order.
+template <int G>
+__global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks,
+                                                              const uint8_t* __restrict__ labels, const float* __restrict__ logits, size_t ld_logits,
+                                                              float* __restrict__ probs, size_t ld_probs, float* __restrict__ losses,
+                                                              double* __restrict__ partial) {
+  constexpr int GPB = 256 / G;
+  __shared__ double s_l[256];
+  __shared__ unsigned s_c[256], s_n[256];
+  const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int nch = (ncls + 3) >> 2;
+  double l = 0.0; unsigned c = 0, n = 0;
+  for (size_t row = begin + (size_t)blockIdx.x * GPB + gid; row < end; row += (size_t)gridDim.x * GPB) {
+    if (masks && masks[row] != 1) continue;  // uniform within the group
+    const float4* x4 = reinterpret_cast<const float4*>(logits + row * ld_logits);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ch = gl + G * k;
+      float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (ch < nch) t = x4[ch];
+      const int col = ch * 4;
+      v[4 * k + 0] = col + 0 < ncls ? t.x : -INFINITY; v[4 * k + 1] = col + 1 < ncls ? t.y : -INFINITY;
+      v[4 * k + 2] = col + 2 < ncls ? t.z : -INFINITY; v[4 * k + 3] = col + 3 < ncls ? t.w : -INFINITY;
+    }
+    float mx = -INFINITY; int am = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) { if (v[4 * k + i] > mx) { mx = v[4 * k + i]; am = (gl + G * k) * 4 + i; } }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const float omx = __shfl_xor_sync(gmask, mx, o);
+      const int oam = __shfl_xor_sync(gmask, am, o);
+      if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
+    }
+    float e[16], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { e[i] = expf(v[i] - mx); sum += e[i]; }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
+    const int lab = labels[row];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ch = gl + G * k;
+      if (ch < nch) {
+        float4 pr;
+        pr.x = e[4 * k + 0] / sum; pr.y = e[4 * k + 1] / sum; pr.z = e[4 * k + 2] / sum; pr.w = e[4 * k + 3] / sum;
+        reinterpret_cast<float4*>(probs + row * ld_probs)[ch] = pr;
+        if ((lab >> 2) == ch) {
+          const float pl = (lab & 3) == 0 ? pr.x : ((lab & 3) == 1 ? pr.y : ((lab & 3) == 2 ? pr.z : pr.w));
+          const float ls = -((pl == 0.f) ? logf(1e-10f) : logf(pl));  // math_functions.cpp:531-542
+          losses[row] = ls;
+          l += (double)ls;
+        }
+      }
+    }
+    if (gl == 0) { n += 1; c += (am == lab); }
+  }
+  if (partial == nullptr) return;
+  s_l[threadIdx.x] = l; s_c[threadIdx.x] = c; s_n[threadIdx.x] = n;
+  __syncthreads();
+  if (threadIdx.x < 32) {  // fixed-order fold: lane t adds entries t, t+32, ... then a fixed shuffle tree
+    double tl = 0.0; unsigned tc = 0, tn = 0;
+    for (int i = threadIdx.x; i < 256; i += 32) { tl += s_l[i]; tc += s_c[i]; tn += s_n[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tl += __shfl_down_sync(0xffffffffu, tl, o); tc += __shfl_down_sync(0xffffffffu, tc, o); tn += __shfl_down_sync(0xffffffffu, tn, o);
+    }
+    if (threadIdx.x == 0) {
+      partial[(size_t)blockIdx.x * 3 + 0] = tl; partial[(size_t)blockIdx.x * 3 + 1] = (double)tc; partial[(size_t)blockIdx.x * 3 + 2] = (double)tn;
+    }
+  }
+}
+
+// grad = (probs - onehot) / denom, evaluated in double then rounded (softmax_loss_layer.cpp:31), same row grouping
+template <int G>
+__global__ void __launch_bounds__(256) softmax_ce_bwd_rows_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks,
+                                                                  const uint8_t* __restrict__ labels, const float* __restrict__ probs, size_t ld_probs,
+                                                                  float* __restrict__ grad, size_t ld_grad, double denom) {
+  constexpr int GPB = 256 / G;
+  const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+  const int nch = (ncls + 3) >> 2;
+  for (size_t row = begin + (size_t)blockIdx.x * GPB + gid; row < end; row += (size_t)gridDim.x * GPB) {
+    if (masks && masks[row] != 1) continue;
+    const int lab = labels[row];
+    for (int ch = gl; ch < nch; ch += G) {
+      const float4 pr = reinterpret_cast<const float4*>(probs + row * ld_probs)[ch];
+      const int col = ch * 4;
+      float4 g;
+      g.x = (float)(((double)pr.x - (lab == col + 0 ? 1.0 : 0.0)) / denom); g.y = (float)(((double)pr.y - (lab == col + 1 ? 1.0 : 0.0)) / denom);
+      g.z = (float)(((double)pr.z - (lab == col + 2 ? 1.0 : 0.0)) / denom); g.w = (float)(((double)pr.w - (lab == col + 3 ? 1.0 : 0.0)) / denom);
+      reinterpret_cast<float4*>(grad + row * ld_grad)[ch] = g;
+    }
+  }
+}
+
+// final fold of the per-CTA partials, one warp, fixed order
+__global__ void loss_acc_stage2_warp(int nparts, const double* __restrict__ partial, float* __restrict__ stats) {
   double tl = 0.0, tc = 0.0, tn = 0.0;
-  for (int p = 0; p < nparts; p++) { tl += partial[p * 3 + 0]; tc += partial[p * 3 + 1]; tn += partial[p * 3 + 2]; }
-  stats[0] = tn > 0.0 ? (float)(tl / tn) : 0.f;
-  stats[1] = (float)tc / (float)tn;  // accuracy_all / float(num_samples), math_functions.cpp:91
-  stats[2] = (float)tn;
+  for (int p = threadIdx.x; p < nparts; p += 32) { tl += partial[p * 3 + 0]; tc += partial[p * 3 + 1]; tn += partial[p * 3 + 2]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tl += __shfl_down_sync(0xffffffffu, tl, o); tc += __shfl_down_sync(0xffffffffu, tc, o); tn += __shfl_down_sync(0xffffffffu, tn, o);
+  }
+  if (threadIdx.x == 0) {
+    stats[0] = tn > 0.0 ? (float)(tl / tn) : 0.f;
+    stats[1] = (float)tc / (float)tn;  // accuracy_all / float(num_samples), math_functions.cpp:91
+    stats[2] = (float)tn;
+  }
 }
 
 // optimizer.cpp:22-35 — eps inside the sqrt; b1_t/b2_t are the powers BEFORE this call's post-multiply.
@@ -281,14 +388,62 @@ int gai_d_l2norm(int n, int dim, const float* feat_in, const float* grad_in, flo
   return gai_d_l2norm_ld(n, dim, feat_in, (size_t)dim, grad_in, (size_t)dim, grad_out, (size_t)dim, stream);
 }
 
+// rows are 128-bit addressable (pitch and base multiples of 4 floats, room for the tail group) and fit 4 float4 per lane
+static bool loss_vec_ok(int ncls, const float* a, size_t lda, const float* b, size_t ldb) {
+  const size_t need = (size_t)((ncls + 3) / 4) * 4;
+  return ncls <= 512 && lda % 4 == 0 && ldb % 4 == 0 && lda >= need && ldb >= need && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(b) % 16 == 0;
+}
+static int loss_group(int ncls) {  // lanes per row: one float4 per lane up to 32 lanes (128 classes), then up to 4 per lane
+  const int nch = (ncls + 3) / 4;
+  int G = 4;
+  while (G < 32 && G < nch) G <<= 1;
+  return G;
+}
+static int softmax_ce_forward_impl(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                                   size_t ld_logits, float* probs, size_t ld_probs, float* losses, float* stats_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && probs && losses && ld_logits >= (size_t)ncls && ld_probs >= (size_t)ncls);
+  cudaStream_t st = gai::S(stream);
+  const size_t rows = end - begin;
+  if (rows && loss_vec_ok(ncls, logits, ld_logits, probs, ld_probs)) {
+    const int G = loss_group(ncls);
+    size_t blocks = (rows * G + 255) / 256;
+    const size_t cap = (size_t)gai::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    double* partial = nullptr;
+    if (stats_d) {
+      void* ws = nullptr;
+      int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws);
+      if (rc != GAI_OK) return rc;
+      partial = reinterpret_cast<double*>(ws);
+    }
+    const unsigned gb = (unsigned)blocks;
+    if (G == 4) softmax_ce_rows_kernel<4><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, partial);
+    else if (G == 8) softmax_ce_rows_kernel<8><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, partial);
+    else if (G == 16) softmax_ce_rows_kernel<16><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, partial);
+    else softmax_ce_rows_kernel<32><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, partial);
+    GAI_LAUNCH_CHECK();
+    if (stats_d) {
+      loss_acc_stage2_warp<<<1, 32, 0, st>>>((int)blocks, partial, stats_d);
+      GAI_LAUNCH_CHECK();
+    }
+    return GAI_OK;
+  }
+  if (rows) {
+    softmax_ce_fwd_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses);
+    GAI_LAUNCH_CHECK();
+  }
+  if (stats_d) return gai_masked_loss_accuracy_ld(ncls, begin, end, masks, labels, logits, ld_logits, losses, stats_d, stream);
+  return GAI_OK;
+}
 int gai_softmax_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                               size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream) {
-  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && logits && probs && losses && ld_logits >= (size_t)ncls && ld_probs >= (size_t)ncls);
-  if (begin == end) return GAI_OK;
-  softmax_ce_fwd_kernel<<<(unsigned)(((end - begin) * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits,
-                                                                                                    ld_logits, probs, ld_probs, losses);
-  GAI_LAUNCH_CHECK();
-  return GAI_OK;
+  return softmax_ce_forward_impl(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, nullptr, stream);
+}
+int gai_softmax_ce_forward_stats_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                                    size_t ld_logits, float* probs, size_t ld_probs, float* losses, float* stats_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(stats_d != nullptr);
+  return softmax_ce_forward_impl(ncls, begin, end, masks, labels, logits, ld_logits, probs, ld_probs, losses, stats_d, stream);
 }
 int gai_softmax_ce_forward(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits, float* probs,
                            float* losses, gai_stream_t stream) {
@@ -298,8 +453,24 @@ int gai_softmax_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t
                                size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream) {
   GAI_CHECK_ARG(ncls > 0 && begin <= end && labels && probs && grad_out && denom > 0 && ld_grad >= (size_t)ncls && ld_probs >= (size_t)ncls);
   if (begin == end) return GAI_OK;
-  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, probs, ld_probs,
-                                                                                         grad_out, (double)denom, ld_grad);
+  cudaStream_t st = gai::S(stream);
+  if (loss_vec_ok(ncls, probs, ld_probs, grad_out, ld_grad)) {
+    const int nch = (ncls + 3) / 4;
+    int G = 4;
+    while (G < 32 && G < nch) G <<= 1;
+    size_t blocks = ((end - begin) * G + 255) / 256;
+    const size_t cap = (size_t)gai::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const unsigned gb = (unsigned)blocks;
+    if (G == 4) softmax_ce_bwd_rows_kernel<4><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, probs, ld_probs, grad_out, ld_grad, (double)denom);
+    else if (G == 8) softmax_ce_bwd_rows_kernel<8><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, probs, ld_probs, grad_out, ld_grad, (double)denom);
+    else if (G == 16) softmax_ce_bwd_rows_kernel<16><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, probs, ld_probs, grad_out, ld_grad, (double)denom);
+    else softmax_ce_bwd_rows_kernel<32><<<gb, 256, 0, st>>>(ncls, begin, end, masks, labels, probs, ld_probs, grad_out, ld_grad, (double)denom);
+    GAI_LAUNCH_CHECK();
+    return GAI_OK;
+  }
+  softmax_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, st>>>(ncls, begin, end, masks, labels, probs, ld_probs, grad_out, (double)denom,
+                                                                            ld_grad);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -326,7 +497,7 @@ int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_
   if (rc != GAI_OK) return rc;
   loss_acc_stage1<<<nparts, 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, ld_logits, losses, reinterpret_cast<double*>(ws));
   GAI_LAUNCH_CHECK();
-  loss_acc_stage2<<<1, 32, 0, gai::S(stream)>>>(nparts, reinterpret_cast<const double*>(ws), stats_d);
+  loss_acc_stage2_warp<<<1, 32, 0, gai::S(stream)>>>(nparts, reinterpret_cast<const double*>(ws), stats_d);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -454,11 +625,15 @@ static int wgrad_cat_or_simt(const gai::WgradCat& q, cudaStream_t st) {
   const int mode = gai::g_gemm_mode;
   if (mode != 1) {
     int rc = gai::gemm_tc_wgrad_cat(q, mode == 3 ? 1 : 3, st);
-    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+    if (rc != GAI_ERR_UNSUPPORTED) return rc;
   }
+  // widths the two-operand kernel declines (more than 512 accumulator columns in all): two plain products, each on the tensor
+  // cores when its own shape fits, otherwise SIMT
   for (int i = 0; i < 2; i++) {
     const int a = q.dual == 1 ? i : 0, b = q.dual == 2 ? i : 0;
-    int rc = gai::gemm_simt(q.Kx[a], q.My[b], q.nrows, q.A[a], q.lda[a], q.B[b], q.ldb[b], q.C[i], q.ldc[i], 1, 0, 0, 0, st);
+    int rc = GAI_ERR_UNSUPPORTED;
+    if (mode != 1) rc = gai::gemm_tc_wgrad(q.Kx[a], q.My[b], q.nrows, q.A[a], q.lda[a], q.B[b], q.ldb[b], q.C[i], q.ldc[i], 0, 0, mode == 3 ? 1 : 3, st);
+    if (rc == GAI_ERR_UNSUPPORTED && mode < 2) rc = gai::gemm_simt(q.Kx[a], q.My[b], q.nrows, q.A[a], q.lda[a], q.B[b], q.ldb[b], q.C[i], q.ldc[i], 1, 0, 0, 0, st);
     if (rc != GAI_OK) return rc;
   }
   return GAI_OK;

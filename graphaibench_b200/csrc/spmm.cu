@@ -41,6 +41,7 @@ struct SpmmArgs {
   int mode, flags;
   int out_vec;       // 1: out/addend rows are 16-byte aligned and F % 4 == 0 -> float4 epilogue
   uint32_t hub_threshold;
+  int hub_per;       // hub rows: float4 chunks per CTA column block (gridDim.y blocks cover nchunks)
 };
 
 // out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
@@ -264,8 +265,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-// ES = edges per stage (32, 16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(nchunks,128) float4.
-template <int MODE, int ES>
+// ES = edges per stage (32, 16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(hub_per,128) float4.
+// CL = lanes along the column-chunk dimension of one gather instruction (the other 32/CL lanes cover consecutive edges):
+//   CL = 32  one edge per instruction, 32 chunks wide — column blocks of 32..128 chunks
+//   CL = 8   four edges per instruction, 8 chunks (one 128-byte line per neighbour row) wide — the row's columns are split
+//            into blocks of <= 8 chunks handled by gridDim.y CTAs: the sequential add chain of a 94 K-edge row stays
+//            sequential per column, but its gather is spread over several SMs with every lane busy.
+template <int MODE, int ES, int CL>
 __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(const SpmmArgs a, const uint32_t* __restrict__ hub_rows) {
   extern __shared__ float4 ring[];
   __shared__ uint64_t full_bar[HUB_PROD_WARPS], empty_bar[HUB_PROD_WARPS];
@@ -276,7 +282,10 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
   const size_t ld4 = (size_t)a.ld_in >> 2;
-  const int nch_max = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
+  const int cb_begin = (int)blockIdx.y * a.hub_per;
+  const int cb_end = a.nchunks < cb_begin + a.hub_per ? a.nchunks : cb_begin + a.hub_per;
+  if (cb_begin >= cb_end) return;  // uniform for the CTA
+  const int nch_max = (cb_end - cb_begin) < HUB_MAX_CHUNKS ? (cb_end - cb_begin) : HUB_MAX_CHUNKS;
   const size_t slot_stride = (size_t)ES * nch_max;
   uint32_t blk = 0;  // column-block index; slot p has been used blk * uses(p) times before this block (mbarrier phase bookkeeping)
 
@@ -285,8 +294,8 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
   }
   __syncthreads();
 
-  for (int cb = 0; cb < a.nchunks; cb += HUB_MAX_CHUNKS) {
-    const int nch = (a.nchunks - cb) < HUB_MAX_CHUNKS ? (a.nchunks - cb) : HUB_MAX_CHUNKS;
+  for (int cb = cb_begin; cb < cb_end; cb += HUB_MAX_CHUNKS) {
+    const int nch = (cb_end - cb) < HUB_MAX_CHUNKS ? (cb_end - cb) : HUB_MAX_CHUNKS;
     if (warp >= HUB_CONS_WARPS) {
       // ---------------- producers ----------------
       const int pw = warp - HUB_CONS_WARPS;
@@ -310,25 +319,29 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
           if (lane < ES && nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight_t<MODE>(a, wrow, (uint32_t)nidx, c); }
         }
         mbar_wait(&empty_bar[pw], ((round0 + r) & 1) ^ 1);
-        for (int ch0 = 0; ch0 < nch; ch0 += 32) {
-          const int ch = ch0 + lane;
+        constexpr int EL = 32 / CL;  // edges per gather instruction
+        const int cl = lane % CL, el = lane / CL;
+        for (int ch0 = 0; ch0 < nch; ch0 += CL) {
+          const int ch = ch0 + cl;
           const bool chv = ch < nch;
-          constexpr int UB = ES < 8 ? ES : 8;
+          constexpr int UB = (ES / EL) < 8 ? (ES / EL) : 8;  // independent loads in flight per lane
 #pragma unroll
-          for (int j0 = 0; j0 < ES; j0 += UB) {
+          for (int j0 = 0; j0 < ES; j0 += UB * EL) {
             float4 x[UB]; float ww[UB];
 #pragma unroll
             for (int u = 0; u < UB; u++) {
-              const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j0 + u);
-              ww[u] = __shfl_sync(0xffffffffu, cur_w, j0 + u);
-              if (chv && j0 + u < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + ch);
+              const int j = j0 + u * EL + el;
+              const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j & 31);
+              ww[u] = __shfl_sync(0xffffffffu, cur_w, j & 31);
+              if (chv && j < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + ch);
             }
 #pragma unroll
             for (int u = 0; u < UB; u++) {
-              if (chv && j0 + u < cnt) {
+              const int j = j0 + u * EL + el;
+              if (chv && j < cnt) {
                 float4 p;
                 p.x = __fmul_rn(ww[u], x[u].x); p.y = __fmul_rn(ww[u], x[u].y); p.z = __fmul_rn(ww[u], x[u].z); p.w = __fmul_rn(ww[u], x[u].w);
-                slot[(size_t)(j0 + u) * nch + ch] = p;
+                slot[(size_t)j * nch + ch] = p;
               }
             }
           }
@@ -451,29 +464,36 @@ int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
   }
 }
 
-template <int MODE, int ES>
-int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, cudaStream_t st) {
+template <int MODE, int ES, int CL>
+int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, unsigned nsplit, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<MODE, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    GAI_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<MODE, ES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
     configured = true;
   }
   const ListSel sel = select_list(a, g);
-  spmm_hub_kernel<MODE, ES><<<sel.n_hub, HUB_THREADS, smem, st>>>(a, sel.hub_rows);
+  spmm_hub_kernel<MODE, ES, CL><<<dim3(sel.n_hub, nsplit), HUB_THREADS, smem, st>>>(a, sel.hub_rows);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
 
 template <int MODE>
-int launch_hub_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+int launch_hub_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
+  // widths up to 512 floats: column blocks of <= 8 chunks (one 128-byte line per neighbour row), one CTA each
+  if (a.nchunks <= 128) {
+    const unsigned nsplit = (unsigned)((a.nchunks + 7) / 8);
+    a.hub_per = (int)((a.nchunks + nsplit - 1) / nsplit);
+    return launch_hub_es<MODE, 32, 8>(a, g, (size_t)HUB_PROD_WARPS * 32 * a.hub_per * sizeof(float4), nsplit, st);
+  }
+  a.hub_per = a.nchunks;
   const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
   // largest stage size in {32, 16, 8, 4} edges whose 16-slot ring fits 200 KB of shared memory (longer stages amortise the
   // consumer's per-stage barrier round trip over more in-order adds)
   auto bytes = [&](int es) { return (size_t)HUB_PROD_WARPS * es * nch * sizeof(float4); };
-  if (bytes(32) <= HUB_RING_CAP) return launch_hub_es<MODE, 32>(a, g, bytes(32), st);
-  if (bytes(16) <= HUB_RING_CAP) return launch_hub_es<MODE, 16>(a, g, bytes(16), st);
-  if (bytes(8) <= HUB_RING_CAP) return launch_hub_es<MODE, 8>(a, g, bytes(8), st);
-  return launch_hub_es<MODE, 4>(a, g, bytes(4), st);
+  if (bytes(32) <= HUB_RING_CAP) return launch_hub_es<MODE, 32, 32>(a, g, bytes(32), 1, st);
+  if (bytes(16) <= HUB_RING_CAP) return launch_hub_es<MODE, 16, 32>(a, g, bytes(16), 1, st);
+  if (bytes(8) <= HUB_RING_CAP) return launch_hub_es<MODE, 8, 32>(a, g, bytes(8), 1, st);
+  return launch_hub_es<MODE, 4, 32>(a, g, bytes(4), 1, st);
 }
 
 int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
@@ -505,6 +525,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.F = F; a.nchunks = (F + 3) / 4; a.ld_out = ld_out; a.row_begin = rb; a.row_end = re;
   a.mode = mode; a.flags = flags;
   a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
+  a.hub_per = a.nchunks;
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
   if ((ld_in % 4 == 0) && aligned16(in) && ld_in >= a.nchunks * 4) {
     // rows are 128-bit loadable as stored; when F % 4 != 0 the tail chunk also reads the (ld_in - F) padding columns of

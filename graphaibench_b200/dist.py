@@ -370,14 +370,24 @@ class DistGnn:
 
         self.W, self.Ws, self.dW, self.dWs = [], [], [], []
         self.feat_in, self.grad_in, self.T, self.A, self.Tm, self.D = [], [], [], [], [], []
+        # every weight gradient is a view of one flat buffer: ONE all-reduce per step instead of one per matrix
+        n_w = sum(dims[l] * dims[l + 1] for l in range(self.L)) * (2 if arch == "sage" else 1)
+        self.dW_flat = torch.zeros(n_w, dtype=torch.float32, device=dev)
+        off = 0
+
+        def wview(din, dout):
+            nonlocal off
+            v = self.dW_flat[off: off + din * dout].view(din, dout)
+            off += din * dout
+            return v
         for l in range(self.L):
             din, dout = dims[l], dims[l + 1]
             tf = din > dout
             self.W.append(torch.from_numpy(gmodel.glorot(din, dout, 1)).to(dev))        # seeds: graph_conv_layer.cpp:13,18
-            self.dW.append(torch.zeros(din, dout, device=dev))
+            self.dW.append(wview(din, dout))
             if arch == "sage":
                 self.Ws.append(torch.from_numpy(gmodel.glorot(din, dout, 2)).to(dev))
-                self.dWs.append(torch.zeros(din, dout, device=dev))
+                self.dWs.append(wview(din, dout))
             # the matrices an aggregation gathers from carry the halo rows (m rows); row stride is a multiple of 4 floats so
             # every gather is a 128-bit load without a staging copy
             self.feat_in.append(buf(m if not tf else n, din))
@@ -565,8 +575,7 @@ class DistGnn:
             self._forward_layer(l)
         if n:
             with self._scope("LOSS", "fwd+reduce", 4.0 * n * (3 * self.dims[-1] + 2)):
-                ops.softmax_ce_forward(self.logits[:n], self.labels, self.mask, 0, n, self.probs, self.losses)
-                ops.masked_loss_accuracy(self.logits[:n], self.labels, self.mask, 0, n, self.losses, self.stats)
+                ops.softmax_ce_forward_stats(self.logits[:n], self.labels, self.mask, 0, n, self.probs, self.losses, self.stats)
         st = self.stats.to(torch.float64)
         cnt = st[2] if n else torch.zeros((), dtype=torch.float64, device=st.device)
         tot = torch.stack([st[0] * cnt, st[1] * cnt, cnt]) if n else torch.zeros(3, dtype=torch.float64, device=st.device)
@@ -585,11 +594,8 @@ class DistGnn:
         for l in range(self.L - 1, -1, -1):
             self._backward_layer(l)
         if self.comm.world > 1:
-            with self._scope("ALLREDUCE", "dW", 0.0):
-                for l in range(self.L):
-                    self.comm.all_reduce_sum(self.dW[l])
-                    if self.arch == "sage":
-                        self.comm.all_reduce_sum(self.dWs[l])
+            with self._scope("ALLREDUCE", "dW", 4.0 * self.dW_flat.numel()):
+                self.comm.all_reduce_sum(self.dW_flat)
 
     def update(self):
         for l in range(self.L):

@@ -396,9 +396,11 @@ loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cl
 }
 
 void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
-  gai_host::OpScope sc("LOSS", "fwd", 8.0 * (end - begin) * num_cls, 0);
-  die_on(gai_softmax_ce_forward_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, stream()),
-         "gai_softmax_ce_forward");
+  // one pass over the logits also yields the loss mean and the accuracy get_prediction_loss() reports (forward_prop calls the two back to back)
+  gai_host::OpScope sc("LOSS", "fwd+stats", 4.0 * (end - begin) * (2 * num_cls + 2), 0);
+  die_on(gai_softmax_ce_forward_stats_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, d_stats,
+                                         stream()), "gai_softmax_ce_forward_stats");
+  stats_begin = begin; stats_end = end; stats_masks = masks; stats_valid = true;
 }
 void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
   gai_host::OpScope sc("LOSS", "bwd", 8.0 * (end - begin) * num_cls, 0);
@@ -407,11 +409,12 @@ void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float
                                     stream()), "gai_softmax_ce_backward");
 }
 acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
-  {
+  if (!(stats_valid && stats_begin == begin && stats_end == end && stats_masks == masks)) {  // not preceded by forward() on the same rows
     gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin) * (num_cls + 1), 0);
     die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), d_losses, d_stats, stream()),
            "gai_masked_loss_accuracy");
   }
+  stats_valid = false;
   float h[3] = {0, 0, 0};
   copy_float_to_host(3, d_stats, h);
   (void)count;  // the reference asserts masked-row count == count; the count comes back as a float here

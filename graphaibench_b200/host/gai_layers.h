@@ -230,6 +230,10 @@ class softmax_loss_layer : public loss_layer {
 
  private:
   acc_t last_acc = 0;
+  // rows the statistics in d_stats were computed over by the last forward()
+  size_t stats_begin = 0, stats_end = 0;
+  mask_t* stats_masks = nullptr;
+  bool stats_valid = false;
 };
 
 float masked_accuracy_single(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);

@@ -236,6 +236,13 @@ def softmax_ce_forward(logits, labels, masks, begin, end, probs, losses):
                                           probs.stride(0), _f32(losses), _stream()), "gai_softmax_ce_forward_ld")
 
 
+def softmax_ce_forward_stats(logits, labels, masks, begin, end, probs, losses, stats):
+    """softmax_ce_forward + masked_loss_accuracy in one pass over the logits: stats = {mean loss, accuracy, count}."""
+    check(lib().gai_softmax_ce_forward_stats_ld(logits.shape[1], begin, end, _p(masks), _p(labels), _f32(logits), logits.stride(0), _f32(probs),
+                                                probs.stride(0), _f32(losses), _f32(stats), _stream()), "gai_softmax_ce_forward_stats_ld")
+    return stats
+
+
 def softmax_ce_backward(probs, labels, masks, begin, end, grad):
     if begin == end:
         return

@@ -195,6 +195,10 @@ int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* 
 /* The three loss entry points with explicit row pitches for logits / probs / grad (denom = the reference's end - begin). */
 int gai_softmax_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                               size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream);
+/* forward + the statistics of gai_masked_loss_accuracy over the same rows in one pass over the logits (forward_prop, net.cpp:458-476,
+ * calls the two back to back): stats_d = {mean loss, accuracy, count}. */
+int gai_softmax_ce_forward_stats_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
+                                    size_t ld_logits, float* probs, size_t ld_probs, float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
 int gai_softmax_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* probs,
                                size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream);
 int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
