@@ -31,6 +31,9 @@ _SIGS = {
     "gai_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "gai_memcpy2d": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, c_stream]),
     "gai_stream_sync": (C.c_int, [c_stream]),
+    "gai_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "gai_stream_destroy": (C.c_int, [c_stream]),
+    "gai_stream_wait_event": (C.c_int, [c_stream, C.c_void_p]),
     "gai_host_alloc_pinned": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "gai_host_free_pinned": (C.c_int, [C.c_void_p]),
     "gai_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),

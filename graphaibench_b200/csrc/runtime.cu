@@ -111,6 +111,19 @@ int gai_memcpy2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_
 }
 int gai_memcpy_d2d(void* dst, const void* src, size_t bytes, gai_stream_t s) { if (bytes) GAI_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, gai::S(s))); return GAI_OK; }
 int gai_stream_sync(gai_stream_t s) { GAI_CUDA(cudaStreamSynchronize(gai::S(s))); return GAI_OK; }
+int gai_stream_create(gai_stream_t* s) {
+  GAI_CHECK_ARG(s != nullptr);
+  cudaStream_t st = nullptr;
+  GAI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = reinterpret_cast<gai_stream_t>(st);
+  return GAI_OK;
+}
+int gai_stream_destroy(gai_stream_t s) { if (s) GAI_CUDA(cudaStreamDestroy(gai::S(s))); return GAI_OK; }
+int gai_stream_wait_event(gai_stream_t s, void* ev) {
+  GAI_CHECK_ARG(ev != nullptr);
+  GAI_CUDA(cudaStreamWaitEvent(gai::S(s), reinterpret_cast<cudaEvent_t>(ev), 0));
+  return GAI_OK;
+}
 int gai_host_alloc_pinned(void** p, size_t bytes) { GAI_CHECK_ARG(p != nullptr); GAI_CUDA(cudaMallocHost(p, bytes ? bytes : 1)); return GAI_OK; }
 int gai_host_free_pinned(void* p) { if (p) GAI_CUDA(cudaFreeHost(p)); return GAI_OK; }
 

@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                  const float ww = __shfl_sync(gmask, w, j + u, G);
+                  // mean aggregation: every edge of the row carries the same 1/deg_i — no broadcast needed
+                  const float ww = MODE == M_MEAN ? wrow : __shfl_sync(gmask, w, j + u, G);
 #pragma unroll
                   for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }
                 }
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                  const float ww = __shfl_sync(gmask, w, j + u, G);
+                  const float ww = MODE == M_MEAN ? wrow : __shfl_sync(gmask, w, j + u, G);
                   if (j + u < cnt) {
 #pragma unroll
                     for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }

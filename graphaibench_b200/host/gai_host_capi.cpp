@@ -12,6 +12,7 @@ struct ModelBase {
   virtual void update() = 0;
   virtual float evaluate(const char* which) = 0;
   virtual void refresh(const float* feats) = 0;
+  virtual void prefetch(const float* feats) = 0;
   // device pointer + logical element count; cols/ld != 0 for per-vertex tensors stored with a row pitch
   virtual float* tensor(const char* name, int layer, size_t* n, size_t* cols, size_t* ld) = 0;
 };
@@ -24,6 +25,7 @@ struct Box : ModelBase {
   void update() override { m.update_weights(m.shared_optimizer()); }
   float evaluate(const char* which) override { return m.evaluate(which); }
   void refresh(const float* feats) override { m.refresh_inputs_from_host(feats); }
+  void prefetch(const float* feats) override { m.prefetch_features_from_host(feats); }
   float* extra(GCN_layer&, const std::string&, size_t*) { return nullptr; }
   float* extra(SAGE_layer&, const std::string&, size_t*) { return nullptr; }
   float* extra(GAT_layer& y, const std::string& name, size_t* n) {
@@ -84,6 +86,7 @@ void gai_model_backward(void* m) { ((ModelBase*)m)->backward(); }
 void gai_model_update(void* m) { ((ModelBase*)m)->update(); }
 float gai_model_evaluate(void* m, const char* which) { return ((ModelBase*)m)->evaluate(which); }
 void gai_model_refresh_inputs(void* m, const float* feats_h) { ((ModelBase*)m)->refresh(feats_h); }
+void gai_model_prefetch_features(void* m, const float* feats_h) { ((ModelBase*)m)->prefetch(feats_h); }
 int64_t gai_model_tensor_size(void* m, const char* name, int layer) {
   size_t n = 0, cols = 0, ld = 0;
   return ((ModelBase*)m)->tensor(name, layer, &n, &cols, &ld) ? (int64_t)n : -1;

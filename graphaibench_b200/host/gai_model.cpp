@@ -106,21 +106,57 @@ void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
 }
 
 template <typename L>
-void Model<L>::refresh_inputs_from_host(const float* feats_h) {
+void Model<L>::stage_pinned(const float* feats_h) {
   // All five inputs are staged once in page-locked host memory so that the per-step copies are true async DMA.
-  static void* pin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (pinned_inputs[0]) return;
   const size_t bytes[5] = {sizeof(float) * input_features.size(), labels.size(), masks_train.size(),
                            sizeof(index_t) * (training_graph->size() + 1), sizeof(index_t) * training_graph->sizeEdges()};
   const void* srcs[5] = {feats_h ? (const void*)feats_h : (const void*)input_features.data(), labels.data(), masks_train.data(),
                          training_graph->row_start_host_ptr(), training_graph->edge_dst_host_ptr()};
-  void* dsts[5] = {d_input_features, d_labels, d_masks_train, (void*)training_graph->row_start_ptr(), (void*)training_graph->edge_dst_ptr()};
   for (int i = 0; i < 5; i++) {
-    if (!pin[i]) {
-      die_on(gai_host_alloc_pinned(&pin[i], bytes[i]), "gai_host_alloc_pinned");
-      memcpy(pin[i], srcs[i], bytes[i]);
-    }
-    die_on(gai_memcpy_h2d(dsts[i], pin[i], bytes[i], stream()), "gai_memcpy_h2d");
+    die_on(gai_host_alloc_pinned(&pinned_inputs[i], bytes[i]), "gai_host_alloc_pinned");
+    memcpy(pinned_inputs[i], srcs[i], bytes[i]);
   }
+}
+
+template <typename L>
+void Model<L>::refresh_inputs_from_host(const float* feats_h) {
+  stage_pinned(feats_h);
+  const size_t bytes[5] = {sizeof(float) * input_features.size(), labels.size(), masks_train.size(),
+                           sizeof(index_t) * (training_graph->size() + 1), sizeof(index_t) * training_graph->sizeEdges()};
+  void* dsts[5] = {d_input_features, d_labels, d_masks_train, (void*)training_graph->row_start_ptr(), (void*)training_graph->edge_dst_ptr()};
+  for (int i = 1; i < 5; i++) die_on(gai_memcpy_h2d(dsts[i], pinned_inputs[i], bytes[i], stream()), "gai_memcpy_h2d");
+  if (prefetch_pending) {  // the features of this step were sent ahead: order the compute stream behind the copy and swap buffers
+    die_on(gai_stream_wait_event(stream(), ev_ready), "gai_stream_wait_event");
+    feat_cur ^= 1;
+    d_input_features = d_feat_buf[feat_cur];
+    layer_gconv[0].set_feat_in(d_input_features);
+    prefetch_pending = false;
+  } else {
+    die_on(gai_memcpy_h2d(d_input_features, pinned_inputs[0], bytes[0], stream()), "gai_memcpy_h2d");
+  }
+}
+
+template <typename L>
+void Model<L>::prefetch_features_from_host(const float* feats_h) {
+  stage_pinned(feats_h);
+  const size_t bytes = sizeof(float) * input_features.size();
+  if (!copy_stream) {
+    die_on(gai_stream_create(&copy_stream), "gai_stream_create");
+    die_on(gai_event_create(&ev_ready), "gai_event_create");
+    die_on(gai_event_create(&ev_free), "gai_event_create");
+    d_feat_buf[0] = d_input_features;
+    void* p = nullptr;
+    die_on(gai_malloc(&p, bytes), "gai_malloc");
+    d_feat_buf[1] = reinterpret_cast<float*>(p);
+  }
+  if (prefetch_pending) return;  // one step ahead at most
+  // the spare buffer was last read by the step before the current one: everything enqueued so far must finish first
+  die_on(gai_event_record(ev_free, stream()), "gai_event_record");
+  die_on(gai_stream_wait_event(copy_stream, ev_free), "gai_stream_wait_event");
+  die_on(gai_memcpy_h2d(d_feat_buf[feat_cur ^ 1], pinned_inputs[0], bytes, copy_stream), "gai_memcpy_h2d");
+  die_on(gai_event_record(ev_ready, copy_stream), "gai_event_record");
+  prefetch_pending = true;
 }
 
 template <typename L>

@@ -35,6 +35,10 @@ class Model {
   // Re-upload the epoch's inputs (features, labels, masks, CSR) from host memory: the reference's host->device boundary
   // (net.cpp:186-187, 207-227), exposed so that an end-to-end step can include it.
   void refresh_inputs_from_host(const float* feats_h_pinned);
+  // Start copying the NEXT step's feature matrix (the bulk of the inputs) into a second device buffer on a copy stream, behind
+  // everything already enqueued on the compute stream; the following refresh_inputs_from_host() swaps it in instead of
+  // copying in line, so the transfer overlaps the current step's kernels.
+  void prefetch_features_from_host(const float* feats_h_pinned);
   int num_conv_layers() const { return num_layers; }
   gconv_layer& conv_layer(int l) { return layer_gconv[l]; }
   dense_layer* dense() { return layer_dense; }
@@ -62,6 +66,13 @@ class Model {
   std::vector<label_t> labels;
   std::vector<mask_t> masks_train, masks_test, masks_val;
   float* d_input_features = nullptr;
+  float* d_feat_buf[2] = {nullptr, nullptr};  // double-buffered input features (prefetch_features_from_host)
+  int feat_cur = 0;
+  bool prefetch_pending = false;
+  void* copy_stream = nullptr;
+  void *ev_ready = nullptr, *ev_free = nullptr;
+  void* pinned_inputs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void stage_pinned(const float* feats_h);
   label_t* d_labels = nullptr;
   mask_t *d_masks_train = nullptr, *d_masks_test = nullptr, *d_masks_val = nullptr;
 

@@ -34,6 +34,7 @@ def hostlib():
         L.gai_model_evaluate.argtypes = [C.c_void_p, C.c_char_p]
         L.gai_model_evaluate.restype = C.c_float
         L.gai_model_refresh_inputs.argtypes = [C.c_void_p, C.c_void_p]
+        L.gai_model_prefetch_features.argtypes = [C.c_void_p, C.c_void_p]
         L.gai_model_tensor_size.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.gai_model_tensor_size.restype = C.c_int64
         L.gai_model_get.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]
@@ -109,6 +110,10 @@ class GnnModel:
 
     def refresh_inputs(self, feats_host_ptr=None):
         self.L.gai_model_refresh_inputs(self.h, feats_host_ptr)
+
+    def prefetch_inputs(self, feats_host_ptr=None):
+        """Start the next step's host->device feature copy on a copy stream (swapped in by the next refresh_inputs())."""
+        self.L.gai_model_prefetch_features(self.h, feats_host_ptr)
 
     def get(self, name, layer=0):
         n = self.L.gai_model_tensor_size(self.h, name.encode(), layer)

@@ -52,6 +52,11 @@ int gai_memcpy_d2d(void* dst, const void* src, size_t bytes, gai_stream_t stream
 /* Pitched copy in either direction (host or device pointers, cudaMemcpyDefault): `rows` rows of width_bytes. */
 int gai_memcpy2d(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, gai_stream_t stream);
 int gai_stream_sync(gai_stream_t stream);
+/* A second stream + cross-stream ordering, for callers that overlap the next step's host->device input copy with the current
+ * step's kernels (the reference copies synchronously on the legacy default stream, net.cpp:207-227). */
+int gai_stream_create(gai_stream_t* stream);
+int gai_stream_destroy(gai_stream_t stream);
+int gai_stream_wait_event(gai_stream_t stream, void* ev);
 int gai_host_alloc_pinned(void** p_h, size_t bytes);
 int gai_host_free_pinned(void* p_h);
 

@@ -6,7 +6,7 @@ OURS='regex:spmm_|gemm_|sgemm_|wgrad_|pad_|prep_b|splitk|adam_k|relu_k|softmax_c
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
-# second epoch's hot kernels (skip the first epoch's 17 matching launches), all sections
-ncu --set full --clock-control none --import-source on -k 'regex:spmm_rows|spmm_hub|gemm_tc' -s 17 -c 17 -f -o gpurun_out/${TAG}_hot \
+# second epoch's hot kernels (skip the first epoch: 14 matching launches per SAGE epoch), all sections
+ncu --set full --clock-control none --import-source on -k 'regex:spmm_rows|spmm_hub|gemm_tc' -s ${HOT_SKIP:-14} -c ${HOT_COUNT:-14} -f -o gpurun_out/${TAG}_hot \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_hot.log 2>&1
 ls -la gpurun_out/
