@@ -105,11 +105,134 @@ __device__ __forceinline__ float edge_weight_t(const SpmmArgs& a, float wrow, ui
   return __ldg(a.vals + __ldg(a.perm + idx));
 }
 
+// ---- hub rows inside the persistent light-row kernel --------------------------------------------------------------------
+// A hub item = (hub row, column block of <= 8 float4 chunks). A whole 256-thread CTA of the persistent kernel takes one item at a
+// time before it turns to the light-row claims: warp 0 adds in edge order (one lane per chunk), warps 1..7 gather + scale stages
+// of 32 edges into a 7-slot shared-memory ring (mbarrier full/empty pairs), four edges per gather instruction so that every lane
+// carries a 128-bit load. The longest rows come first in the item list, so their sequential add chains start at t = 0 and run
+// underneath the rest of the kernel; no second kernel, stream or event is involved and no SM is ever reserved for hub rows.
+constexpr int HI_PW = 7;    // producer warps
+constexpr int HI_ES = 32;   // edges per stage
+constexpr int HI_CL = 8;    // chunk lanes per gather instruction
+constexpr int HI_UB = 4;    // gathers in flight per lane (64-register budget of the persistent kernel)
+struct HubShared {
+  float4 ring[HI_PW][HI_ES * HI_CL];
+  uint64_t full_bar[HI_PW], empty_bar[HI_PW];
+  uint32_t round0[HI_PW];  // uses of each slot by the items this CTA has already processed (mbarrier phase bookkeeping)
+  unsigned long long item;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+
+template <int MODE>
+__device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh) {
+  const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const size_t ld4 = (size_t)a.ld_in >> 2;
+  if (warp > 0) {
+    // ---------------- producers ----------------
+    const int pw = warp - 1;
+    const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
+    float4* slot = sh.ring[pw];
+    const uint32_t round0 = sh.round0[pw];
+    uint32_t c = 0; float w = 0.0f;
+    {
+      const uint32_t idx = s + (uint32_t)pw * HI_ES + lane;
+      if (idx < e) { c = __ldg(a.colidx + idx); w = edge_weight_t<MODE>(a, wrow, idx, c); }
+    }
+    constexpr int EL = 32 / HI_CL;
+    const int cl = lane % HI_CL, el = lane / HI_CL;
+    const bool chv = cl < nch;
+    for (uint32_t k = pw, r = 0; k < nstages; k += HI_PW, r++) {
+      const uint32_t base = s + k * HI_ES;
+      const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
+      const uint32_t cur_c = c; const float cur_w = w;
+      c = 0; w = 0.0f;
+      {
+        const uint64_t nidx = (uint64_t)base + (uint64_t)HI_PW * HI_ES + lane;
+        if (nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight_t<MODE>(a, wrow, (uint32_t)nidx, c); }
+      }
+      mbar_wait(&sh.empty_bar[pw], ((round0 + r) & 1) ^ 1);
+#pragma unroll
+      for (int j0 = 0; j0 < HI_ES; j0 += HI_UB * EL) {
+        float4 x[HI_UB]; float ww[HI_UB];
+#pragma unroll
+        for (int u = 0; u < HI_UB; u++) {
+          const int j = j0 + u * EL + el;
+          const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
+          ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
+          if (chv && j < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + cl);
+        }
+#pragma unroll
+        for (int u = 0; u < HI_UB; u++) {
+          const int j = j0 + u * EL + el;
+          if (chv && j < cnt) {
+            float4 p;
+            p.x = __fmul_rn(ww[u], x[u].x); p.y = __fmul_rn(ww[u], x[u].y); p.z = __fmul_rn(ww[u], x[u].z); p.w = __fmul_rn(ww[u], x[u].w);
+            slot[j * HI_CL + cl] = p;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.full_bar[pw]);
+    }
+  } else {
+    // ---------------- consumer: in-order add, one float4 chunk per lane ----------------
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < nstages; k++) {
+      const int pw = k % HI_PW;
+      const uint32_t r = k / HI_PW;
+      const uint32_t base = s + k * HI_ES;
+      const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
+      mbar_wait(&sh.full_bar[pw], (sh.round0[pw] + r) & 1);
+      if (lane < nch) {
+        const float4* tile = sh.ring[pw] + lane;
+        if (cnt == HI_ES) {
+          constexpr int SB = 8;
+          float4 p[2][SB];
+#pragma unroll
+          for (int j = 0; j < SB; j++) p[0][j] = tile[j * HI_CL];
+#pragma unroll
+          for (int b = 0; b < HI_ES / SB; b++) {
+            if (b + 1 < HI_ES / SB) {
+#pragma unroll
+              for (int j = 0; j < SB; j++) p[(b + 1) & 1][j] = tile[((b + 1) * SB + j) * HI_CL];
+            }
+#pragma unroll
+            for (int j = 0; j < SB; j++) acc_add(acc, p[b & 1][j]);
+          }
+        } else {
+          for (int j = 0; j < cnt; j++) acc_add(acc, tile[j * HI_CL]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.empty_bar[pw]);
+    }
+    if (lane < nch) store_chunk(a, row, cb + lane, acc);
+  }
+}
+
 constexpr int SLOTS = 32;  // work-list entries per claim
 
 template <int MODE, int G, int K>
 __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, const uint32_t* __restrict__ order, const uint32_t* __restrict__ claim_ptr,
-                                                         unsigned long long n_claims, unsigned long long* __restrict__ counter) {
+                                                         unsigned long long n_claims, unsigned long long* __restrict__ counter,
+                                                         const uint32_t* __restrict__ hub_rows, unsigned long long n_hub_items, int hub_nsplit) {
   constexpr int RPW = 32 / G;                                  // rows in flight per warp
   constexpr int UMAX = (K == 1) ? 8 : (K == 2 ? 4 : 2);
   constexpr int U = G < UMAX ? G : UMAX;                       // independent neighbour rows in flight per lane
@@ -124,6 +247,33 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
   bool act[K];
 #pragma unroll
   for (int k = 0; k < K; k++) { act[k] = (gl + G * k) < a.nchunks; chunk[k] = act[k] ? gl + G * k : 0; }
+
+  // ---- hub items first (counter[1]), CTA-wide ----
+  if (n_hub_items != 0) {
+    __shared__ HubShared hub_sh;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < HI_PW; i++) { mbar_init(&hub_sh.full_bar[i], 1); mbar_init(&hub_sh.empty_bar[i], 1); hub_sh.round0[i] = 0; }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (;;) {
+      __syncthreads();  // previous item fully drained (ring, round0) / barriers initialised
+      if (threadIdx.x == 0) hub_sh.item = atomicAdd(counter + 1, 1ull);
+      __syncthreads();
+      const unsigned long long item = hub_sh.item;
+      if (item >= n_hub_items) break;  // uniform
+      const uint32_t hrow = __ldg(hub_rows + item / (unsigned)hub_nsplit);
+      const int cb = (int)(item % (unsigned)hub_nsplit) * a.hub_per;
+      const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
+      if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
+      const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
+      hub_item_cta<MODE>(a, hrow, hs, he, cb, nch, hub_sh);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
+        for (int i = 0; i < HI_PW; i++) hub_sh.round0[i] += (nst + HI_PW - 1 - i) / HI_PW;
+      }
+    }
+  }
 
   for (;;) {
     unsigned long long claim = 0;
@@ -250,21 +400,6 @@ constexpr int HUB_MAX_CHUNKS = 128;  // column block = 512 floats
 #endif
 constexpr int HUB_MIN_CTAS = GAI_HUB_MIN_CTAS;
 constexpr size_t HUB_RING_CAP = (HUB_MIN_CTAS == 1 ? 200 : 100) * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
 
 // ES = edges per stage (32, 16, 8 or 4). Dynamic smem: HUB_PROD_WARPS * ES * min(hub_per,128) float4.
 // CL = lanes along the column-chunk dimension of one gather instruction (the other 32/CL lanes cover consecutive edges):
@@ -424,33 +559,46 @@ ListSel select_list(const SpmmArgs& a, const gai_csr* g) {
   return {nullptr, nullptr, g->hub_rows, g->n_hub, (n_rows + SLOTS - 1) / SLOTS, false};
 }
 
+// widths whose hub rows are handled inside the persistent kernel (column blocks of <= 8 chunks, up to 16 blocks)
+inline bool hub_fused(const SpmmArgs& a) { return a.nchunks <= 128; }
+
 template <int MODE>
-int launch_rows_mode(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
+int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   // listed calls walk a degree-ordered list (hub rows sit at its head and are skipped by offset); other row-range calls walk
   // the range in natural order
   const ListSel sel = select_list(a, g);
   const uint32_t* order = sel.order;
   const unsigned long long claims = sel.n_claims;
-  if (claims == 0) return GAI_OK;
+  unsigned long long hub_items = 0;
+  int nsplit = 1;
+  if (sel.n_hub != 0 && hub_fused(a)) {
+    nsplit = (a.nchunks + 7) / 8;
+    a.hub_per = (a.nchunks + nsplit - 1) / nsplit;
+    hub_items = (unsigned long long)sel.n_hub * (unsigned)nsplit;
+  }
+  if (claims == 0 && hub_items == 0) return GAI_OK;
   const uint32_t* claim_ptr = sel.claim_ptr;
   int G = 4;
   while (G < 32 && G < a.nchunks) G <<= 1;
   int K = 1;
   if (G == 32) { K = (a.nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
   unsigned long long ctas = (claims + 7) / 8;
+  if (ctas < hub_items) ctas = hub_items;
   const unsigned long long persistent = (unsigned long long)gai::sm_count() * 4;
   if (ctas > persistent) ctas = persistent;
   const unsigned grid = (unsigned)ctas;
-  // rotating work counters: launches on one stream are ordered; the rotation keeps up to 16 launches that overlap on
-  // different streams (interior / boundary rows of the 1D partition) from sharing a counter
-  unsigned long long* ctr = g->row_counters + (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 16u);
-  GAI_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
-  if (G == 4) spmm_rows_kernel<MODE, 4, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
-  else if (G == 8) spmm_rows_kernel<MODE, 8, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
-  else if (G == 16) spmm_rows_kernel<MODE, 16, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
-  else if (K == 1) spmm_rows_kernel<MODE, 32, 1><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
-  else if (K == 2) spmm_rows_kernel<MODE, 32, 2><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
-  else spmm_rows_kernel<MODE, 32, 4><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr);
+  // rotating work-counter pairs {light-row claims, hub items}: launches on one stream are ordered; the rotation keeps up to 8
+  // launches that overlap on different streams (interior / boundary rows of the 1D partition) from sharing a pair
+  unsigned long long* ctr = g->row_counters + 2 * (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 8u);
+  GAI_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
+#define GAI_ROWS_LAUNCH(GG, KK) spmm_rows_kernel<MODE, GG, KK><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit)
+  if (G == 4) GAI_ROWS_LAUNCH(4, 1);
+  else if (G == 8) GAI_ROWS_LAUNCH(8, 1);
+  else if (G == 16) GAI_ROWS_LAUNCH(16, 1);
+  else if (K == 1) GAI_ROWS_LAUNCH(32, 1);
+  else if (K == 2) GAI_ROWS_LAUNCH(32, 2);
+  else GAI_ROWS_LAUNCH(32, 4);
+#undef GAI_ROWS_LAUNCH
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -480,12 +628,7 @@ int launch_hub_es(const SpmmArgs& a, const gai_csr* g, size_t smem, unsigned nsp
 
 template <int MODE>
 int launch_hub_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
-  // widths up to 512 floats: column blocks of <= 8 chunks (one 128-byte line per neighbour row), one CTA each
-  if (a.nchunks <= 128) {
-    const unsigned nsplit = (unsigned)((a.nchunks + 7) / 8);
-    a.hub_per = (int)((a.nchunks + nsplit - 1) / nsplit);
-    return launch_hub_es<MODE, 32, 8>(a, g, (size_t)HUB_PROD_WARPS * 32 * a.hub_per * sizeof(float4), nsplit, st);
-  }
+  // only widths beyond 512 floats come here (narrower rows are hub items of the persistent kernel)
   a.hub_per = a.nchunks;
   const int nch = a.nchunks < HUB_MAX_CHUNKS ? a.nchunks : HUB_MAX_CHUNKS;
   // largest stage size in {32, 16, 8, 4} edges whose 16-slot ring fits 200 KB of shared memory (longer stages amortise the
@@ -549,7 +692,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   // Hub rows go first, on a high-priority side stream (fork/join with events): their CTAs are the long poles (one
   // 94 K-edge row is ~0.3 ms of in-order adds), the persistent light-row warps on `st` fill the other SMs meanwhile.
   int rc = GAI_OK;
-  const bool has_hub = select_list(a, g).n_hub != 0;
+  const bool has_hub = select_list(a, g).n_hub != 0 && !hub_fused(a);
   if (has_hub) {
     if (!g->aux_stream) {
       int lo = 0, hi = 0;
