@@ -191,6 +191,15 @@ METRIC = "GraphSAGE full-graph training throughput (CSR edges trained per second
 UNIT = "Medges/s"
 
 
+def measured_traffic(op):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel(s) behind `op`, from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py from profiles/r1_hot_kernels.csv); None if that op was not captured."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(op)
+    except (OSError, ValueError):
+        return None
+
+
 def roofline_from_profile(prof, peaks, n_epochs):
     """Dominant op class by device time; achieved = algorithmic bytes (or flops) / event time for its heaviest shape."""
     by_bucket = {}
@@ -202,8 +211,11 @@ def roofline_from_profile(prof, peaks, n_epochs):
     top = rows[0]
     ms = top["ms"] / top["calls"]
     gbs = top["bytes"] / top["calls"] / (ms * 1e-3) / 1e9
-    out = {"kernel": f"{dom} {top['shape']}", "share_of_step": by_bucket[dom] / total, "launch_ms": ms, "traffic": None,
+    out = {"kernel": f"{dom} {top['shape']}", "share_of_step": by_bucket[dom] / total, "launch_ms": ms, "traffic": measured_traffic(f"{dom} {top['shape']}"),
            "peak_source": peaks["source"]}
+    if dom in ("AGGR", "ATTN_FWD", "ATTN_BWD"):
+        out["model"] = ("algorithmic bytes = gather model of SURVEY.md 8d (every neighbour row counted once per edge); L2 hits make it an upper bound on "
+                        "DRAM traffic, so achieved can exceed the HBM peak; `traffic` = dram__bytes_read+write per launch from the committed ncu capture")
     tfl = top["flops"] / top["calls"] / (ms * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops"] / 2.0
     if dom == "LINEAR" and tfl / tf32_peak > gbs / peaks["hbm_gbs"]:

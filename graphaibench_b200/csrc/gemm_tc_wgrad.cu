@@ -16,6 +16,7 @@
 //       shared A, two B   [dWn | dWs] = H^T · [dY | dZ]   the B parts sit side by side in the N dimension (own TMA maps)
 //     (SAGE keeps W_neigh and W_self apart, sage_layer.cpp:37-47; the reference runs two sgemm calls.)
 // HBM-bound by design: bytes = 4·n·(Kx + My), tensor work = 3 · 2·n·128·ceil(Kx/128)·My.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace gai {
@@ -30,6 +31,7 @@ constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 
 constexpr int WG_SPLIT_WARPS = 8;
 
 struct WgArgs {
+  int debug;  // GAI_TC_DEBUG (timing experiments only): 4 = no hi/lo split, 8 = no MMA issue
   float* partial;  // [grid][Kx_total][My_total], parts concatenated
   size_t nrows;
   size_t blocks_per_cta;  // k-blocks per CTA
@@ -112,7 +114,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
         const uint32_t b_hi = a_hi + 2 * g.a_bytes;
         const uint32_t b_lo = b_hi + g.b_bytes;
 #pragma unroll
-        for (int kg = 0; kg < WG_BK / 8; kg++) {
+        for (int kg = 0; kg < ((g.debug & 8) ? 0 : WG_BK / 8); kg++) {
           const uint32_t koff = kg * 1024;  // 8 rows x 128 B
           for (int t = 0; t < g.mt; t++) {
             const uint32_t toff = (uint32_t)t * 4u * WG_BOX + koff;
@@ -150,7 +152,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
     for (uint32_t it = 0; it < nkb; it++) {
       const int s = it % g.stages;
       mbar_wait(&full_bar[s], (it / g.stages) & 1);
-      if (g.passes == 3) {
+      if (g.passes == 3 && !(g.debug & 4)) {
         uint4* ahi = reinterpret_cast<uint4*>(smem + (size_t)s * g.stage_bytes);
         uint4* bhi = ahi + 2 * a_u4;
         const uint32_t a_live0 = (uint32_t)g.nbox_at[0] * BOX_U4;
@@ -245,6 +247,8 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   WgArgs g;
   memset(&g, 0, sizeof(g));
   g.nrows = nrows; g.passes = passes;
+  static const int debug_knobs = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+  g.debug = debug_knobs;
   g.dual_a = na == 2;
   if (na == 2) {
     g.mt = 2;

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 N = 2_449_029
 
 
-def run(knob, n):
+def run(knob, n, only=""):
     import torch
     from graphaibench_b200 import ops
     dev = "cuda:0"
@@ -41,7 +41,9 @@ def run(knob, n):
         "wgrad two_b 256 x 47,47": (lambda: ops.wgrad_two_b(h256, g48a, g48b), 4.0 * n * (256 + 94)),
     }
     for name, (fn, nbytes) in cases.items():
-        if knob and name.startswith("wgrad"):
+        if name.startswith("wgrad") and (knob & 3):
+            continue
+        if only and not name.startswith(only):
             continue
         for _ in range(3):
             fn()
@@ -61,10 +63,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--knob", type=int, default=None)
     ap.add_argument("--rows", type=int, default=N)
+    ap.add_argument("--only", default="", help="case-name prefix filter")
     a = ap.parse_args()
     if a.knob is not None:
-        run(a.knob, a.rows)
+        run(a.knob, a.rows, a.only)
     else:
         for k in [int(v) for v in os.environ.get("GAI_PROBE_KNOBS", "0,1,2,4,8,3,7,15").split(",")]:
             env = dict(os.environ, GAI_TC_DEBUG=str(k))
-            subprocess.run([sys.executable, os.path.abspath(__file__), "--knob", str(k), "--rows", str(a.rows)], env=env, check=False)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--knob", str(k), "--rows", str(a.rows), "--only", a.only], env=env, check=False)
