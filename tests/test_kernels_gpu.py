@@ -215,7 +215,7 @@ def test_gat_forward_backward_vs_reference_golden(T, ops, golden, small_graph):
     assert np.array_equal(z2.cpu().numpy(), dz.cpu().numpy())
 
 
-@pytest.mark.parametrize("F", [64, 256])
+@pytest.mark.parametrize("F", [64, 256, 512])
 def test_gat_wide_vs_oracle(T, ops, liborc, small_graph, F):
     from oracle import model as om
     g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.add_selfloop()
