@@ -66,9 +66,11 @@ _SIGS = {
     "gai_matmul_ld": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t,
                                 C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "gai_matmul_kcat": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t,
-                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, C.c_int, c_f32p, C.c_size_t, c_stream]),
+                                  c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, c_stream]),
+    "gai_matmul_relu_bits": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int,
+                                       C.c_void_p, C.c_size_t, c_stream]),
     "gai_matmul_mask": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int,
-                                  c_f32p, C.c_size_t, C.c_int, c_stream]),
+                                  C.c_void_p, C.c_size_t, C.c_int, c_stream]),
     "gai_matmul_ncat": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,
                                   c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_int, c_stream]),
     "gai_wgrad_two_a": (C.c_int, [C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_size_t,

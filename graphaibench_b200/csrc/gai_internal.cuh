@@ -55,8 +55,10 @@ struct GemmCat {
   float* C[2] = {nullptr, nullptr};
   size_t ldc[2] = {0, 0};
   int accum = 0, flags = 0;
-  const float* mask = nullptr;  // GAI_EPI_MASK: C = mask > 0 ? C : 0 (nn == 1)
+  const float* mask = nullptr;  // GAI_EPI_MASK: C = mask > 0 ? C : 0 (nn == 1); with GAI_EPI_BITMASK: uint32 sign-bit words, ldmask in words
   size_t ldmask = 0;
+  uint32_t* bits_out = nullptr; // with GAI_EPI_RELU: also write the sign bits of C (one word per row and 32-column chunk)
+  size_t ld_bits = 0;
 };
 // Concatenated weight gradients (gemm_tc_wgrad.cu): C_i = A_i^T · B_i over nrows rows; dual = 1: two A parts (<= 128 columns
 // each) against B_0; dual = 2: A_0 against two B parts; dual = 0: the plain product.

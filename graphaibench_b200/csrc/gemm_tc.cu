@@ -48,6 +48,10 @@ struct TcArgs {
   int noff1, nouts;
   const float* mask;
   size_t ldmask;
+  const uint32_t* mask_bits;  // GAI_EPI_BITMASK: the mask as sign bits, one word per (row, 32-column chunk)
+  size_t ld_mask_bits;
+  uint32_t* bits_out;         // ReLU epilogue also writes the sign bits of C
+  size_t ld_bits_out;
   size_t M;
   int n_mma;       // tile width rounded up to a multiple of 16 (UMMA N)
   int nkb0;        // k-blocks of the first K part
@@ -208,9 +212,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           float* cp = Cj + (row0 + rsub) * ld + cbase + csub;
           const size_t step = 4 * ld;
           float4 x[8];  // "+C" or mask operands, requested before the accumulator is read back (their latency overlaps the transpose)
+          uint32_t wb[8];  // sign-bit words of the lane's 8 rows (GAI_EPI_BITMASK)
           if (g.accum) {
 #pragma unroll
             for (int i = 0; i < 8; i++) if (on && i * 4 + rsub < nrows) x[i] = *reinterpret_cast<const float4*>(cp + i * step);
+          } else if (g.mask_bits != nullptr) {
+            const uint32_t* bp = g.mask_bits + (row0 + rsub) * g.ld_mask_bits + (cbase >> 5);
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (i * 4 + rsub < nrows) wb[i] = __ldg(bp + i * 4 * g.ld_mask_bits);
           } else if (g.mask != nullptr) {
             const float* mp = g.mask + (row0 + rsub) * g.ldmask + cbase + csub;
 #pragma unroll
@@ -232,6 +241,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 *reinterpret_cast<float4*>(cp + i * step) = v;
               }
             }
+          } else if (g.mask_bits != nullptr) {
+            const int sh = 4 * (lane & 7);  // the lane's four columns within the 32-column word
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (on && i * 4 + rsub < nrows) {
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+                const uint32_t nib = wb[i] >> sh;
+                v.x = (nib & 1u) ? v.x : 0.f; v.y = (nib & 2u) ? v.y : 0.f; v.z = (nib & 4u) ? v.z : 0.f; v.w = (nib & 8u) ? v.w : 0.f;
+                *reinterpret_cast<float4*>(cp + i * step) = v;
+              }
+            }
+          } else if (g.bits_out != nullptr) {
+            // ReLU + the sign bits of the activation, one 32-bit word per (row, 32-column chunk): the layer above masks its input
+            // gradient with 1 bit per element instead of re-reading the activation (78 MB instead of 2.5 GB on C2)
+            // each lane collects the 4-bit signs of its 8 rows (nibble i = row i*4 + rsub, its own 4 columns); an 8 x 8 nibble
+            // transpose among the 8 lanes of a row group (3 shuffles) then leaves lane l with the full 32-column word of row l*4 + rsub
+            uint32_t W = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const bool rv = i * 4 + rsub < nrows;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on && rv) v = *reinterpret_cast<const float4*>(sp + i * 4 * EPI_PITCH);
+              if (relu) { v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f; v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f; }
+              W |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << (4 * i);
+              if (on && rv) *reinterpret_cast<float4*>(cp + i * step) = v;
+            }
+#pragma unroll
+            for (int sidx = 0; sidx < 3; sidx++) {
+              const int sft = 4 >> sidx;  // 4, 2, 1
+              const uint32_t mlo = sft == 4 ? 0x0000FFFFu : (sft == 2 ? 0x00FF00FFu : 0x0F0F0F0Fu);
+              const bool hi = (lane & sft) != 0;
+              const uint32_t send = hi ? (W & mlo) : ((W & ~mlo) >> (4 * sft));
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, sft);
+              W = hi ? ((W & ~mlo) | recv) : ((W & mlo) | (recv << (4 * sft)));
+            }
+            const int rl = (lane & 7) * 4 + rsub;
+            if (rl < nrows && !(g.debug & 2)) g.bits_out[(row0 + rl) * g.ld_bits_out + (cbase >> 5)] = W;
           } else if (g.mask != nullptr) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -417,7 +463,18 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   TcArgs g;
   memset(&g, 0, sizeof(g));
   for (int j = 0; j < q.nn; j++) { g.C[j] = q.C[j]; g.ldc[j] = q.ldc[j]; g.N[j] = (int)q.N[j]; }
-  g.noff1 = noff1; g.nouts = q.nn; g.mask = (q.flags & GAI_EPI_MASK) ? q.mask : nullptr; g.ldmask = q.ldmask;
+  g.noff1 = noff1; g.nouts = q.nn; g.ldmask = q.ldmask;
+  const bool bitmask = (q.flags & GAI_EPI_MASK) && (q.flags & GAI_EPI_BITMASK);
+  g.mask = ((q.flags & GAI_EPI_MASK) && !bitmask) ? q.mask : nullptr;
+  g.mask_bits = bitmask ? reinterpret_cast<const uint32_t*>(q.mask) : nullptr; g.ld_mask_bits = q.ldmask;
+  g.bits_out = q.bits_out; g.ld_bits_out = q.ld_bits;
+  if (bitmask || q.bits_out) {
+    // sign-bit words are read / written by the 128-bit epilogue path only: one output, 16-byte aligned rows, every chunk whole
+    const bool whole = (q.N[0] % 4 == 0) || ((q.flags & GAI_EPI_PADDED) && q.ldc[0] >= (q.N[0] + 3) / 4 * 4);
+    if (q.nn != 1 || q.accum || q.ldc[0] % 4 != 0 || reinterpret_cast<uintptr_t>(q.C[0]) % 16 != 0 || !whole) return GAI_ERR_UNSUPPORTED;
+    if (q.bits_out && ((q.flags & GAI_EPI_MASK) || q.ld_bits < (q.N[0] + 31) / 32)) return GAI_ERR_UNSUPPORTED;
+    if (bitmask && q.ldmask < (q.N[0] + 31) / 32) return GAI_ERR_UNSUPPORTED;
+  }
   g.M = M; g.n_mma = n_mma; g.nkb0 = nkb[0]; g.num_kb = num_kb; g.last_steps[0] = last_steps[0]; g.last_steps[1] = last_steps[1];
   static const int debug_knobs = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
   g.debug = debug_knobs;

@@ -68,6 +68,27 @@ __global__ void d_relu_ld_kernel(size_t rows, int F, const float* __restrict__ g
   }
 }
 
+// sign bits of a row-major matrix: bits[r, c / 32] bit (c % 32) = data[r, c] > 0 (one warp per word group; fallback for shapes the
+// tensor-core epilogue does not take), and the matching mask: out = bit ? grad : 0
+__global__ void sign_bits_kernel(size_t rows, int F, const float* __restrict__ data, size_t ldd, uint32_t* __restrict__ bits, size_t ldb) {
+  const int nw = (F + 31) / 32;
+  const size_t total = rows * (size_t)nw;
+  const int lane = threadIdx.x & 31;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += ((size_t)gridDim.x * blockDim.x) >> 5) {
+    const size_t r = w / nw;
+    const int c = (int)(w % nw) * 32 + lane;
+    const unsigned b = __ballot_sync(0xffffffffu, c < F && data[r * ldd + c] > 0.f);
+    if (lane == 0) bits[r * ldb + w % nw] = b;
+  }
+}
+__global__ void d_relu_bits_kernel(size_t rows, int F, float* __restrict__ grad, size_t ldg, const uint32_t* __restrict__ bits, size_t ldb) {
+  const size_t total = rows * (size_t)F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / F, c = i % F;
+    if (!((bits[r * ldb + (c >> 5)] >> (c & 31)) & 1u)) grad[r * ldg + c] = 0.f;
+  }
+}
+
 __global__ void fill_kernel(size_t n, float value, float* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = value;
@@ -549,14 +570,27 @@ int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, cons
   return gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, transA, transB, accum, flags, st);
 }
 
+static int sign_bits(size_t rows, int F, const float* data, size_t ldd, uint32_t* bits, size_t ldb, cudaStream_t st) {
+  sign_bits_kernel<<<grid_for(rows * ((F + 31) / 32) * 32, 256), 256, 0, st>>>(rows, F, data, ldd, bits, ldb);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+static int d_relu_bits(size_t rows, int F, float* grad, size_t ldg, const uint32_t* bits, size_t ldb, cudaStream_t st) {
+  d_relu_bits_kernel<<<grid_for(rows * F, 256), 256, 0, st>>>(rows, F, grad, ldg, bits, ldb);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+
 int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t ldb1, size_t z2, const float* A2,
                     size_t lda2, const float* B2, size_t ldb2, float* C, size_t ldc, int transB, int flags, const float* mask, size_t ldmask,
-                    gai_stream_t stream) {
+                    uint32_t* relu_bits, size_t ld_bits, gai_stream_t stream) {
   if (x == 0 || y == 0) return GAI_OK;
   GAI_CHECK_ARG(A1 && B1 && A2 && B2 && C && z1 > 0 && z2 > 0);
   GAI_CHECK_ARG(lda1 >= z1 && lda2 >= z2 && ldc >= y && ldb1 >= (transB ? z1 : y) && ldb2 >= (transB ? z2 : y));
-  GAI_CHECK_ARG((flags & ~(GAI_EPI_RELU | GAI_EPI_MASK | GAI_EPI_PADDED)) == 0);
-  GAI_CHECK_ARG(!(flags & GAI_EPI_MASK) || (mask && ldmask >= y && !(flags & GAI_EPI_RELU)));
+  GAI_CHECK_ARG((flags & ~(GAI_EPI_RELU | GAI_EPI_MASK | GAI_EPI_PADDED | GAI_EPI_BITMASK)) == 0);
+  const bool bitmask = (flags & GAI_EPI_MASK) && (flags & GAI_EPI_BITMASK);
+  GAI_CHECK_ARG(!(flags & GAI_EPI_MASK) || (mask && ldmask >= (bitmask ? (y + 31) / 32 : y) && !(flags & GAI_EPI_RELU)));
+  GAI_CHECK_ARG(!relu_bits || ((flags & GAI_EPI_RELU) && ld_bits >= (y + 31) / 32));
   cudaStream_t st = gai::S(stream);
   const int mode = gai::g_gemm_mode;
   if (mode != 1) {
@@ -564,27 +598,28 @@ int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1,
     q.M = x; q.nk = 2; q.tb = transB;
     q.A[0] = A1; q.lda[0] = lda1; q.K[0] = z1; q.B[0][0] = B1; q.ldb[0][0] = ldb1;
     q.A[1] = A2; q.lda[1] = lda2; q.K[1] = z2; q.B[1][0] = B2; q.ldb[1][0] = ldb2;
-    q.N[0] = y; q.C[0] = C; q.ldc[0] = ldc; q.flags = flags; q.mask = mask; q.ldmask = ldmask;
+    q.N[0] = y; q.C[0] = C; q.ldc[0] = ldc; q.flags = flags; q.mask = mask; q.ldmask = ldmask; q.bits_out = relu_bits; q.ld_bits = ld_bits;
     int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
     if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
   }
-  // shapes the tensor-core kernel declines (few rows, wide outputs): the same sum as two SIMT products + the mask pass
+  // shapes the tensor-core kernel declines (few rows, wide outputs): the same sum as two SIMT products + the mask / sign-bit pass
   const int relu = (flags & GAI_EPI_MASK) ? 0 : (flags & GAI_EPI_RELU);
   int rc = gai::gemm_simt(x, y, z1, A1, lda1, B1, ldb1, C, ldc, 0, transB, 0, 0, st);
   if (rc != GAI_OK) return rc;
   rc = gai::gemm_simt(x, y, z2, A2, lda2, B2, ldb2, C, ldc, 0, transB, 1, relu, st);
   if (rc != GAI_OK) return rc;
-  if (flags & GAI_EPI_MASK) {
-    rc = gai_d_relu_ld(x, (int)y, C, ldc, mask, ldmask, C, ldc, stream);
-    if (rc != GAI_OK) return rc;
-  }
+  if (bitmask) return d_relu_bits(x, (int)y, C, ldc, reinterpret_cast<const uint32_t*>(mask), ldmask, st);
+  if (flags & GAI_EPI_MASK) return gai_d_relu_ld(x, (int)y, C, ldc, mask, ldmask, C, ldc, stream);
+  if (relu_bits) return sign_bits(x, (int)y, C, ldc, relu_bits, ld_bits, st);
   return GAI_OK;
 }
 
 int gai_matmul_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int transB,
                     const float* mask, size_t ldmask, int flags, gai_stream_t stream) {
   if (x == 0 || y == 0) return GAI_OK;
-  GAI_CHECK_ARG(A && B && C && mask && z > 0 && lda >= z && ldc >= y && ldmask >= y && ldb >= (transB ? z : y) && (flags & ~GAI_EPI_PADDED) == 0);
+  const bool bitmask = (flags & GAI_EPI_BITMASK) != 0;
+  GAI_CHECK_ARG(A && B && C && mask && z > 0 && lda >= z && ldc >= y && ldmask >= (bitmask ? (y + 31) / 32 : y) && ldb >= (transB ? z : y) &&
+                (flags & ~(GAI_EPI_PADDED | GAI_EPI_BITMASK)) == 0);
   cudaStream_t st = gai::S(stream);
   const int mode = gai::g_gemm_mode;
   if (mode != 1) {
@@ -597,7 +632,28 @@ int gai_matmul_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, co
   }
   int rc = gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, 0, transB, 0, 0, st);
   if (rc != GAI_OK) return rc;
+  if (bitmask) return d_relu_bits(x, (int)y, C, ldc, reinterpret_cast<const uint32_t*>(mask), ldmask, st);
   return gai_d_relu_ld(x, (int)y, C, ldc, mask, ldmask, C, ldc, stream);
+}
+
+// C = ReLU(A·B) and the sign bits of C in one pass (aggregate-first GCN forward, gcn_layer.cpp:20-24 + the mask the layer above needs)
+int gai_matmul_relu_bits(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int flags,
+                         uint32_t* relu_bits, size_t ld_bits, gai_stream_t stream) {
+  if (x == 0 || y == 0) return GAI_OK;
+  GAI_CHECK_ARG(A && B && C && relu_bits && z > 0 && lda >= z && ldc >= y && ldb >= y && ld_bits >= (y + 31) / 32 && (flags & ~GAI_EPI_PADDED) == 0);
+  cudaStream_t st = gai::S(stream);
+  const int mode = gai::g_gemm_mode;
+  if (mode != 1) {
+    gai::GemmCat q;
+    q.M = x;
+    q.A[0] = A; q.lda[0] = lda; q.K[0] = z; q.B[0][0] = B; q.ldb[0][0] = ldb;
+    q.N[0] = y; q.C[0] = C; q.ldc[0] = ldc; q.flags = GAI_EPI_RELU | flags; q.bits_out = relu_bits; q.ld_bits = ld_bits;
+    int rc = gai::gemm_tc_cat(q, mode == 3 ? 1 : 3, st);
+    if (rc != GAI_ERR_UNSUPPORTED || mode >= 2) return rc;
+  }
+  int rc = gai::gemm_simt(x, y, z, A, lda, B, ldb, C, ldc, 0, 0, 0, GAI_EPI_RELU, st);
+  if (rc != GAI_OK) return rc;
+  return sign_bits(x, (int)y, C, ldc, relu_bits, ld_bits, st);
 }
 
 int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,

@@ -369,7 +369,7 @@ class DistGnn:
             return torch.zeros(max(rows, 1), _ceil4(width), dtype=torch.float32, device=dev)
 
         self.W, self.Ws, self.dW, self.dWs = [], [], [], []
-        self.feat_in, self.grad_in, self.T, self.A, self.Tm, self.D = [], [], [], [], [], []
+        self.feat_in, self.grad_in, self.T, self.A, self.Tm, self.D, self.bits = [], [], [], [], [], [], []
         # every weight gradient is a view of one flat buffer: ONE all-reduce per step instead of one per matrix
         n_w = sum(dims[l] * dims[l + 1] for l in range(self.L)) * (2 if arch == "sage" else 1)
         self.dW_flat = torch.zeros(n_w, dtype=torch.float32, device=dev)
@@ -396,6 +396,9 @@ class DistGnn:
             self.A.append(buf(n, din) if not tf else None)         # Â·X (aggregate first), kept for dW
             self.Tm.append(buf(m, din) if (not tf and l > 0) else None)  # G·Wᵀ before the transposed aggregation
             self.D.append(buf(n, dout) if tf else None)            # Âᵀ·G
+            # sign bits of the activation (aggregate-first layers apply ReLU in a transform epilogue that also emits them): the layer
+            # above masks its input gradient with 1 bit per element instead of re-reading the activation
+            self.bits.append(torch.zeros(max(n, 1), (dout + 31) // 32, dtype=torch.int32, device=dev) if (not tf and l < self.L - 1) else None)
         ncls = dims[-1]
         self.logits = buf(n, ncls)[:, :ncls]     # rows padded to 4 floats like every tall buffer; the loss kernels take the pitch
         self.probs = buf(n, ncls)[:, :ncls]
@@ -468,13 +471,18 @@ class DistGnn:
             self._exchange(B)
             self._spmm(B, F, out, transposed, flags, addend, (0, p.n_loc))
 
-    def _mm(self, A, B, out, transA=False, transB=False, accum=False, flags=0, mask=None):
+    def _mm(self, A, B, out, transA=False, transB=False, accum=False, flags=0, mask=None, mask_bits=None, relu_bits=None):
         x, z = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
         y = out.shape[1]
-        with self._scope("LINEAR", f"{x}x{y}x{z}" + (" TA" if transA else "") + (" TB" if transB else "") + (" mask" if mask is not None else ""),
+        tag = " bitmask" if mask_bits is not None else (" mask" if mask is not None else (" relu+bits" if relu_bits is not None else ""))
+        with self._scope("LINEAR", f"{x}x{y}x{z}" + (" TA" if transA else "") + (" TB" if transB else "") + tag,
                          4.0 * (x * z + z * y + x * y * (2 if accum or mask is not None else 1)), 2.0 * x * y * z):
-            if mask is not None:
+            if mask_bits is not None:
+                self.ops.matmul_mask(A, B, mask_bits, out=out, transB=transB, flags=self._pad(out) | self.ops.EPI_BITMASK)
+            elif mask is not None:
                 self.ops.matmul_mask(A, B, mask, out=out, transB=transB, flags=self._pad(out))
+            elif relu_bits is not None:
+                self.ops.matmul_relu_bits(A, B, relu_bits, out=out, flags=self._pad(out))
             else:
                 self.ops.matmul(A, B, out=out, transA=transA, transB=transB, accum=accum, flags=flags | (0 if transA else self._pad(out)))
 
@@ -482,12 +490,18 @@ class DistGnn:
         # every tall buffer of this class has rows padded to 4 floats (buf()): the transforms may use 128-bit stores throughout
         return self.ops.EPI_PADDED if out.stride(0) % 4 == 0 and out.stride(0) >= _ceil4(out.shape[1]) else 0
 
-    def _mm_kcat(self, A1, B1, A2, B2, out, transB=False, flags=0, mask=None):
+    def _mm_kcat(self, A1, B1, A2, B2, out, transB=False, flags=0, mask=None, mask_bits=None, relu_bits=None):
         x, z1, z2, y = A1.shape[0], A1.shape[1], A2.shape[1], out.shape[1]
-        with self._scope("LINEAR", f"{x}x{y}x{z1}+{z2}" + (" TB" if transB else "") + " kcat" + (" mask" if mask is not None else ""),
+        tag = " bitmask" if mask_bits is not None else (" mask" if mask is not None else "")
+        with self._scope("LINEAR", f"{x}x{y}x{z1}+{z2}" + (" TB" if transB else "") + " kcat" + tag,
                          4.0 * (x * (z1 + z2) + (z1 + z2) * y + x * y * (2 if mask is not None else 1)), 2.0 * x * y * (z1 + z2)):
-            self.ops.matmul_kcat(A1, B1, A2, B2, out=out, transB=transB, flags=flags | self._pad(out) | (self.ops.EPI_MASK if mask is not None else 0),
-                                 mask=mask)
+            f = flags | self._pad(out)
+            if mask_bits is not None:
+                f |= self.ops.EPI_MASK | self.ops.EPI_BITMASK
+            elif mask is not None:
+                f |= self.ops.EPI_MASK
+            self.ops.matmul_kcat(A1, B1, A2, B2, out=out, transB=transB, flags=f, mask=mask_bits if mask_bits is not None else mask,
+                                 relu_bits=relu_bits)
 
     def _out_buffer(self, l):
         return self.logits if l == self.L - 1 else self.feat_in[l + 1]
@@ -521,8 +535,11 @@ class DistGnn:
             A = self.A[l]
             static = l == 0 and self.static_input_halo
             self._aggregate(X, din, A[:n], exchange=not static)
+            bits = self.bits[l][:n] if self.bits[l] is not None else None
             if self.arch == "sage":
-                self._mm_kcat(A[:n, :din], self.W[l], X[:n, :din], self.Ws[l], out, flags=relu)
+                self._mm_kcat(A[:n, :din], self.W[l], X[:n, :din], self.Ws[l], out, flags=relu, relu_bits=bits)
+            elif bits is not None:
+                self._mm(A[:n, :din], self.W[l], out, relu_bits=bits)
             else:
                 self._mm(A[:n, :din], self.W[l], out, flags=relu)
 
@@ -548,10 +565,13 @@ class DistGnn:
                 self._mm(X[:n, :din], D[:n, :dout], self.dW[l], transA=True)
             if l > 0:
                 mask = X[:n, :din] if self._premasked(l - 1) else None   # X = output of layer l-1 (post-ReLU)
+                mbits = self.bits[l - 1][:n] if (mask is not None and self.bits[l - 1] is not None) else None
+                if mbits is not None:
+                    mask = None
                 if sage:
-                    self._mm_kcat(D[:n, :dout], self.W[l], G[:n, :dout], self.Ws[l], gout, transB=True, mask=mask)
+                    self._mm_kcat(D[:n, :dout], self.W[l], G[:n, :dout], self.Ws[l], gout, transB=True, mask=mask, mask_bits=mbits)
                 else:
-                    self._mm(D[:n, :dout], self.W[l], gout, transB=True, mask=mask)
+                    self._mm(D[:n, :dout], self.W[l], gout, transB=True, mask=mask, mask_bits=mbits)
         else:
             A = self.A[l]
             if sage:

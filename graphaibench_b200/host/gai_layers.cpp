@@ -54,20 +54,35 @@ static void mm(size_t x, size_t y, size_t z, const float* A, size_t lda, const f
 }
 // C = A1·op(B1) + A2·op(B2) in one pass; mask != NULL folds the d_relu of the layer below into the epilogue
 static void mm_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t z2, const float* A2, size_t lda2,
-                    const float* B2, float* C, size_t ldc, bool tb, int flags, const float* mask, size_t ldmask) {
-  gai_host::OpScope sc("LINEAR", shape(x, y, z1) + "+" + std::to_string(z2) + (tb ? " TB" : "") + " kcat" + (mask ? " mask" : ""),
-                       4.0 * ((double)x * (z1 + z2) + (double)(z1 + z2) * y + (double)x * y * (mask ? 2 : 1)), 2.0 * (double)x * y * (z1 + z2));
-  const size_t ldb1 = tb ? z1 : y, ldb2 = tb ? z2 : y;
+                    const float* B2, float* C, size_t ldc, bool tb, int flags, const float* mask, size_t ldmask, const uint32_t* mask_bits = nullptr,
+                    uint32_t* relu_bits = nullptr) {
+  const bool masked = mask || mask_bits;
+  gai_host::OpScope sc("LINEAR", shape(x, y, z1) + "+" + std::to_string(z2) + (tb ? " TB" : "") + " kcat" + (mask_bits ? " bitmask" : (mask ? " mask" : "")),
+                       4.0 * ((double)x * (z1 + z2) + (double)(z1 + z2) * y + (double)x * y * (mask ? 2 : 1)) + (mask_bits || relu_bits ? (double)x * y / 8 : 0),
+                       2.0 * (double)x * y * (z1 + z2));
+  const size_t ldb1 = tb ? z1 : y, ldb2 = tb ? z2 : y, ldw = bits_pitch(y);
   const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && (!mask || (ldmask % 4 == 0 && ldmask >= pitch4(y)))) ? GAI_EPI_PADDED : 0;
-  die_on(gai_matmul_kcat(x, y, z1, A1, lda1, B1, ldb1, z2, A2, lda2, B2, ldb2, C, ldc, tb, flags | padded | (mask ? GAI_EPI_MASK : 0), mask, ldmask,
+  const float* mptr = mask_bits ? reinterpret_cast<const float*>(mask_bits) : mask;
+  die_on(gai_matmul_kcat(x, y, z1, A1, lda1, B1, ldb1, z2, A2, lda2, B2, ldb2, C, ldc, tb,
+                         flags | padded | (masked ? GAI_EPI_MASK : 0) | (mask_bits ? GAI_EPI_BITMASK : 0), mptr, mask_bits ? ldw : ldmask, relu_bits, ldw,
                          stream()), "gai_matmul_kcat");
 }
 static void mm_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, float* C, size_t ldc, bool tb, const float* mask,
-                    size_t ldmask) {
-  gai_host::OpScope sc("LINEAR", shape(x, y, z) + (tb ? " TB" : "") + " mask", 4.0 * ((double)x * z + (double)z * y + 2.0 * (double)x * y),
-                       2.0 * (double)x * y * z);
-  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && ldmask % 4 == 0 && ldmask >= pitch4(y)) ? GAI_EPI_PADDED : 0;
-  die_on(gai_matmul_mask(x, y, z, A, lda, B, tb ? z : y, C, ldc, tb, mask, ldmask, padded, stream()), "gai_matmul_mask");
+                    size_t ldmask, const uint32_t* mask_bits = nullptr) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z) + (tb ? " TB" : "") + (mask_bits ? " bitmask" : " mask"),
+                       4.0 * ((double)x * z + (double)z * y + (mask_bits ? 1.0 : 2.0) * (double)x * y) + (mask_bits ? (double)x * y / 8 : 0), 2.0 * (double)x * y * z);
+  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && (mask_bits || (ldmask % 4 == 0 && ldmask >= pitch4(y)))) ? GAI_EPI_PADDED : 0;
+  if (mask_bits)
+    die_on(gai_matmul_mask(x, y, z, A, lda, B, tb ? z : y, C, ldc, tb, reinterpret_cast<const float*>(mask_bits), bits_pitch(y), padded | GAI_EPI_BITMASK,
+                           stream()), "gai_matmul_mask");
+  else
+    die_on(gai_matmul_mask(x, y, z, A, lda, B, tb ? z : y, C, ldc, tb, mask, ldmask, padded, stream()), "gai_matmul_mask");
+}
+// C = ReLU(A·B) + the sign bits of C for the layer above
+static void mm_relu_bits(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, float* C, size_t ldc, uint32_t* bits) {
+  gai_host::OpScope sc("LINEAR", shape(x, y, z) + " relu+bits", 4.0 * ((double)x * z + (double)z * y + (double)x * y) + (double)x * y / 8, 2.0 * (double)x * y * z);
+  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  die_on(gai_matmul_relu_bits(x, y, z, A, lda, B, y, C, ldc, padded, bits, bits_pitch(y), stream()), "gai_matmul_relu_bits");
 }
 // C1 = A·B1, C2 = A·B2, A read once
 static void mm_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y, const float* B1, float* C1, size_t ldc1, const float* B2, float* C2,
@@ -202,6 +217,8 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
   if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * pitch4(din));
   if (id > 0) feat_in = float_malloc_device_zero(n * ld_in);
   grad_in = float_malloc_device_zero(n * ld_out);
+  // aggregate-first layers apply ReLU in a dense-transform epilogue, which also emits the sign bits the layer above masks with
+  if (act && !transform_first) d_relu_bits = reinterpret_cast<uint32_t*>(float_malloc_device_zero(n * bits_pitch(dout)));
   optm = new adam(lr);
 }
 
@@ -258,7 +275,8 @@ void GCN_layer::forward(float* feat_out) {
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, relu, nullptr);
   } else {      // aggregate first; ReLU rides the GEMM epilogue
     aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
-    mm(x, z, y, d_in_temp1, ldt, d_W_neigh, z, feat_out, ld_out, false, false, false, relu);
+    if (is_act && d_relu_bits) mm_relu_bits(x, z, y, d_in_temp1, ldt, d_W_neigh, feat_out, ld_out, d_relu_bits);
+    else mm(x, z, y, d_in_temp1, ldt, d_W_neigh, z, feat_out, ld_out, false, false, false, relu);
   }
 }
 
@@ -268,7 +286,7 @@ void GCN_layer::backward(float* feat_out, float* grad_out) {
   if (y > z) {
     aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
     if (level_ > 0) {
-      if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in);
+      if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in, mask_bits_in);
       else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
     }
     mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);
@@ -303,7 +321,8 @@ void SAGE_layer::forward(float* feat_out) {
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, GAI_EPI_ADD | relu, feat_out);
   } else {
     aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
-    mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, feat_in, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0);
+    mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, feat_in, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0, nullptr,
+            is_act ? d_relu_bits : nullptr);
   }
 }
 
@@ -314,7 +333,8 @@ void SAGE_layer::backward(float* feat_out, float* grad_out) {
     aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
     wgrad_two_b(x, y, feat_in, ld_in, z, grad_in, ld_out, d_W_self_grad, d_out_temp, ld_out, d_W_neigh_grad);
     if (level_ > 0)
-      mm_kcat(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_in, ld_out, d_W_self, grad_out, ld_in, true, 0, mask_grad_out ? feat_in : nullptr, ld_in);
+      mm_kcat(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_in, ld_out, d_W_self, grad_out, ld_in, true, 0,
+              (mask_grad_out && !mask_bits_in) ? feat_in : nullptr, ld_in, mask_grad_out ? mask_bits_in : nullptr);
   } else {
     wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad, feat_in, ld_in, d_W_self_grad);
     if (level_ > 0) {
@@ -348,7 +368,7 @@ void GAT_layer::backward(float* feat_out, float* grad_out) {
   if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   aggr.d_aggregate((int)z, *graph, d_out_temp, grad_in, d_out_temp);  // dZ overwrites Z (gat_layer.cpp:33-36)
   if (level_ != 0) {
-    if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in);
+    if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in, mask_bits_in);
     else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
   }
   mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);

@@ -45,6 +45,8 @@ struct adam : public optimizer {
 
 // Row pitch of every per-vertex activation / gradient buffer the layer classes own (floats).
 inline size_t pitch4(size_t dim) { return (dim + 3) / 4 * 4; }
+// Words per row of a sign-bit matrix (one bit per activation, GAI_EPI_BITMASK).
+inline size_t bits_pitch(size_t dim) { return (dim + 31) / 32; }
 
 // ---- aggregators --------------------------------------------------------------------------------------------------
 // aggregate / d_aggregate keep the reference signatures (dense rows, aggregator.h:21-88); the *_ld forms take row pitches
@@ -122,6 +124,10 @@ class graph_conv_layer {
   bool can_mask_grad_out() const;                 // this layer's last backward op on grad_out is a dense transform
   void set_mask_grad_out(bool on) { mask_grad_out = on; }
   void set_grad_premasked(bool on) { grad_premasked = on; }
+  // Sign bits of this layer's activation (written by its forward when ReLU runs in a dense-transform epilogue; NULL otherwise) and
+  // the bits of the layer below, which this layer's masked input gradient reads instead of the activation itself.
+  const uint32_t* relu_bits() const { return d_relu_bits; }
+  void set_mask_bits(const uint32_t* bits) { mask_bits_in = bits; }
   bool has_activation() const { return is_act; }
 
  protected:
@@ -132,6 +138,8 @@ class graph_conv_layer {
   net_phase phase_ = net_phase::TRAIN;
   size_t ld_in = 0, ld_out = 0;  // row pitches of feat_in / (grad_in, out_temp, the feat_out this layer writes)
   bool mask_grad_out = false, grad_premasked = false;
+  uint32_t* d_relu_bits = nullptr;
+  const uint32_t* mask_bits_in = nullptr;
   float *feat_in = nullptr, *grad_in = nullptr;
   float *d_in_temp = nullptr, *d_in_temp1 = nullptr, *d_out_temp = nullptr;
   float *d_W_neigh = nullptr, *d_W_neigh_grad = nullptr, *d_W_self = nullptr, *d_W_self_grad = nullptr;

@@ -174,6 +174,7 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   for (int l = 1; l < num_layers; l++) {
     if (layer_gconv[l - 1].has_activation() && layer_gconv[l].can_mask_grad_out()) {
       layer_gconv[l].set_mask_grad_out(true);
+      layer_gconv[l].set_mask_bits(layer_gconv[l - 1].relu_bits());  // NULL: mask with the activation itself
       layer_gconv[l - 1].set_grad_premasked(true);
     }
   }

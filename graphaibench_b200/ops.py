@@ -9,7 +9,7 @@ import torch
 
 from ._abi import check, lib
 
-EPI_NONE, EPI_RELU, EPI_ADD, EPI_MASK, EPI_PADDED = 0, 1, 2, 4, 8
+EPI_NONE, EPI_RELU, EPI_ADD, EPI_MASK, EPI_PADDED, EPI_BITMASK = 0, 1, 2, 4, 8, 16
 
 
 def _stream():
@@ -153,15 +153,27 @@ def matmul(A, B, out=None, transA=False, transB=False, accum=False, flags=0):
     return out
 
 
-def matmul_kcat(A1, B1, A2, B2, out=None, transB=False, flags=0, mask=None):
-    """C = A1·op(B1) + A2·op(B2) in one pass (gai_matmul_kcat); flags: EPI_RELU, or EPI_MASK with `mask` (d_relu by the activation)."""
+def matmul_kcat(A1, B1, A2, B2, out=None, transB=False, flags=0, mask=None, relu_bits=None):
+    """C = A1·op(B1) + A2·op(B2) in one pass (gai_matmul_kcat); flags: EPI_RELU (relu_bits: int32 [x, ceil(y/32)] receives the sign bits of C),
+    or EPI_MASK with `mask` (d_relu by the activation; with EPI_BITMASK `mask` is such a sign-bit tensor)."""
     x, z1, z2 = A1.shape[0], A1.shape[1], A2.shape[1]
     y = B1.shape[0] if transB else B1.shape[1]
     if out is None:
         out = torch.empty(x, y, dtype=torch.float32, device=A1.device)
     check(lib().gai_matmul_kcat(x, y, z1, _f32(A1), A1.stride(0), _f32(B1), B1.stride(0), z2, _f32(A2), A2.stride(0), _f32(B2), B2.stride(0),
-                                _f32(out), out.stride(0), int(transB), flags, _f32(mask) if mask is not None else None,
-                                mask.stride(0) if mask is not None else 0, _stream()), "gai_matmul_kcat")
+                                _f32(out), out.stride(0), int(transB), flags, _p(mask), mask.stride(0) if mask is not None else 0,
+                                _p(relu_bits), relu_bits.stride(0) if relu_bits is not None else 0, _stream()), "gai_matmul_kcat")
+    return out
+
+
+def matmul_relu_bits(A, B, relu_bits, out=None, flags=0):
+    """C = ReLU(A·B) and the sign bits of C (gai_matmul_relu_bits)."""
+    x, z = A.shape
+    y = B.shape[1]
+    if out is None:
+        out = torch.empty(x, y, dtype=torch.float32, device=A.device)
+    check(lib().gai_matmul_relu_bits(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), flags, _p(relu_bits),
+                                     relu_bits.stride(0), _stream()), "gai_matmul_relu_bits")
     return out
 
 
@@ -171,7 +183,7 @@ def matmul_mask(A, B, mask, out=None, transB=False, flags=0):
     y = B.shape[0] if transB else B.shape[1]
     if out is None:
         out = torch.empty(x, y, dtype=torch.float32, device=A.device)
-    check(lib().gai_matmul_mask(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), int(transB), _f32(mask),
+    check(lib().gai_matmul_mask(x, y, z, _f32(A), A.stride(0), _f32(B), B.stride(0), _f32(out), out.stride(0), int(transB), _p(mask),
                                 mask.stride(0), flags, _stream()), "gai_matmul_mask")
     return out
 

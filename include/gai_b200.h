@@ -105,6 +105,8 @@ const uint32_t* gai_csr_transpose_perm(gai_csr_t g);
  * out[i, 0:F] = epilogue( sum_{e in row i} w_e * in[col_e, 0:F] ), i in [row_begin, row_end).
  * flags: GAI_EPI_ADD  -> add `addend[i, :]` (ld = ld_out) after the sum;  GAI_EPI_RELU -> max(.,0) last. */
 enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2, GAI_EPI_MASK = 4 /* dense transforms only: see gai_matmul_kcat */,
+       GAI_EPI_BITMASK = 16 /* with GAI_EPI_MASK: `mask` points to uint32 sign-bit words, one per row and 32-column chunk (bit c % 32 of
+                               word c / 32 = activation[row, c] > 0), ldmask in words — written by the ReLU epilogue of the layer below */,
        GAI_EPI_PADDED = 8 /* dense transforms only: the rows of C (and of the mask) are padded to a multiple of 4 floats (ldc % 4 == 0,
                              ldc >= round_up(y, 4)); the transform may overwrite the padding columns with zeros (all stores 128-bit) */ };
 /* GCN_Aggregator::aggregate == d_aggregate (src/gnn/gconv/gcn_aggregator.cpp:23-77): w_e = norm_i * norm_j. */
@@ -145,11 +147,15 @@ int gai_matmul_ld(size_t x, size_t y, size_t z, const float* A, size_t lda, cons
  * mask[i,j] <= 0 (d_relu by the forward activation, math_functions.cpp:453-463, applied before C is ever written). */
 int gai_matmul_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1, const float* B1, size_t ldb1, size_t z2, const float* A2,
                     size_t lda2, const float* B2, size_t ldb2, float* C, size_t ldc, int transB, int flags, const float* mask, size_t ldmask,
+                    uint32_t* relu_bits /* NULL, or with GAI_EPI_RELU: sign-bit words of C written in the same pass */, size_t ld_bits,
                     gai_stream_t stream);
 /* Input gradient with the previous layer's d_relu folded into the epilogue: C[x×y] = mask > 0 ? A[x×z]·op(B) : 0
  * (gcn_layer.cpp:51-54 followed by the d_relu of the layer below, gcn_layer.cpp:38-40 / math_functions.cpp:453-463). */
 int gai_matmul_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int transB,
-                    const float* mask, size_t ldmask, int flags /* 0 or GAI_EPI_PADDED */, gai_stream_t stream);
+                    const float* mask, size_t ldmask, int flags /* GAI_EPI_PADDED, GAI_EPI_BITMASK */, gai_stream_t stream);
+/* C[x×y] = ReLU(A[x×z]·B[z×y]) and the sign-bit words of C (ld_bits >= ceil(y / 32)) in one pass. */
+int gai_matmul_relu_bits(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, int flags,
+                         uint32_t* relu_bits, size_t ld_bits, gai_stream_t stream);
 /* N-concatenated transform: C1[x×y1] = A[x×z]·B1[z×y1], C2[x×y2] = A·B2[z×y2] with A read once (SAGE transform-first
  * forward: H·W_neigh for the aggregation and H·W_self for the self term, sage_layer.cpp:26-30). */
 int gai_matmul_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y1, const float* B1, size_t ldb1, float* C1, size_t ldc1, size_t y2,

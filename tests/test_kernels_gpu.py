@@ -354,6 +354,26 @@ def test_matmul_kcat_vs_oracle(T, ops, liborc, shape, padded):
         ops.matmul(dA1, dev(T, B1), out=full[:, :y], transB=bool(tb), flags=ops.EPI_PADDED)
         ops.matmul(dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), accum=True, flags=ops.EPI_RELU | ops.EPI_PADDED)
         close(full[:, :y].cpu().numpy(), np.maximum(ref, 0))
+        # sign bits: the ReLU epilogue writes one bit per activation, the masked input gradient of the layer above reads them back
+        nw = (y + 31) // 32
+        bits = T.zeros(x, nw, dtype=T.int32, device="cuda")
+        ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), flags=ops.EPI_RELU | ops.EPI_PADDED, relu_bits=bits)
+        act = full[:, :y].cpu().numpy().copy()
+        close(act, np.maximum(ref, 0))
+        want = np.zeros((x, nw * 32), bool); want[:, :y] = act > 0
+        got = np.unpackbits(bits.cpu().numpy().view(np.uint8), axis=1, bitorder="little").astype(bool)
+        assert np.array_equal(got, want), "sign bits differ from (activation > 0)"
+        ops.matmul_kcat(dA1, dev(T, B1), dA2, dev(T, B2), out=full[:, :y], transB=bool(tb), flags=ops.EPI_MASK | ops.EPI_BITMASK | ops.EPI_PADDED, mask=bits)
+        close(full[:, :y].cpu().numpy(), np.where(act > 0, ref, 0))
+        ops.matmul_mask(dA1, dev(T, B1), bits, out=full[:, :y], transB=bool(tb), flags=ops.EPI_PADDED | ops.EPI_BITMASK)
+        close(full[:, :y].cpu().numpy(), np.where(act > 0, ref1, 0))
+        if not tb:
+            bits2 = T.zeros(x, nw, dtype=T.int32, device="cuda")
+            ops.matmul_relu_bits(dA1, dev(T, B1), bits2, out=full[:, :y], flags=ops.EPI_PADDED)
+            a1 = full[:, :y].cpu().numpy()
+            close(a1, np.maximum(ref1, 0))
+            want2 = np.zeros((x, nw * 32), bool); want2[:, :y] = a1 > 0
+            assert np.array_equal(np.unpackbits(bits2.cpu().numpy().view(np.uint8), axis=1, bitorder="little").astype(bool), want2)
 
 
 @pytest.mark.parametrize("shape", [(20000, 256, 47, 47), (5000, 100, 64, 33), (4096, 128, 128, 100), (3000, 50, 7, 9)])
