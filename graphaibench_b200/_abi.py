@@ -57,6 +57,8 @@ _SIGS = {
     "gai_csr_transpose_perm": (C.c_void_p, [C.c_void_p]),
     "gai_spmm_gcn": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
     "gai_spmm_mean": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
+    "gai_spmm_gcn_masked": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_int, c_stream]),
+    "gai_spmm_mean_masked": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_int, c_stream]),
     "gai_spmm_edge": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_u32p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
     "gai_spmm_gcn_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
     "gai_spmm_mean_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),

@@ -42,6 +42,8 @@ struct SpmmArgs {
   int out_vec;       // 1: out/addend rows are 16-byte aligned and F % 4 == 0 -> float4 epilogue
   uint32_t hub_threshold;
   int hub_per;       // hub rows: float4 chunks per CTA column block (gridDim.y blocks cover nchunks)
+  const uint32_t* mask_bits;  // optional d_relu of the layer below: out = bit ? out : 0, one sign bit per element (GAI_EPI_BITMASK)
+  int ld_bits;                // words per row
 };
 
 // out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
@@ -53,6 +55,10 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int
       r.x = __fadd_rn(r.x, ad.x); r.y = __fadd_rn(r.y, ad.y); r.z = __fadd_rn(r.z, ad.z); r.w = __fadd_rn(r.w, ad.w);
     }
     if (a.flags & GAI_EPI_RELU) { r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f; r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f; }
+    if (a.mask_bits) {
+      const uint32_t nib = __ldg(a.mask_bits + (size_t)row * a.ld_bits + (chunk >> 3)) >> ((chunk & 7) * 4);
+      r.x = (nib & 1u) ? r.x : 0.f; r.y = (nib & 2u) ? r.y : 0.f; r.z = (nib & 4u) ? r.z : 0.f; r.w = (nib & 8u) ? r.w : 0.f;
+    }
     *reinterpret_cast<float4*>(a.out + o) = r;
   } else {
     const float v[4] = {r.x, r.y, r.z, r.w};
@@ -62,6 +68,7 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int
         float t = v[k];
         if (a.flags & GAI_EPI_ADD) t = __fadd_rn(t, a.addend[o + k]);
         if (a.flags & GAI_EPI_RELU) t = t > 0.f ? t : 0.f;
+        if (a.mask_bits) { const int c = chunk * 4 + k; if (!((__ldg(a.mask_bits + (size_t)row * a.ld_bits + (c >> 5)) >> (c & 31)) & 1u)) t = 0.f; }
         a.out[o + k] = t;
       }
     }
@@ -652,7 +659,8 @@ int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
 }
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
-                  int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
+                  int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream, const uint32_t* mask_bits = nullptr,
+                  int ld_bits = 0) {
   GAI_CHECK_ARG(g != nullptr);
   GAI_CHECK_ARG(rb <= re && re <= g->nv);
   if (re == rb) return GAI_OK;  // empty graph / empty row range: nothing to do (buffers may be NULL)
@@ -670,6 +678,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.mode = mode; a.flags = flags;
   a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   a.hub_per = a.nchunks;
+  a.mask_bits = mask_bits; a.ld_bits = ld_bits;
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
   if ((ld_in % 4 == 0) && aligned16(in) && ld_in >= a.nchunks * 4) {
     // rows are 128-bit loadable as stored; when F % 4 != 0 the tail chunk also reads the (ld_in - F) padding columns of
@@ -727,6 +736,17 @@ int gai_spmm_mean(gai_csr_t g, int F, const float* in, int ld_in, float* out, in
 int gai_spmm_edge(gai_csr_t g, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
   GAI_CHECK_ARG(g != nullptr);
   return spmm_dispatch(g, perm ? M_EDGE_PERM : M_EDGE, 0, g->nv, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream);
+}
+int gai_spmm_gcn_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend,
+                        const uint32_t* mask_bits, int ld_bits, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr && mask_bits != nullptr && ld_bits >= (F + 31) / 32);
+  return spmm_dispatch(g, M_GCN, 0, g->nv, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream, mask_bits, ld_bits);
+}
+int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend,
+                         const uint32_t* mask_bits, int ld_bits, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr && mask_bits != nullptr && ld_bits >= (F + 31) / 32);
+  return spmm_dispatch(g, transposed ? M_MEAN_T : M_MEAN, 0, g->nv, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream, mask_bits,
+                       ld_bits);
 }
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t rb, uint32_t re, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
   return spmm_dispatch(g, M_GCN, rb, re, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream);

@@ -137,8 +137,13 @@ void GCN_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_
   die_on(gai_spmm_gcn(g.device(), len, in, (int)ld_in, out, (int)ld_out, flags, addend, stream()), "gai_spmm_gcn");
 }
 // the normalised adjacency is symmetric, so the derivative is the same product (gcn_aggregator.cpp:35-46)
-void GCN_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend) {
-  aggregate_ld(len, g, grad_in, ld_in, grad_out, ld_out, flags, addend);
+void GCN_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
+                                    const uint32_t* mask_bits) {
+  if (!mask_bits) { aggregate_ld(len, g, grad_in, ld_in, grad_out, ld_out, flags, addend); return; }
+  gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len) + " bitmask", spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + g.size() * len / 8.0,
+                       2.0 * g.sizeEdges() * len);
+  die_on(gai_spmm_gcn_masked(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend, mask_bits, (int)bits_pitch(len), stream()),
+         "gai_spmm_gcn_masked");
 }
 void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) { aggregate(len, g, grad_in, grad_out); }
@@ -148,9 +153,15 @@ void SAGE_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld
   gai_host::OpScope sc("AGGR", "mean F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
   die_on(gai_spmm_mean(g.device(), len, in, (int)ld_in, out, (int)ld_out, 0, flags, addend, stream()), "gai_spmm_mean");
 }
-void SAGE_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend) {
-  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_mean(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, stream()), "gai_spmm_mean(T)");
+void SAGE_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
+                                     const uint32_t* mask_bits) {
+  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len) + (mask_bits ? " bitmask" : ""),
+                       spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + (mask_bits ? g.size() * len / 8.0 : 0), 2.0 * g.sizeEdges() * len);
+  if (mask_bits)
+    die_on(gai_spmm_mean_masked(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, mask_bits, (int)bits_pitch(len), stream()),
+           "gai_spmm_mean_masked(T)");
+  else
+    die_on(gai_spmm_mean(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, stream()), "gai_spmm_mean(T)");
 }
 void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {
@@ -220,6 +231,12 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
   // aggregate-first layers apply ReLU in a dense-transform epilogue, which also emits the sign bits the layer above masks with
   if (act && !transform_first) d_relu_bits = reinterpret_cast<uint32_t*>(float_malloc_device_zero(n * bits_pitch(dout)));
   optm = new adam(lr);
+}
+
+template <typename A>
+bool graph_conv_layer<A>::can_mask_grad_out_bits() const {
+  // aggregate-first GCN / SAGE layers end their backward with an aggregation, whose epilogue can apply a sign-bit mask
+  return level_ > 0 && dim_in <= dim_out && !std::is_same<A, GAT_Aggregator>::value;
 }
 
 template <typename A>
@@ -293,7 +310,7 @@ void GCN_layer::backward(float* feat_out, float* grad_out) {
   } else {
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
-      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_NONE, nullptr);
+      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_NONE, nullptr, mask_grad_out ? mask_bits_in : nullptr);
     }
     mm(y, z, x, d_in_temp1, ldt, grad_in, ld_out, d_W_neigh_grad, z, true, false);
   }
@@ -340,7 +357,7 @@ void SAGE_layer::backward(float* feat_out, float* grad_out) {
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
       mm(x, y, z, grad_in, ld_out, d_W_self, z, grad_out, ld_in, false, true);
-      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_ADD, grad_out);
+      aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_ADD, grad_out, mask_grad_out ? mask_bits_in : nullptr);
     }
   }
 }

@@ -65,7 +65,8 @@ class GCN_Aggregator : public aggregator {
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
   void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
-  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend);
+  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend,
+                      const uint32_t* mask_bits = nullptr);
 };
 
 class SAGE_Aggregator : public aggregator {
@@ -74,7 +75,8 @@ class SAGE_Aggregator : public aggregator {
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
   void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
-  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend);
+  void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend,
+                      const uint32_t* mask_bits = nullptr);
 };
 
 class GAT_Aggregator : public aggregator {
@@ -122,6 +124,7 @@ class graph_conv_layer {
   // d_relu fusion across the layer boundary: the layer above writes this layer's grad_in already masked by this layer's
   // activation (the GEMM epilogue reads its own feat_in = this layer's output), so backward() skips the separate pass.
   bool can_mask_grad_out() const;                 // this layer's last backward op on grad_out is a dense transform
+  bool can_mask_grad_out_bits() const;            // ... or an aggregation, which can mask with the lower layer's sign bits only
   void set_mask_grad_out(bool on) { mask_grad_out = on; }
   void set_grad_premasked(bool on) { grad_premasked = on; }
   // Sign bits of this layer's activation (written by its forward when ReLU runs in a dense-transform epilogue; NULL otherwise) and

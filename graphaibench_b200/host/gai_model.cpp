@@ -172,7 +172,8 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   layer_gconv[0].set_feat_in(d_input_features);
   // d_relu of layer l-1 (gcn_layer.cpp:38-40) rides the epilogue of the transform that produces its grad_in in layer l
   for (int l = 1; l < num_layers; l++) {
-    if (layer_gconv[l - 1].has_activation() && layer_gconv[l].can_mask_grad_out()) {
+    if (layer_gconv[l - 1].has_activation() &&
+        (layer_gconv[l].can_mask_grad_out() || (layer_gconv[l].can_mask_grad_out_bits() && layer_gconv[l - 1].relu_bits()))) {
       layer_gconv[l].set_mask_grad_out(true);
       layer_gconv[l].set_mask_bits(layer_gconv[l - 1].relu_bits());  // NULL: mask with the activation itself
       layer_gconv[l - 1].set_grad_premasked(true);

@@ -117,6 +117,13 @@ int gai_spmm_mean(gai_csr_t g, int F, const float* in, int ld_in, float* out, in
 /* update_all with explicit per-edge values (src/gnn/gconv/gat_aggregator.cpp:26-45; spmm(), math_functions.cpp:206-219).
  * If perm != NULL the value used for edge e is vals[perm[e]] (transposed attention without materialising it). */
 int gai_spmm_edge(gai_csr_t g, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
+/* Aggregation whose epilogue also applies the d_relu of the layer below (out = bit ? out : 0) from sign-bit words written by that
+ * layer's ReLU epilogue (GAI_EPI_BITMASK layout): the last op of an aggregate-first layer's backward (gcn_layer.cpp:55-58 followed by
+ * gcn_layer.cpp:38-40 of the layer below). */
+int gai_spmm_gcn_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend,
+                        const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
+int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend,
+                         const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
 /* Row-range variants for the 1D partition (interior rows first, boundary rows after the halo arrives). */
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
 int gai_spmm_mean_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend, gai_stream_t stream);

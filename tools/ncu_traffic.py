@@ -5,7 +5,7 @@ N-cat transform, AGGR mean F=47, [loss], AGGR meanT F=47, two-B dW, K-cat+mask t
 import csv, json, sys
 rows = list(csv.DictReader(open(sys.argv[1])))
 names = ["AGGR mean F=100", "LINEAR 2449029x256x100+100 kcat", "LINEAR 2449029x47x256 ncat2", "AGGR mean F=47", "AGGR meanT F=47",
-         "LINEAR 256x47x2449029 TA two_b", "LINEAR 2449029x256x47+47 TB kcat mask", "LINEAR 100x256x2449029 TA two_a"]
+         "LINEAR 256x47x2449029 TA two_b", "LINEAR 2449029x256x47+47 TB kcat bitmask", "LINEAR 100x256x2449029 TA two_a"]
 kinds = ["spmm_rows", "gemm_tc_kernel", "gemm_tc_kernel", "spmm_rows", "spmm_rows", "gemm_tc_wgrad", "gemm_tc_kernel", "gemm_tc_wgrad"]
 # find the first launch of the epoch: an spmm_rows kernel followed by two gemm_tc_kernel launches
 start = next(i for i in range(len(rows) - 2) if "spmm_rows" in rows[i]["kernel"] and "gemm_tc_kernel" in rows[i + 1]["kernel"] and "gemm_tc_kernel" in rows[i + 2]["kernel"])
