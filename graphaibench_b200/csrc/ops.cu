@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t b
   const int gid = threadIdx.x / G, gl = threadIdx.x % G;
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int nch = (ncls + 3) >> 2;
+  const int kk = (nch + G - 1) / G;
   double l = 0.0; unsigned c = 0, n = 0;
   for (size_t row = begin + (size_t)blockIdx.x * GPB + gid; row < end; row += (size_t)gridDim.x * GPB) {
     if (masks && masks[row] != 1) continue;  // uniform within the group
@@ -228,18 +229,22 @@ __global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t b
     float v[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const int ch = gl + G * k;
-      float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (ch < nch) t = x4[ch];
-      const int col = ch * 4;
-      v[4 * k + 0] = col + 0 < ncls ? t.x : -INFINITY; v[4 * k + 1] = col + 1 < ncls ? t.y : -INFINITY;
-      v[4 * k + 2] = col + 2 < ncls ? t.z : -INFINITY; v[4 * k + 3] = col + 3 < ncls ? t.w : -INFINITY;
+      if (k < kk) {  // kk = float4 chunks per lane actually needed (warp-uniform): 1 for up to 4*G classes
+        const int ch = gl + G * k;
+        float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (ch < nch) t = x4[ch];
+        const int col = ch * 4;
+        v[4 * k + 0] = col + 0 < ncls ? t.x : -INFINITY; v[4 * k + 1] = col + 1 < ncls ? t.y : -INFINITY;
+        v[4 * k + 2] = col + 2 < ncls ? t.z : -INFINITY; v[4 * k + 3] = col + 3 < ncls ? t.w : -INFINITY;
+      }
     }
     float mx = -INFINITY; int am = 0x7fffffff;
 #pragma unroll
     for (int k = 0; k < 4; k++)
+      if (k < kk) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) { if (v[4 * k + i] > mx) { mx = v[4 * k + i]; am = (gl + G * k) * 4 + i; } }
+        for (int i = 0; i < 4; i++) { if (v[4 * k + i] > mx) { mx = v[4 * k + i]; am = (gl + G * k) * 4 + i; } }
+      }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
       const float omx = __shfl_xor_sync(gmask, mx, o);
@@ -248,14 +253,18 @@ __global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t b
     }
     float e[16], sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; i++) { e[i] = expf(v[i] - mx); sum += e[i]; }
+    for (int k = 0; k < 4; k++)
+      if (k < kk) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { e[4 * k + i] = expf(v[4 * k + i] - mx); sum += e[4 * k + i]; }
+      }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
     const int lab = labels[row];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int ch = gl + G * k;
-      if (ch < nch) {
+      if (k < kk && ch < nch) {
         float4 pr;
         pr.x = e[4 * k + 0] / sum; pr.y = e[4 * k + 1] / sum; pr.z = e[4 * k + 2] / sum; pr.w = e[4 * k + 3] / sum;
         reinterpret_cast<float4*>(probs + row * ld_probs)[ch] = pr;
