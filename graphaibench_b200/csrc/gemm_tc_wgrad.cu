@@ -25,7 +25,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int WG_BK = 16;                 // rows per k-block
+constexpr int WG_BK = 16;                 // rows per k-block (8-row blocks measured 40 % slower: twice the TMA boxes and barrier hand-offs per byte)
 constexpr uint32_t WG_BOX = WG_BK * 128;  // bytes per TMA box
 constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 splitters + epilogue
 constexpr int WG_SPLIT_WARPS = 8;
@@ -84,20 +84,29 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    // ---------------- TMA producer: lane 0 owns the barriers, every box of a stage is issued by its own lane ----------------
+    {
+      const int nA0 = g.nbox_at[0], nA1 = g.nbox_at[1], nB = g.nbox_b;
       for (uint32_t it = 0; it < nkb; it++) {
         const int s = it % g.stages;
-        mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+        if (lane == 0) {
+          mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nA0 + nA1 + nB) * WG_BOX);
+        }
+        __syncwarp();
         uint8_t* st = smem + (size_t)s * g.stage_bytes;
-        const int row = (int)((kb0 + it) * WG_BK);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(g.nbox_at[0] + g.nbox_at[1] + g.nbox_b) * WG_BOX);
-        for (int c = 0; c < g.nbox_at[0]; c++) tma_load_2d(st + (size_t)c * WG_BOX, &map_a0, c * 32, row, &full_bar[s]);
-        for (int c = 0; c < g.nbox_at[1]; c++)
-          tma_load_2d(st + (size_t)(4 + c) * WG_BOX, g.dual_a ? &map_a1 : &map_a0, (g.dual_a ? c : 4 + c) * 32, row, &full_bar[s]);
         uint8_t* sb = st + 2 * g.a_bytes;
-        for (int c = 0; c < g.nbox_b0; c++) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b0, c * 32, row, &full_bar[s]);
-        for (int c = g.nbox_b0; c < g.nbox_b; c++) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b1, (c - g.nbox_b0) * 32, row, &full_bar[s]);
+        const int row = (int)((kb0 + it) * WG_BK);
+        if (lane < nA0) {
+          tma_load_2d(st + (size_t)lane * WG_BOX, &map_a0, lane * 32, row, &full_bar[s]);
+        } else if (lane < nA0 + nA1) {
+          const int c = lane - nA0;
+          tma_load_2d(st + (size_t)(4 + c) * WG_BOX, g.dual_a ? &map_a1 : &map_a0, (g.dual_a ? c : 4 + c) * 32, row, &full_bar[s]);
+        } else if (lane < nA0 + nA1 + nB) {
+          const int c = lane - nA0 - nA1;
+          if (c < g.nbox_b0) tma_load_2d(sb + (size_t)c * WG_BOX, &map_b0, c * 32, row, &full_bar[s]);
+          else tma_load_2d(sb + (size_t)c * WG_BOX, &map_b1, (c - g.nbox_b0) * 32, row, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
