@@ -43,6 +43,8 @@ def build_cuda(force=False, verbose=False):
                    "-I", CSRC, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
+            for d in os.environ.get("GAI_NVCC_DEFINES", "").split():  # build-time experiments, e.g. GAI_NVCC_DEFINES=-DGAI_GATHER_NOALLOC
+                cmd.insert(1, d)
             procs.append((s, subprocess.Popen(cmd)))
     for s, p in procs:
         if p.wait() != 0:

@@ -103,6 +103,17 @@ __device__ __forceinline__ void acc_add(float4& acc, const float4& p) {
   acc.x = __fadd_rn(acc.x, p.x); acc.y = __fadd_rn(acc.y, p.y); acc.z = __fadd_rn(acc.z, p.z); acc.w = __fadd_rn(acc.w, p.w);
 }
 
+// 128-bit gather of a neighbour-row chunk. GAI_GATHER_NOALLOC (build-time experiment): read-only path without L1 allocation.
+__device__ __forceinline__ float4 gather4(const float4* p) {
+#ifdef GAI_GATHER_NOALLOC
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <int MODE>
 __device__ __forceinline__ float edge_weight_t(const SpmmArgs& a, float wrow, uint32_t idx, uint32_t c) {
   if (MODE == M_GCN) return __fmul_rn(wrow, __ldg(a.norm + c));  // b = a_i * a_j (gcn_aggregator.cpp:66)
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
                   const float4* src = in4 + (size_t)cc * ld4;
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = __ldg(src + ch[k]);
+                  for (int k = 0; k < K; k++) x[u][k] = gather4(src + ch[k]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
                   const float4* src = in4 + (size_t)cc * ld4;
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? __ldg(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
