@@ -222,6 +222,9 @@ def roofline_from_profile(prof, peaks, n_epochs):
         out.update({"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak})
     else:
         out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]})
+    if out.get("traffic"):  # the measured side of the SURVEY.md 8d triple: DRAM bytes of the same launch / the same event time
+        out["dram_GBps"] = out["traffic"] / (ms * 1e-3) / 1e9
+        out["dram_frac"] = out["dram_GBps"] / peaks["hbm_gbs"]
     breakdown = {b: round(v / n_epochs, 4) for b, v in sorted(by_bucket.items(), key=lambda kv: -kv[1])}
     per_shape = [{"op": f"{r['bucket']} {r['shape']}", "ms": round(r["ms"] / r["calls"], 4), "calls_per_step": r["calls"] / n_epochs,
                   "GBps": round(r["bytes"] / r["calls"] / (r["ms"] / r["calls"] * 1e-3) / 1e9, 1),
