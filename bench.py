@@ -243,7 +243,10 @@ def ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         with quiet_stdout():  # NCCL announces its version on stdout at communicator creation
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            # the collectives run on a HIGH-PRIORITY stream: when the halo all-to-all and the persistent interior-row aggregation
+            # become runnable together, the collective's few CTAs must be placed first or they wait for the aggregation to drain
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=os.environ.get("GAI_NCCL_HIGH_PRIO", "1") != "0")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
             dist.barrier()
     from graphaibench_b200 import _abi, build, model as gmodel
     if rank == 0:
@@ -353,7 +356,8 @@ def ours_partitioned(args, world, rank, local, L, peaks):
     stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        m = gdist.DistGnn("sage", plan, sh["feats"][loc], sh["labels"][loc], mask, int(split[1] - split[0]), dims, lr=C2["lr"])
+        m = gdist.DistGnn("sage", plan, sh["feats"][loc], sh["labels"][loc], mask, int(split[1] - split[0]), dims, lr=C2["lr"],
+                          overlap=os.environ.get("GAI_DIST_OVERLAP", "1") != "0")
         # pinned host copies of this rank's inputs for the end-to-end step
         host = {k: v.cpu().pin_memory() for k, v in dict(feats=sh["feats"][loc], labels=m.labels, mask=m.mask, rowptr=plan.rowptr, colidx=plan.colidx).items()}
         dev_scratch = {k: torch.empty_like(v, device="cuda") for k, v in host.items() if k != "feats"}

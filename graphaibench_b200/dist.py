@@ -416,19 +416,29 @@ class DistGnn:
         return self.timer.scope(bucket, shape, nbytes, flops) if self.timer is not None else _NoScope()
 
     # -- pieces --
+    def _pack(self, B):
+        """Owners copy the rows their peers need into the contiguous send buffer (gai_gather_rows)."""
+        p = self.plan
+        ld = B.shape[1]
+        send = self.sendbuf.reshape(-1)[: max(p.n_send, 1) * ld].view(-1, ld)
+        if p.n_send:
+            self.ops.gather_rows(p.send_ids, B, out=send[: p.n_send])
+        return send
+
+    def _a2a(self, B, send):
+        """One all-to-all-v straight into B's halo block."""
+        p = self.plan
+        self.comm.all_to_all_rows(send[: p.n_send], p.send_counts, B[p.n_loc:], p.recv_counts)
+        self.exchanges += 1
+        self.exchange_bytes += 4 * B.shape[1] * p.n_halo
+
     def _exchange(self, B):
         """Halo rows of B[m, ld] <- the owners' rows. Pack + one all-to-all-v straight into B's halo block."""
         p = self.plan
         if self.comm.world == 1:
             return
-        ld = B.shape[1]
-        send = self.sendbuf.reshape(-1)[: max(p.n_send, 1) * ld].view(-1, ld)
-        with self._scope("HALO", f"pack+all-to-all W={ld}", 4.0 * ld * p.n_halo):
-            if p.n_send:
-                self.ops.gather_rows(p.send_ids, B, out=send[: p.n_send])
-            self.comm.all_to_all_rows(send[: p.n_send], p.send_counts, B[p.n_loc:], p.recv_counts)
-        self.exchanges += 1
-        self.exchange_bytes += 4 * ld * p.n_halo
+        with self._scope("HALO", f"pack+all-to-all W={B.shape[1]}", 4.0 * B.shape[1] * p.n_halo):
+            self._a2a(B, self._pack(B))
 
     def _spmm(self, B, F, out, transposed, flags, addend, rows):
         if rows[0] == rows[1]:
@@ -456,15 +466,20 @@ class DistGnn:
                 self._spmm(B, F, out, transposed, flags, addend, (0, p.n_loc))
             return
         if self.overlap and p.n_int:
+            # Order matters: the persistent aggregation kernel fills every SM, so a collective launched after it would only start
+            # when it drains. The all-to-all is therefore enqueued FIRST (its few CTAs become resident as soon as the pack is done)
+            # and the interior rows — which need nothing from the peers — start behind the pack on a side stream and take the
+            # remaining SMs while the halo rows travel over NVLink.
             main = torch.cuda.current_stream()
+            send = self._pack(B)
             ev = torch.cuda.Event()
             ev.record(main)
+            self._a2a(B, send)
             self.side.wait_event(ev)
             with torch.cuda.stream(self.side):
                 self._spmm(B, F, out, transposed, flags, addend, (0, p.n_int))
                 done = torch.cuda.Event()
                 done.record(self.side)
-            self._exchange(B)
             self._spmm(B, F, out, transposed, flags, addend, (p.n_int, p.n_loc))
             main.wait_event(done)
         else:
