@@ -224,15 +224,24 @@ __global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t b
   const int kk = (nch + G - 1) / G;
   double l = 0.0; unsigned c = 0, n = 0;
   for (size_t row = begin + (size_t)blockIdx.x * GPB + gid; row < end; row += (size_t)gridDim.x * GPB) {
-    if (masks && masks[row] != 1) continue;  // uniform within the group
+    // the mask byte, the label and the logits are requested together (rows of [begin, end) are always readable): testing the mask
+    // first would put two dependent memory round trips on every row
+    const unsigned mk = masks ? masks[row] : 1u;
+    const int lab = labels[row];
     const float4* x4 = reinterpret_cast<const float4*>(logits + row * ld_logits);
+    float4 tq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      tq[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (k < kk && gl + G * k < nch) tq[k] = x4[gl + G * k];
+    }
+    if (mk != 1u) continue;  // uniform within the group
     float v[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (k < kk) {  // kk = float4 chunks per lane actually needed (warp-uniform): 1 for up to 4*G classes
         const int ch = gl + G * k;
-        float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (ch < nch) t = x4[ch];
+        const float4 t = tq[k];
         const int col = ch * 4;
         v[4 * k + 0] = col + 0 < ncls ? t.x : -INFINITY; v[4 * k + 1] = col + 1 < ncls ? t.y : -INFINITY;
         v[4 * k + 2] = col + 2 < ncls ? t.z : -INFINITY; v[4 * k + 3] = col + 3 < ncls ? t.w : -INFINITY;
@@ -260,7 +269,6 @@ __global__ void __launch_bounds__(256) softmax_ce_rows_kernel(int ncls, size_t b
       }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
-    const int lab = labels[row];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int ch = gl + G * k;
@@ -303,10 +311,13 @@ __global__ void __launch_bounds__(256) softmax_ce_bwd_rows_kernel(int ncls, size
   const int gid = threadIdx.x / G, gl = threadIdx.x % G;
   const int nch = (ncls + 3) >> 2;
   for (size_t row = begin + (size_t)blockIdx.x * GPB + gid; row < end; row += (size_t)gridDim.x * GPB) {
-    if (masks && masks[row] != 1) continue;
+    const unsigned mk = masks ? masks[row] : 1u;
     const int lab = labels[row];
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gl < nch) p0 = reinterpret_cast<const float4*>(probs + row * ld_probs)[gl];  // requested before the mask is known
+    if (mk != 1u) continue;
     for (int ch = gl; ch < nch; ch += G) {
-      const float4 pr = reinterpret_cast<const float4*>(probs + row * ld_probs)[ch];
+      const float4 pr = ch == gl ? p0 : reinterpret_cast<const float4*>(probs + row * ld_probs)[ch];
       const int col = ch * 4;
       float4 g;
       g.x = (float)(((double)pr.x - (lab == col + 0 ? 1.0 : 0.0)) / denom); g.y = (float)(((double)pr.y - (lab == col + 1 ? 1.0 : 0.0)) / denom);
