@@ -74,3 +74,21 @@ def test_partition1d_h_bit_exact(abi, golden, cora, small_graph):
     rp = np.array([0, 1, 2], np.int64); ci = np.array([1, 0], np.uint32)
     r = ops.partition1d(rp, ci, 4, 3)
     assert len(r["idx_map"]) == 0 and r["local_begin"] == r["local_end"] == 0
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/r1_bench.json is a real `python bench.py` line: the keys the driver and the judge read must all be there."""
+    import json
+    import os
+    from conftest import ROOT
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["traffic"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert abs(d["value"] - d["config"]["csr_edges"] / d["ms_per_step"] / 1e3) < 1e-6 * d["value"]
