@@ -91,6 +91,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
+  // N >> 3 in bits [17,23), M >> 4 in bits [24,29)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // MMAs of one k-block into accumulator `acc` (one thread), then the commits that release the stage / publish the accumulator
+  auto issue_kblock = [&](int kb, int s, int acc) {
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+    const uint32_t a_hi = smem_u32(smem + (size_t)s * g.stage_bytes);
+    const uint32_t a_lo = a_hi + A_BYTES;
+    const uint32_t b_hi = a_hi + 2 * A_BYTES;
+    const uint32_t b_lo = b_hi + g.b_tile_bytes;
+    // the last k-block of a part holds K mod 32 live columns: the all-zero k-steps behind them are not issued
+    const int steps = kb == g.nkb0 - 1 ? g.last_steps[0] : (kb == g.num_kb - 1 ? g.last_steps[1] : BK / 8);
+    for (int k = 0; k < ((g.debug & 8) ? 0 : steps); k++) {
+      const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along the swizzled 128-byte row
+      const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+      if (g.passes == 3) {
+        umma_tf32(d_tmem, make_desc_k128(a_lo + koff), make_desc_k128(b_hi + koff), idesc, first);
+        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_lo + koff), idesc, 1u);
+        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, 1u);
+      } else {
+        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, first);
+      }
+    }
+    umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
+    if (kb == g.num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+  };
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
@@ -114,39 +140,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
-      // N >> 3 in bits [17,23), M >> 4 in bits [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
         const int acc = tcount & 1;
         mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < g.num_kb; kb++, it++) {
           const int s = it % g.stages;
           mbar_wait(&conv_bar[s], (it / g.stages) & 1);
           tcgen05_fence_after();
-          const uint32_t a_hi = smem_u32(smem + (size_t)s * g.stage_bytes);
-          const uint32_t a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_BYTES;
-          const uint32_t b_lo = b_hi + g.b_tile_bytes;
-          // the last k-block of a part holds K mod 32 live columns: the all-zero k-steps behind them are not issued
-          const int steps = kb == g.nkb0 - 1 ? g.last_steps[0] : (kb == g.num_kb - 1 ? g.last_steps[1] : BK / 8);
-          for (int k = 0; k < ((g.debug & 8) ? 0 : steps); k++) {
-            const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along the swizzled 128-byte row
-            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-            if (g.passes == 3) {
-              umma_tf32(d_tmem, make_desc_k128(a_lo + koff), make_desc_k128(b_hi + koff), idesc, first);
-              umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_lo + koff), idesc, 1u);
-              umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, first);
-            }
-          }
-          umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
+          issue_kblock(kb, s, acc);
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
       }
     }
   } else if (warp >= 8) {
