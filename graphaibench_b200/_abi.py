@@ -98,6 +98,10 @@ _SIGS = {
     "gai_softmax_ce_backward": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_stream]),
     "gai_softmax_ce_backward_scaled": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, C.c_int, C.c_uint64, c_stream]),
     "gai_masked_loss_accuracy": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "gai_sigmoid_ce_forward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, c_f32p, c_stream]),
+    "gai_sigmoid_ce_backward_ld": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_uint64, c_stream]),
+    "gai_masked_loss_mean": (C.c_int, [C.c_size_t, C.c_size_t, c_u8p, c_f32p, c_f32p, c_stream]),
+    "gai_masked_f1_micro": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, c_u8p, c_u8p, c_f32p, C.c_size_t, c_f32p, c_stream]),
     "gai_adam_update": (C.c_int, [C.c_size_t, c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, c_stream]),
     "gai_partition1d_h": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -342,6 +342,81 @@ __global__ void loss_acc_stage2_warp(int nparts, const double* __restrict__ part
   }
 }
 
+// ---- sigmoid (multi-label) loss: sigmoid_loss_layer::forward/backward (src/layers/sigmoid_loss_layer.cpp:4-36), sigmoid and
+// sigmoid_cross_entropy with the reference's mixed float/double expressions (math_functions.cpp:517-521,553-559). One warp per row;
+// labels are [nv x ncls] multi-hot bytes.
+__global__ void sigmoid_ce_fwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                      const float* __restrict__ logits, size_t ld_logits, float* __restrict__ probs, size_t ld_probs,
+                                      float* __restrict__ losses) {
+  const size_t row = begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= end) return;
+  if (masks && masks[row] != 1) return;
+  const float* x = logits + row * ld_logits;
+  const uint8_t* y = labels + row * (size_t)ncls;
+  float loss = 0.f;
+  for (int j = lane; j < ncls; j += 32) {
+    const float p = x[j];
+    probs[row * ld_probs + j] = (float)(1.0 / (1.0 + (double)expf(-p)));
+    const int pos = p >= 0.f ? 1 : 0;
+    const float e = expf((float)((double)p - 2.0 * (double)p * (double)pos));
+    loss -= __fsub_rn(__fmul_rn(p, (float)y[j] - (float)pos), logf((float)(1.0 + (double)e)));
+  }
+  loss = warp_sum(loss);
+  if (lane == 0) losses[row] = loss;
+}
+__global__ void sigmoid_ce_bwd_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                      const float* __restrict__ probs, size_t ld_probs, float* __restrict__ grad, size_t ld_grad, float denom) {
+  const size_t n = (end - begin) * ncls;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = begin + k / ncls;
+    const int j = (int)(k % ncls);
+    if (masks && masks[row] != 1) continue;
+    grad[row * ld_grad + j] = __fdiv_rn(probs[row * ld_probs + j] - (float)labels[row * (size_t)ncls + j], denom);  // sigmoid_loss_layer.cpp:29
+  }
+}
+// mean of losses over the masked rows (sigmoid_loss_layer::get_prediction_loss): per-CTA double partials, fixed-order fold
+__global__ void loss_mean_stage1(size_t begin, size_t end, const uint8_t* __restrict__ masks, const float* __restrict__ losses,
+                                 double* __restrict__ partial) {
+  __shared__ double s_l[256];
+  __shared__ unsigned s_n[256];
+  double l = 0.0; unsigned n = 0;
+  for (size_t row = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; row < end; row += (size_t)gridDim.x * blockDim.x)
+    if (!masks || masks[row] == 1) { l += (double)losses[row]; n++; }
+  s_l[threadIdx.x] = l; s_n[threadIdx.x] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tl = 0.0; unsigned tn = 0;
+    for (int i = 0; i < 256; i++) { tl += s_l[i]; tn += s_n[i]; }
+    partial[(size_t)blockIdx.x * 3 + 0] = tl; partial[(size_t)blockIdx.x * 3 + 1] = 0.0; partial[(size_t)blockIdx.x * 3 + 2] = (double)tn;
+  }
+}
+// micro-F1 at threshold 0.5 over the (row, class) pairs of the masked rows (masked_f1_score, math_functions.cpp:580-623): integer
+// counts (deterministic), then 2PR/(P+R) in double
+__global__ void f1_count_kernel(int ncls, size_t begin, size_t end, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ labels,
+                                const float* __restrict__ preds, size_t ld_preds, unsigned long long* __restrict__ counts /*tp, fp, fn*/) {
+  unsigned tp = 0, fp = 0, fn = 0;
+  const size_t n = (end - begin) * ncls;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = begin + k / ncls;
+    const int j = (int)(k % ncls);
+    if (masks && masks[row] != 1) continue;
+    const bool pos = preds[row * ld_preds + j] > 0.5f;
+    const uint8_t y = labels[row * (size_t)ncls + j];
+    tp += (y == 1 && pos); fp += (y == 0 && pos); fn += (y == 1 && !pos);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tp += __shfl_xor_sync(0xffffffffu, tp, o); fp += __shfl_xor_sync(0xffffffffu, fp, o); fn += __shfl_xor_sync(0xffffffffu, fn, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(counts + 0, (unsigned long long)tp); atomicAdd(counts + 1, (unsigned long long)fp); atomicAdd(counts + 2, (unsigned long long)fn); }
+}
+__global__ void f1_final_kernel(const unsigned long long* __restrict__ counts, float* __restrict__ f1) {
+  const double tp = (double)counts[0], fp = (double)counts[1], fn = (double)counts[2];
+  const double prec = tp + fp > 0 ? tp / (tp + fp) : 0.0, rec = tp + fn > 0 ? tp / (tp + fn) : 0.0;
+  *f1 = (float)(rec + prec > 0.0 ? 2.0 * (rec * prec) / (rec + prec) : 0.0);
+}
+
 // optimizer.cpp:22-35 — eps inside the sqrt; b1_t/b2_t are the powers BEFORE this call's post-multiply.
 __global__ void adam_kernel(size_t n, const float* __restrict__ dW, float* __restrict__ W, float* __restrict__ m, float* __restrict__ v,
                             float lr, float b1, float b2, float b1_t, float b2_t, float eps) {
@@ -545,6 +620,56 @@ int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_
 int gai_masked_loss_accuracy(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                              const float* losses, float* stats_d, gai_stream_t stream) {
   return gai_masked_loss_accuracy_ld(ncls, begin, end, masks, labels, logits, (size_t)ncls, losses, stats_d, stream);
+}
+
+int gai_sigmoid_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* logits,
+                              size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels_multi && logits && probs && losses && ld_logits >= (size_t)ncls && ld_probs >= (size_t)ncls);
+  if (begin == end) return GAI_OK;
+  sigmoid_ce_fwd_kernel<<<(unsigned)(((end - begin) * 32 + 255) / 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels_multi, logits,
+                                                                                                    ld_logits, probs, ld_probs, losses);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_sigmoid_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* probs,
+                               size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels_multi && probs && grad_out && denom > 0 && ld_grad >= (size_t)ncls && ld_probs >= (size_t)ncls);
+  if (begin == end) return GAI_OK;
+  sigmoid_ce_bwd_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels_multi, probs, ld_probs,
+                                                                                         grad_out, ld_grad, (float)denom);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_masked_loss_mean(size_t begin, size_t end, const uint8_t* masks, const float* losses, float* stats_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(begin <= end && losses && stats_d);
+  size_t blocks = (end - begin + 255) / 256;
+  const size_t cap = (size_t)gai::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  void* ws = nullptr;
+  int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws);
+  if (rc != GAI_OK) return rc;
+  loss_mean_stage1<<<(unsigned)blocks, 256, 0, gai::S(stream)>>>(begin, end, masks, losses, reinterpret_cast<double*>(ws));
+  GAI_LAUNCH_CHECK();
+  loss_acc_stage2_warp<<<1, 32, 0, gai::S(stream)>>>((int)blocks, reinterpret_cast<const double*>(ws), stats_d);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_masked_f1_micro(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* preds, size_t ld_preds,
+                        float* f1_d, gai_stream_t stream) {
+  GAI_CHECK_ARG(ncls > 0 && begin <= end && labels_multi && preds && f1_d && ld_preds >= (size_t)ncls);
+  void* ws = nullptr;
+  int rc = gai::workspace(sizeof(unsigned long long) * 4, &ws);
+  if (rc != GAI_OK) return rc;
+  GAI_CUDA(cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 4, gai::S(stream)));
+  if (begin != end) {
+    f1_count_kernel<<<grid_for((end - begin) * ncls, 256), 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels_multi, preds, ld_preds,
+                                                                                    reinterpret_cast<unsigned long long*>(ws));
+    GAI_LAUNCH_CHECK();
+  }
+  f1_final_kernel<<<1, 1, 0, gai::S(stream)>>>(reinterpret_cast<const unsigned long long*>(ws), f1_d);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
 }
 
 int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, float lr, float b1, float b2, float b1_t, float b2_t, float eps,

@@ -459,6 +459,37 @@ acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t c
   return h[0];
 }
 
+void sigmoid_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
+  gai_host::OpScope sc("LOSS", "sigmoid fwd", 4.0 * (end - begin) * (2 * num_cls + 1) + (double)(end - begin) * num_cls, 0);
+  die_on(gai_sigmoid_ce_forward_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, stream()),
+         "gai_sigmoid_ce_forward");
+}
+void sigmoid_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
+  gai_host::OpScope sc("LOSS", "sigmoid bwd", 8.0 * (end - begin) * num_cls, 0);
+  if (begin == end) return;
+  die_on(gai_sigmoid_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, pitch4(num_cls), grad_out, pitch4(num_cls), (uint64_t)(end - begin),
+                                    stream()), "gai_sigmoid_ce_backward");
+}
+acc_t sigmoid_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
+  {
+    gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin), 0);
+    die_on(gai_masked_loss_mean(begin, end, masks, d_losses, d_stats, stream()), "gai_masked_loss_mean");
+  }
+  float h[3] = {0, 0, 0};
+  copy_float_to_host(3, d_stats, h);
+  (void)count;
+  return h[0];
+}
+
+float masked_accuracy_multi(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
+  static float* d_f1 = nullptr;
+  if (!d_f1) d_f1 = float_malloc_device_zero(4);
+  die_on(gai_masked_f1_micro(num_classes, begin, end, masks, ground_truth, preds, pitch4(num_classes), d_f1, stream()), "gai_masked_f1_micro");
+  float h = 0.f;
+  copy_float_to_host(1, d_f1, &h);
+  return h;
+}
+
 // preds: the loss layer's feat_in (rows pitched to 4 floats, as every layer-owned buffer)
 float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
   static float* scratch = nullptr;

@@ -247,4 +247,17 @@ class softmax_loss_layer : public loss_layer {
   bool stats_valid = false;
 };
 
+// the output layer for multi-label classification (include/layers/sigmoid_loss_layer.h, src/layers/sigmoid_loss_layer.cpp:4-55);
+// labels are [nv x ncls] multi-hot bytes on the device
+class sigmoid_loss_layer : public loss_layer {
+ public:
+  sigmoid_loss_layer(int nv, int ncls, label_t* ptr) : loss_layer(nv, ncls, ptr) {}
+  void forward(size_t begin, size_t end, mask_t* masks) override;
+  void backward(size_t begin, size_t end, mask_t* masks, float* grad_out) override;
+  acc_t get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) override;
+};
+
 float masked_accuracy_single(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);
+// micro-F1 at threshold 0.5 (masked_accuracy_multi -> masked_f1_score, math_functions.cpp:94-97,580-623); preds: the loss layer's
+// feat_out (sigmoid outputs, rows pitched to 4 floats), ground_truth: [nv x ncls] multi-hot
+float masked_accuracy_multi(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);

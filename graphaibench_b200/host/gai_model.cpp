@@ -44,7 +44,6 @@ void Model<L>::load_data(int argc, char* argv[]) {
     inductive = atoi(argv[12]) != 0;
   }
   assert(num_layers >= 2);
-  if (is_sigmoid) { std::cerr << "sigmoid (multi-label) loss is not built yet\n"; std::exit(1); }
   if (subg_size > 0 || inductive) { std::cerr << "subgraph sampling / inductive training is out of scope of this build\n"; std::exit(1); }
   full_graph = new Graph(true);
   Reader reader(dataset_name);
@@ -179,7 +178,8 @@ void Model<L>::construct_network() {  // net.cpp:422-453
       layer_gconv[l - 1].set_grad_premasked(true);
     }
   }
-  layer_loss = new softmax_loss_layer(nv, num_cls, d_labels);
+  if (is_sigmoid) layer_loss = new sigmoid_loss_layer(nv, num_cls, d_labels);  // net.cpp:447-451
+  else layer_loss = new softmax_loss_layer(nv, num_cls, d_labels);
   opt_ = new adam(lrate);  // net.cpp:362
   sync();
 }
@@ -208,6 +208,8 @@ acc_t Model<L>::forward_prop(acc_t& loss) {
   run_forward_layers();
   layer_loss->forward(train_begin, train_end, d_masks_train);
   loss = layer_loss->get_prediction_loss(train_begin, train_end, train_count, d_masks_train);
+  if (is_sigmoid)  // net.cpp:495-497
+    return masked_accuracy_multi((int)train_begin, (int)train_end, (int)train_count, num_cls, d_masks_train, layer_loss->get_feat_out(), d_labels);
   return static_cast<softmax_loss_layer*>(layer_loss)->last_accuracy();  // same reduction pass as the loss mean
 }
 
@@ -215,6 +217,13 @@ template <typename L>
 acc_t Model<L>::evaluate(std::string type) {
   set_netphases(net_phase::TEST);
   run_forward_layers();
+  if (is_sigmoid) {  // net.cpp:569-572: the loss layer's forward produces the sigmoid outputs the F1 score thresholds
+    const bool test = type == "test";
+    const size_t b = test ? test_begin : val_begin, e = test ? test_end : val_end, c = test ? test_count : val_count;
+    mask_t* mk = test ? d_masks_test : d_masks_val;
+    layer_loss->forward(b, e, mk);
+    return masked_accuracy_multi((int)b, (int)e, (int)c, num_cls, mk, layer_loss->get_feat_out(), d_labels);
+  }
   if (type == "test") return masked_accuracy_single((int)test_begin, (int)test_end, (int)test_count, num_cls, d_masks_test, layer_loss->get_feat_in(), d_labels);
   return masked_accuracy_single((int)val_begin, (int)val_end, (int)val_count, num_cls, d_masks_val, layer_loss->get_feat_in(), d_labels);
 }

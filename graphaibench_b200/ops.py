@@ -275,6 +275,30 @@ def masked_loss_accuracy(logits, labels, masks, begin, end, losses, stats=None):
     return stats
 
 
+def sigmoid_ce_forward(logits, labels_multi, masks, begin, end, probs, losses):
+    """sigmoid_loss_layer::forward: probs = sigmoid(logits), losses[i] = multi-label cross-entropy; labels_multi uint8 [nv, ncls]."""
+    check(lib().gai_sigmoid_ce_forward_ld(logits.shape[1], begin, end, _p(masks), _p(labels_multi), _f32(logits), logits.stride(0), _f32(probs),
+                                          probs.stride(0), _f32(losses), _stream()), "gai_sigmoid_ce_forward_ld")
+
+
+def sigmoid_ce_backward(probs, labels_multi, masks, begin, end, grad, denom=None):
+    check(lib().gai_sigmoid_ce_backward_ld(probs.shape[1], begin, end, _p(masks), _p(labels_multi), _f32(probs), probs.stride(0), _f32(grad),
+                                           grad.stride(0), denom if denom is not None else max(end - begin, 1), _stream()), "gai_sigmoid_ce_backward_ld")
+
+
+def masked_loss_mean(losses, masks, begin, end):
+    stats = torch.empty(3, dtype=torch.float32, device=losses.device)
+    check(lib().gai_masked_loss_mean(begin, end, _p(masks), _f32(losses), _f32(stats), _stream()), "gai_masked_loss_mean")
+    return stats
+
+
+def masked_f1_micro(preds, labels_multi, masks, begin, end):
+    out = torch.empty(1, dtype=torch.float32, device=preds.device)
+    check(lib().gai_masked_f1_micro(preds.shape[1], begin, end, _p(masks), _p(labels_multi), _f32(preds), preds.stride(0), _f32(out), _stream()),
+          "gai_masked_f1_micro")
+    return out
+
+
 def adam_update(dW, W, m, v, lr, b1_t, b2_t, b1=0.9, b2=0.999, eps=1e-8):
     check(lib().gai_adam_update(W.numel(), _f32(dW), _f32(W), _f32(m), _f32(v), lr, b1, b2, b1_t, b2_t, eps, _stream()), "gai_adam_update")
 

@@ -222,6 +222,20 @@ int gai_softmax_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t
 int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels, const float* logits,
                                 size_t ld_logits, const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
 
+/* ---- sigmoid_loss_layer (multi-label; src/layers/sigmoid_loss_layer.cpp:4-55, sigmoid / sigmoid_cross_entropy
+ *      math_functions.cpp:517-521,553-559) and masked_accuracy_multi = micro-F1 at threshold 0.5 (math_functions.cpp:94-97,580-623).
+ * labels_multi: [nv x ncls] multi-hot bytes (Reader::bin_read_vlabels(labels, false), reader.cpp:347-412).
+ * forward : probs = sigmoid(logits), losses[i] = sum_j sigmoid cross-entropy, rows of [begin,end) with masks[i]==1.
+ * backward: grad = (probs - y) / (float)denom  (the reference divides by end - begin).
+ * gai_masked_loss_mean: stats_d = {mean of losses over the masked rows, 0, count}.  gai_masked_f1_micro: *f1_d = micro-F1. */
+int gai_sigmoid_ce_forward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* logits,
+                              size_t ld_logits, float* probs, size_t ld_probs, float* losses, gai_stream_t stream);
+int gai_sigmoid_ce_backward_ld(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* probs,
+                               size_t ld_probs, float* grad_out, size_t ld_grad, uint64_t denom, gai_stream_t stream);
+int gai_masked_loss_mean(size_t begin, size_t end, const uint8_t* masks, const float* losses, float* stats_d /*3 floats*/, gai_stream_t stream);
+int gai_masked_f1_micro(int ncls, size_t begin, size_t end, const uint8_t* masks, const uint8_t* labels_multi, const float* preds, size_t ld_preds,
+                        float* f1_d, gai_stream_t stream);
+
 /* ---- adam::update (src/utilities/optimizer.cpp:22-35; GPU twin optimizer.cu:5-36).  The caller owns m, v and
  *      the running powers b1_t/b2_t (they advance once per update() call on the reference's optimiser object). */
 int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, float lr, float b1, float b2, float b1_t, float b2_t,

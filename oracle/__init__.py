@@ -72,6 +72,8 @@ def liborc():
         L.orc_d_relu.argtypes = [C.c_size_t, f32p, f32p, f32p]
         L.orc_softmax_loss.argtypes = [C.c_int, f32p, u8p, C.c_void_p, C.c_size_t, C.c_size_t, f32p, f32p, C.c_void_p, C.c_void_p]
         L.orc_softmax_loss.restype = C.c_float
+        L.orc_sigmoid_loss.argtypes = [C.c_int, f32p, u8p, C.c_void_p, C.c_size_t, C.c_size_t, f32p, f32p, C.c_void_p, C.c_void_p]
+        L.orc_sigmoid_loss.restype = C.c_float
         L.orc_adam.argtypes = [C.c_size_t, f32p, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_float]
         L.orc_l2norm.argtypes = [C.c_int, C.c_int, f32p, f32p]
         L.orc_d_l2norm.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p]
@@ -109,6 +111,9 @@ def libref():
         L.ref_matmul.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int]
         L.ref_softmax_loss.argtypes = [C.c_int, C.c_int, f32p, u8p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_softmax_loss.restype = C.c_float
+        L.ref_sigmoid_loss.argtypes = [C.c_int, C.c_int, f32p, u8p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+        L.ref_sigmoid_loss.restype = C.c_float
         L.ref_adam_steps.argtypes = [C.c_size_t, C.c_float, C.c_int, f32p, f32p]
         L.ref_model_new.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, u8p, i64p, C.c_int]
         L.ref_model_new.restype = C.c_void_p

@@ -249,6 +249,43 @@ float orc_softmax_loss(int ncls, const float* logits, const uint8_t* labels, con
   return count ? total / (float)count : 0.0f;
 }
 
+/* ---- sigmoid_loss_layer::forward/backward/get_prediction_loss (src/layers/sigmoid_loss_layer.cpp:4-55), sigmoid and
+ * sigmoid_cross_entropy (src/utilities/math_functions.cpp:517-521,553-559, with their mixed float/double arithmetic) and
+ * masked_accuracy_multi = micro-F1 over (row, class) pairs at threshold 0.5 (math_functions.cpp:94-97,580-623).
+ * labels: [nv x ncls] multi-hot. grad = (p - y) / (float)(end - begin) on masked rows, others untouched. Returns the mean loss. */
+float orc_sigmoid_loss(int ncls, const float* logits, const uint8_t* labels, const uint8_t* masks, size_t begin, size_t end,
+                       float* probs, float* losses, float* grad, float* f1) {
+  float total = 0.0f;
+  size_t count = 0;
+  long tp = 0, fp = 0, fn = 0;
+  for (size_t i = begin; i < end; i++) {
+    if (masks && masks[i] != 1) continue;
+    const float* x = logits + (size_t)ncls * i;
+    const uint8_t* y = labels + (size_t)ncls * i;
+    float* p = probs + (size_t)ncls * i;
+    float loss = 0.0f;
+    for (int j = 0; j < ncls; j++) {
+      p[j] = (float)(1. / (1. + expf(-x[j])));
+      loss -= x[j] * ((float)y[j] - (x[j] >= 0.)) - logf((float)(1. + expf((float)(x[j] - 2. * x[j] * (x[j] >= 0.)))));
+    }
+    losses[i] = loss;
+    total += loss;
+    count++;
+    if (grad)
+      for (int j = 0; j < ncls; j++) grad[(size_t)ncls * i + j] = (p[j] - (float)y[j]) / (float)(end - begin);
+    for (int j = 0; j < ncls; j++) {
+      if (y[j] == 1 && p[j] > 0.5) tp++;
+      else if (y[j] == 0 && p[j] > 0.5) fp++;
+      else if (y[j] == 1 && p[j] <= 0.5) fn++;
+    }
+  }
+  if (f1) {
+    const double prec = tp + fp > 0 ? (double)tp / (double)(tp + fp) : 0., rec = tp + fn > 0 ? (double)tp / (double)(tp + fn) : 0.;
+    *f1 = (float)(rec + prec > 0. ? 2. * (rec * prec) / (rec + prec) : 0.);
+  }
+  return count ? total / (float)count : 0.0f;
+}
+
 /* ---- adam::update: src/utilities/optimizer.cpp:22-35 (eps inside the sqrt; b1_t/b2_t advance per call) */
 void orc_adam(size_t n, const float* dW, float* W, float* m, float* v, float alpha, float b1, float b2, float* b1_t, float* b2_t, float eps) {
   for (size_t i = 0; i < n; i++) {

@@ -17,6 +17,7 @@
 #include "net.h"
 #include "math_functions.hh"
 #include "softmax_loss_layer.h"
+#include "sigmoid_loss_layer.h"
 
 std::map<char, double> time_ops;  // reference global (defined in train.cpp:3, which is not linked here)
 
@@ -211,6 +212,20 @@ float ref_softmax_loss(int nv, int ncls, const float* logits, const uint8_t* lab
   if (probs) memcpy(probs, l.get_feat_out(), sizeof(float) * nv * ncls);
   if (grad) l.backward(begin, end, (mask_t*)masks, grad);
   if (acc) *acc = masked_accuracy_single(begin, end, count, ncls, (mask_t*)masks, l.get_feat_in(), (label_t*)labels);
+  return loss;
+}
+// sigmoid (multi-label) loss on caller-supplied logits (src/layers/sigmoid_loss_layer.cpp:4-55) and the micro-F1 the reference
+// reports as "accuracy" (masked_accuracy_multi -> masked_f1_score, math_functions.cpp:94-97,580-623). labels: [nv x ncls] multi-hot.
+float ref_sigmoid_loss(int nv, int ncls, const float* logits, const uint8_t* labels, const uint8_t* masks, size_t begin, size_t end,
+                       size_t count, float* probs, float* losses, float* grad, float* f1) {
+  sigmoid_loss_layer l(nv, ncls, (label_t*)labels);
+  memcpy(l.get_feat_in(), logits, sizeof(float) * nv * ncls);
+  l.forward(begin, end, (mask_t*)masks);
+  float loss = l.get_prediction_loss(begin, end, count, (mask_t*)masks);
+  if (probs) memcpy(probs, l.get_feat_out(), sizeof(float) * nv * ncls);
+  if (losses) for (size_t i = begin; i < end; i++) losses[i] = sigmoid_cross_entropy(ncls, (label_t*)labels + (size_t)ncls * i, logits + (size_t)ncls * i);
+  if (grad) l.backward(begin, end, (mask_t*)masks, grad);
+  if (f1) *f1 = masked_accuracy_multi(begin, end, count, ncls, (mask_t*)masks, l.get_feat_out(), (label_t*)labels);
   return loss;
 }
 // One Adam step with a fresh optimizer advanced `prior_calls` times (src/utilities/optimizer.cpp:22-35).

@@ -424,3 +424,30 @@ def test_wgrad_two_b_vs_fp64(T, ops, shape, padded):
     c1, c2 = ops.wgrad_two_b(dev(T, A), dev(T, B1)[:, :y1], dev(T, B2)[:, :y2])
     close(c1.cpu().numpy(), A.astype(np.float64).T @ B1[:, :y1].astype(np.float64), 5e-6)
     close(c2.cpu().numpy(), A.astype(np.float64).T @ B2[:, :y2].astype(np.float64), 5e-6)
+
+
+def test_sigmoid_loss_and_f1_vs_reference_golden(T, ops):
+    """Multi-label loss kernels against vectors from the live reference (tests/golden/sigmoid.npz): probabilities / losses / gradient within
+    1e-6 (device expf / logf differ from glibc in the last bit), micro-F1 equal, through dense and pitched row layouts."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "sigmoid.npz"))
+    x, y, m, b, e = z["x"], z["y"], z["m"], int(z["b"]), int(z["e"])
+    nv, nc = x.shape
+    sel = m.astype(bool); sel[:b] = False; sel[e:] = False
+    for pitch in (nc, (nc + 3) // 4 * 4):
+        logits = T.zeros(nv, pitch, device="cuda"); logits[:, :nc] = dev(T, x)
+        probs = T.zeros(nv, pitch, device="cuda"); grad = T.zeros(nv, pitch, device="cuda"); losses = T.zeros(nv, device="cuda")
+        dy, dm = dev(T, y), dev(T, m)
+        ops.sigmoid_ce_forward(logits[:, :nc], dy, dm, b, e, probs[:, :nc], losses)
+        ops.sigmoid_ce_backward(probs[:, :nc], dy, dm, b, e, grad[:, :nc])
+        p = probs[:, :nc].cpu().numpy(); l = losses.cpu().numpy(); g = grad[:, :nc].cpu().numpy()
+        np.testing.assert_allclose(p[sel], z["probs"][sel], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(l[sel], z["losses"][sel], rtol=2e-6)
+        # p - y cancels where p ~ y: the bar is norm-wise (1e-6 of the largest gradient entry), as for every fp32 tensor in this suite
+        np.testing.assert_allclose(g, z["grad"], rtol=1e-6, atol=1e-6 * float(np.abs(z["grad"]).max()))
+        assert (g[~sel] == 0).all(), "rows outside the masked range keep their gradient"
+        st = ops.masked_loss_mean(losses, dm, b, e).cpu().numpy()
+        assert abs(st[0] - float(z["loss"])) <= 2e-6 * float(z["loss"]) and st[2] == sel.sum()
+        f1 = float(ops.masked_f1_micro(probs[:, :nc], dy, dm, b, e).cpu()[0])
+        assert abs(f1 - float(z["f1"])) < 1e-6

@@ -106,3 +106,29 @@ def test_medium_graph_layers_match_oracle(gm, arch, dims, layers):
     # Adam divides by sqrt(v): weights whose gradient is ~0 amplify last-bit gradient differences up to a fraction of lr per step
     for k in range(layers):
         close(m.get("W", k), o.layers[k].W, 2e-3)
+
+
+def test_cli_sigmoid_loss_on_cora(gm, cora, tmp_path):
+    """`gpu_train_gcn cora 60 1 sigmoid` (multi-hot labels, sigmoid cross-entropy, micro-F1 as accuracy; net.cpp:20,447-451,495-497,569-572)
+    against the reference's own CPU binary run in the build container:
+        oracle/_ref/cpu_train_gcn cora 60 8 sigmoid  ->  Epoch 0 train_loss 4.852 train_acc 0.236, Epoch 59 train_loss 1.577 train_acc 0.462,
+        Test accuracy 0.175."""
+    from graphaibench_b200 import datagen
+    d = tmp_path / "cora"
+    datagen.write_dataset(str(d), cora["rowptr64"], cora["colidx"], cora["feats"], cora["labels"], cora["ncls"], cora["split"])
+    env = dict(os.environ, DATASET_PATH=str(tmp_path) + "/")
+    out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_gcn"), "cora", "60", "1", "sigmoid"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Using multi-class (multi-hot) labels" in out.stdout
+    lines = out.stdout.splitlines()
+
+    def epoch(n):
+        f = [l for l in lines if l.startswith(f"Epoch {n:3d} ")][0].split()
+        return float(f[f.index("train_loss") + 1]), float(f[f.index("train_acc") + 1])
+    l0, a0 = epoch(0)
+    l59, a59 = epoch(59)
+    assert abs(l0 - 4.852) <= 0.002 and abs(a0 - 0.236) <= 0.002
+    assert abs(l59 - 1.577) <= 0.01 and abs(a59 - 0.462) <= 0.01
+    test = float([l for l in lines if l.startswith("Test accuracy:")][0].split()[2])
+    assert abs(test - 0.175) <= 0.01

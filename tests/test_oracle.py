@@ -150,3 +150,21 @@ def test_restatement_against_live_reference(small_graph):
     L.ref_matmul(300, 40, 70, A.reshape(-1), B.reshape(-1), c1.reshape(-1), 0, 0, 0)
     oracle.liborc().orc_gemm(300, 40, 70, A.reshape(-1), B.reshape(-1), c2.reshape(-1), 0, 0, 0)
     assert np.abs(c1 - c2).max() <= 1e-5 * np.abs(c1).max()
+
+
+def test_sigmoid_loss_restatement_matches_reference_golden(liborc):
+    """orc_sigmoid_loss (sigmoid_loss_layer.cpp:4-55, math_functions.cpp:517-521,553-559,580-623) against vectors generated from the live
+    reference (tests/golden/make_golden_sigmoid.py): probabilities, per-row losses, gradient, mean loss and micro-F1, bit for bit."""
+    import ctypes as C
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "sigmoid.npz"))
+    x, y, m, b, e = z["x"], z["y"], z["m"], int(z["b"]), int(z["e"])
+    nv, nc = x.shape
+    probs = np.zeros((nv, nc), np.float32); losses = np.zeros(nv, np.float32); grad = np.zeros((nv, nc), np.float32); f1 = C.c_float()
+    loss = liborc.orc_sigmoid_loss(nc, x.reshape(-1), y.reshape(-1), m.ctypes.data_as(C.c_void_p), b, e, probs.reshape(-1), losses,
+                                   grad.ctypes.data_as(C.c_void_p), C.byref(f1))
+    sel = m.astype(bool); sel[:b] = False; sel[e:] = False
+    assert np.array_equal(probs[sel], z["probs"][sel]) and np.array_equal(losses[sel], z["losses"][sel]) and np.array_equal(grad, z["grad"])
+    # the reference adds the per-row losses under an OpenMP reduction (sigmoid_loss_layer.cpp:38-47): order, hence the last bit, is free
+    assert abs(np.float32(loss) - z["loss"]) <= 1e-6 * z["loss"] and np.float32(f1.value) == z["f1"]
