@@ -84,6 +84,8 @@ _SIGS = {
     "gai_get_gemm_mode": (C.c_int, []),
     "gai_relu": (C.c_int, [C.c_size_t, c_f32p, c_f32p, c_stream]),
     "gai_d_relu": (C.c_int, [C.c_size_t, c_f32p, c_f32p, c_f32p, c_stream]),
+    "gai_dropout": (C.c_int, [C.c_size_t, C.c_float, C.c_float, C.c_uint64, C.c_uint64, c_f32p, c_u8p, c_f32p, c_stream]),
+    "gai_d_dropout": (C.c_int, [C.c_size_t, C.c_float, c_f32p, c_u8p, c_f32p, c_stream]),
     "gai_fill": (C.c_int, [C.c_size_t, C.c_float, c_f32p, c_stream]),
     "gai_l2norm": (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_stream]),
     "gai_d_l2norm": (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),

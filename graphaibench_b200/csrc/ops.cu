@@ -89,6 +89,29 @@ __global__ void d_relu_bits_kernel(size_t rows, int F, float* __restrict__ grad,
   }
 }
 
+// dropout / d_dropout (math_functions.cpp:404-440): out = in * (float)mask * scale, mask ~ Bernoulli(1 - rate) per element, redrawn on
+// every call. The reference draws from a /dev/urandom-seeded boost mt19937 (random.cpp:6-20), i.e. it is not reproducible; here the
+// mask is a counter-based hash of (seed, call, element index): reproducible, order-independent, no generator state.
+__device__ __forceinline__ uint32_t mix_u64(uint64_t z) {
+  z = (z ^ (z >> 33)) * 0xff51afd7ed558ccdULL;
+  z = (z ^ (z >> 33)) * 0xc4ceb9fe1a85ec53ULL;
+  return (uint32_t)((z ^ (z >> 33)) >> 32);
+}
+__global__ void dropout_kernel(size_t n, float keep, float scale, uint64_t seed, uint64_t call, const float* __restrict__ in,
+                               uint8_t* __restrict__ mask, float* __restrict__ out) {
+  const uint64_t base = seed * 0x9E3779B97F4A7C15ULL + call * 0xD1B54A32D192ED03ULL;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float u = (float)(mix_u64(base + (uint64_t)i * 0x2545F4914F6CDD1DULL) >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+    const uint8_t m = u < keep ? 1 : 0;
+    mask[i] = m;
+    out[i] = __fmul_rn(__fmul_rn(in[i], (float)m), scale);
+  }
+}
+__global__ void d_dropout_kernel(size_t n, float scale, const float* __restrict__ in, const uint8_t* __restrict__ mask, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fmul_rn(__fmul_rn(in[i], (float)mask[i]), scale);
+}
+
 __global__ void fill_kernel(size_t n, float value, float* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = value;
@@ -473,6 +496,20 @@ int gai_d_relu_ld(size_t rows, int F, const float* grad, size_t ld_grad, const f
   GAI_CHECK_ARG(grad && data && out && ld_grad >= (size_t)F && ld_data >= (size_t)F && ld_out >= (size_t)F);
   if (ld_grad == (size_t)F && ld_data == (size_t)F && ld_out == (size_t)F) return gai_d_relu(rows * F, grad, data, out, stream);
   d_relu_ld_kernel<<<grid_for(rows * F, 256), 256, 0, gai::S(stream)>>>(rows, F, grad, ld_grad, data, ld_data, out, ld_out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_dropout(size_t n, float rate, float scale, uint64_t seed, uint64_t call, const float* in, uint8_t* mask, float* out, gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(in && mask && out && rate >= 0.f && rate < 1.f);
+  dropout_kernel<<<grid_for(n, 256, 4), 256, 0, gai::S(stream)>>>(n, 1.0f - rate, scale, seed, call, in, mask, out);
+  GAI_LAUNCH_CHECK();
+  return GAI_OK;
+}
+int gai_d_dropout(size_t n, float scale, const float* in, const uint8_t* mask, float* out, gai_stream_t stream) {
+  if (n == 0) return GAI_OK;
+  GAI_CHECK_ARG(in && mask && out);
+  d_dropout_kernel<<<grid_for(n, 256, 4), 256, 0, gai::S(stream)>>>(n, scale, in, mask, out);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

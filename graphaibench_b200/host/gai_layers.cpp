@@ -205,7 +205,6 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
       feat_dropout_rate(feat_drop), score_dropout_rate(score_drop) {
   assert(feat_dropout_rate >= 0.f && feat_dropout_rate < 1.f);
   assert(score_dropout_rate >= 0.f && score_dropout_rate < 1.f);
-  if (feat_dropout_rate > 0.f) { std::cerr << "feature dropout is not supported yet (all reference configs run 0)\n"; std::exit(1); }
   feat_scale = 1.f / (1.f - feat_dropout_rate);
   const size_t n = (size_t)nv;
   d_W_neigh = upload_glorot(din, dout, 1);  // seeds: graph_conv_layer.cpp:13,18
@@ -228,9 +227,32 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
   if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * pitch4(din));
   if (id > 0) feat_in = float_malloc_device_zero(n * ld_in);
   grad_in = float_malloc_device_zero(n * ld_out);
+  if (feat_dropout_rate > 0.f) {  // dropout_mask + in_temp of the reference (graph_conv_layer.cpp:33-38)
+    d_drop_in = float_malloc_device_zero(n * ld_in);
+    void* mp = nullptr;
+    die_on(gai_malloc(&mp, n * ld_in), "gai_malloc");
+    d_dropout_mask = reinterpret_cast<uint8_t*>(mp);
+  }
   // aggregate-first layers apply ReLU in a dense-transform epilogue, which also emits the sign bits the layer above masks with
   if (act && !transform_first) d_relu_bits = reinterpret_cast<uint32_t*>(float_malloc_device_zero(n * bits_pitch(dout)));
   optm = new adam(lr);
+}
+
+// in_data of the reference's forward (gcn_layer.cpp:15-19): the dropped-out input in the TRAIN phase, feat_in otherwise
+template <typename A>
+const float* graph_conv_layer<A>::forward_input() {
+  if (!(feat_dropout_rate > 0.f && phase_ == net_phase::TRAIN)) return feat_in;
+  gai_host::OpScope sc("DROPOUT", "fwd n=" + std::to_string((size_t)num_samples * ld_in), 9.0 * num_samples * ld_in, 0);
+  die_on(gai_dropout((size_t)num_samples * ld_in, feat_dropout_rate, feat_scale, 0x5eedULL + (uint64_t)level_, dropout_calls++, feat_in, d_dropout_mask,
+                     d_drop_in, stream()), "gai_dropout");
+  return d_drop_in;
+}
+// grad_out *= mask * scale (gcn_layer.cpp:58-59)
+template <typename A>
+void graph_conv_layer<A>::backward_dropout(float* grad_out) {
+  if (level_ == 0 || !(feat_dropout_rate > 0.f) || grad_out == nullptr) return;
+  gai_host::OpScope sc("DROPOUT", "bwd n=" + std::to_string((size_t)num_samples * ld_in), 9.0 * num_samples * ld_in, 0);
+  die_on(gai_d_dropout((size_t)num_samples * ld_in, feat_scale, grad_out, d_dropout_mask, grad_out, stream()), "gai_d_dropout");
 }
 
 template <typename A>
@@ -287,11 +309,12 @@ GCN_layer::GCN_layer(int id, int nv, int din, int dout, Graph* g, bool act, floa
 void GCN_layer::forward(float* feat_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
+  const float* in_data = forward_input();
   if (y > z) {  // transform first: aggregate at the narrower width; ReLU rides the SpMM epilogue
-    mm(x, z, y, feat_in, ld_in, d_W_neigh, z, d_out_temp, ld_out);
+    mm(x, z, y, in_data, ld_in, d_W_neigh, z, d_out_temp, ld_out);
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, relu, nullptr);
   } else {      // aggregate first; ReLU rides the GEMM epilogue
-    aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
     if (is_act && d_relu_bits) mm_relu_bits(x, z, y, d_in_temp1, ldt, d_W_neigh, feat_out, ld_out, d_relu_bits);
     else mm(x, z, y, d_in_temp1, ldt, d_W_neigh, z, feat_out, ld_out, false, false, false, relu);
   }
@@ -306,7 +329,7 @@ void GCN_layer::backward(float* feat_out, float* grad_out) {
       if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in, mask_bits_in);
       else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
     }
-    mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);
+    mm(y, z, x, feat_dropout_rate > 0.f ? d_drop_in : feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);  // gcn_layer.cpp:48-50
   } else {
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
@@ -314,6 +337,7 @@ void GCN_layer::backward(float* feat_out, float* grad_out) {
     }
     mm(y, z, x, d_in_temp1, ldt, grad_in, ld_out, d_W_neigh_grad, z, true, false);
   }
+  backward_dropout(grad_out);
 }
 
 void GCN_layer::update_weight(optimizer* opt) { opt->update_gpu((size_t)dim_in * dim_out, d_W_neigh_grad, d_W_neigh); }  // shared optimiser (gcn_layer.cpp:62-66)
@@ -333,12 +357,13 @@ SAGE_layer::SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, fl
 void SAGE_layer::forward(float* feat_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
+  const float* in_data = forward_input();
   if (y > z) {
-    mm_ncat(x, y, feat_in, ld_in, z, d_W_neigh, d_out_temp, ld_out, d_W_self, feat_out, ld_out);
+    mm_ncat(x, y, in_data, ld_in, z, d_W_neigh, d_out_temp, ld_out, d_W_self, feat_out, ld_out);
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, GAI_EPI_ADD | relu, feat_out);
   } else {
-    aggr.aggregate_ld((int)y, *graph, feat_in, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
-    mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, feat_in, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0, nullptr,
+    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, in_data, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0, nullptr,
             is_act ? d_relu_bits : nullptr);
   }
 }
@@ -346,20 +371,22 @@ void SAGE_layer::forward(float* feat_out) {
 void SAGE_layer::backward(float* feat_out, float* grad_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
   if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
+  const float* in_data = feat_dropout_rate > 0.f ? d_drop_in : feat_in;  // sage_layer.cpp:35-36
   if (y > z) {
     aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
-    wgrad_two_b(x, y, feat_in, ld_in, z, grad_in, ld_out, d_W_self_grad, d_out_temp, ld_out, d_W_neigh_grad);
+    wgrad_two_b(x, y, in_data, ld_in, z, grad_in, ld_out, d_W_self_grad, d_out_temp, ld_out, d_W_neigh_grad);
     if (level_ > 0)
       mm_kcat(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_in, ld_out, d_W_self, grad_out, ld_in, true, 0,
               (mask_grad_out && !mask_bits_in) ? feat_in : nullptr, ld_in, mask_grad_out ? mask_bits_in : nullptr);
   } else {
-    wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad, feat_in, ld_in, d_W_self_grad);
+    wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad, in_data, ld_in, d_W_self_grad);
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
       mm(x, y, z, grad_in, ld_out, d_W_self, z, grad_out, ld_in, false, true);
       aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_ADD, grad_out, mask_grad_out ? mask_bits_in : nullptr);
     }
   }
+  backward_dropout(grad_out);
 }
 
 void SAGE_layer::update_weight(optimizer*) {  // the layer's own optimiser, neighbour then self (sage_layer.cpp:55-59)
@@ -376,7 +403,7 @@ GAT_layer::GAT_layer(int id, int nv, int din, int dout, Graph* g, bool act, floa
 
 void GAT_layer::forward(float* feat_out) {
   const size_t x = num_samples, y = dim_in, z = dim_out;
-  mm(x, z, y, feat_in, ld_in, d_W_neigh, z, d_out_temp, ld_out);
+  mm(x, z, y, forward_input(), ld_in, d_W_neigh, z, d_out_temp, ld_out);
   aggr.aggregate_fused((int)z, *graph, d_out_temp, feat_out, is_act ? GAI_EPI_RELU : GAI_EPI_NONE, nullptr);
 }
 
@@ -388,7 +415,8 @@ void GAT_layer::backward(float* feat_out, float* grad_out) {
     if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in, mask_bits_in);
     else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
   }
-  mm(y, z, x, feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);
+  mm(y, z, x, feat_dropout_rate > 0.f ? d_drop_in : feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);  // gat_layer.cpp:32
+  backward_dropout(grad_out);
 }
 
 void GAT_layer::update_weight(optimizer* opt) {

@@ -143,6 +143,12 @@ class graph_conv_layer {
   bool mask_grad_out = false, grad_premasked = false;
   uint32_t* d_relu_bits = nullptr;
   const uint32_t* mask_bits_in = nullptr;
+  // feature dropout (feat_dropout_rate > 0): the dropped-out input of the last training forward and its mask
+  float* d_drop_in = nullptr;
+  uint8_t* d_dropout_mask = nullptr;
+  unsigned long long dropout_calls = 0;
+  const float* forward_input();
+  void backward_dropout(float* grad_out);
   float *feat_in = nullptr, *grad_in = nullptr;
   float *d_in_temp = nullptr, *d_in_temp1 = nullptr, *d_out_temp = nullptr;
   float *d_W_neigh = nullptr, *d_W_neigh_grad = nullptr, *d_W_self = nullptr, *d_W_self_grad = nullptr;

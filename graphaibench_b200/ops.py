@@ -218,6 +218,20 @@ def wgrad_two_b(A, B1, B2, out1=None, out2=None):
     return c1, c2
 
 
+def dropout(x, rate, seed, call, out=None, mask=None):
+    """out = x * mask / (1 - rate), mask ~ Bernoulli(1 - rate) from hash(seed, call, index) (gai_dropout). Returns (out, mask uint8)."""
+    out = torch.empty_like(x) if out is None else out
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if mask is None else mask
+    check(lib().gai_dropout(x.numel(), rate, 1.0 / (1.0 - rate), seed, call, _f32(x), _p(mask), _f32(out), _stream()), "gai_dropout")
+    return out, mask
+
+
+def d_dropout(grad, mask, rate, out=None):
+    out = torch.empty_like(grad) if out is None else out
+    check(lib().gai_d_dropout(grad.numel(), 1.0 / (1.0 - rate), _f32(grad), _p(mask), _f32(out), _stream()), "gai_d_dropout")
+    return out
+
+
 def relu(x, out=None):
     out = torch.empty_like(x) if out is None else out
     check(lib().gai_relu(x.numel(), _f32(x), _f32(out), _stream()), "gai_relu")

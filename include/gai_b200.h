@@ -185,6 +185,11 @@ int gai_get_gemm_mode(void);
 int gai_relu(size_t n, const float* in, float* out, gai_stream_t stream);
 int gai_d_relu(size_t n, const float* grad, const float* data, float* out, gai_stream_t stream);
 int gai_fill(size_t n, float value, float* out, gai_stream_t stream); /* init_const_gpu, math_functions.cu:12-19 */
+/* dropout_cpu / d_dropout_cpu (math_functions.cpp:417-440): out = in * (float)mask * scale with mask ~ Bernoulli(1 - rate) per element.
+ * The reference's generator is seeded from /dev/urandom (not reproducible); here mask = hash(seed, call, index): pass a new `call` for
+ * every redraw (the reference redraws on every training forward). */
+int gai_dropout(size_t n, float rate, float scale, uint64_t seed, uint64_t call, const float* in, uint8_t* mask, float* out, gai_stream_t stream);
+int gai_d_dropout(size_t n, float scale, const float* in, const uint8_t* mask, float* out, gai_stream_t stream);
 
 /* ---- l2norm_layer (src/layers/l2norm_layer.cpp:19-64; l2norm/d_l2norm math_functions.cu:158-205) ---- */
 int gai_l2norm(int n, int dim, const float* in, float* out, gai_stream_t stream);

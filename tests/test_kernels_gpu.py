@@ -451,3 +451,25 @@ def test_sigmoid_loss_and_f1_vs_reference_golden(T, ops):
         assert abs(st[0] - float(z["loss"])) <= 2e-6 * float(z["loss"]) and st[2] == sel.sum()
         f1 = float(ops.masked_f1_micro(probs[:, :nc], dy, dm, b, e).cpu()[0])
         assert abs(f1 - float(z["f1"])) < 1e-6
+
+
+def test_dropout_mask_algebra_and_statistics(T, ops):
+    """dropout_cpu / d_dropout_cpu (math_functions.cpp:417-440): out = in * mask * scale exactly, the mask is Bernoulli(1 - rate), redrawn
+    per call, reproducible for the same (seed, call). The reference's generator is /dev/urandom-seeded, so only the algebra and the
+    statistics can be pinned."""
+    n, rate = 1 << 20, 0.3
+    x = T.randn(n, device="cuda")
+    out, mask = ops.dropout(x, rate, seed=7, call=0)
+    scale = np.float32(1.0 / (1.0 - rate))
+    want = (x.cpu().numpy() * mask.cpu().numpy().astype(np.float32)) * scale
+    assert np.array_equal(out.cpu().numpy(), want)
+    keep = float(mask.float().mean())
+    assert abs(keep - (1 - rate)) < 3e-3, keep
+    out2, mask2 = ops.dropout(x, rate, seed=7, call=0)
+    assert T.equal(mask, mask2) and T.equal(out, out2)
+    _, mask3 = ops.dropout(x, rate, seed=7, call=1)
+    agree = float((mask3 == mask).float().mean())
+    assert abs(agree - ((1 - rate) ** 2 + rate ** 2)) < 5e-3, agree  # independent redraw
+    g = T.randn(n, device="cuda")
+    dg = ops.d_dropout(g, mask, rate)
+    assert np.array_equal(dg.cpu().numpy(), (g.cpu().numpy() * mask.cpu().numpy().astype(np.float32)) * scale)

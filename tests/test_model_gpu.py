@@ -132,3 +132,23 @@ def test_cli_sigmoid_loss_on_cora(gm, cora, tmp_path):
     assert abs(l59 - 1.577) <= 0.01 and abs(a59 - 0.462) <= 0.01
     test = float([l for l in lines if l.startswith("Test accuracy:")][0].split()[2])
     assert abs(test - 0.175) <= 0.01
+
+
+def test_cli_feature_dropout_on_cora(gm, cora, tmp_path):
+    """`gpu_train_gcn cora 200 1 softmax 16 0 0.5 0.02` (feature dropout 0.5, argv as net.cpp:13-64). Dropout is stochastic in the reference
+    too (/dev/urandom seed): its CPU binary gives test accuracy 0.800 / 0.801 and a final train loss of 0.026 / 0.032 on two runs (0.795 and
+    0.005 without dropout), so the check is a band: the regularised regime, not the rate-0 trajectory."""
+    from graphaibench_b200 import datagen
+    d = tmp_path / "cora"
+    datagen.write_dataset(str(d), cora["rowptr64"], cora["colidx"], cora["feats"], cora["labels"], cora["ncls"], cora["split"])
+    env = dict(os.environ, DATASET_PATH=str(tmp_path) + "/")
+    out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_gcn"), "cora", "200", "1", "softmax", "16", "0", "0.5", "0.02"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "feat_drop = 0.5" in out.stdout
+    lines = out.stdout.splitlines()
+    last = [l for l in lines if l.startswith("Epoch 199 ")][0].split()
+    loss = float(last[last.index("train_loss") + 1])
+    test = float([l for l in lines if l.startswith("Test accuracy:")][0].split()[2])
+    assert 0.012 <= loss <= 0.08, loss
+    assert 0.775 <= test <= 0.825, test
