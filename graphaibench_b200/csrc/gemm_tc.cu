@@ -480,7 +480,11 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
     if (bitmask && q.ldmask < (q.N[0] + 31) / 32) return GAI_ERR_UNSUPPORTED;
   }
   g.M = M; g.n_mma = n_mma; g.nkb0 = nkb[0]; g.num_kb = num_kb; g.last_steps[0] = last_steps[0]; g.last_steps[1] = last_steps[1];
-  static const int debug_knobs = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+  static const int debug_knobs = [] {
+    const int k = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+    if (k) fprintf(stderr, "libgai_b200: GAI_TC_DEBUG=%d — timing experiment, dense-transform RESULTS ARE WRONG (tools/gemm_probe.py only)\n", k);
+    return k;
+  }();
   g.debug = debug_knobs;
   g.stages = stages; g.passes = passes; g.accum = q.accum; g.flags = q.flags; g.stage_bytes = stage_bytes; g.b_tile_bytes = b_tile_bytes;
   if ((q.flags & GAI_EPI_MASK) && !q.mask) return set_error(GAI_ERR_ARG, "gemm_tc", "GAI_EPI_MASK without a mask matrix");

@@ -256,7 +256,11 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   WgArgs g;
   memset(&g, 0, sizeof(g));
   g.nrows = nrows; g.passes = passes;
-  static const int debug_knobs = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+  static const int debug_knobs = [] {
+    const int k = getenv("GAI_TC_DEBUG") ? atoi(getenv("GAI_TC_DEBUG")) : 0;
+    if (k) fprintf(stderr, "libgai_b200: GAI_TC_DEBUG=%d — timing experiment, dense-transform RESULTS ARE WRONG (tools/gemm_probe.py only)\n", k);
+    return k;
+  }();
   g.debug = debug_knobs;
   g.dual_a = na == 2;
   if (na == 2) {
