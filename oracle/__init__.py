@@ -117,6 +117,8 @@ def libref():
         L.ref_adam_steps.argtypes = [C.c_size_t, C.c_float, C.c_int, f32p, f32p]
         L.ref_model_new.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, u8p, i64p, C.c_int]
         L.ref_model_new.restype = C.c_void_p
+        L.ref_model_new_sigmoid.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, u8p, i64p, C.c_int]
+        L.ref_model_new_sigmoid.restype = C.c_void_p
         L.ref_model_train_epoch.argtypes = [C.c_void_p, C.POINTER(C.c_float)]; L.ref_model_train_epoch.restype = C.c_float
         L.ref_model_forward.argtypes = [C.c_void_p, C.POINTER(C.c_float)]; L.ref_model_forward.restype = C.c_float
         L.ref_model_backward.argtypes = [C.c_void_p]
@@ -134,14 +136,15 @@ ARCH_ID = {"gcn": 0, "sage": 1, "gat": 2}
 class RefModel:
     """The reference's Model<L> driven in memory (see ref_harness.cpp)."""
 
-    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02, threads=1):
+    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02, threads=1, sigmoid=False):
         L = libref()
         nv = len(rowptr) - 1
         rp = np.ascontiguousarray(rowptr, np.uint32)
         ci = np.ascontiguousarray(colidx, np.uint32)
         self.g = L.ref_graph_new(nv, len(ci), rp, ci)
         feats = np.ascontiguousarray(feats, np.float32)
-        self.h = L.ref_model_new(ARCH_ID[arch], self.g, nv, feats.shape[1], dim_hid, num_cls, num_layers, lr, feats,
+        new = L.ref_model_new_sigmoid if sigmoid else L.ref_model_new
+        self.h = new(ARCH_ID[arch], self.g, nv, feats.shape[1], dim_hid, num_cls, num_layers, lr, feats,
                                  np.ascontiguousarray(labels, np.uint8), np.ascontiguousarray(split9, np.int64), threads)
         self.L = L
 

@@ -183,8 +183,9 @@ class ConvLayer:
 class OracleModel:
     """Model<L> for subg_size == 0, softmax loss (src/gnn/net.cpp)."""
 
-    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02):
+    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02, sigmoid=False):
         self.arch = arch
+        self.sigmoid = sigmoid  # argv[4] == "sigmoid": multi-hot labels, sigmoid_loss_layer, micro-F1 as accuracy (net.cpp:20,447-451)
         self.g = Graph(rowptr, colidx)
         if arch != "sage":
             self.g.add_selfloop()  # net.cpp:96
@@ -194,6 +195,11 @@ class OracleModel:
         self.feats = _f(feats).reshape(-1)
         dim_init = np.asarray(feats).shape[1]
         self.labels = np.ascontiguousarray(labels, np.uint8)
+        if sigmoid:  # Reader::bin_read_vlabels(labels, false), reader.cpp:347-412
+            hot = np.zeros((len(self.labels), num_cls), np.uint8)
+            ok = self.labels < num_cls
+            hot[np.nonzero(ok)[0], self.labels[ok]] = 1
+            self.labels = np.ascontiguousarray(hot.reshape(-1))
         (self.tb, self.te, self.tc, self.vb, self.ve, self.vc, self.sb, self.se, self.sc) = [int(v) for v in split9]
         self.masks = {}
         for name, (b, e) in {"train": (self.tb, self.te), "val": (self.vb, self.ve), "test": (self.sb, self.se)}.items():
@@ -227,19 +233,21 @@ class OracleModel:
         else:
             Ls[-1].forward(self.logits)
 
+    def _loss(self, mask, b, e, grad):
+        fn = liborc().orc_sigmoid_loss if self.sigmoid else liborc().orc_softmax_loss
+        acc = C.c_float()
+        loss = fn(self.ncls, self.logits, self.labels, mask.ctypes.data_as(C.c_void_p), b, e, self.probs, self.losses,
+                  grad.ctypes.data_as(C.c_void_p) if grad is not None else None, C.byref(acc))
+        return float(loss), float(acc.value)
+
     def forward(self):
         self._forward_layers()
-        acc = C.c_float()
-        loss = liborc().orc_softmax_loss(self.ncls, self.logits, self.labels, self.masks["train"].ctypes.data_as(C.c_void_p),
-                                         self.tb, self.te, self.probs, self.losses, None, C.byref(acc))
-        return float(loss), float(acc.value)
+        return self._loss(self.masks["train"], self.tb, self.te, None)
 
     def backward(self):  # net.cpp:580-615
         Ls = self.layers
         last_grad = self.d_grad_in if self.use_dense else Ls[-1].grad_in
-        acc = C.c_float()
-        liborc().orc_softmax_loss(self.ncls, self.logits, self.labels, self.masks["train"].ctypes.data_as(C.c_void_p),
-                                  self.tb, self.te, self.probs, self.losses, last_grad.ctypes.data_as(C.c_void_p), C.byref(acc))
+        self._loss(self.masks["train"], self.tb, self.te, last_grad)
         if self.use_dense:  # dense_layer.cpp:57-72 (updates its own weights inside backward), l2norm_layer.cpp:40-64
             matmul(self.hid, self.ncls, self.nv, self.d_feat_in, self.d_grad_in, self.d_W_grad, True)
             matmul(self.nv, self.hid, self.ncls, self.d_grad_in, self.d_W, self.l2_grad_in, False, True)
@@ -265,6 +273,8 @@ class OracleModel:
     def evaluate(self, which="test"):  # net.cpp:506-577 (softmax branch: argmax over logits only)
         self._forward_layers()
         b, e = (self.vb, self.ve) if which == "val" else (self.sb, self.se)
+        if self.sigmoid:  # net.cpp:569-572: loss forward over the range, then micro-F1 of the sigmoid outputs
+            return self._loss(self.masks["val" if which == "val" else "test"], b, e, None)[1]
         lg = self.logits.reshape(self.nv, self.ncls)[b:e]
         pred = np.argmax(lg, axis=1)
         return float(np.float32(np.sum(pred == self.labels[b:e])) / np.float32(e - b))

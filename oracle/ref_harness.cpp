@@ -43,7 +43,7 @@ struct ModelBox : ModelBase {
   Model<L>* m;
   optimizer* opt;
   ModelBox(Graph* g, int nv, int dim_init, int dim_hid, int num_cls, int num_layers, float lr,
-           const float* feats, const uint8_t* labels, const int64_t* split, int threads) {
+           const float* feats, const uint8_t* labels, const int64_t* split, int threads, bool sigmoid = false) {
     omp_set_num_threads(threads);
     openblas_set_num_threads(threads);
     m = (Model<L>*)operator new(sizeof(Model<L>));
@@ -52,7 +52,12 @@ struct ModelBox : ModelBase {
     new (&m->dataset_name) std::string("harness");
     new (&m->layer_gconv) std::vector<L>();
     new (&m->input_features) std::vector<float>(feats, feats + (size_t)nv * dim_init);
-    new (&m->labels) std::vector<label_t>(labels, labels + nv);
+    if (sigmoid) {  // multi-hot [nv x num_cls] from the class ids, as Reader::bin_read_vlabels(labels, false) (reader.cpp:347-412)
+      new (&m->labels) std::vector<label_t>((size_t)nv * num_cls, 0);
+      for (int v = 0; v < nv; v++) if (labels[v] < num_cls) m->labels[(size_t)v * num_cls + labels[v]] = 1;
+    } else {
+      new (&m->labels) std::vector<label_t>(labels, labels + nv);
+    }
     new (&m->masks_train) std::vector<mask_t>(nv, 0);
     new (&m->masks_test) std::vector<mask_t>(nv, 0);
     new (&m->masks_val) std::vector<mask_t>(nv, 0);
@@ -65,7 +70,7 @@ struct ModelBox : ModelBase {
     m->train_begin = split[0]; m->train_end = split[1]; m->train_count = split[2];
     m->val_begin = split[3]; m->val_end = split[4]; m->val_count = split[5];
     m->test_begin = split[6]; m->test_end = split[7]; m->test_count = split[8];
-    m->is_sigmoid = false; m->use_gpu = false; m->inductive = false;
+    m->is_sigmoid = sigmoid; m->use_gpu = false; m->inductive = false;
     m->arch = arch_of<L>::value;
     // src/gnn/net.cpp:67-71
     m->use_l2norm = (m->arch == gnn_arch::GAT);
@@ -245,6 +250,14 @@ void* ref_model_new(int arch, void* g, int nv, int dim_init, int dim_hid, int nu
   if (arch == 0) return new ModelBox<GCN_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads);
   if (arch == 1) return new ModelBox<SAGE_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads);
   if (arch == 2) return new ModelBox<GAT_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads);
+  return NULL;
+}
+// the same with the sigmoid (multi-label) loss layer and micro-F1 as accuracy (argv[4] == "sigmoid", net.cpp:20,447-451)
+void* ref_model_new_sigmoid(int arch, void* g, int nv, int dim_init, int dim_hid, int num_cls, int num_layers, float lr,
+                            const float* feats, const uint8_t* labels, const int64_t* split9, int threads) {
+  if (arch == 0) return new ModelBox<GCN_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads, true);
+  if (arch == 1) return new ModelBox<SAGE_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads, true);
+  if (arch == 2) return new ModelBox<GAT_layer>((Graph*)g, nv, dim_init, dim_hid, num_cls, num_layers, lr, feats, labels, split9, threads, true);
   return NULL;
 }
 float ref_model_train_epoch(void* m, float* loss) { return ((ModelBase*)m)->train_epoch(loss); }
