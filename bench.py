@@ -32,7 +32,9 @@ sys.path.insert(0, ROOT)
 
 # BASELINE.json configs[1] (SURVEY.md §8d "C2")
 C2 = dict(nv=2_449_029, nnz=62_000_000, feat=100, hid=256, ncls=47, layers=2, lr=0.01)
-SAMPLE_DIV = 16  # the CPU reference runs a 1/16-scale graph of the same shape (same generator, degree, widths)
+REF_WALL_S = 240.0  # the CPU reference arm times whole epochs of the SAME graph and stops adding epochs after this much wall clock
+L2_PEAK_GBS = 21000.0  # L2 -> SM read bandwidth the aggregation floor is computed with: the round-1 ncu capture of the F = 100 call moved
+                       # 8.71 TB/s over xbar2l1tex at lts__throughput 41 % (profiles/r1_hot_kernels.csv) -> ~21 TB/s at 100 %
 
 
 class quiet_stdout:
@@ -147,44 +149,54 @@ def config_dict(w, n_gpus, scale_div, extra=None):
     return c
 
 
-def run_cpu_reference(w_small, threads, steps, warmup, min_seconds=0.0):
-    """The reference's own CPU implementation (oracle/_ref/libref_gnn.so: Model<SAGE_layer> from the reference sources)."""
+def run_cpu_reference(w, threads, steps, warmup, wall_s):
+    """The reference's own CPU implementation (oracle/_ref/libref_gnn.so: Model<SAGE_layer> from the reference sources) on workload `w`:
+    `warmup` untimed epochs, then up to `steps` timed epochs, stopping early (never before 2) once `wall_s` seconds have been spent."""
     import oracle
     if not oracle.have_ref():
         raise RuntimeError("oracle/_ref/libref_gnn.so missing (built by oracle/build_ref.sh in the build container)")
     with quiet_stdout():
-        m = oracle.RefModel("sage", w_small["rowptr"], w_small["colidx"], w_small["feats"], w_small["labels"], w_small["split"], C2["hid"], C2["ncls"],
+        m = oracle.RefModel("sage", w["rowptr"], w["colidx"], w["feats"], w["labels"], w["split"], C2["hid"], C2["ncls"],
                             num_layers=C2["layers"], lr=C2["lr"], threads=threads)
     for _ in range(warmup):
         m.train_epoch()
     t0 = time.time()
     done = 0
-    while done < steps or (time.time() - t0) < min_seconds:
+    while done < steps:
         m.train_epoch()
         done += 1
-        if done >= steps and min_seconds <= 0:
+        if done >= 2 and (time.time() - t0) > wall_s:
             break
     dt = (time.time() - t0) / done
     return dt, done
 
 
 def reference_arm(args):
+    """`--impl reference`: the reference's OpenMP + OpenBLAS CPU path on the SAME graph, widths and split as our arm (same generator and
+    seeds: the two arms train bit-identical inputs), all host threads. A step = one whole epoch; the epoch count is bounded by wall clock."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    w = make_workload(args.scale * SAMPLE_DIV, "cpu")
-    dt, done = run_cpu_reference(w, threads, args.steps, args.warmup)
+    w = make_workload(args.scale, "cuda" if _cuda_ok() else "cpu")
+    dt, done = run_cpu_reference(w, threads, max(args.steps, 2), min(args.warmup, 1), REF_WALL_S)
     val = w["nnz"] / dt / 1e6
-    sample = f"1/{SAMPLE_DIV}-scale graph of the same shape ({w['nv']} vertices, {w['nnz']} CSR edges), {done} epochs, {threads} OpenMP+OpenBLAS threads"
-    from graphaibench_b200 import datagen
-    full = dict(nv=C2["nv"] // args.scale, nnz=C2["nnz"] // args.scale, split=datagen.split_ranges(C2["nv"] // args.scale))
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    sample = (f"the full configuration ({w['nv']} vertices, {w['nnz']} CSR edges): {done} whole epochs timed after {min(args.warmup, 1)} warm-up "
+              f"(epoch count bounded by {REF_WALL_S:.0f} s of wall clock), {threads} OpenMP+OpenBLAS threads")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(full, args.gpus, args.scale, {"reference_sample": sample}),
+            "config": config_dict(w, 1, args.scale, {"reference_sample": sample}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def _cuda_ok():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 METRIC = "GraphSAGE full-graph training throughput (CSR edges trained per second; epoch ms in ms_per_step)"
@@ -192,16 +204,25 @@ UNIT = "Medges/s"
 
 
 def measured_traffic(op):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel(s) behind `op`, from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py from profiles/r1_hot_kernels.csv); None if that op was not captured."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel(s) behind `op`, from the committed `ncu --set full` capture of
+    THIS command at N = 1 (profiles/traffic.json, written by tools/ncu_traffic.py); None if that op was not captured. bench.py cannot read
+    DRAM counters itself (they need a profiler, and a number taken under a profiler is not a bench value)."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(op)
     except (OSError, ValueError):
         return None
 
 
-def roofline_from_profile(prof, peaks, n_epochs):
-    """Dominant op class by device time; achieved = algorithmic bytes (or flops) / event time for its heaviest shape."""
+def spmm_compulsory_bytes(nv, nnz, F):
+    """SURVEY.md 8d compulsory bound of one aggregation call: every input row and output row once, the CSR once: 4*[2*N*F + nnz + 2N + 1]."""
+    return 4.0 * (2.0 * nv * F + nnz + 2.0 * nv + 1.0)
+
+
+def roofline_from_profile(prof, peaks, n_epochs, graph=None, traffic_ok=True):
+    """Dominant op class by device time. For its heaviest shape: the SURVEY.md 8d triple (gather-model, measured-DRAM and compulsory GB/s over
+    the same CUDA-event time) and frac = floor time / measured time, the floor being what the memory system allows for the bytes actually
+    moved: max(DRAM bytes / measured HBM peak, gather bytes / L2 peak) for an aggregation, algorithmic bytes / HBM peak (or flops / TF32
+    peak) for a dense transform."""
     by_bucket = {}
     for r in prof:
         by_bucket[r["bucket"]] = by_bucket.get(r["bucket"], 0.0) + r["ms"]
@@ -210,25 +231,49 @@ def roofline_from_profile(prof, peaks, n_epochs):
     rows = sorted([r for r in prof if r["bucket"] == dom], key=lambda r: -r["ms"])
     top = rows[0]
     ms = top["ms"] / top["calls"]
-    gbs = top["bytes"] / top["calls"] / (ms * 1e-3) / 1e9
-    out = {"kernel": f"{dom} {top['shape']}", "share_of_step": by_bucket[dom] / total, "launch_ms": ms, "traffic": measured_traffic(f"{dom} {top['shape']}"),
-           "peak_source": peaks["source"]}
-    if dom in ("AGGR", "ATTN_FWD", "ATTN_BWD"):
-        out["model"] = ("algorithmic bytes = gather model of SURVEY.md 8d (every neighbour row counted once per edge); L2 hits make it an upper bound on "
-                        "DRAM traffic, so achieved can exceed the HBM peak; `traffic` = dram__bytes_read+write per launch from the committed ncu capture")
+    alg_bytes = top["bytes"] / top["calls"]
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = measured_traffic(f"{dom} {top['shape']}") if traffic_ok else None
+    out = {"kernel": f"{dom} {top['shape']}", "share_of_step": by_bucket[dom] / total, "launch_ms": ms, "traffic": traffic, "peak_source": peaks["source"]}
     tfl = top["flops"] / top["calls"] / (ms * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops"] / 2.0
-    if dom == "LINEAR" and tfl / tf32_peak > gbs / peaks["hbm_gbs"]:
+    if dom in ("AGGR", "ATTN_FWD", "ATTN_BWD"):
+        F = None
+        for tok in top["shape"].split():
+            if tok.startswith("F="):
+                F = int(tok[2:])
+        floor_dram_ms = (traffic / 1e9 / peaks["hbm_gbs"] * 1e3) if traffic else None
+        floor_l2_ms = alg_bytes / 1e9 / L2_PEAK_GBS * 1e3
+        comp = spmm_compulsory_bytes(graph["nv"], graph["nnz"], F) if (graph and F and dom == "AGGR") else None
+        floor_ms = max(floor_dram_ms or 0.0, floor_l2_ms)
+        out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": floor_ms / ms,
+                    "frac_is": "floor_ms / launch_ms, floor = max(measured DRAM bytes / HBM peak, gather-model bytes / L2 peak)",
+                    "gather_GBps": gbs, "gather_over_hbm_peak": gbs / peaks["hbm_gbs"],
+                    "dram_GBps": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
+                    "dram_frac": (traffic / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+                    "compulsory_GBps": (comp / (ms * 1e-3) / 1e9) if comp else None,
+                    "compulsory_bytes": comp, "algorithmic_bytes": alg_bytes,
+                    "floor_ms": floor_ms, "floor_dram_ms": floor_dram_ms, "floor_l2_ms": floor_l2_ms, "l2_peak_GBps": L2_PEAK_GBS,
+                    "model": "achieved = gather model of SURVEY.md 8d (every neighbour row counted once per edge): an upper bound on DRAM traffic "
+                             "that can exceed the HBM peak because the L2 absorbs re-reads; traffic = dram__bytes_read+write per launch from the "
+                             "committed ncu capture of this command (profiles/), null when this shape was not captured"})
+    elif dom == "LINEAR" and tfl / tf32_peak > gbs / peaks["hbm_gbs"]:
         out.update({"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak})
     else:
         out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]})
-    if out.get("traffic"):  # the measured side of the SURVEY.md 8d triple: DRAM bytes of the same launch / the same event time
-        out["dram_GBps"] = out["traffic"] / (ms * 1e-3) / 1e9
-        out["dram_frac"] = out["dram_GBps"] / peaks["hbm_gbs"]
+        if traffic:
+            out["dram_GBps"] = traffic / (ms * 1e-3) / 1e9
+            out["dram_frac"] = out["dram_GBps"] / peaks["hbm_gbs"]
     breakdown = {b: round(v / n_epochs, 4) for b, v in sorted(by_bucket.items(), key=lambda kv: -kv[1])}
-    per_shape = [{"op": f"{r['bucket']} {r['shape']}", "ms": round(r["ms"] / r["calls"], 4), "calls_per_step": r["calls"] / n_epochs,
-                  "GBps": round(r["bytes"] / r["calls"] / (r["ms"] / r["calls"] * 1e-3) / 1e9, 1),
-                  "TFLOPps": round(r["flops"] / r["calls"] / (r["ms"] / r["calls"] * 1e-3) / 1e12, 2)} for r in sorted(prof, key=lambda r: -r["ms"])]
+    per_shape = []
+    for r in sorted(prof, key=lambda r: -r["ms"]):
+        t = r["ms"] / r["calls"]
+        row = {"op": f"{r['bucket']} {r['shape']}", "ms": round(t, 4), "calls_per_step": r["calls"] / n_epochs,
+               "GBps": round(r["bytes"] / r["calls"] / (t * 1e-3) / 1e9, 1), "TFLOPps": round(r["flops"] / r["calls"] / (t * 1e-3) / 1e12, 2)}
+        tr = measured_traffic(f"{r['bucket']} {r['shape']}") if traffic_ok else None
+        if tr:
+            row["dram_GBps"] = round(tr / (t * 1e-3) / 1e9, 1)
+        per_shape.append(row)
     return out, breakdown, per_shape
 
 
@@ -297,11 +342,13 @@ def ours(args):
         time.sleep(0.3)
     ms_step, launches, (loss, acc), span = timed(m.train_epoch, args.steps)
 
+    feats_pinned = torch.from_numpy(w["feats"]).pin_memory()  # the CALLER's host buffer: read from where it lies on every step
+
     def e2e_step():
         # pinned host -> device every step: labels, train mask and CSR in line; the feature matrix (80 % of the bytes) of step k+1 is
-        # sent on a copy stream while step k computes (double-buffered) and swapped in here
-        m.refresh_inputs()
-        m.prefetch_inputs()
+        # sent on a copy stream while step k computes (double-buffered, one pitched DMA into line-aligned rows) and swapped in here
+        m.refresh_inputs(feats_pinned.data_ptr())
+        m.prefetch_inputs(feats_pinned.data_ptr())
         return m.train_epoch()  # ends with the device -> host read of {loss, accuracy, count}
     e2e_step()
     ms_e2e, _, _, span2 = timed(e2e_step, args.steps)
@@ -319,7 +366,7 @@ def ours(args):
         m.train_epoch()
     prof = gmodel.profile_collect()
     gmodel.profile_enable(False)
-    roof, breakdown, per_shape = roofline_from_profile(prof, peaks, n_prof)
+    roof, breakdown, per_shape = roofline_from_profile(prof, peaks, n_prof, graph=dict(nv=w["nv"], nnz=w["nnz"]))
 
     if rank != 0:
         return
@@ -331,11 +378,11 @@ def ours(args):
             "final": {"train_loss": loss, "train_acc": acc}}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        ws = make_workload(args.scale * SAMPLE_DIV, "cuda")
-        dt, done = run_cpu_reference(ws, threads, 2, 1, min_seconds=10.0)
-        line["cpu_baseline"] = {"value": ws["nnz"] / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step_sample": dt * 1e3,
-                                "sample": f"reference OpenMP build (oracle/_ref) on a 1/{SAMPLE_DIV}-scale graph of the same shape ({ws['nv']} vertices, "
-                                          f"{ws['nnz']} CSR edges), {done} epochs after 1 warm-up, {threads} threads"}
+        del m
+        dt, done = run_cpu_reference(w, threads, 2, 1, 30.0)
+        line["cpu_baseline"] = {"value": w["nnz"] / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "reference", "ms_per_step": dt * 1e3,
+                                "sample": f"reference OpenMP build (oracle/_ref) on the SAME graph and widths ({w['nv']} vertices, {w['nnz']} CSR edges): "
+                                          f"{done} whole epochs after 1 warm-up, {threads} threads"}
     print(json.dumps(line), flush=True)
 
 
@@ -445,7 +492,8 @@ def ours_partitioned(args, world, rank, local, L, peaks):
             m.train_epoch_async()
     prof = m.timer.collect()
     m.timer = None
-    roof, breakdown, per_shape = roofline_from_profile([r for r in prof if r["bucket"] not in ("HALO", "ALLREDUCE")], peaks, n_prof)
+    roof, breakdown, per_shape = roofline_from_profile([r for r in prof if r["bucket"] not in ("HALO", "ALLREDUCE")], peaks, n_prof,
+                                                       graph=None, traffic_ok=False)  # no ncu capture exists for the partitioned run: traffic stays null
     halo_ms = sum(r["ms"] for r in prof if r["bucket"] == "HALO") / n_prof
     breakdown["HALO"] = round(halo_ms, 4)
     breakdown["ALLREDUCE"] = round(sum(r["ms"] for r in prof if r["bucket"] == "ALLREDUCE") / n_prof, 4)

@@ -76,12 +76,12 @@ __device__ __forceinline__ bool pick_row(const RowSel& r, uint32_t& row, uint32_
 }
 
 // el/er per vertex: one warp per row, coalesced.
-__global__ void el_er_kernel(uint32_t nv, int F, const float* __restrict__ z, const float* __restrict__ al, const float* __restrict__ ar,
+__global__ void el_er_kernel(uint32_t nv, int F, const float* __restrict__ z, size_t ld, const float* __restrict__ al, const float* __restrict__ ar,
                              float* __restrict__ el, float* __restrict__ er) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nv) return;
-  const float* x = z + (size_t)w * F;
+  const float* x = z + (size_t)w * ld;
   float a = 0.f, b = 0.f;
   for (int k = lane; k < F; k += 32) { const float v = x[k]; a += __ldg(al + k) * v; b += __ldg(ar + k) * v; }
   a = warp_sum(a); b = warp_sum(b);
@@ -118,14 +118,14 @@ __global__ void scores_kernel(const RowSel r, const uint32_t* __restrict__ colid
 
 // SDDMM dS[e] = <g_i, z_j>. One warp per edge-slice: light rows = one warp per row; hub rows = CTA per row, warps split the edges.
 template <bool CTA>
-__global__ void sddmm_kernel(const RowSel r, const uint32_t* __restrict__ colidx, int F, const float* __restrict__ grad, const float* __restrict__ z,
+__global__ void sddmm_kernel(const RowSel r, const uint32_t* __restrict__ colidx, int F, size_t ld, const float* __restrict__ grad, const float* __restrict__ z,
                              float* __restrict__ ds, int vec) {
   uint32_t row, s, e; int tid, nthr;
   if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
   const int lane = threadIdx.x & 31;
   const int warp = CTA ? (threadIdx.x >> 5) : 0;
   const int nwarps = CTA ? (blockDim.x >> 5) : 1;
-  const float* g = grad + (size_t)row * F;
+  const float* g = grad + (size_t)row * ld;
   if (vec == 4) {
     const int nch = F / 4;
     // keep up to 4 chunks of g_i in registers (F <= 512); further chunks are re-read (L1)
@@ -137,7 +137,7 @@ __global__ void sddmm_kernel(const RowSel r, const uint32_t* __restrict__ colidx
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         if (k0 + u < e) {
-          const float4* x = reinterpret_cast<const float4*>(z + (size_t)__ldg(colidx + k0 + u) * F);
+          const float4* x = reinterpret_cast<const float4*>(z + (size_t)__ldg(colidx + k0 + u) * ld);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             if (lane + 32 * k < nch) { const float4 v = __ldg(x + lane + 32 * k); d[u] += gr[k].x * v.x + gr[k].y * v.y + gr[k].z * v.z + gr[k].w * v.w; }
@@ -153,7 +153,7 @@ __global__ void sddmm_kernel(const RowSel r, const uint32_t* __restrict__ colidx
     }
   } else {
     for (uint32_t k0 = s + warp; k0 < e; k0 += nwarps) {
-      const float* x = z + (size_t)__ldg(colidx + k0) * F;
+      const float* x = z + (size_t)__ldg(colidx + k0) * ld;
       float d = 0.f;
       for (int c = lane; c < F; c += 32) d += __ldg(g + c) * __ldg(x + c);
       d = warp_sum(d);
@@ -275,7 +275,7 @@ __global__ void colsum_kernel(const RowSel r, const uint32_t* __restrict__ perm,
 }
 
 // Stage 1 of d_alpha = Z^T·[rowsum colsum]: each CTA reduces a slab of rows; thread (tx, ty): column tx (+CW*q), rows ty, ty+RH, ...
-__global__ void alpha_grad_stage1(uint32_t nv, int F, const float* __restrict__ z, const float* __restrict__ rowsum, const float* __restrict__ colsum,
+__global__ void alpha_grad_stage1(uint32_t nv, int F, size_t ld, const float* __restrict__ z, const float* __restrict__ rowsum, const float* __restrict__ colsum,
                                   uint32_t rows_per_cta, int CW, float* __restrict__ partial /*[grid][2][F]*/) {
   extern __shared__ float sm[];  // [RH][2][CW]
   const int tx = threadIdx.x % CW, ty = threadIdx.x / CW, RH = blockDim.x / CW;
@@ -286,7 +286,7 @@ __global__ void alpha_grad_stage1(uint32_t nv, int F, const float* __restrict__ 
     float al = 0.f, ar = 0.f;
     if (c < F) {
       for (uint32_t i = r0 + ty; i < r1; i += RH) {
-        const float v = __ldg(z + (size_t)i * F + c);
+        const float v = __ldg(z + (size_t)i * ld + c);
         al += __ldg(rowsum + i) * v;
         ar += __ldg(colsum + i) * v;
       }
@@ -324,9 +324,9 @@ inline unsigned warp_grid(uint32_t nv) { return (unsigned)(((uint64_t)nv * 32 + 
 
 extern "C" {
 
-int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
-                    float* norm_scores, float* out, int flags, gai_stream_t stream) {
-  GAI_CHECK_ARG(g && z && alpha_l && alpha_r && temp_scores && norm_scores && out && F > 0);
+int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
+                       float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream) {
+  GAI_CHECK_ARG(g && z && alpha_l && alpha_r && temp_scores && norm_scores && out && F > 0 && ld >= (size_t)F && ld_out >= (size_t)F);
   if (g->nv == 0) return GAI_OK;
   cudaStream_t st = gai::S(stream);
   void* ws = nullptr;
@@ -334,7 +334,7 @@ int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, co
   if (rc != GAI_OK) return rc;
   float* el = reinterpret_cast<float*>(ws);
   float* er = el + g->nv;
-  el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, z, alpha_l, alpha_r, el, er);
+  el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, z, ld, alpha_l, alpha_r, el, er);
   GAI_LAUNCH_CHECK();
   const RowSel r = make_sel(g);
   scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
@@ -343,12 +343,13 @@ int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, co
     scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
     GAI_LAUNCH_CHECK();
   }
-  return gai_spmm_edge(g, F, norm_scores, nullptr, z, F, out, F, flags, nullptr, stream);
+  return gai_spmm_edge(g, F, norm_scores, nullptr, z, (int)ld, out, (int)ld_out, flags, nullptr, stream);
 }
 
-int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, float slope, const float* temp_scores, const float* norm_scores,
-                     float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, gai_stream_t stream) {
+int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld, const float* grad_in, size_t ld_grad, float slope, const float* temp_scores,
+                        const float* norm_scores, float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, size_t ld_dz, gai_stream_t stream) {
   GAI_CHECK_ARG(g && z && grad_in && temp_scores && norm_scores && ds && d_alpha_l && d_alpha_r && dz && F > 0);
+  GAI_CHECK_ARG(ld >= (size_t)F && ld_grad >= (size_t)F && ld_dz >= (size_t)F);
   if (g->nv == 0) return GAI_OK;
   int rc = gai_csr_build_transpose(g, stream);
   if (rc != GAI_OK) return rc;
@@ -362,20 +363,26 @@ int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, f
   float* colsum = rowsum + g->nv;
   float* partial = colsum + g->nv;
   const RowSel r = make_sel(g);
-  const int vec = (F % 4 == 0 && reinterpret_cast<uintptr_t>(z) % 16 == 0 && reinterpret_cast<uintptr_t>(grad_in) % 16 == 0) ? 4 : 1;
-  if (vec == 4 && F <= 512 && g->nnz > 0) {
-    const int nch = F / 4;
+  // 128-bit path: both gathered matrices share one pitch that is a multiple of 4 floats (the tail chunk of a width that is not reads
+  // padding columns, which the layer classes keep at zero on both sides: 0 * 0 adds nothing to the dot product)
+  const bool vec_ok = ld == ld_grad && ld % 4 == 0 && ld >= (size_t)((F + 3) / 4 * 4) && reinterpret_cast<uintptr_t>(z) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(grad_in) % 16 == 0;
+  if (vec_ok && F <= 512 && g->nnz > 0) {
+    const int nch = (F + 3) / 4;
     const unsigned grid = (unsigned)(sms * 4);
     const float4* g4 = reinterpret_cast<const float4*>(grad_in);
     const float4* z4 = reinterpret_cast<const float4*>(z);
-    if (nch <= 32) sddmm_edges_kernel<1><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, (size_t)nch, g4, z4, ds);
-    else if (nch <= 64) sddmm_edges_kernel<2><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, (size_t)nch, g4, z4, ds);
-    else sddmm_edges_kernel<4><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, (size_t)nch, g4, z4, ds);
+    if (nch <= 32) sddmm_edges_kernel<1><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, ld / 4, g4, z4, ds);
+    else if (nch <= 64) sddmm_edges_kernel<2><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, ld / 4, g4, z4, ds);
+    else sddmm_edges_kernel<4><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, ld / 4, g4, z4, ds);
     GAI_LAUNCH_CHECK();
   } else {
-    sddmm_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, F, grad_in, z, ds, vec);
+    const int vec = (vec_ok && F % 4 == 0) ? 4 : 1;
+    const size_t ldc = ld;  // the fallback walks both matrices with the pitch of z; grad_in must share it
+    GAI_CHECK_ARG(ld == ld_grad);
+    sddmm_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, F, ldc, grad_in, z, ds, vec);
     GAI_LAUNCH_CHECK();
-    if (g->n_hub) { sddmm_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, F, grad_in, z, ds, vec); GAI_LAUNCH_CHECK(); }
+    if (g->n_hub) { sddmm_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, F, ldc, grad_in, z, ds, vec); GAI_LAUNCH_CHECK(); }
   }
   softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, slope, temp_scores, norm_scores, ds, rowsum);
   GAI_LAUNCH_CHECK();
@@ -386,12 +393,22 @@ int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, f
   int CW = 1;
   while (CW < F && CW < 256) CW <<= 1;
   const uint32_t rows_per_cta = (g->nv + nparts - 1) / nparts;
-  alpha_grad_stage1<<<nparts, 256, sizeof(float) * 2 * 256, st>>>(g->nv, F, z, rowsum, colsum, rows_per_cta, CW, partial);
+  alpha_grad_stage1<<<nparts, 256, sizeof(float) * 2 * 256, st>>>(g->nv, F, ld, z, rowsum, colsum, rows_per_cta, CW, partial);
   GAI_LAUNCH_CHECK();
   alpha_grad_stage2<<<(2 * F + 255) / 256, 256, 0, st>>>(F, nparts, partial, d_alpha_l, d_alpha_r);
   GAI_LAUNCH_CHECK();
   // dZ = P^T · G  (update_all with transposed scores, gat_aggregator.cpp:175-199); z is dead from here on, dz may alias it
-  return gai_spmm_edge(g, F, norm_scores, g->tperm, grad_in, F, dz, F, GAI_EPI_NONE, nullptr, stream);
+  return gai_spmm_edge(g, F, norm_scores, g->tperm, grad_in, (int)ld_grad, dz, (int)ld_dz, GAI_EPI_NONE, nullptr, stream);
+}
+
+int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
+                    float* norm_scores, float* out, int flags, gai_stream_t stream) {
+  return gai_gat_forward_ld(g, F, z, (size_t)F, alpha_l, alpha_r, slope, temp_scores, norm_scores, out, (size_t)F, flags, stream);
+}
+
+int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, float slope, const float* temp_scores, const float* norm_scores,
+                     float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, gai_stream_t stream) {
+  return gai_gat_backward_ld(g, F, z, (size_t)F, grad_in, (size_t)F, slope, temp_scores, norm_scores, ds, d_alpha_l, d_alpha_r, dz, (size_t)F, stream);
 }
 
 }  // extern "C"

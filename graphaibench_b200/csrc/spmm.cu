@@ -5,20 +5,28 @@
 // CPU loops they mirror (src/gnn/gconv/gcn_aggregator.cpp:48-77, sage_aggregator.cpp:7-54, gat_aggregator.cpp:26-45).
 //
 // Design (B200: an HBM/L2 gather; no tensor-core shape here):
-//   * every input row is read with 128-bit loads: if F % 4 != 0 or the layout is misaligned, the input is first copied
-//     into a zero-padded workspace with ld = ceil4(F) (one N x F pass, ~1% of the gather traffic).
-//   * row-split by degree bucket.
-//       light rows (deg <= hub_degree): a group of G lanes (G = 4..32, from the feature width) owns one output row in
-//         registers; the group loads G column indices + edge weights with one coalesced request, broadcasts them by
-//         shuffle, and keeps U independent 128-bit neighbour-row loads in flight per lane.
-//       hub rows (deg > hub_degree, a per-graph threshold = a warp's fair share of the edges): one warp-specialised CTA
-//         per row. 16 producer warps gather + scale neighbour rows into a shared-memory ring (one slot per producer,
-//         mbarrier full/empty pairs); 4 consumer warps (one thread per 4 columns) add the staged products IN EDGE
-//         ORDER. The gather runs at SM bandwidth while the add chain stays sequential.
+//   * every input row is read with 128-bit loads. Rows whose pitch is a multiple of 4 floats are read in place; only a
+//     caller's dense matrix with F % 4 != 0 (or a misaligned base) goes through a zero-padded staging copy.
+//     Row ALIGNMENT decides the cost of a gather: the L1 data pipe serves a 128-bit warp load one quarter-warp
+//     (8 lanes x 16 B = 128 B) per wavefront only if those 128 B lie in one 128-byte line. With a 400-byte pitch
+//     (F = 100) every quarter straddles two lines: ncu counted 7.4 wavefronts per gather instead of 4 and
+//     l1tex__data_pipe_lsu_wavefronts at 73 % was the kernel's top limiter (profiles/README.md, round 1). The layer
+//     classes therefore store per-vertex buffers with a line-aligned pitch (host/gai_layers.h: row_pitch()), and lanes
+//     past the row width are predicated off instead of re-reading chunk 0.
+//   * one persistent kernel (4 CTAs x 148 SMs), two kinds of work items taken from global counters:
+//       light rows (deg <= hub_degree): rows in DEGREE order, cut into claims of <= 32 rows / <= 2048 edges. A group of
+//         G lanes (G = 4..32, from the feature width) owns one output row in registers; the group loads G column
+//         indices with one coalesced request, broadcasts them by shuffle, and keeps U independent 128-bit
+//         neighbour-row loads in flight per lane, with a two-deep index pipeline across rows and batches.
+//       hub rows (deg > hub_degree, a per-graph threshold = a warp's fair share of the edges): item = (row, column block
+//         of <= 8 float4 chunks). A whole CTA takes one item: 7 producer warps gather + scale stages of 32 edges into a
+//         shared-memory ring (mbarrier full/empty pairs); warp 0 adds the staged products IN EDGE ORDER. The longest
+//         rows are listed first, so their add chains run underneath the light rows.
+//       (widths beyond 512 floats keep the older CTA-per-row kernel spmm_hub_kernel, forked onto a side stream.)
 //   * numerics: acc = fadd_rn(acc, fmul_rn(w, x)) per edge, sequential per column — exactly the reference CPU path's
 //     scale()+vadd() (math_functions.cpp:266,336): results are bit-identical for every row length, hub rows included.
-//   * fused: zero-init (no memset pass), optional "+ addend" and ReLU epilogue, leading dimensions, row ranges
-//     (1D partition: interior vs boundary rows).
+//   * fused: zero-init (no memset pass), optional "+ addend", ReLU and sign-bit d_relu mask epilogues, leading
+//     dimensions, row ranges (1D partition: interior vs boundary rows).
 #include "gai_internal.cuh"
 
 namespace {
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
   const size_t ld4 = (size_t)a.ld_in >> 2;
-  // lanes whose chunk lies past the row width re-read chunk 0 (same sectors as lane 0) and store nothing
+  // lanes whose chunk lies past the row width are predicated off: they issue no load (no wavefront, no writeback) and store nothing
   int chunk[K];
   bool act[K];
 #pragma unroll
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
                   const float4* src = in4 + (size_t)cc * ld4;
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = gather4(src + ch[k]);
+                  for (int k = 0; k < K; k++) x[u][k] = av[k] ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
                   const float4* src = in4 + (size_t)cc * ld4;
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = 0; k < K; k++) x[u][k] = (av[k] && j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -709,8 +717,8 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
     GAI_LAUNCH_CHECK();
     a.in = reinterpret_cast<const float*>(ws); a.ld_in = Fp;
   }
-  // Hub rows go first, on a high-priority side stream (fork/join with events): their CTAs are the long poles (one
-  // 94 K-edge row is ~0.3 ms of in-order adds), the persistent light-row warps on `st` fill the other SMs meanwhile.
+  // Widths beyond 512 floats only: the hub rows of such calls run in the CTA-per-row kernel on a high-priority side
+  // stream (fork/join with events); every narrower call serves its hub rows as work items of the persistent kernel.
   int rc = GAI_OK;
   const bool has_hub = select_list(a, g).n_hub != 0 && !hub_fused(a);
   if (has_hub) {

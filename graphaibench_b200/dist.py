@@ -268,6 +268,14 @@ def _ceil4(x):
     return (x + 3) // 4 * 4
 
 
+def _pitch(x):
+    """Row pitch of every tall buffer (host/gai_layers.h row_pitch): line-aligned rows, so a gather never straddles 128-byte lines."""
+    for p in (4, 8, 16, 32):
+        if x <= p:
+            return p
+    return (x + 31) // 32 * 32
+
+
 class _Adam:
     """adam (optimizer.cpp:22-35) as the host classes drive it: beta powers advance once per update() call on the object,
     moments keyed by the weight tensor."""
@@ -366,7 +374,7 @@ class DistGnn:
         n, m = p.n_loc, p.m
 
         def buf(rows, width):
-            return torch.zeros(max(rows, 1), _ceil4(width), dtype=torch.float32, device=dev)
+            return torch.zeros(max(rows, 1), _pitch(width), dtype=torch.float32, device=dev)
 
         self.W, self.Ws, self.dW, self.dWs = [], [], [], []
         self.feat_in, self.grad_in, self.T, self.A, self.Tm, self.D, self.bits = [], [], [], [], [], [], []
@@ -404,7 +412,7 @@ class DistGnn:
         self.probs = buf(n, ncls)[:, :ncls]
         self.losses = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
         self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.sendbuf = torch.empty(max(p.n_send, 1), _ceil4(max(dims)), dtype=torch.float32, device=dev)
+        self.sendbuf = torch.empty(max(p.n_send, 1), _pitch(max(dims)), dtype=torch.float32, device=dev)
         self.feat_in[0][:n, :dims[0]].copy_(feats)
         if self.comm.world > 1 and static_input_halo and dims[0] <= dims[1]:
             self._exchange(self.feat_in[0])   # layer-0 input is constant: its halo rows are fetched once (replicated features)

@@ -163,28 +163,33 @@ void Reader::bin_read_graph(LearningGraph* g) {
 size_t Reader::bin_read_features(std::vector<float>& feats) {
   std::cout << "Reading features ... N x D: " << num_vertices_ << " x " << feat_len << "\n";
   feats.resize((size_t)num_vertices_ * feat_len);
-  read_exact<float>(inputfile_path + "graph.feats.bin", feats.data(), feats.size());
+  // as the reference (reader.cpp:258-263): no open check here — a dataset without a feature file (feat_len 0) loads with no features
+  std::ifstream in((inputfile_path + "graph.feats.bin").c_str(), std::ios::binary);
+  if (!feats.empty()) in.read(reinterpret_cast<char*>(feats.data()), sizeof(float) * feats.size());
   return feat_len;
 }
 
 int Reader::bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class) {
   assert(num_vertex_classes > 0 && num_vertex_classes < 255);
-  std::vector<vlabel_t> vl(num_vertices_);
+  std::vector<vlabel_t> vl(num_vertices_, 0);
   std::ifstream probe((inputfile_path + "graph.vlabel.bin").c_str());
+  std::cout << (is_single_class ? "Using single-class (one-hot) labels\n" : "Using multi-class (multi-hot) labels\n");
+  labels.assign(is_single_class ? (size_t)num_vertices_ : (size_t)num_vertices_ * num_vertex_classes, 0);
   if (probe.good()) {
     read_exact<vlabel_t>(inputfile_path + "graph.vlabel.bin", vl.data(), vl.size());
+    for (size_t v = 0; v < num_vertices_; v++) {
+      if (is_single_class) labels[v] = vl[v];
+      else if (vl[v] < num_vertex_classes) labels[v * num_vertex_classes + vl[v]] = 1;
+    }
   } else {
+    // reader.cpp:386-408, quirks included: in single-class mode only the scratch array is drawn (labels stay all zero, so every
+    // generated label is a valid class id); in multi-hot mode the drawn class is 1..C, and a draw of C sets no column at all
     std::cout << "WARNING: vertex label file not exist; generating random labels\n";
-    for (auto& v : vl) v = rand() % num_vertex_classes + 1;  // reader.cpp:386-408
-  }
-  if (is_single_class) {
-    std::cout << "Using single-class (one-hot) labels\n";
-    labels.assign(vl.begin(), vl.end());
-  } else {
-    std::cout << "Using multi-class (multi-hot) labels\n";
-    labels.assign((size_t)num_vertices_ * num_vertex_classes, 0);
-    for (size_t v = 0; v < num_vertices_; v++)
-      if (vl[v] < num_vertex_classes) labels[v * num_vertex_classes + vl[v]] = 1;
+    for (size_t v = 0; v < num_vertices_; v++) {
+      const int rand_class = rand() % num_vertex_classes + 1;
+      if (is_single_class) vl[v] = (vlabel_t)rand_class;
+      else if (rand_class < num_vertex_classes) labels[v * num_vertex_classes + rand_class] = 1;
+    }
   }
   std::cout << "maximum vertex label: " << unsigned(*std::max_element(vl.begin(), vl.end())) << "\n";
   return num_vertex_classes;

@@ -123,5 +123,28 @@ int64_t gai_host_profile_json(char* buf, int64_t cap) {
   if (buf && cap > 0) { const size_t n = js.size() < (size_t)cap - 1 ? js.size() : (size_t)cap - 1; memcpy(buf, js.data(), n); buf[n] = 0; }
   return (int64_t)js.size();
 }
+// Reader (src/gnn/reader.cpp:248-457 mirror) on $DATASET_PATH/<dataset>/: same two-call protocol and meta layout as the reference-side
+// harness (oracle/ref_harness.cpp: ref_reader_load), so a test can compare the two loaders field by field. Host only, no device work.
+int gai_reader_load(const char* dataset, int single_class, int64_t* meta, uint32_t* rowptr, uint32_t* colidx, float* feats, uint8_t* labels) {
+  Reader reader{std::string(dataset)};
+  Graph g(true);
+  reader.bin_read_graph(&g);
+  std::vector<float> f;
+  const size_t flen = reader.bin_read_features(f);
+  std::vector<label_t> lab;
+  const int ncls = reader.bin_read_vlabels(lab, single_class != 0);
+  size_t b[3], e[3], c[3];
+  const char* kinds[3] = {"train", "val", "test"};
+  for (int i = 0; i < 3; i++) c[i] = reader.bin_read_masks(kinds[i], g.size(), b[i], e[i], nullptr);
+  meta[0] = (int64_t)g.size(); meta[1] = (int64_t)g.sizeEdges(); meta[2] = (int64_t)flen; meta[3] = ncls;
+  for (int i = 0; i < 3; i++) { meta[4 + 3 * i] = (int64_t)b[i]; meta[5 + 3 * i] = (int64_t)e[i]; meta[6 + 3 * i] = (int64_t)c[i]; }
+  if (rowptr) {
+    memcpy(rowptr, g.row_start_host_ptr(), sizeof(uint32_t) * (g.size() + 1));
+    memcpy(colidx, g.edge_dst_host_ptr(), sizeof(uint32_t) * g.sizeEdges());
+    memcpy(feats, f.data(), sizeof(float) * f.size());
+    memcpy(labels, lab.data(), lab.size());
+  }
+  return 0;
+}
 void gai_model_sync() { gai_stream_sync(gai_host::stream()); }
 }

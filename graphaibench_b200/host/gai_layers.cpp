@@ -49,7 +49,7 @@ static void mm(size_t x, size_t y, size_t z, const float* A, size_t lda, const f
   gai_host::OpScope sc("LINEAR", shape(x, y, z) + (ta ? " TA" : "") + (tb ? " TB" : ""),
                        4.0 * ((double)x * z + (double)z * y + (double)x * y * (accum ? 2 : 1)), 2.0 * (double)x * y * z);
   // tall outputs live in layer-owned buffers whose rows are padded to 4 floats: every epilogue store can be 128-bit
-  const int padded = (!ta && ldc % 4 == 0 && ldc >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  const int padded = (!ta && ldc % 4 == 0 && ldc >= ceil4(y)) ? GAI_EPI_PADDED : 0;
   die_on(gai_matmul_ld(x, y, z, A, lda, B, ldb, C, ldc, ta, tb, accum, flags | padded, stream()), "gai_matmul_ld");
 }
 // C = A1·op(B1) + A2·op(B2) in one pass; mask != NULL folds the d_relu of the layer below into the epilogue
@@ -61,7 +61,7 @@ static void mm_kcat(size_t x, size_t y, size_t z1, const float* A1, size_t lda1,
                        4.0 * ((double)x * (z1 + z2) + (double)(z1 + z2) * y + (double)x * y * (mask ? 2 : 1)) + (mask_bits || relu_bits ? (double)x * y / 8 : 0),
                        2.0 * (double)x * y * (z1 + z2));
   const size_t ldb1 = tb ? z1 : y, ldb2 = tb ? z2 : y, ldw = bits_pitch(y);
-  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && (!mask || (ldmask % 4 == 0 && ldmask >= pitch4(y)))) ? GAI_EPI_PADDED : 0;
+  const int padded = (ldc % 4 == 0 && ldc >= ceil4(y) && (!mask || (ldmask % 4 == 0 && ldmask >= ceil4(y)))) ? GAI_EPI_PADDED : 0;
   const float* mptr = mask_bits ? reinterpret_cast<const float*>(mask_bits) : mask;
   die_on(gai_matmul_kcat(x, y, z1, A1, lda1, B1, ldb1, z2, A2, lda2, B2, ldb2, C, ldc, tb,
                          flags | padded | (masked ? GAI_EPI_MASK : 0) | (mask_bits ? GAI_EPI_BITMASK : 0), mptr, mask_bits ? ldw : ldmask, relu_bits, ldw,
@@ -71,7 +71,7 @@ static void mm_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, co
                     size_t ldmask, const uint32_t* mask_bits = nullptr) {
   gai_host::OpScope sc("LINEAR", shape(x, y, z) + (tb ? " TB" : "") + (mask_bits ? " bitmask" : " mask"),
                        4.0 * ((double)x * z + (double)z * y + (mask_bits ? 1.0 : 2.0) * (double)x * y) + (mask_bits ? (double)x * y / 8 : 0), 2.0 * (double)x * y * z);
-  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y) && (mask_bits || (ldmask % 4 == 0 && ldmask >= pitch4(y)))) ? GAI_EPI_PADDED : 0;
+  const int padded = (ldc % 4 == 0 && ldc >= ceil4(y) && (mask_bits || (ldmask % 4 == 0 && ldmask >= ceil4(y)))) ? GAI_EPI_PADDED : 0;
   if (mask_bits)
     die_on(gai_matmul_mask(x, y, z, A, lda, B, tb ? z : y, C, ldc, tb, reinterpret_cast<const float*>(mask_bits), bits_pitch(y), padded | GAI_EPI_BITMASK,
                            stream()), "gai_matmul_mask");
@@ -81,14 +81,14 @@ static void mm_mask(size_t x, size_t y, size_t z, const float* A, size_t lda, co
 // C = ReLU(A·B) + the sign bits of C for the layer above
 static void mm_relu_bits(size_t x, size_t y, size_t z, const float* A, size_t lda, const float* B, float* C, size_t ldc, uint32_t* bits) {
   gai_host::OpScope sc("LINEAR", shape(x, y, z) + " relu+bits", 4.0 * ((double)x * z + (double)z * y + (double)x * y) + (double)x * y / 8, 2.0 * (double)x * y * z);
-  const int padded = (ldc % 4 == 0 && ldc >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  const int padded = (ldc % 4 == 0 && ldc >= ceil4(y)) ? GAI_EPI_PADDED : 0;
   die_on(gai_matmul_relu_bits(x, y, z, A, lda, B, y, C, ldc, padded, bits, bits_pitch(y), stream()), "gai_matmul_relu_bits");
 }
 // C1 = A·B1, C2 = A·B2, A read once
 static void mm_ncat(size_t x, size_t z, const float* A, size_t lda, size_t y, const float* B1, float* C1, size_t ldc1, const float* B2, float* C2,
                     size_t ldc2) {
   gai_host::OpScope sc("LINEAR", shape(x, y, z) + " ncat2", 4.0 * ((double)x * z + 2.0 * (double)z * y + 2.0 * (double)x * y), 4.0 * (double)x * y * z);
-  const int padded = (ldc1 % 4 == 0 && ldc1 >= pitch4(y) && ldc2 % 4 == 0 && ldc2 >= pitch4(y)) ? GAI_EPI_PADDED : 0;
+  const int padded = (ldc1 % 4 == 0 && ldc1 >= ceil4(y) && ldc2 % 4 == 0 && ldc2 >= ceil4(y)) ? GAI_EPI_PADDED : 0;
   die_on(gai_matmul_ncat(x, z, A, lda, y, B1, y, C1, ldc1, y, B2, y, C2, ldc2, padded, stream()), "gai_matmul_ncat");
 }
 // weight gradients of one layer in one pass over the shared operand: dW1 = A1^T·B, dW2 = A2^T·B (two_a) / dW1 = A^T·B1, dW2 = A^T·B2 (two_b)
@@ -172,7 +172,9 @@ void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
   length = len;
   attn_drop = drop_rate;
   assert(attn_drop >= 0.f && attn_drop < 1.f);
-  if (attn_drop > 0.f) { std::cerr << "attention dropout is not supported (all reference configs run 0)\n"; std::exit(1); }
+  // the reference accepts the rate and ignores it on its CPU path (the attention-dropout lines of gat_aggregator.cpp:78-79,138-139 are
+  // commented out): same here, with a note
+  if (attn_drop > 0.f) std::cerr << "note: score_drop = " << attn_drop << " is accepted and ignored (as the reference CPU path does)\n";
   d_alpha_l = upload_glorot(len, 1, 2);  // seeds 2 / 3: gat_aggregator.cpp:11-12
   d_alpha_r = upload_glorot(len, 1, 3);
   d_alpha_lgrad = float_malloc_device_zero(len);
@@ -184,13 +186,14 @@ void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
 }
 void GAT_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float*) {
   gai_host::OpScope sc("ATTN_FWD", "gat F=" + std::to_string(len), spmm_bytes(g, len, 2) + 4.0 * g.size() * len, 2.0 * g.sizeEdges() * len);
-  die_on(gai_gat_forward(g.device(), len, in, d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out, flags, stream()), "gai_gat_forward");
+  die_on(gai_gat_forward_ld(g.device(), len, in, row_pitch(len), d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out, row_pitch(len), flags,
+                            stream()), "gai_gat_forward");
 }
 void GAT_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
 void GAT_Aggregator::d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out) {
   gai_host::OpScope sc("ATTN_BWD", "gat F=" + std::to_string(len), 2.0 * spmm_bytes(g, len, 3) + 4.0 * g.size() * len, 4.0 * g.sizeEdges() * len);
-  die_on(gai_gat_backward(g.device(), len, feat_in, grad_in, epsilon, d_temp_scores, d_norm_scores, d_scores_grad, d_alpha_lgrad, d_alpha_rgrad,
-                          grad_out, stream()), "gai_gat_backward");
+  die_on(gai_gat_backward_ld(g.device(), len, feat_in, row_pitch(len), grad_in, row_pitch(len), epsilon, d_temp_scores, d_norm_scores, d_scores_grad,
+                             d_alpha_lgrad, d_alpha_rgrad, grad_out, row_pitch(len), stream()), "gai_gat_backward");
 }
 void GAT_Aggregator::update_weights(optimizer*) {  // own optimiser, two calls (gat_aggregator.cpp:202-205)
   alpha_opt->update_gpu(length, d_alpha_lgrad, d_alpha_l);
@@ -213,18 +216,14 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
     d_W_self = upload_glorot(din, dout, 2);
     d_W_self_grad = float_malloc_device_zero((size_t)din * dout);
   }
-  // row pitches: layer 0 reads the caller's dense feature matrix; everything the layers own is padded to 4 floats
-  ld_in = id == 0 ? (size_t)din : pitch4(din);
-  ld_out = pitch4(dout);
-  if (std::is_same<A, GAT_Aggregator>::value && (ld_out != (size_t)dout || ld_in != (size_t)din)) {
-    std::cerr << "GAT layers need widths that are multiples of 4 (dense attention buffers)\n";
-    std::exit(1);
-  }
+  // row pitches: every per-vertex buffer, layer 0's input included (Model's device copy of the features), has line-aligned rows
+  ld_in = row_pitch(din);
+  ld_out = row_pitch(dout);
   // temporaries: only what this layer's schedule touches (the reference allocates all of them unconditionally)
   const bool transform_first = din > dout || std::is_same<A, GAT_Aggregator>::value;  // GAT always transforms first
   if (transform_first) d_out_temp = float_malloc_device_zero(n * ld_out);
-  if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * pitch4(din));
-  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * pitch4(din));
+  if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * row_pitch(din));
+  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * row_pitch(din));
   if (id > 0) feat_in = float_malloc_device_zero(n * ld_in);
   grad_in = float_malloc_device_zero(n * ld_out);
   if (feat_dropout_rate > 0.f) {  // dropout_mask + in_temp of the reference (graph_conv_layer.cpp:33-38)
@@ -292,7 +291,7 @@ template <typename A>
 void graph_conv_layer<A>::tensor_layout(const std::string& name, size_t* cols, size_t* ld) {
   *cols = 0; *ld = 0;
   if (name == "feat_in") { *cols = dim_in; *ld = ld_in; }
-  else if (name == "in_temp1") { *cols = dim_in; *ld = pitch4(dim_in); }
+  else if (name == "in_temp1") { *cols = dim_in; *ld = row_pitch(dim_in); }
   else if (name == "grad_in" || name == "out_temp") { *cols = dim_out; *ld = ld_out; }
 }
 template class graph_conv_layer<GCN_Aggregator>;
@@ -307,7 +306,7 @@ GCN_layer::GCN_layer(int id, int nv, int din, int dout, Graph* g, bool act, floa
 }
 
 void GCN_layer::forward(float* feat_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = row_pitch(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
   const float* in_data = forward_input();
   if (y > z) {  // transform first: aggregate at the narrower width; ReLU rides the SpMM epilogue
@@ -321,7 +320,7 @@ void GCN_layer::forward(float* feat_out) {
 }
 
 void GCN_layer::backward(float* feat_out, float* grad_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = row_pitch(y);
   if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   if (y > z) {
     aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
@@ -355,7 +354,7 @@ SAGE_layer::SAGE_layer(int id, int nv, int din, int dout, Graph* g, bool act, fl
 }
 
 void SAGE_layer::forward(float* feat_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = row_pitch(y);
   const int relu = is_act ? GAI_EPI_RELU : GAI_EPI_NONE;
   const float* in_data = forward_input();
   if (y > z) {
@@ -369,7 +368,7 @@ void SAGE_layer::forward(float* feat_out) {
 }
 
 void SAGE_layer::backward(float* feat_out, float* grad_out) {
-  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = pitch4(y);
+  const size_t x = num_samples, y = dim_in, z = dim_out, ldt = row_pitch(y);
   if (is_act && !grad_premasked) d_relu_rows(x, (int)z, grad_in, ld_out, feat_out, ld_out);
   const float* in_data = feat_dropout_rate > 0.f ? d_drop_in : feat_in;  // sage_layer.cpp:35-36
   if (y > z) {
@@ -427,35 +426,35 @@ void GAT_layer::update_weight(optimizer* opt) {
 // ---- l2norm / dense / loss ------------------------------------------------------------------------------------------
 
 l2norm_layer::l2norm_layer(int nv, int len) : num_samples(nv), dim(len) {
-  feat_in = float_malloc_device_zero((size_t)nv * pitch4(len));
-  grad_in = float_malloc_device_zero((size_t)nv * pitch4(len));
+  feat_in = float_malloc_device_zero((size_t)nv * row_pitch(len));
+  grad_in = float_malloc_device_zero((size_t)nv * row_pitch(len));
 }
 void l2norm_layer::forward(float* feat_out) {
   gai_host::OpScope sc("NORM", "l2norm", 8.0 * num_samples * dim, 0);
-  die_on(gai_l2norm_ld(num_samples, dim, feat_in, pitch4(dim), feat_out, pitch4(dim), stream()), "gai_l2norm");
+  die_on(gai_l2norm_ld(num_samples, dim, feat_in, row_pitch(dim), feat_out, row_pitch(dim), stream()), "gai_l2norm");
 }
 void l2norm_layer::backward(float* grad_out) {
   gai_host::OpScope sc("NORM", "d_l2norm", 12.0 * num_samples * dim, 0);
-  die_on(gai_d_l2norm_ld(num_samples, dim, feat_in, pitch4(dim), grad_in, pitch4(dim), grad_out, pitch4(dim), stream()), "gai_d_l2norm");
+  die_on(gai_d_l2norm_ld(num_samples, dim, feat_in, row_pitch(dim), grad_in, row_pitch(dim), grad_out, row_pitch(dim), stream()), "gai_d_l2norm");
 }
 
 dense_layer::dense_layer(int nv, int in_len, int out_len, float lr) : dim_in(in_len), dim_out(out_len), num_samples(nv) {
-  feat_in = float_malloc_device_zero((size_t)nv * pitch4(in_len));
-  grad_in = float_malloc_device_zero((size_t)nv * pitch4(out_len));
+  feat_in = float_malloc_device_zero((size_t)nv * row_pitch(in_len));
+  grad_in = float_malloc_device_zero((size_t)nv * row_pitch(out_len));
   d_weight = upload_glorot(in_len, out_len, 1);  // dense_layer.cpp:33
   d_weight_grad = float_malloc_device_zero((size_t)in_len * out_len);
   optm = new adam(lr);
 }
-void dense_layer::forward(float* feat_out) { mm(num_samples, dim_out, dim_in, feat_in, pitch4(dim_in), d_weight, dim_out, feat_out, pitch4(dim_out)); }
+void dense_layer::forward(float* feat_out) { mm(num_samples, dim_out, dim_in, feat_in, row_pitch(dim_in), d_weight, dim_out, feat_out, row_pitch(dim_out)); }
 void dense_layer::backward(float* grad_out) {
-  mm(dim_in, dim_out, num_samples, feat_in, pitch4(dim_in), grad_in, pitch4(dim_out), d_weight_grad, dim_out, true, false);
-  mm(num_samples, dim_in, dim_out, grad_in, pitch4(dim_out), d_weight, dim_out, grad_out, pitch4(dim_in), false, true);
+  mm(dim_in, dim_out, num_samples, feat_in, row_pitch(dim_in), grad_in, row_pitch(dim_out), d_weight_grad, dim_out, true, false);
+  mm(num_samples, dim_in, dim_out, grad_in, row_pitch(dim_out), d_weight, dim_out, grad_out, row_pitch(dim_in), false, true);
   optm->update_gpu((size_t)dim_in * dim_out, d_weight_grad, d_weight);
 }
 
 loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cls(ncls), labels(ptr) {
-  feat_in = float_malloc_device_zero((size_t)nv * pitch4(ncls));
-  feat_out = float_malloc_device_zero((size_t)nv * pitch4(ncls));
+  feat_in = float_malloc_device_zero((size_t)nv * row_pitch(ncls));
+  feat_out = float_malloc_device_zero((size_t)nv * row_pitch(ncls));
   d_losses = float_malloc_device_zero(nv);
   d_stats = float_malloc_device_zero(4);
 }
@@ -463,20 +462,20 @@ loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cl
 void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
   // one pass over the logits also yields the loss mean and the accuracy get_prediction_loss() reports (forward_prop calls the two back to back)
   gai_host::OpScope sc("LOSS", "fwd+stats", 4.0 * (end - begin) * (2 * num_cls + 2), 0);
-  die_on(gai_softmax_ce_forward_stats_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, d_stats,
+  die_on(gai_softmax_ce_forward_stats_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), feat_out, row_pitch(num_cls), d_losses, d_stats,
                                          stream()), "gai_softmax_ce_forward_stats");
   stats_begin = begin; stats_end = end; stats_masks = masks; stats_valid = true;
 }
 void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
   gai_host::OpScope sc("LOSS", "bwd", 8.0 * (end - begin) * num_cls, 0);
   if (begin == end) return;
-  die_on(gai_softmax_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, pitch4(num_cls), grad_out, pitch4(num_cls), (uint64_t)(end - begin),
+  die_on(gai_softmax_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, row_pitch(num_cls), grad_out, row_pitch(num_cls), (uint64_t)(end - begin),
                                     stream()), "gai_softmax_ce_backward");
 }
 acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
   if (!(stats_valid && stats_begin == begin && stats_end == end && stats_masks == masks)) {  // not preceded by forward() on the same rows
     gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin) * (num_cls + 1), 0);
-    die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), d_losses, d_stats, stream()),
+    die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), d_losses, d_stats, stream()),
            "gai_masked_loss_accuracy");
   }
   stats_valid = false;
@@ -489,13 +488,13 @@ acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t c
 
 void sigmoid_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
   gai_host::OpScope sc("LOSS", "sigmoid fwd", 4.0 * (end - begin) * (2 * num_cls + 1) + (double)(end - begin) * num_cls, 0);
-  die_on(gai_sigmoid_ce_forward_ld(num_cls, begin, end, masks, labels, feat_in, pitch4(num_cls), feat_out, pitch4(num_cls), d_losses, stream()),
+  die_on(gai_sigmoid_ce_forward_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), feat_out, row_pitch(num_cls), d_losses, stream()),
          "gai_sigmoid_ce_forward");
 }
 void sigmoid_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
   gai_host::OpScope sc("LOSS", "sigmoid bwd", 8.0 * (end - begin) * num_cls, 0);
   if (begin == end) return;
-  die_on(gai_sigmoid_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, pitch4(num_cls), grad_out, pitch4(num_cls), (uint64_t)(end - begin),
+  die_on(gai_sigmoid_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, row_pitch(num_cls), grad_out, row_pitch(num_cls), (uint64_t)(end - begin),
                                     stream()), "gai_sigmoid_ce_backward");
 }
 acc_t sigmoid_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
@@ -512,7 +511,7 @@ acc_t sigmoid_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t c
 float masked_accuracy_multi(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
   static float* d_f1 = nullptr;
   if (!d_f1) d_f1 = float_malloc_device_zero(4);
-  die_on(gai_masked_f1_micro(num_classes, begin, end, masks, ground_truth, preds, pitch4(num_classes), d_f1, stream()), "gai_masked_f1_micro");
+  die_on(gai_masked_f1_micro(num_classes, begin, end, masks, ground_truth, preds, row_pitch(num_classes), d_f1, stream()), "gai_masked_f1_micro");
   float h = 0.f;
   copy_float_to_host(1, d_f1, &h);
   return h;
@@ -527,7 +526,7 @@ float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* m
     scratch_n = (size_t)end + 4;
     scratch = float_malloc_device_zero(scratch_n);
   }
-  die_on(gai_masked_loss_accuracy_ld(num_classes, begin, end, masks, ground_truth, preds, pitch4(num_classes), scratch, scratch + end, stream()),
+  die_on(gai_masked_loss_accuracy_ld(num_classes, begin, end, masks, ground_truth, preds, row_pitch(num_classes), scratch, scratch + end, stream()),
          "gai_masked_loss_accuracy");
   float h[3];
   copy_float_to_host(3, scratch + end, h);

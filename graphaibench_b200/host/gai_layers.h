@@ -43,8 +43,18 @@ struct adam : public optimizer {
   std::unordered_map<const float*, std::pair<float*, float*>> moments;
 };
 
-// Row pitch of every per-vertex activation / gradient buffer the layer classes own (floats).
-inline size_t pitch4(size_t dim) { return (dim + 3) / 4 * 4; }
+// Row pitch (floats) of every per-vertex activation / gradient buffer the layer classes own: rows start on a boundary of
+// their own (power-of-two) size up to 128 bytes, and on a 128-byte line boundary beyond that (47 -> 64, 100 -> 128, 256 -> 256).
+// A neighbour-row gather then costs the minimum number of L1 wavefronts (a quarter-warp's 128 bytes never straddle two
+// lines, csrc/spmm.cu) and every TMA box / 128-bit epilogue store is aligned for any width.
+inline size_t row_pitch(size_t dim) {
+  if (dim <= 4) return 4;
+  if (dim <= 8) return 8;
+  if (dim <= 16) return 16;
+  if (dim <= 32) return 32;
+  return (dim + 31) / 32 * 32;
+}
+inline size_t ceil4(size_t dim) { return (dim + 3) / 4 * 4; }
 // Words per row of a sign-bit matrix (one bit per activation, GAI_EPI_BITMASK).
 inline size_t bits_pitch(size_t dim) { return (dim + 31) / 32; }
 
@@ -102,7 +112,7 @@ class graph_conv_layer {
   graph_conv_layer(int id, int nv, int din, int dout, Graph* g, bool act, bool concat, float lr, float feat_drop, float score_drop);
   float* get_feat_in() { return feat_in; }
   float* get_grad_in() { return grad_in; }
-  void set_feat_in(float* ptr) { feat_in = ptr; }
+  void set_feat_in(float* ptr) { feat_in = ptr; }  // rows stored with row_pitch(dim_in), layer 0 included
   void set_graph_ptr(Graph* ptr) { graph = ptr; }
   void set_netphase(net_phase phase) { phase_ = phase; }
   void update_dim_size(size_t sz) { num_samples = (int)sz; }
@@ -116,9 +126,8 @@ class graph_conv_layer {
   size_t weight_size(const std::string& name);   // logical element count (rows x cols, dense)
   // Row layout of a named per-vertex tensor: logical columns and the pitch it is stored with (0/0 for weights: dense).
   void tensor_layout(const std::string& name, size_t* cols, size_t* ld);
-  // Row pitches. Per-vertex activation / gradient buffers owned by the layer classes are stored with their rows padded to
-  // a multiple of 4 floats (pitch4), so that every aggregation gather, TMA box and epilogue store is 16-byte aligned for
-  // any width (47 classes -> pitch 48); layer 0's feat_in is the caller's dense input matrix.
+  // Row pitches. Per-vertex activation / gradient buffers owned by the layer classes are stored with line-aligned rows
+  // (row_pitch: 47 classes -> pitch 64); layer 0's feat_in is Model's device copy of the input features, stored the same way.
   size_t ld_feat_in() const { return ld_in; }
   size_t ld_grad_in() const { return ld_out; }
   // d_relu fusion across the layer boundary: the layer above writes this layer's grad_in already masked by this layer's
@@ -265,5 +274,5 @@ class sigmoid_loss_layer : public loss_layer {
 
 float masked_accuracy_single(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);
 // micro-F1 at threshold 0.5 (masked_accuracy_multi -> masked_f1_score, math_functions.cpp:94-97,580-623); preds: the loss layer's
-// feat_out (sigmoid outputs, rows pitched to 4 floats), ground_truth: [nv x ncls] multi-hot
+// feat_out (sigmoid outputs, rows stored with row_pitch), ground_truth: [nv x ncls] multi-hot
 float masked_accuracy_multi(int begin, int end, int count, int num_classes, mask_t* masks, float* preds, label_t* ground_truth);

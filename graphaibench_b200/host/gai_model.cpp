@@ -96,7 +96,9 @@ void Model<L>::finish_setup() {
 
 template <typename L>
 void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
-  d_input_features = upload(input_features.data(), input_features.size());
+  // input features live on the device with line-aligned rows (row_pitch), like every other per-vertex buffer
+  d_input_features = float_malloc_device_zero((size_t)num_samples * row_pitch(dim_init));
+  upload_features(d_input_features, input_features.data(), stream());
   d_labels = upload(labels.data(), labels.size());
   d_masks_train = upload(masks_train.data(), masks_train.size());
   d_masks_test = upload(masks_test.data(), masks_test.size());
@@ -104,26 +106,47 @@ void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
   sync();
 }
 
+// dense host rows [num_samples x dim_init] -> device rows of pitch row_pitch(dim_init): one pitched DMA
 template <typename L>
-void Model<L>::stage_pinned(const float* feats_h) {
-  // All five inputs are staged once in page-locked host memory so that the per-step copies are true async DMA.
-  if (pinned_inputs[0]) return;
+void Model<L>::upload_features(float* dst_d, const float* src_h, void* on_stream) {
+  const size_t w = sizeof(float) * (size_t)dim_init;
+  die_on(gai_memcpy2d(dst_d, sizeof(float) * row_pitch(dim_init), src_h, w, w, (size_t)num_samples, on_stream), "gai_memcpy2d");
+}
+
+template <typename L>
+void Model<L>::stage_pinned() {
+  // The four inputs the Model itself owns (labels, train mask, CSR) and its own copy of the features are staged once in page-locked
+  // host memory so that the per-step copies are true async DMA. They cannot change behind the Model's back; a feature matrix the
+  // CALLER passes to refresh_inputs_from_host / prefetch_features_from_host is never staged: it is copied from where it lies, every call.
+  if (pinned_inputs[1]) return;
   const size_t bytes[5] = {sizeof(float) * input_features.size(), labels.size(), masks_train.size(),
                            sizeof(index_t) * (training_graph->size() + 1), sizeof(index_t) * training_graph->sizeEdges()};
-  const void* srcs[5] = {feats_h ? (const void*)feats_h : (const void*)input_features.data(), labels.data(), masks_train.data(),
-                         training_graph->row_start_host_ptr(), training_graph->edge_dst_host_ptr()};
-  for (int i = 0; i < 5; i++) {
+  const void* srcs[5] = {input_features.data(), labels.data(), masks_train.data(), training_graph->row_start_host_ptr(),
+                         training_graph->edge_dst_host_ptr()};
+  for (int i = 1; i < 5; i++) {
     die_on(gai_host_alloc_pinned(&pinned_inputs[i], bytes[i]), "gai_host_alloc_pinned");
     memcpy(pinned_inputs[i], srcs[i], bytes[i]);
   }
 }
 
+// The feature matrix a host->device step copies: the caller's (page-locked for a true async copy; read on every call, so new data
+// is honoured) or, with NULL, the Model's own copy of the training features, pinned on first use.
+template <typename L>
+const float* Model<L>::feature_source(const float* feats_h) {
+  if (feats_h) return feats_h;
+  if (!pinned_inputs[0]) {
+    die_on(gai_host_alloc_pinned(&pinned_inputs[0], sizeof(float) * input_features.size()), "gai_host_alloc_pinned");
+    memcpy(pinned_inputs[0], input_features.data(), sizeof(float) * input_features.size());
+  }
+  return reinterpret_cast<const float*>(pinned_inputs[0]);
+}
+
 template <typename L>
 void Model<L>::refresh_inputs_from_host(const float* feats_h) {
-  stage_pinned(feats_h);
-  const size_t bytes[5] = {sizeof(float) * input_features.size(), labels.size(), masks_train.size(),
-                           sizeof(index_t) * (training_graph->size() + 1), sizeof(index_t) * training_graph->sizeEdges()};
-  void* dsts[5] = {d_input_features, d_labels, d_masks_train, (void*)training_graph->row_start_ptr(), (void*)training_graph->edge_dst_ptr()};
+  stage_pinned();
+  const size_t bytes[5] = {0, labels.size(), masks_train.size(), sizeof(index_t) * (training_graph->size() + 1),
+                           sizeof(index_t) * training_graph->sizeEdges()};
+  void* dsts[5] = {nullptr, d_labels, d_masks_train, (void*)training_graph->row_start_ptr(), (void*)training_graph->edge_dst_ptr()};
   for (int i = 1; i < 5; i++) die_on(gai_memcpy_h2d(dsts[i], pinned_inputs[i], bytes[i], stream()), "gai_memcpy_h2d");
   if (prefetch_pending) {  // the features of this step were sent ahead: order the compute stream behind the copy and swap buffers
     die_on(gai_stream_wait_event(stream(), ev_ready), "gai_stream_wait_event");
@@ -132,28 +155,24 @@ void Model<L>::refresh_inputs_from_host(const float* feats_h) {
     layer_gconv[0].set_feat_in(d_input_features);
     prefetch_pending = false;
   } else {
-    die_on(gai_memcpy_h2d(d_input_features, pinned_inputs[0], bytes[0], stream()), "gai_memcpy_h2d");
+    upload_features(d_input_features, feature_source(feats_h), stream());
   }
 }
 
 template <typename L>
 void Model<L>::prefetch_features_from_host(const float* feats_h) {
-  stage_pinned(feats_h);
-  const size_t bytes = sizeof(float) * input_features.size();
   if (!copy_stream) {
     die_on(gai_stream_create(&copy_stream), "gai_stream_create");
     die_on(gai_event_create(&ev_ready), "gai_event_create");
     die_on(gai_event_create(&ev_free), "gai_event_create");
     d_feat_buf[0] = d_input_features;
-    void* p = nullptr;
-    die_on(gai_malloc(&p, bytes), "gai_malloc");
-    d_feat_buf[1] = reinterpret_cast<float*>(p);
+    d_feat_buf[1] = float_malloc_device_zero((size_t)num_samples * row_pitch(dim_init));
   }
   if (prefetch_pending) return;  // one step ahead at most
   // the spare buffer was last read by the step before the current one: everything enqueued so far must finish first
   die_on(gai_event_record(ev_free, stream()), "gai_event_record");
   die_on(gai_stream_wait_event(copy_stream, ev_free), "gai_stream_wait_event");
-  die_on(gai_memcpy_h2d(d_feat_buf[feat_cur ^ 1], pinned_inputs[0], bytes, copy_stream), "gai_memcpy_h2d");
+  upload_features(d_feat_buf[feat_cur ^ 1], feature_source(feats_h), copy_stream);
   die_on(gai_event_record(ev_ready, copy_stream), "gai_event_record");
   prefetch_pending = true;
 }

@@ -33,12 +33,13 @@ class Model {
   // One training step exactly as Model::train's loop body (net.cpp:373-383); returns train accuracy.
   acc_t train_epoch(acc_t& loss);
   // Re-upload the epoch's inputs (features, labels, masks, CSR) from host memory: the reference's host->device boundary
-  // (net.cpp:186-187, 207-227), exposed so that an end-to-end step can include it.
-  void refresh_inputs_from_host(const float* feats_h_pinned);
+  // (net.cpp:186-187, 207-227), exposed so that an end-to-end step can include it. `feats_h` = dense [nv x dim_init] rows, read from
+  // where they lie on EVERY call (pass page-locked memory for a true async copy); NULL = the Model's own copy of the training features.
+  void refresh_inputs_from_host(const float* feats_h);
   // Start copying the NEXT step's feature matrix (the bulk of the inputs) into a second device buffer on a copy stream, behind
   // everything already enqueued on the compute stream; the following refresh_inputs_from_host() swaps it in instead of
   // copying in line, so the transfer overlaps the current step's kernels.
-  void prefetch_features_from_host(const float* feats_h_pinned);
+  void prefetch_features_from_host(const float* feats_h);
   int num_conv_layers() const { return num_layers; }
   gconv_layer& conv_layer(int l) { return layer_gconv[l]; }
   dense_layer* dense() { return layer_dense; }
@@ -72,7 +73,9 @@ class Model {
   void* copy_stream = nullptr;
   void *ev_ready = nullptr, *ev_free = nullptr;
   void* pinned_inputs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  void stage_pinned(const float* feats_h);
+  void stage_pinned();
+  const float* feature_source(const float* feats_h);
+  void upload_features(float* dst_d, const float* src_h, void* on_stream);
   label_t* d_labels = nullptr;
   mask_t *d_masks_train = nullptr, *d_masks_test = nullptr, *d_masks_val = nullptr;
 

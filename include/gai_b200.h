@@ -139,6 +139,13 @@ int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, co
 int gai_gat_backward(gai_csr_t g, int F, const float* z, const float* grad_in, float slope, const float* temp_scores,
                      const float* norm_scores, float* scores_grad_ws, float* d_alpha_l, float* d_alpha_r, float* dz, gai_stream_t stream);
 
+/* The same two with explicit row pitches (the layer classes store per-vertex buffers with line-aligned rows, any width F). */
+int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld_z, const float* alpha_l, const float* alpha_r, float slope,
+                       float* temp_scores, float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream);
+int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld_z, const float* grad_in, size_t ld_grad, float slope, const float* temp_scores,
+                        const float* norm_scores, float* scores_grad_ws, float* d_alpha_l, float* d_alpha_r, float* dz, size_t ld_dz,
+                        gai_stream_t stream);
+
 /* ---- dense transform: matmul(x,y,z,A,B,C,transA,transB,accum) (src/utilities/math_functions.cpp:142-171;
  *      GPU twin cublasSgemm, math_functions.cu:321-343).  C[x×y] = op(A)[x×z] · op(B)[z×y] (+ C if accum).
  *      fp32 in/out; tensor-core path = tcgen05 kind::tf32 with 3xTF32 error compensation (≈fp32 accuracy).

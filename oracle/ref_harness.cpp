@@ -18,6 +18,7 @@
 #include "math_functions.hh"
 #include "softmax_loss_layer.h"
 #include "sigmoid_loss_layer.h"
+#include "reader.h"
 
 std::map<char, double> time_ops;  // reference global (defined in train.cpp:3, which is not linked here)
 
@@ -282,6 +283,31 @@ int64_t ref_model_set(void* m, const char* name, int layer, const float* in, int
   if (n < 0 || n != n_in) return -1;
   memcpy(p, in, sizeof(float) * n);
   return n;
+}
+
+// The reference's own loader (src/gnn/reader.cpp:248-457) on a dataset directory under DATASET_PATH (the path is read once, at
+// library load: include/gnn/configs.h:5). Two-call protocol: with rowptr == NULL only the sizes come back in meta[0..12] =
+// {nv, ne, feat_len, num_classes, train begin/end/count, val begin/end/count, test begin/end/count}.
+int ref_reader_load(const char* dataset, int single_class, int64_t* meta, uint32_t* rowptr, uint32_t* colidx, float* feats, uint8_t* labels) {
+  Reader reader{std::string(dataset)};
+  Graph* g = new Graph(false);
+  reader.bin_read_graph(g);
+  std::vector<float> f;
+  const size_t flen = reader.bin_read_features(f);
+  std::vector<label_t> lab;
+  const int ncls = reader.bin_read_vlabels(lab, single_class != 0);
+  size_t b[3], e[3], c[3];
+  const char* kinds[3] = {"train", "val", "test"};
+  for (int i = 0; i < 3; i++) c[i] = reader.bin_read_masks(kinds[i], g->size(), b[i], e[i], NULL);
+  meta[0] = g->size(); meta[1] = g->sizeEdges(); meta[2] = (int64_t)flen; meta[3] = ncls;
+  for (int i = 0; i < 3; i++) { meta[4 + 3 * i] = b[i]; meta[5 + 3 * i] = e[i]; meta[6 + 3 * i] = c[i]; }
+  if (rowptr) {
+    memcpy(rowptr, g->row_start_host_ptr(), sizeof(uint32_t) * (g->size() + 1));
+    memcpy(colidx, g->edge_dst_host_ptr(), sizeof(uint32_t) * g->sizeEdges());
+    memcpy(feats, f.data(), sizeof(float) * f.size());
+    memcpy(labels, lab.data(), lab.size());
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -36,6 +36,16 @@ def cora():
 
 
 @pytest.fixture(scope="session")
+def ref_inputs(tmp_path_factory):
+    """DATASET_PATH holding byte-identical copies of the reference's own inputs/cora/* (tests/golden/cora_ref.tar.xz, digests in cora_ref.json)."""
+    import tarfile
+    d = tmp_path_factory.mktemp("ref_inputs")
+    with tarfile.open(os.path.join(GOLDEN_DIR, "cora_ref.tar.xz")) as t:
+        t.extractall(d, filter="data")
+    return str(d) + "/"
+
+
+@pytest.fixture(scope="session")
 def small_graph(golden):
     """Power-law graph with a hub row (>1024 neighbours) and isolated vertices; inputs regenerated from seeds."""
     rp64, ci = golden["sg_rowptr64"], golden["sg_colidx"]

@@ -76,6 +76,43 @@ def test_partition1d_h_bit_exact(abi, golden, cora, small_graph):
     assert len(r["idx_map"]) == 0 and r["local_begin"] == r["local_end"] == 0
 
 
+def test_argument_errors_are_reported_not_executed(abi):
+    """Error behaviour of the C ABI (the reference asserts / exits; this layer returns GAI_ERR_ARG with a message and touches nothing).
+    All of these are rejected before any CUDA call, so they run without a device."""
+    L = abi.lib()
+    ARG = 2
+    h = C.c_void_p()
+    rp = np.zeros(2, np.uint32)
+    # NULL outputs / inputs
+    assert L.gai_csr_create(1, 0, rp.ctypes.data_as(C.c_void_p), None, None, None) == ARG
+    assert L.gai_csr_create(1, 0, None, None, None, C.byref(h)) == ARG
+    # nnz >= 2^32: the 32-bit column-offset layout cannot address it (reference: eidType is 64-bit on disk, 32-bit in LearningGraph)
+    assert L.gai_csr_create(1, 1 << 32, rp.ctypes.data_as(C.c_void_p), rp.ctypes.data_as(C.c_void_p), None, C.byref(h)) == ARG
+    assert b"nnz" in L.gai_last_error()
+    # rowptr[nv] must equal nnz
+    assert L.gai_csr_create(1, 5, rp.ctypes.data_as(C.c_void_p), rp.ctypes.data_as(C.c_void_p), None, C.byref(h)) == ARG
+    # NULL graph handles on every aggregation entry point
+    assert L.gai_spmm_gcn(None, 4, None, 4, None, 4, 0, None, None) == ARG
+    assert L.gai_spmm_mean(None, 4, None, 4, None, 4, 0, 0, None, None) == ARG
+    assert L.gai_spmm_edge(None, 4, None, None, None, 4, None, 4, 0, None, None) == ARG
+    assert L.gai_gat_forward_ld(None, 4, None, 4, None, None, 0.2, None, None, None, 4, 0, None) == ARG
+    assert L.gai_csr_set_norms(None, None, None, None) == ARG
+    assert L.gai_csr_set_row_segments(None, 0, None, None) == ARG
+    assert L.gai_csr_build_transpose(None, None) == ARG
+    # accessors on a NULL handle are total functions
+    assert L.gai_csr_nv(None) == 0 and L.gai_csr_nnz(None) == 0 and L.gai_csr_rowptr(None) is None
+    assert L.gai_csr_destroy(None) == 0 and L.gai_free(None) == 0
+    # partition: bad part index / part count
+    rp64 = np.array([0, 1, 2], np.int64); ci = np.array([1, 0], np.uint32)
+    m, ne = C.c_int64(), C.c_int64()
+    assert L.gai_partition1d_h(2, rp64.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), 0, 0, None, None, None, C.byref(m), C.byref(ne),
+                               None, None) == ARG
+    assert L.gai_partition1d_h(2, rp64.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p), 2, 2, None, None, None, C.byref(m), C.byref(ne),
+                               None, None) == ARG
+    # out-parameters that must not be NULL
+    assert L.gai_device_count(None) == ARG and L.gai_malloc(None, 16) == ARG and L.gai_event_create(None) == ARG
+
+
 def test_committed_bench_line_has_the_contract_keys():
     """profiles/r1_bench.json is a real `python bench.py` line: the keys the driver and the judge read must all be there."""
     import json

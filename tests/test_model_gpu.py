@@ -52,17 +52,16 @@ def test_cora_training_matches_reference(gm, golden, cora, arch, epochs):
     losses = np.array(losses, np.float32)
     assert abs(losses[0] - ref_losses[0]) <= 1e-5 * ref_losses[0]
     np.testing.assert_allclose(losses[:10], ref_losses[:10], rtol=2e-4)
-    np.testing.assert_allclose(losses, ref_losses, rtol=0.05, atol=2e-4)  # long trajectories drift in the last digits
+    # long trajectories drift in the last digits (200 Adam steps amplify 1e-6 differences of the first gradients): 1 % on every epoch's loss
+    np.testing.assert_allclose(losses, ref_losses, rtol=0.01, atol=1e-4)
     assert abs(m.evaluate("test") - float(golden[f"cora_{arch}_test_acc"])) < 1e-6, "final test accuracy differs from the reference"
     assert abs(m.evaluate("val") - float(golden[f"cora_{arch}_val_acc"])) < 1e-6
 
 
-def test_cli_binary_on_cora(gm, golden, cora, tmp_path):
-    """The reference's CLI contract: DATASET_PATH + positional argv, 'Test accuracy:' line (train.cpp:9-41)."""
-    from graphaibench_b200 import datagen
-    d = tmp_path / "cora"
-    datagen.write_dataset(str(d), cora["rowptr64"], cora["colidx"], cora["feats"], cora["labels"], cora["ncls"], cora["split"])
-    env = dict(os.environ, DATASET_PATH=str(tmp_path) + "/")
+def test_cli_binary_on_cora(gm, golden, ref_inputs):
+    """The reference's CLI contract: DATASET_PATH + positional argv, 'Test accuracy:' line (train.cpp:9-41), on the REFERENCE's own
+    dataset files (byte-identical copies of inputs/cora/*, tests/golden/cora_ref.tar.xz)."""
+    env = dict(os.environ, DATASET_PATH=ref_inputs)
     out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_gcn"), "cora", "200", "1", "softmax"], env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -108,15 +107,12 @@ def test_medium_graph_layers_match_oracle(gm, arch, dims, layers):
         close(m.get("W", k), o.layers[k].W, 2e-3)
 
 
-def test_cli_sigmoid_loss_on_cora(gm, cora, tmp_path):
+def test_cli_sigmoid_loss_on_cora(gm, ref_inputs):
     """`gpu_train_gcn cora 60 1 sigmoid` (multi-hot labels, sigmoid cross-entropy, micro-F1 as accuracy; net.cpp:20,447-451,495-497,569-572)
     against the reference's own CPU binary run in the build container:
         oracle/_ref/cpu_train_gcn cora 60 8 sigmoid  ->  Epoch 0 train_loss 4.852 train_acc 0.236, Epoch 59 train_loss 1.577 train_acc 0.462,
         Test accuracy 0.175."""
-    from graphaibench_b200 import datagen
-    d = tmp_path / "cora"
-    datagen.write_dataset(str(d), cora["rowptr64"], cora["colidx"], cora["feats"], cora["labels"], cora["ncls"], cora["split"])
-    env = dict(os.environ, DATASET_PATH=str(tmp_path) + "/")
+    env = dict(os.environ, DATASET_PATH=ref_inputs)
     out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_gcn"), "cora", "60", "1", "sigmoid"], env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -134,14 +130,11 @@ def test_cli_sigmoid_loss_on_cora(gm, cora, tmp_path):
     assert abs(test - 0.175) <= 0.01
 
 
-def test_cli_feature_dropout_on_cora(gm, cora, tmp_path):
+def test_cli_feature_dropout_on_cora(gm, ref_inputs):
     """`gpu_train_gcn cora 200 1 softmax 16 0 0.5 0.02` (feature dropout 0.5, argv as net.cpp:13-64). Dropout is stochastic in the reference
     too (/dev/urandom seed): its CPU binary gives test accuracy 0.800 / 0.801 and a final train loss of 0.026 / 0.032 on two runs (0.795 and
     0.005 without dropout), so the check is a band: the regularised regime, not the rate-0 trajectory."""
-    from graphaibench_b200 import datagen
-    d = tmp_path / "cora"
-    datagen.write_dataset(str(d), cora["rowptr64"], cora["colidx"], cora["feats"], cora["labels"], cora["ncls"], cora["split"])
-    env = dict(os.environ, DATASET_PATH=str(tmp_path) + "/")
+    env = dict(os.environ, DATASET_PATH=ref_inputs)
     out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_gcn"), "cora", "200", "1", "softmax", "16", "0", "0.5", "0.02"], env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -152,3 +145,31 @@ def test_cli_feature_dropout_on_cora(gm, cora, tmp_path):
     test = float([l for l in lines if l.startswith("Test accuracy:")][0].split()[2])
     assert 0.012 <= loss <= 0.08, loss
     assert 0.775 <= test <= 0.825, test
+
+
+def test_refresh_inputs_reads_the_callers_buffer_every_call(gm):
+    """refresh_inputs_from_host / prefetch_features_from_host must honour the host data passed on EVERY call, not a copy
+    staged on the first one. Two different feature matrices through one model must give the losses of two freshly built models."""
+    import ctypes
+    from graphaibench_b200 import datagen
+    nv, F, hid, ncls = 5000, 100, 32, 7
+    rp64, ci = datagen.rmat_csr(nv, 60000, seed=21)
+    rp = rp64.astype(np.uint32)
+    fa, fb = datagen.features(nv, F, seed=22), datagen.features(nv, F, seed=23)
+    labels = np.random.default_rng(24).integers(0, ncls, nv).astype(np.uint8)
+    split = datagen.split_ranges(nv)
+    la = gm.GnnModel("sage", rp, ci, fa, labels, split, hid, ncls).forward()[0]
+    lb = gm.GnnModel("sage", rp, ci, fb, labels, split, hid, ncls).forward()[0]
+    assert abs(la - lb) > 1e-4 * abs(la), "the two feature sets must be distinguishable"
+    m = gm.GnnModel("sage", rp, ci, fa, labels, split, hid, ncls)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    m.refresh_inputs(ptr(fb))
+    assert m.forward()[0] == lb
+    m.refresh_inputs(ptr(fa))
+    assert m.forward()[0] == la
+    m.prefetch_inputs(ptr(fb)); m.refresh_inputs(ptr(fb))     # the copy-stream path swaps the prefetched buffer in
+    assert m.forward()[0] == lb
+    m.prefetch_inputs(ptr(fa)); m.refresh_inputs(ptr(fa))
+    assert m.forward()[0] == la
+    m.refresh_inputs(None)                                    # NULL = the model's own copy of its training features
+    assert m.forward()[0] == la
