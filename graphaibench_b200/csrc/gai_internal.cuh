@@ -34,9 +34,11 @@ static inline cudaStream_t S(gai_stream_t s) { return reinterpret_cast<cudaStrea
 // Number of SMs of the current device (148 on B200); cached.
 int sm_count();
 
-// Library-owned scratch (split-K partials, reductions). Grown on demand, never shrunk; one per device.
-int workspace(size_t bytes, void** out);          // slot 0: split-K partials, GAT per-vertex scratch, reductions
-int workspace_slot(int slot, size_t bytes, void** out);  // slot 1: SpMM padded-input staging
+// Library-owned scratch (split-K partials, reductions). Grown on demand, never shrunk; one per (device, stream, slot): work on two
+// streams (two models, the ranks of an in-process partitioned run, a side stream) never shares a scratch buffer, and growing one
+// waits for that stream only.
+int workspace(size_t bytes, void** out, cudaStream_t st);          // slot 0: split-K partials, GAT per-vertex scratch, reductions
+int workspace_slot(int slot, size_t bytes, void** out, cudaStream_t st);  // slot 1: SpMM padded-input staging, slot 2: dense-transform operands
 
 // Hub threshold: rows longer than a warp's fair share of the edges (nnz / resident warp slots), clamped to [1024, 8192],
 // go to the CTA-per-row kernels; everything else is one lane-group per row.

@@ -330,7 +330,7 @@ int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld, const floa
   if (g->nv == 0) return GAI_OK;
   cudaStream_t st = gai::S(stream);
   void* ws = nullptr;
-  int rc = gai::workspace(sizeof(float) * 2 * (size_t)g->nv, &ws);
+  int rc = gai::workspace(sizeof(float) * 2 * (size_t)g->nv, &ws, st);
   if (rc != GAI_OK) return rc;
   float* el = reinterpret_cast<float*>(ws);
   float* er = el + g->nv;
@@ -357,7 +357,7 @@ int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld, const flo
   const int sms = gai::sm_count();
   const int nparts = (int)((g->nv + 255) / 256 < (uint32_t)(4 * sms) ? (g->nv + 255) / 256 : (uint32_t)(4 * sms));
   void* ws = nullptr;
-  rc = gai::workspace(sizeof(float) * (2 * (size_t)g->nv + (size_t)nparts * 2 * F), &ws);
+  rc = gai::workspace(sizeof(float) * (2 * (size_t)g->nv + (size_t)nparts * 2 * F), &ws, st);
   if (rc != GAI_OK) return rc;
   float* rowsum = reinterpret_cast<float*>(ws);
   float* colsum = rowsum + g->nv;

@@ -161,7 +161,7 @@ int gemm_simt(size_t M, size_t N, size_t K, const float* A, size_t lda, const fl
   g.partial = nullptr;
   if (splits > 1) {
     void* ws = nullptr;
-    int rc = workspace(sizeof(float) * (size_t)splits * M * N, &ws);
+    int rc = workspace(sizeof(float) * (size_t)splits * M * N, &ws, st);
     if (rc != GAI_OK) return rc;
     g.partial = reinterpret_cast<float*>(ws);
   }

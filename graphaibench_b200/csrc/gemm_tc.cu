@@ -426,7 +426,7 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   }
   const size_t b_elems = ((size_t)n_mma * k_pad + 63) / 64 * 64;
   void* ws = nullptr;
-  int rc = workspace_slot(2, sizeof(float) * (2 * b_elems + pad_elems) + 256, &ws);
+  int rc = workspace_slot(2, sizeof(float) * (2 * b_elems + pad_elems) + 256, &ws, st);
   if (rc != GAI_OK) return rc;
   float* bhi = reinterpret_cast<float*>(ws);
   float* blo = bhi + b_elems;

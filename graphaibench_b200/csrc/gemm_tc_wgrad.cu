@@ -295,7 +295,7 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
-  int rc = workspace(sizeof(float) * grid * g.Kx * g.My, &ws);
+  int rc = workspace(sizeof(float) * grid * g.Kx * g.My, &ws, st);
   if (rc != GAI_OK) return rc;
   g.partial = reinterpret_cast<float*>(ws);
   const float* src[4] = {q.A[0], na == 2 ? q.A[1] : q.A[0], q.B[0], nb == 2 ? q.B[1] : q.B[0]};
@@ -307,7 +307,7 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
     if (used[i] && !tma_ok(src[i], ld[i])) pad_elems += (nrows * ((cols[i] + 3) / 4 * 4) + 63) / 64 * 64;
   if (pad_elems) {
     void* ws2 = nullptr;
-    rc = workspace_slot(2, sizeof(float) * pad_elems + 512, &ws2);
+    rc = workspace_slot(2, sizeof(float) * pad_elems + 512, &ws2, st);
     if (rc != GAI_OK) return rc;
     float* p = reinterpret_cast<float*>(ws2);
     const size_t cap = (size_t)sm_count() * 32;

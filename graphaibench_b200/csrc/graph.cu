@@ -225,6 +225,7 @@ uint64_t gai_csr_nnz(gai_csr_t g) { return g ? g->nnz : 0; }
 const uint32_t* gai_csr_rowptr(gai_csr_t g) { return g ? g->rowptr : nullptr; }
 const uint32_t* gai_csr_colidx(gai_csr_t g) { return g ? g->colidx : nullptr; }
 const float* gai_csr_vertex_norm(gai_csr_t g) { return g ? g->norm_gcn : nullptr; }
+const float* gai_csr_mean_norm(gai_csr_t g) { return g ? g->norm_mean : nullptr; }
 uint32_t gai_csr_num_hub_rows(gai_csr_t g) { return g ? g->n_hub : 0; }
 
 int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream) {

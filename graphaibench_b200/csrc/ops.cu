@@ -566,7 +566,7 @@ static int softmax_ce_forward_impl(int ncls, size_t begin, size_t end, const uin
     double* partial = nullptr;
     if (stats_d) {
       void* ws = nullptr;
-      int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws);
+      int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws, gai::S(stream));
       if (rc != GAI_OK) return rc;
       partial = reinterpret_cast<double*>(ws);
     }
@@ -646,7 +646,7 @@ int gai_masked_loss_accuracy_ld(int ncls, size_t begin, size_t end, const uint8_
   if (nparts > cap) nparts = cap;
   if (nparts < 1) nparts = 1;
   void* ws = nullptr;
-  int rc = gai::workspace(sizeof(double) * 3 * (size_t)nparts, &ws);
+  int rc = gai::workspace(sizeof(double) * 3 * (size_t)nparts, &ws, gai::S(stream));
   if (rc != GAI_OK) return rc;
   loss_acc_stage1<<<nparts, 256, 0, gai::S(stream)>>>(ncls, begin, end, masks, labels, logits, ld_logits, losses, reinterpret_cast<double*>(ws));
   GAI_LAUNCH_CHECK();
@@ -684,7 +684,7 @@ int gai_masked_loss_mean(size_t begin, size_t end, const uint8_t* masks, const f
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   void* ws = nullptr;
-  int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws);
+  int rc = gai::workspace(sizeof(double) * 3 * blocks, &ws, gai::S(stream));
   if (rc != GAI_OK) return rc;
   loss_mean_stage1<<<(unsigned)blocks, 256, 0, gai::S(stream)>>>(begin, end, masks, losses, reinterpret_cast<double*>(ws));
   GAI_LAUNCH_CHECK();
@@ -696,7 +696,7 @@ int gai_masked_f1_micro(int ncls, size_t begin, size_t end, const uint8_t* masks
                         float* f1_d, gai_stream_t stream) {
   GAI_CHECK_ARG(ncls > 0 && begin <= end && labels_multi && preds && f1_d && ld_preds >= (size_t)ncls);
   void* ws = nullptr;
-  int rc = gai::workspace(sizeof(unsigned long long) * 4, &ws);
+  int rc = gai::workspace(sizeof(unsigned long long) * 4, &ws, gai::S(stream));
   if (rc != GAI_OK) return rc;
   GAI_CUDA(cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 4, gai::S(stream)));
   if (begin != end) {

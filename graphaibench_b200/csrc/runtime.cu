@@ -3,6 +3,7 @@
 // and its exit-on-error macros (include/utils/cutils.h:133-174) with int status codes.
 #include <mutex>
 #include <map>
+#include <tuple>
 #include "gai_internal.cuh"
 
 namespace gai {
@@ -39,18 +40,18 @@ int sm_count() {
 
 struct Ws { void* p = nullptr; size_t bytes = 0; };
 static std::mutex g_ws_mu;
-static std::map<std::pair<int, int>, Ws> g_ws;
+static std::map<std::tuple<int, cudaStream_t, int>, Ws> g_ws;
 
-int workspace(size_t bytes, void** out) { return workspace_slot(0, bytes, out); }
+int workspace(size_t bytes, void** out, cudaStream_t st) { return workspace_slot(0, bytes, out, st); }
 
-int workspace_slot(int slot, size_t bytes, void** out) {
+int workspace_slot(int slot, size_t bytes, void** out, cudaStream_t st) {
   int dev = 0;
   GAI_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_ws_mu);
-  Ws& w = g_ws[std::make_pair(dev, slot)];
+  Ws& w = g_ws[std::make_tuple(dev, st, slot)];
   if (w.bytes < bytes) {
     if (w.p) {
-      GAI_CUDA(cudaDeviceSynchronize());
+      GAI_CUDA(cudaStreamSynchronize(st));  // only work on this stream can still be reading the old buffer
       GAI_CUDA(cudaFree(w.p));
       w.p = nullptr; w.bytes = 0;
     }

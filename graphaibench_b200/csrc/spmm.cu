@@ -7,12 +7,10 @@
 // Design (B200: an HBM/L2 gather; no tensor-core shape here):
 //   * every input row is read with 128-bit loads. Rows whose pitch is a multiple of 4 floats are read in place; only a
 //     caller's dense matrix with F % 4 != 0 (or a misaligned base) goes through a zero-padded staging copy.
-//     Row ALIGNMENT decides the cost of a gather: the L1 data pipe serves a 128-bit warp load one quarter-warp
-//     (8 lanes x 16 B = 128 B) per wavefront only if those 128 B lie in one 128-byte line. With a 400-byte pitch
-//     (F = 100) every quarter straddles two lines: ncu counted 7.4 wavefronts per gather instead of 4 and
-//     l1tex__data_pipe_lsu_wavefronts at 73 % was the kernel's top limiter (profiles/README.md, round 1). The layer
-//     classes therefore store per-vertex buffers with a line-aligned pitch (host/gai_layers.h: row_pitch()), and lanes
-//     past the row width are predicated off instead of re-reading chunk 0.
+//     Lanes past the row width are predicated off (no load, no wavefront, no writeback) instead of re-reading chunk 0.
+//     What bounds the kernel (ncu, profiles/README.md round 2): L2 -> SM bandwidth (8.7 TB/s of the ~12 TB/s LTS cap for F = 100) and
+//     the latency of the gathers behind it (occupancy 48 % at 64 registers, long_scoreboard the top stall) — not the L1 data pipe:
+//     128-byte-aligned row pitches cut its wavefronts by a third and changed nothing (the larger footprint cost the hit rates).
 //   * one persistent kernel (4 CTAs x 148 SMs), two kinds of work items taken from global counters:
 //       light rows (deg <= hub_degree): rows in DEGREE order, cut into claims of <= 32 rows / <= 2048 edges. A group of
 //         G lanes (G = 4..32, from the feature width) owns one output row in registers; the group loads G column
@@ -707,7 +705,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
     // gather source must be 128-bit loadable: stage a zero-padded copy (all nv rows can be neighbours)
     const int Fp = a.nchunks * 4;
     void* ws = nullptr;
-    int rc = gai::workspace_slot(1, sizeof(float) * (size_t)g->nv * Fp, &ws);
+    int rc = gai::workspace_slot(1, sizeof(float) * (size_t)g->nv * Fp, &ws, st);
     if (rc != GAI_OK) return rc;
     const size_t total = (size_t)g->nv * Fp;
     size_t blocks = (total + 255) / 256;
@@ -766,6 +764,13 @@ int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* 
   GAI_CHECK_ARG(g != nullptr && mask_bits != nullptr && ld_bits >= (F + 31) / 32);
   return spmm_dispatch(g, transposed ? M_MEAN_T : M_MEAN, 0, g->nv, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream, mask_bits,
                        ld_bits);
+}
+int gai_spmm_rows_ex(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in,
+                     float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, gai_stream_t stream) {
+  GAI_CHECK_ARG(mode >= M_GCN && mode <= M_EDGE_PERM);
+  GAI_CHECK_ARG(mode != M_EDGE_PERM || perm != nullptr);
+  GAI_CHECK_ARG(mask_bits == nullptr || ld_bits >= (F + 31) / 32);
+  return spmm_dispatch(g, mode, rb, re, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream, mask_bits, ld_bits);
 }
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t rb, uint32_t re, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
   return spmm_dispatch(g, M_GCN, rb, re, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream);

@@ -269,11 +269,8 @@ def _ceil4(x):
 
 
 def _pitch(x):
-    """Row pitch of every tall buffer (host/gai_layers.h row_pitch): line-aligned rows, so a gather never straddles 128-byte lines."""
-    for p in (4, 8, 16, 32):
-        if x <= p:
-            return p
-    return (x + 31) // 32 * 32
+    """Row pitch of every tall buffer (host/gai_layers.h row_pitch): rows padded to 4 floats."""
+    return _ceil4(x)
 
 
 class _Adam:

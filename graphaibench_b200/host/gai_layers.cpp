@@ -216,7 +216,7 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
     d_W_self = upload_glorot(din, dout, 2);
     d_W_self_grad = float_malloc_device_zero((size_t)din * dout);
   }
-  // row pitches: every per-vertex buffer, layer 0's input included (Model's device copy of the features), has line-aligned rows
+  // row pitches: every per-vertex buffer, layer 0's input included (Model's device copy of the features), has rows padded to 4 floats
   ld_in = row_pitch(din);
   ld_out = row_pitch(dout);
   // temporaries: only what this layer's schedule touches (the reference allocates all of them unconditionally)

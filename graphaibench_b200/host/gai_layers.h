@@ -43,17 +43,12 @@ struct adam : public optimizer {
   std::unordered_map<const float*, std::pair<float*, float*>> moments;
 };
 
-// Row pitch (floats) of every per-vertex activation / gradient buffer the layer classes own: rows start on a boundary of
-// their own (power-of-two) size up to 128 bytes, and on a 128-byte line boundary beyond that (47 -> 64, 100 -> 128, 256 -> 256).
-// A neighbour-row gather then costs the minimum number of L1 wavefronts (a quarter-warp's 128 bytes never straddle two
-// lines, csrc/spmm.cu) and every TMA box / 128-bit epilogue store is aligned for any width.
-inline size_t row_pitch(size_t dim) {
-  if (dim <= 4) return 4;
-  if (dim <= 8) return 8;
-  if (dim <= 16) return 16;
-  if (dim <= 32) return 32;
-  return (dim + 31) / 32 * 32;
-}
+// Row pitch (floats) of every per-vertex activation / gradient buffer the layer classes own: rows padded to a multiple of 4 floats
+// (47 classes -> pitch 48), so that every aggregation gather, TMA box and epilogue store is 16-byte aligned for any width.
+// Measured and rejected (round 2, profiles/README.md): 128-byte-aligned rows (47 -> 64, 100 -> 128). They cut the L1 wavefronts of a
+// gather by a third (a quarter-warp's 128 bytes no longer straddle two lines) but the aggregation is bound by L2 bandwidth and latency,
+// not by the L1 data pipe, and the larger footprint lowered the L2 / L1 hit rates: F = 100 unchanged, F = 47 5-10 % slower.
+inline size_t row_pitch(size_t dim) { return (dim + 3) / 4 * 4; }
 inline size_t ceil4(size_t dim) { return (dim + 3) / 4 * 4; }
 // Words per row of a sign-bit matrix (one bit per activation, GAI_EPI_BITMASK).
 inline size_t bits_pitch(size_t dim) { return (dim + 31) / 32; }
@@ -126,8 +121,8 @@ class graph_conv_layer {
   size_t weight_size(const std::string& name);   // logical element count (rows x cols, dense)
   // Row layout of a named per-vertex tensor: logical columns and the pitch it is stored with (0/0 for weights: dense).
   void tensor_layout(const std::string& name, size_t* cols, size_t* ld);
-  // Row pitches. Per-vertex activation / gradient buffers owned by the layer classes are stored with line-aligned rows
-  // (row_pitch: 47 classes -> pitch 64); layer 0's feat_in is Model's device copy of the input features, stored the same way.
+  // Row pitches. Per-vertex activation / gradient buffers owned by the layer classes are stored with rows padded to 4 floats
+  // (row_pitch: 47 classes -> pitch 48); layer 0's feat_in is Model's device copy of the input features, stored the same way.
   size_t ld_feat_in() const { return ld_in; }
   size_t ld_grad_in() const { return ld_out; }
   // d_relu fusion across the layer boundary: the layer above writes this layer's grad_in already masked by this layer's

@@ -96,7 +96,7 @@ void Model<L>::finish_setup() {
 
 template <typename L>
 void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
-  // input features live on the device with line-aligned rows (row_pitch), like every other per-vertex buffer
+  // input features live on the device with rows of pitch row_pitch(dim_init), like every other per-vertex buffer
   d_input_features = float_malloc_device_zero((size_t)num_samples * row_pitch(dim_init));
   upload_features(d_input_features, input_features.data(), stream());
   d_labels = upload(labels.data(), labels.size());
@@ -106,11 +106,14 @@ void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
   sync();
 }
 
-// dense host rows [num_samples x dim_init] -> device rows of pitch row_pitch(dim_init): one pitched DMA
+// dense host rows [num_samples x dim_init] -> device rows of pitch row_pitch(dim_init): one linear DMA when the width is a multiple of
+// 4 floats (every BASELINE.json shape), a pitched one otherwise (measured: a pitched host->device copy of 400-byte rows runs at
+// ~4 GB/s, so wide matrices whose width is not a multiple of 4 should be padded on the host)
 template <typename L>
 void Model<L>::upload_features(float* dst_d, const float* src_h, void* on_stream) {
   const size_t w = sizeof(float) * (size_t)dim_init;
-  die_on(gai_memcpy2d(dst_d, sizeof(float) * row_pitch(dim_init), src_h, w, w, (size_t)num_samples, on_stream), "gai_memcpy2d");
+  if (row_pitch(dim_init) == (size_t)dim_init) die_on(gai_memcpy_h2d(dst_d, src_h, w * (size_t)num_samples, on_stream), "gai_memcpy_h2d");
+  else die_on(gai_memcpy2d(dst_d, sizeof(float) * row_pitch(dim_init), src_h, w, w, (size_t)num_samples, on_stream), "gai_memcpy2d");
 }
 
 template <typename L>

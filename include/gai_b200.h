@@ -88,6 +88,7 @@ uint64_t gai_csr_nnz(gai_csr_t g);
 const uint32_t* gai_csr_rowptr(gai_csr_t g);   /* LearningGraph::row_start_ptr (lgraph.h:173) */
 const uint32_t* gai_csr_colidx(gai_csr_t g);   /* LearningGraph::edge_dst_ptr  (lgraph.h:175) */
 const float* gai_csr_vertex_norm(gai_csr_t g); /* LearningGraph::vertex_data_ptr (lgraph.h:179) */
+const float* gai_csr_mean_norm(gai_csr_t g);   /* 1 / deg (sage_aggregator.cpp:17,41); with gai_csr_vertex_norm: the arrays a partitioned rank exposes to its peers */
 /* Override the per-vertex normalisers with values computed elsewhere (1D partition: norms come from GLOBAL degrees). */
 int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream);
 uint32_t gai_csr_num_hub_rows(gai_csr_t g);
@@ -124,6 +125,10 @@ int gai_spmm_gcn_masked(gai_csr_t g, int F, const float* in, int ld_in, float* o
                         const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
 int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend,
                          const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
+/* Every aggregation form over a row range, in one entry point (what the partitioned layer classes call: rows [0, n_masters) of a local
+ * CSR whose column ids run over masters + halo). mode: 0 GCN, 1 mean, 2 transposed mean, 3 edge values, 4 edge values through perm. */
+int gai_spmm_rows_ex(gai_csr_t g, int mode, uint32_t row_begin, uint32_t row_end, int F, const float* vals, const uint32_t* perm, const float* in,
+                     int ld_in, float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
 /* Row-range variants for the 1D partition (interior rows first, boundary rows after the halo arrives). */
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
 int gai_spmm_mean_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend, gai_stream_t stream);
@@ -260,8 +265,40 @@ int gai_adam_update(size_t n, const float* dW, float* W, float* m, float* v, flo
 int gai_partition1d_h(uint32_t nv, const int64_t* rowptr_h, const uint32_t* colidx_h, int nparts, int part, uint32_t* idx_map_h,
                       int64_t* sub_rowptr_h, uint32_t* sub_colidx_h, int64_t* m_out, int64_t* ne_out, uint32_t* local_begin, uint32_t* local_end);
 
-/* ---- halo exchange over NVLink peer memory (multi-GPU; no reference counterpart: the reference GNN path is
- *      single-GPU).  dst_rows[k, 0:F] = src[ids[k], 0:F] where `src` may be a peer-mapped pointer. */
+/* ---- multi-GPU: halo exchange and reductions over NVLink peer memory (csrc/peers.cu) ---------------------------------
+ * No reference counterpart on the GNN path (single-GPU); the partition these serve follows
+ * PartitionedGraph::edgecut_induced_partition1D (src/partitioner/graph_partition.cc:128-178): S = ceil(N / P), rank p owns the
+ * global ids [p*S, min((p+1)*S, N)), a rank's matrices hold its masters in ascending global id (row = id - p*S) followed by its halo
+ * rows in ascending global id.
+ * One rank per GPU: one process each (torchrun) or one host thread each (gpu_train_* with GAI_PARTS). Buffers other ranks read are
+ * registered collectively; ranks exchange {pid, pointer, cudaIpcMemHandle} through the caller's bootstrap all-gather. */
+typedef struct gai_peers* gai_peers_t;
+typedef struct gai_halo_plan* gai_halo_plan_t;
+/* Bootstrap collective supplied by the caller (torch.distributed, threads, ...): every rank passes `bytes` bytes, every rank receives
+ * the nranks blocks in rank order. Only used at set-up time. */
+typedef void (*gai_allgather_fn)(void* ctx, const void* send, size_t bytes, void* recv_all);
+int gai_peers_create(int rank, int nranks, gai_allgather_fn allgather, void* ctx, gai_stream_t stream, gai_peers_t* out);
+int gai_peers_destroy(gai_peers_t p);
+int gai_peers_rank(gai_peers_t p);
+int gai_peers_world(gai_peers_t p);
+/* Collective: every rank registers its instance of the same logical buffer (a whole cudaMalloc allocation), in the same order. */
+int gai_peers_register(gai_peers_t p, void* dptr, int* id_out);
+/* Flag barrier in peer memory, enqueued on `stream`: everything this rank enqueued before it is visible to every rank's work behind it. */
+int gai_peers_barrier(gai_peers_t p, gai_stream_t stream);
+/* Synchronises `stream`; GAI_ERR_CUDA if a barrier gave up waiting for a peer (a rank died). */
+int gai_peers_error(gai_peers_t p, gai_stream_t stream);
+/* halo_gids_h: this rank's distinct remote neighbours, strictly ascending global ids (grouped by owner as a consequence). */
+int gai_halo_plan_create(gai_peers_t p, uint32_t nv_global, uint32_t n_halo, const uint32_t* halo_gids_h, gai_stream_t stream, gai_halo_plan_t* out);
+int gai_halo_plan_destroy(gai_halo_plan_t h);
+enum { GAI_PULL_NO_BARRIER_BEFORE = 1, GAI_PULL_NO_BARRIER_AFTER = 2 };
+/* Rows [dst_row_offset, dst_row_offset + n_halo) of this rank's instance of buffer `buf_id` <- the owners' rows, read through the mapped
+ * peer pointers (row pitch ld floats on every rank, F live columns). barrier - pull - barrier unless `flags` drops one. */
+int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld, size_t dst_row_offset, int flags, gai_stream_t stream);
+/* sum = 1: out[i] = sum over ranks (rank order, identical bits everywhere) of buffer `buf_id`[i], i < n   (weight-gradient all-reduce);
+ * sum = 0: out[q*n + i] = rank q's buffer[i]                                                              (all-gather of small vectors).
+ * `out` is a private buffer, not the registered one. barrier - combine - barrier. */
+int gai_peers_combine(gai_peers_t p, int buf_id, size_t n, int sum, float* out, gai_stream_t stream);
+/* dst_rows[k, 0:F] = src[ids[k], 0:F] (local row gather; `src` may be a peer-mapped pointer). */
 int gai_gather_rows(size_t n_ids, const uint32_t* ids, int F, const float* src, int ld_src, float* dst, int ld_dst, gai_stream_t stream);
 
 #ifdef __cplusplus

@@ -51,9 +51,25 @@ def tensor(chk, kind, name, layer):
     return np.asarray(getattr(y, name)).ravel()
 
 
-def test_c2_full_size_step_matches_reference(env):
-    """BASELINE.json configs[1] at full size, the exact bench.py workload (same generator and seeds)."""
+def exact_wgrad(a, g, nv):
+    """fp64 A^T·G over all rows, chunked on the GPU: the exact value both implementations approximate."""
     import torch
+    a = a.reshape(nv, -1); g = g.reshape(nv, -1)
+    out = torch.zeros(a.shape[1], g.shape[1], dtype=torch.float64, device="cuda")
+    step = 1 << 18
+    for r in range(0, nv, step):
+        out += torch.from_numpy(a[r:r + step]).cuda().double().t() @ torch.from_numpy(g[r:r + step]).cuda().double()
+    return out.cpu().numpy().ravel()
+
+
+def test_c2_full_size_step_matches_reference(env):
+    """BASELINE.json configs[1] at full size, the exact bench.py workload (same generator and seeds).
+
+    Activations, input gradients and the loss are held to 1e-5 / 2e-5 against the reference. The four weight gradients are sums over
+    2.45 M rows: fp32 accumulation order alone moves such a sum by ~eps*sqrt(rows) ~ 1e-4 of its norm, and the reference's own value
+    (OpenBLAS sgemm, blocked fp32) sits that far from the exact product. They are therefore judged against the EXACT fp64 product of the
+    same operands: this implementation must be within 2e-5 of it, must be at least as close to it as the reference is, and must agree
+    with the reference to within the reference's own distance from exact (+ 2e-5)."""
     import bench
     w = bench.make_workload(1, "cuda")
     C2 = bench.C2
@@ -61,21 +77,42 @@ def test_c2_full_size_step_matches_reference(env):
     m = env["model"].GnnModel("sage", w["rowptr"], w["colidx"], w["feats"], w["labels"], w["split"], C2["hid"], C2["ncls"], num_layers=2, lr=C2["lr"])
     chk, kind = env["checker"]("sage", w["rowptr"], w["colidx"], w["feats"], w["labels"], w["split"], C2["hid"], C2["ncls"], 2, C2["lr"])
     l, a = m.forward(); lr_, ar_ = chk.forward()
-    assert abs(l - lr_) <= 1e-5 * abs(lr_), (l, lr_)
-    assert abs(a - ar_) <= 2e-6, (a, ar_)   # accuracy = correct / 1 224 514 rows: at most a couple of argmax ties may flip
+    report = {"loss": (abs(l - lr_) / abs(lr_), 1e-5), "accuracy": (abs(a - ar_), 2e-6)}  # accuracy = correct / 1 224 514 rows
     m.backward(); chk.backward()
     rows = np.random.default_rng(17).integers(0, nv, 4000)
     hubs = np.argsort(np.diff(w["rowptr"].astype(np.int64)))[-8:]
     rows = np.concatenate([rows, hubs])
-    for k, width_in, width_out in ((0, C2["feat"], C2["hid"]), (1, C2["hid"], C2["ncls"])):
-        close(m.get("W_grad", k), tensor(chk, kind, "W_grad", k), 2e-5, f"W_grad[{k}]")
-        close(m.get("W_self_grad", k), tensor(chk, kind, "W_self_grad", k), 2e-5, f"W_self_grad[{k}]")
-        if k > 0:
-            close(m.get("feat_in", k).reshape(nv, width_in)[rows], tensor(chk, kind, "feat_in", k).reshape(nv, width_in)[rows], 1e-5, f"feat_in[{k}]")
-        close(m.get("grad_in", k).reshape(nv, width_out)[rows], tensor(chk, kind, "grad_in", k).reshape(nv, width_out)[rows], 2e-5, f"grad_in[{k}]")
+    F, H, Cn = C2["feat"], C2["hid"], C2["ncls"]
+    ours = {k: {n: m.get(n, k) for n in ("grad_in", "W_grad", "W_self_grad")} for k in (0, 1)}
+    ref = {k: {n: tensor(chk, kind, n, k) for n in ("grad_in", "W_grad", "W_self_grad")} for k in (0, 1)}
+    ours[1]["feat_in"], ref[1]["feat_in"] = m.get("feat_in", 1), tensor(chk, kind, "feat_in", 1)
+    report["feat_in[1] rows"] = (relerr(ours[1]["feat_in"].reshape(nv, H)[rows], ref[1]["feat_in"].reshape(nv, H)[rows]), 1e-5)
+    report["grad_in[0] rows"] = (relerr(ours[0]["grad_in"].reshape(nv, H)[rows], ref[0]["grad_in"].reshape(nv, H)[rows]), 2e-5)
+    report["grad_in[1] rows"] = (relerr(ours[1]["grad_in"].reshape(nv, Cn)[rows], ref[1]["grad_in"].reshape(nv, Cn)[rows]), 2e-5)
+    # operands of the four weight gradients (sage_layer.cpp:37-47): layer 0 aggregates first (dW_n = (AX)^T G, dW_s = X^T G), layer 1
+    # transforms first (dW_n = H^T (A^T G), dW_s = H^T G)
+    operands = {(0, "W_grad"): ("in_temp1", 0, "grad_in", 0), (0, "W_self_grad"): (None, 0, "grad_in", 0),
+                (1, "W_grad"): ("feat_in", 1, "out_temp", 1), (1, "W_self_grad"): ("feat_in", 1, "grad_in", 1)}
+    for (k, name), (an, ak, gn, gk) in operands.items():
+        def side(getter):
+            A = w["feats"] if an is None else getter(an, ak)
+            return exact_wgrad(np.ascontiguousarray(A), getter(gn, gk), nv)
+        ex_ours = side(lambda n, kk: m.get(n, kk))
+        e_ours = relerr(ours[k][name], ex_ours)
+        if kind == "reference":
+            ex_ref = side(lambda n, kk: chk.get(n, kk))
+            e_ref = relerr(ref[k][name], ex_ref)
+            report[f"{name}[{k}] exact-vs-exact (operands agree)"] = (relerr(ex_ours, ex_ref), 2e-5)
+            report[f"{name}[{k}] vs reference"] = (relerr(ours[k][name], ref[k][name]), e_ref + 2e-5)
+            report[f"{name}[{k}] reference vs fp64 (informative)"] = (e_ref, float("inf"))
+        report[f"{name}[{k}] vs fp64"] = (e_ours, 2e-5)
     m.update(); chk.update()
     l2, _ = m.train_epoch(); l2r, _ = chk.train_epoch()
-    assert abs(l2 - l2r) <= 1e-4 * abs(l2r), (l2, l2r)   # second epoch: one Adam step apart from bit-identical initial weights
+    report["loss, epoch 2"] = (abs(l2 - l2r) / abs(l2r), 1e-4)   # one Adam step apart from bit-identical initial weights
+    for k, (err, tol) in report.items():
+        print(f"  {k:58s} {err:.3e}  (bar {tol:.1e})")
+    bad = {k: v for k, v in report.items() if not v[0] <= v[1]}
+    assert not bad, bad
 
 
 def _scaled_case(env, arch, nv, nnz, dims, layers, seed):

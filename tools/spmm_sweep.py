@@ -6,8 +6,8 @@ bandwidth figures of §8d (gather model B_spmm/t, compulsory bound/t) against th
   python tools/spmm_sweep.py [--nv 1000000,4000000] [--deg 16,64] [--feat 16,32,64,128,256,512] [--reps 5] [--modes gcn,mean]
                              [--pitch aligned|dense|both] [--ncu]
 
---pitch   row pitch of the gathered matrix: `aligned` = the layer classes' line-aligned rows (host/gai_layers.h row_pitch: 47 -> 64,
-          100 -> 128), `dense` = pitch F (a caller's dense matrix).
+--pitch   row pitch of the gathered matrix: `pad4` = the layer classes' rows padded to 4 floats (host/gai_layers.h row_pitch: 47 -> 48),
+          `aligned` = 128-byte-aligned rows (47 -> 64, 100 -> 128; measured and rejected), `dense` = pitch F (a caller's dense matrix).
 --ncu     exactly one warm-up and one measured launch per point, in the order printed: run the tool under
           `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:spmm_` and join the per-launch DRAM
           bytes to the points with tools/sweep_join.py (the DRAM column of SURVEY.md 8d's triple; times under ncu are not bench values).
@@ -26,7 +26,8 @@ def main():
     ap.add_argument("--modes", default="gcn,mean")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--max-gb", type=float, default=150.0)
-    ap.add_argument("--pitch", default="aligned", choices=["aligned", "dense", "both"])
+    ap.add_argument("--max-edges", type=float, default=2.2e9, help="skip graphs beyond this many CSR edges (R-MAT generation memory)")
+    ap.add_argument("--pitch", default="pad4", choices=["pad4", "aligned", "dense", "both"])
     ap.add_argument("--ncu", action="store_true")
     args = ap.parse_args()
     import torch
@@ -37,12 +38,15 @@ def main():
         peak = float(json.load(open(p))["hbm_gbs"])
     for nv in [int(x) for x in args.nv.split(",")]:
         for deg in [int(x) for x in args.deg.split(",")]:
+            if nv * deg >= (1 << 32) - nv or nv * deg > args.max_edges:   # 32-bit edge offsets (gai_csr_create); generator memory
+                continue
             rp, ci = datagen.rmat_csr_torch(nv, nv * deg, seed=1, device="cuda")
             rp32 = rp.to(torch.int32); ci32 = ci.to(torch.int32)
             nnz = int(ci32.numel())
             g = ops.DeviceGraph(rp32, ci32, device_arrays=True)
             for F, pitch_kind in [(int(x), k) for x in args.feat.split(",") for k in (("aligned", "dense") if args.pitch == "both" else (args.pitch,))]:
-                pitch = F if pitch_kind == "dense" else (next(p for p in (4, 8, 16, 32) if F <= p) if F <= 32 else (F + 31) // 32 * 32)
+                pitch = F if pitch_kind == "dense" else ((F + 3) // 4 * 4 if pitch_kind == "pad4" else
+                                                         (next(p for p in (4, 8, 16, 32) if F <= p) if F <= 32 else (F + 31) // 32 * 32))
                 if pitch_kind == "dense" and args.pitch == "both" and pitch == F and F % 32 == 0:
                     continue  # identical layouts
                 if 4.0 * (2 * nv * pitch + nnz) / 1e9 > args.max_gb:
