@@ -9,7 +9,9 @@
 // collective and no staging buffer:
 //   peer_barrier_kernel   a flag barrier in peer memory (release store of a sequence number into every peer's flag row, acquire spin
 //                         on the own row). Orders "my buffer is complete" before the peers read it and "the peers are done reading"
-//                         before it is overwritten.
+//                         before it is overwritten. (Ranks that are threads of ONE process may share a device, where a spinning kernel
+//                         and an implicitly synchronising call such as cudaMalloc on another rank's thread could wait for each other:
+//                         there the barrier is a stream synchronise plus a host rendezvous through the bootstrap callback instead.)
 //   halo_pull_kernel      halo rows <- the owners' rows, read straight from the owners' matrices through the mapped pointers into the
 //                         halo block of the local matrix: each halo row crosses NVLink exactly once (peer loads bypass the local L2,
 //                         B300_MICROARCH.md, so gathering from peer memory inside the aggregation would fetch a row once per EDGE).
@@ -33,6 +35,7 @@ struct gai_peers {
   unsigned long long** d_flag_rows = nullptr;  // device array [world]: every rank's flag row
   unsigned long long seq = 0;
   int* d_err = nullptr;
+  bool host_barrier = false;  // every rank lives in this process
 };
 
 struct gai_halo_plan {
@@ -149,6 +152,13 @@ __global__ void peer_reduce_kernel(const ReduceArgs a, size_t n, int sum, float*
 
 int launch_barrier(gai_peers* p, cudaStream_t st) {
   if (p->world == 1) return GAI_OK;
+  if (p->host_barrier) {
+    GAI_CUDA(cudaStreamSynchronize(st));
+    unsigned char token = 0;
+    std::vector<unsigned char> all((size_t)p->world);
+    p->allgather(p->ctx, &token, 1, all.data());
+    return GAI_OK;
+  }
   p->seq++;
   peer_barrier_kernel<<<1, 32, 0, st>>>(p->d_flag_rows, p->rank, p->world, p->seq, p->d_err);
   GAI_LAUNCH_CHECK();
@@ -185,6 +195,10 @@ int gai_peers_register(gai_peers_t p, void* dptr, int* id_out) {
       p->opened.push_back(m);
       ptrs[q] = m;
     }
+  }
+  if (p->local.empty()) {  // first registration (the flag rows, from gai_peers_create): learn whether all ranks share this process
+    p->host_barrier = p->world > 1;
+    for (int q = 0; q < p->world; q++) p->host_barrier = p->host_barrier && all[q].pid == p->pid;
   }
   *id_out = (int)p->local.size();
   p->local.push_back(dptr);
@@ -268,8 +282,9 @@ int gai_halo_plan_destroy(gai_halo_plan_t h) {
   return GAI_OK;
 }
 
-int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld, size_t dst_row_offset, int flags, gai_stream_t stream) {
-  GAI_CHECK_ARG(p != nullptr && h != nullptr && buf_id > 0 && buf_id < (int)p->local.size() && F > 0 && ld >= (size_t)F);
+int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld, float* dst, size_t ld_dst, int flags, gai_stream_t stream) {
+  GAI_CHECK_ARG(p != nullptr && h != nullptr && buf_id > 0 && buf_id < (int)p->local.size() && F > 0 && ld >= (size_t)F && ld_dst >= (size_t)F);
+  GAI_CHECK_ARG(dst != nullptr || h->n_halo == 0);
   cudaStream_t st = gai::S(stream);
   if (p->world == 1) return GAI_OK;
   int rc = GAI_OK;
@@ -280,9 +295,9 @@ int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld
     for (int q = 0; q < p->world; q++) a.src[q] = reinterpret_cast<const float*>(p->peer[buf_id][q]);
     for (int q = 0; q <= GAI_MAX_PEERS; q++) a.seg[q] = h->seg[q];
     a.src_row = h->d_src_row;
-    a.dst = reinterpret_cast<float*>(p->local[buf_id]) + dst_row_offset * ld;
-    a.ld_src = ld; a.ld_dst = ld; a.n_halo = h->n_halo; a.world = p->world; a.F = F;
-    const bool vec = ld % 4 == 0 && reinterpret_cast<uintptr_t>(p->local[buf_id]) % 16 == 0;
+    a.dst = dst;
+    a.ld_src = ld; a.ld_dst = ld_dst; a.n_halo = h->n_halo; a.world = p->world; a.F = F;
+    const bool vec = ld % 4 == 0 && ld_dst % 4 == 0 && reinterpret_cast<uintptr_t>(p->local[buf_id]) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
     if (vec) {
       a.nch = (F + 3) / 4;
       const size_t total = (size_t)h->n_halo * a.nch;

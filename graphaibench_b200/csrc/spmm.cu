@@ -7,10 +7,10 @@
 // Design (B200: an HBM/L2 gather; no tensor-core shape here):
 //   * every input row is read with 128-bit loads. Rows whose pitch is a multiple of 4 floats are read in place; only a
 //     caller's dense matrix with F % 4 != 0 (or a misaligned base) goes through a zero-padded staging copy.
-//     Lanes past the row width are predicated off (no load, no wavefront, no writeback) instead of re-reading chunk 0.
-//     What bounds the kernel (ncu, profiles/README.md round 2): L2 -> SM bandwidth (8.7 TB/s of the ~12 TB/s LTS cap for F = 100) and
-//     the latency of the gathers behind it (occupancy 48 % at 64 registers, long_scoreboard the top stall) — not the L1 data pipe:
-//     128-byte-aligned row pitches cut its wavefronts by a third and changed nothing (the larger footprint cost the hit rates).
+//     What bounds the kernel (ncu + tools/l2_probe.cu, profiles/README.md round 2): the LATENCY of the gathers — 8.7 TB/s of L2 -> SM
+//     traffic for F = 100 against a measured 19 TB/s L2 streaming rate, DRAM at 49 %, occupancy 48 % at 64 registers, long_scoreboard the
+//     top stall: the bytes in flight per SM are capped by the registers that hold them. It is NOT the L1 data pipe: 128-byte-aligned row
+//     pitches cut its wavefronts by a third and changed nothing (the larger footprint cost the hit rates), predicated lanes likewise.
 //   * one persistent kernel (4 CTAs x 148 SMs), two kinds of work items taken from global counters:
 //       light rows (deg <= hub_degree): rows in DEGREE order, cut into claims of <= 32 rows / <= 2048 edges. A group of
 //         G lanes (G = 4..32, from the feature width) owns one output row in registers; the group loads G column
@@ -50,7 +50,16 @@ struct SpmmArgs {
   int hub_per;       // hub rows: float4 chunks per CTA column block (gridDim.y blocks cover nchunks)
   const uint32_t* mask_bits;  // optional d_relu of the layer below: out = bit ? out : 0, one sign bit per element (GAI_EPI_BITMASK)
   int ld_bits;                // words per row
+  // 1D partition: neighbour ids >= n_split are halo vertices, whose rows live in a separate buffer (row = id - n_split, same pitch):
+  // the owners' rows land there (gai_halo_pull) and the matrix itself carries master rows only. n_split = 0xffffffff: one matrix.
+  const float* in_halo;
+  uint32_t n_split;
 };
+
+// base of neighbour row `c` (float4 units)
+__device__ __forceinline__ const float4* row_base(const float4* in4, const float4* halo4, uint32_t n_split, size_t ld4, uint32_t c) {
+  return c < n_split ? in4 + (size_t)c * ld4 : halo4 + (size_t)(c - n_split) * ld4;
+}
 
 // out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
 __device__ __forceinline__ void store_chunk(const SpmmArgs& a, uint32_t row, int chunk, float4 r) {
@@ -167,6 +176,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
   const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
   const size_t ld4 = (size_t)a.ld_in >> 2;
   if (warp > 0) {
     // ---------------- producers ----------------
@@ -200,7 +210,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
           const int j = j0 + u * EL + el;
           const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
           ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
-          if (chv && j < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + cl);
+          if (chv && j < cnt) x[u] = __ldg(row_base(in4, halo4, a.n_split, ld4, cc) + cb + cl);
         }
 #pragma unroll
         for (int u = 0; u < HI_UB; u++) {
@@ -265,8 +275,10 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
   const int gl = lane % G, grp = lane / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
   const size_t ld4 = (size_t)a.ld_in >> 2;
-  // lanes whose chunk lies past the row width are predicated off: they issue no load (no wavefront, no writeback) and store nothing
+  // lanes whose chunk lies past the row width re-read chunk 0 (same sectors as lane 0) and store nothing. Predicating them off instead
+  // was measured slower (round 2: F = 47 calls +4..9 %): the L1 data pipe is not the limiter and the predicate costs issue slots.
   int chunk[K];
   bool act[K];
 #pragma unroll
@@ -361,9 +373,9 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = in4 + (size_t)cc * ld4;
+                  const float4* src = row_base(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = av[k] ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = 0; k < K; k++) x[u][k] = gather4(src + ch[k]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -381,9 +393,9 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = in4 + (size_t)cc * ld4;
+                  const float4* src = row_base(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = (av[k] && j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -441,6 +453,7 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
   const uint32_t nstages = (e - s + ES - 1) / ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
   const size_t ld4 = (size_t)a.ld_in >> 2;
   const int cb_begin = (int)blockIdx.y * a.hub_per;
   const int cb_end = a.nchunks < cb_begin + a.hub_per ? a.nchunks : cb_begin + a.hub_per;
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
               const int j = j0 + u * EL + el;
               const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j & 31);
               ww[u] = __shfl_sync(0xffffffffu, cur_w, j & 31);
-              if (chv && j < cnt) x[u] = __ldg(in4 + (size_t)cc * ld4 + cb + ch);
+              if (chv && j < cnt) x[u] = __ldg(row_base(in4, halo4, a.n_split, ld4, cc) + cb + ch);
             }
 #pragma unroll
             for (int u = 0; u < UB; u++) {
@@ -677,7 +690,7 @@ int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
                   int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream, const uint32_t* mask_bits = nullptr,
-                  int ld_bits = 0) {
+                  int ld_bits = 0, const float* in_halo = nullptr, uint32_t n_split = 0xffffffffu) {
   GAI_CHECK_ARG(g != nullptr);
   GAI_CHECK_ARG(rb <= re && re <= g->nv);
   if (re == rb) return GAI_OK;  // empty graph / empty row range: nothing to do (buffers may be NULL)
@@ -696,7 +709,10 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   a.hub_per = a.nchunks;
   a.mask_bits = mask_bits; a.ld_bits = ld_bits;
+  a.in_halo = in_halo; a.n_split = in_halo ? n_split : 0xffffffffu;
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
+  if (in_halo && !((ld_in % 4 == 0) && aligned16(in) && aligned16(in_halo) && ld_in >= a.nchunks * 4))
+    return gai::set_error(GAI_ERR_ARG, "spmm", "a split (masters | halo) input needs 16-byte aligned rows whose pitch is a multiple of 4 floats");
   if ((ld_in % 4 == 0) && aligned16(in) && ld_in >= a.nchunks * 4) {
     // rows are 128-bit loadable as stored; when F % 4 != 0 the tail chunk also reads the (ld_in - F) padding columns of
     // the row: they land in accumulator lanes that are never stored (store_chunk masks columns >= F)
@@ -766,11 +782,12 @@ int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* 
                        ld_bits);
 }
 int gai_spmm_rows_ex(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in,
-                     float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, gai_stream_t stream) {
+                     float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, const float* in_halo,
+                     uint32_t n_split, gai_stream_t stream) {
   GAI_CHECK_ARG(mode >= M_GCN && mode <= M_EDGE_PERM);
   GAI_CHECK_ARG(mode != M_EDGE_PERM || perm != nullptr);
   GAI_CHECK_ARG(mask_bits == nullptr || ld_bits >= (F + 31) / 32);
-  return spmm_dispatch(g, mode, rb, re, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream, mask_bits, ld_bits);
+  return spmm_dispatch(g, mode, rb, re, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream, mask_bits, ld_bits, in_halo, n_split);
 }
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t rb, uint32_t re, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
   return spmm_dispatch(g, M_GCN, rb, re, F, nullptr, nullptr, in, ld_in, out, ld_out, flags, addend, stream);

@@ -1,4 +1,5 @@
 #include "gai_graph.h"
+#include "gai_dist.h"
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
@@ -7,9 +8,17 @@
 #include <iostream>
 
 namespace gai_host {
-static gai_stream_t g_stream = nullptr;
+static thread_local gai_stream_t g_stream = nullptr;
 gai_stream_t stream() { return g_stream; }
 void set_stream(gai_stream_t s) { g_stream = s; }
+static thread_local bool g_quiet = false;
+void set_quiet(bool quiet) { g_quiet = quiet; }
+std::ostream& out() {
+  struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+  static NullBuf nb;
+  static std::ostream null_stream(&nb);
+  return g_quiet ? null_stream : std::cout;
+}
 void die_on(int status, const char* what) {
   if (status == GAI_OK) return;
   std::fprintf(stderr, "%s failed (status %d): %s\n", what, status, gai_last_error());
@@ -17,8 +26,8 @@ void die_on(int status, const char* what) {
 }
 
 struct Rec { std::string bucket, shape; double bytes, flops; void* e0; void* e1; };
-static bool g_prof = false;
-static std::vector<Rec> g_recs;
+static thread_local bool g_prof = false;
+static thread_local std::vector<Rec> g_recs;
 void profile_enable(bool on) { g_prof = on; }
 bool profile_enabled() { return g_prof; }
 OpScope::OpScope(const char* bucket, const std::string& shape, double bytes, double flops) : idx(-1) {
@@ -100,7 +109,7 @@ LearningGraph* LearningGraph::generate_masked_graph(mask_t* masks) {
     for (index_t e = rowptr_[v]; e < rowptr_[v + 1]; e++)
       if (masks[colidx_[e]] == 1) mg->constructEdge(k++, colidx_[e]);
   }
-  std::cout << "masked graph: num_vertices = " << mg->size() << ", num_edges = " << mg->sizeEdges() << "\n";
+  gai_host::out() << "masked graph: num_vertices = " << mg->size() << ", num_edges = " << mg->sizeEdges() << "\n";
   return mg;
 }
 
@@ -109,7 +118,101 @@ void LearningGraph::alloc_on_device(index_t) {}
 
 void LearningGraph::copy_to_gpu() {
   if (dev_) { gai_csr_destroy(dev_); dev_ = nullptr; }
-  die_on(gai_csr_create(num_vertices_, num_edges_, rowptr_.data(), colidx_.data(), gai_host::stream(), &dev_), "gai_csr_create");
+  if (!comm_) {
+    die_on(gai_csr_create(num_vertices_, num_edges_, rowptr_.data(), colidx_.data(), gai_host::stream(), &dev_), "gai_csr_create");
+    return;
+  }
+  // partitioned: the device CSR spans masters + halo (halo rows are empty); normalisers come from GLOBAL degrees — the masters' rows
+  // are complete, so their degrees are global already; the halo vertices' normalisers are read from their owners
+  const size_t m = rows_with_halo();
+  std::vector<index_t> rp(m + 1);
+  std::copy(rowptr_.begin(), rowptr_.end(), rp.begin());
+  std::fill(rp.begin() + num_vertices_ + 1, rp.end(), rowptr_[num_vertices_]);
+  die_on(gai_csr_create((index_t)m, num_edges_, rp.data(), colidx_.data(), gai_host::stream(), &dev_), "gai_csr_create");
+  const index_t seg[2] = {0, num_vertices_};
+  die_on(gai_csr_set_row_segments(dev_, 1, seg, gai_host::stream()), "gai_csr_set_row_segments");
+  if (plan_) gai_halo_plan_destroy(plan_);
+  die_on(gai_halo_plan_create(comm_->peers(), nv_global_, (uint32_t)halo_gids_.size(), halo_gids_.data(), gai_host::stream(), &plan_), "gai_halo_plan_create");
+  const float* norms[2] = {gai_csr_vertex_norm(dev_), gai_csr_mean_norm(dev_)};
+  for (const float* nrm : norms) {
+    const int id = comm_->register_buffer(nrm);
+    die_on(gai_halo_pull(comm_->peers(), plan_, id, 1, 1, const_cast<float*>(nrm) + num_vertices_, 1, 0, gai_host::stream()), "gai_halo_pull(norms)");
+  }
+}
+
+void LearningGraph::add_selfloop_rows(index_t first) {
+  // lgraph.h:185-218 on rows [first, first + n): the loop id of row r is first + r
+  const index_t n = num_vertices_;
+  std::vector<index_t> rp((size_t)n + 1), ci((size_t)num_edges_ + n);
+  for (index_t r = 0; r < n; r++) {
+    const index_t b = rowptr_[r], e = rowptr_[r + 1], self = first + r;
+    index_t pos = e;
+    for (index_t k = b; k < e; k++)
+      if (colidx_[k] > self) { pos = k; break; }
+    index_t* o = ci.data() + (size_t)b + r;
+    std::copy(colidx_.begin() + b, colidx_.begin() + pos, o);
+    o[pos - b] = self;
+    std::copy(colidx_.begin() + pos, colidx_.begin() + e, o + (pos - b) + 1);
+    rp[r] = b + r;
+  }
+  rp[n] = rowptr_[n] + n;
+  rowptr_.swap(rp);
+  colidx_.swap(ci);
+  num_edges_ += n;
+}
+
+void LearningGraph::partition_rows(gai_host::Comm* comm, index_t nv_global) {
+  partition_rows(comm->world(), comm->rank(), nv_global);
+  comm_ = comm;
+}
+
+void LearningGraph::partition_rows(int world, int rank, index_t nv_global) {
+  const gai_host::OwnerRange own = gai_host::owner_range(nv_global, world, rank);
+  if (own.last - own.first != num_vertices_) {
+    std::cerr << "partition_rows: this rank owns " << own.last - own.first << " vertices but the graph holds " << num_vertices_ << " rows\n";
+    std::exit(EXIT_FAILURE);
+  }
+  nv_global_ = nv_global; first_ = own.first;
+  halo_gids_.clear();
+  for (index_t c : colidx_)
+    if (c < own.first || c >= own.last) halo_gids_.push_back(c);
+  std::sort(halo_gids_.begin(), halo_gids_.end());
+  halo_gids_.erase(std::unique(halo_gids_.begin(), halo_gids_.end()), halo_gids_.end());
+  for (index_t& c : colidx_) {
+    if (c >= own.first && c < own.last) c -= own.first;
+    else c = num_vertices_ + (index_t)(std::lower_bound(halo_gids_.begin(), halo_gids_.end(), c) - halo_gids_.begin());
+  }
+}
+
+void LearningGraph::register_gather_buffer(const float* buf) {
+  if (comm_) comm_->register_buffer(buf);
+}
+
+const float* LearningGraph::halo_exchange(const float* buf, int F, size_t ld) {
+  if (!comm_ || comm_->world() == 1 || halo_gids_.empty()) {
+    if (comm_ && comm_->world() > 1) halo_exchange_into(buf, F, ld, nullptr);  // a rank without halo still takes part in the barriers
+    return nullptr;
+  }
+  const size_t need = halo_gids_.size() * ld;
+  if (need > halo_scratch_floats_) {  // grown on the first epoch only (widest exchanged matrix)
+    if (halo_scratch_) { die_on(gai_stream_sync(gai_host::stream()), "gai_stream_sync"); gai_free(halo_scratch_); }
+    void* p = nullptr;
+    die_on(gai_malloc(&p, sizeof(float) * need), "gai_malloc(halo scratch)");
+    halo_scratch_ = reinterpret_cast<float*>(p);
+    halo_scratch_floats_ = need;
+  }
+  halo_exchange_into(buf, F, ld, halo_scratch_);
+  return halo_scratch_;
+}
+
+void LearningGraph::halo_exchange_into(const float* buf, int F, size_t ld, float* dst) {
+  if (!comm_ || comm_->world() == 1) return;
+  const int id = comm_->id_of(buf);
+  if (id < 0) { std::cerr << "halo_exchange: the gathered matrix was never registered with the peer group\n"; std::exit(EXIT_FAILURE); }
+  gai_host::OpScope sc("HALO", "pull W=" + std::to_string(F), 4.0 * F * halo_gids_.size(), 0);
+  die_on(gai_halo_pull(comm_->peers(), plan_, id, F, ld, dst, ld, 0, gai_host::stream()), "gai_halo_pull");
+  halo_exchanges++;
+  halo_bytes += 4ull * (unsigned long long)F * halo_gids_.size();
 }
 
 void LearningGraph::compute_vertex_data() {
@@ -119,6 +222,8 @@ void LearningGraph::compute_edge_data() { compute_vertex_data(); }
 
 void LearningGraph::dealloc() {
   if (dev_) { gai_csr_destroy(dev_); dev_ = nullptr; }
+  if (plan_) { gai_halo_plan_destroy(plan_); plan_ = nullptr; }
+  if (halo_scratch_) { gai_free(halo_scratch_); halo_scratch_ = nullptr; halo_scratch_floats_ = 0; }
   rowptr_.clear(); rowptr_.shrink_to_fit();
   colidx_.clear(); colidx_.shrink_to_fit();
 }
@@ -139,7 +244,7 @@ void Reader::bin_read_graph(LearningGraph* g) {
   const char* root = std::getenv("DATASET_PATH");
   if (!root) { std::cerr << "DATASET_PATH is not set\n"; std::exit(1); }
   inputfile_path = std::string(root) + dataset_str + "/";
-  std::cout << "input file path: " << inputfile_path << ", graph name: " << dataset_str << "\n";
+  gai_host::out() << "input file path: " << inputfile_path << ", graph name: " << dataset_str << "\n";
   std::ifstream meta((inputfile_path + "graph.meta.txt").c_str());
   if (!meta.good()) { std::cerr << "Failed to open file: " << inputfile_path << "graph.meta.txt\n"; std::exit(1); }
   int vid_size = 0, eid_size = 0, vlabel_size = 0, elabel_size = 0, max_degree = 0;
@@ -157,11 +262,11 @@ void Reader::bin_read_graph(LearningGraph* g) {
   index_t* rp = g->row_start_host_ptr();
   for (size_t i = 0; i <= (size_t)nv; i++) rp[i] = (index_t)rows[i];  // on-disk int64 -> u32 (reader.cpp:445-454)
   g->degree_counting();
-  std::cout << "|V| " << nv << " |E| " << ne << " max_deg " << g->get_max_degree() << "\n";
+  gai_host::out() << "|V| " << nv << " |E| " << ne << " max_deg " << g->get_max_degree() << "\n";
 }
 
 size_t Reader::bin_read_features(std::vector<float>& feats) {
-  std::cout << "Reading features ... N x D: " << num_vertices_ << " x " << feat_len << "\n";
+  gai_host::out() << "Reading features ... N x D: " << num_vertices_ << " x " << feat_len << "\n";
   feats.resize((size_t)num_vertices_ * feat_len);
   // as the reference (reader.cpp:258-263): no open check here — a dataset without a feature file (feat_len 0) loads with no features
   std::ifstream in((inputfile_path + "graph.feats.bin").c_str(), std::ios::binary);
@@ -173,7 +278,7 @@ int Reader::bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class)
   assert(num_vertex_classes > 0 && num_vertex_classes < 255);
   std::vector<vlabel_t> vl(num_vertices_, 0);
   std::ifstream probe((inputfile_path + "graph.vlabel.bin").c_str());
-  std::cout << (is_single_class ? "Using single-class (one-hot) labels\n" : "Using multi-class (multi-hot) labels\n");
+  gai_host::out() << (is_single_class ? "Using single-class (one-hot) labels\n" : "Using multi-class (multi-hot) labels\n");
   labels.assign(is_single_class ? (size_t)num_vertices_ : (size_t)num_vertices_ * num_vertex_classes, 0);
   if (probe.good()) {
     read_exact<vlabel_t>(inputfile_path + "graph.vlabel.bin", vl.data(), vl.size());
@@ -184,26 +289,26 @@ int Reader::bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class)
   } else {
     // reader.cpp:386-408, quirks included: in single-class mode only the scratch array is drawn (labels stay all zero, so every
     // generated label is a valid class id); in multi-hot mode the drawn class is 1..C, and a draw of C sets no column at all
-    std::cout << "WARNING: vertex label file not exist; generating random labels\n";
+    gai_host::out() << "WARNING: vertex label file not exist; generating random labels\n";
     for (size_t v = 0; v < num_vertices_; v++) {
       const int rand_class = rand() % num_vertex_classes + 1;
       if (is_single_class) vl[v] = (vlabel_t)rand_class;
       else if (rand_class < num_vertex_classes) labels[v * num_vertex_classes + rand_class] = 1;
     }
   }
-  std::cout << "maximum vertex label: " << unsigned(*std::max_element(vl.begin(), vl.end())) << "\n";
+  gai_host::out() << "maximum vertex label: " << unsigned(*std::max_element(vl.begin(), vl.end())) << "\n";
   return num_vertex_classes;
 }
 
 size_t Reader::bin_read_masks(std::string mask_type, size_t n, size_t& begin, size_t& end, mask_t*) {
   bool known = false;
   for (const char* d : kDatasets) known = known || dataset_str == d;
-  if (!known) { std::cout << "Dataset currently not supported\n"; std::exit(1); }
+  if (!known) { gai_host::out() << "Dataset currently not supported\n"; std::exit(1); }
   size_t count;
   if (mask_type == "train") { begin = train_begin; end = train_end; count = train_count; }
   else if (mask_type == "val") { begin = val_begin; end = val_end; count = val_count; }
   else { begin = test_begin; end = test_end; count = test_count; }
-  std::cout << mask_type << "_mask range: [" << begin << ", " << end << ") Number of valid samples: " << count << " ("
+  gai_host::out() << mask_type << "_mask range: [" << begin << ", " << end << ") Number of valid samples: " << count << " ("
             << (float)count / (float)n * 100.0f << "%)\n";
   return count;  // the .masks.bin files are not read: ranges come from the meta file (reader.cpp:272-316)
 }

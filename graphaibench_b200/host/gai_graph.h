@@ -8,14 +8,19 @@
 // device errors) so that reference-side callers compile against it unchanged.
 #pragma once
 #include <cstdint>
+#include <ostream>
 #include <string>
 #include <vector>
 #include "gai_b200.h"
 
 namespace gai_host {
+class Comm;
 void die_on(int status, const char* what);  // prints gai_last_error() and exits: the reference's CUDA_CHECK contract
-gai_stream_t stream();                      // the stream every host-class call is issued on
+gai_stream_t stream();                      // the stream every host-class call of THIS THREAD is issued on (one rank per thread)
 void set_stream(gai_stream_t s);
+// Log stream of the reference's progress lines (std::cout) — silenced per thread for the ranks > 0 of a partitioned run.
+std::ostream& out();
+void set_quiet(bool quiet);
 
 // Per-op device timing (the reference's `time_ops` buckets, include/gnn/global.h:42-54, taken with CUDA events on the
 // launching stream instead of gettimeofday around synchronous calls). Off by default; when on, every ABI call the
@@ -60,6 +65,30 @@ class LearningGraph {
   void compute_edge_data();          // per-edge norms are never materialised (computed on the fly from vertex norms)
   void dealloc();
 
+  // ---- 1D partition (one rank's rows; host/gai_dist.h) -----------------------------------------------------------------------
+  // The graph holds the rows of the masters [first, first + size()) with GLOBAL column ids until partition_rows() renumbers them.
+  void add_selfloop_rows(index_t first);   // add_selfloop on a block of rows: global id first + r enters row r at its sorted place
+  // Column ids -> local ids: a master g becomes g - first, a remote neighbour becomes size() + its rank in the ascending list of
+  // distinct remote neighbours (the halo). Edge order inside a row is untouched, so aggregated rows keep the single-GPU bits.
+  void partition_rows(gai_host::Comm* comm, index_t nv_global);
+  void partition_rows(int world, int rank, index_t nv_global);  // the integer part alone (no device, no peer group): tests
+  bool partitioned() const { return comm_ != nullptr; }
+  gai_host::Comm* comm() const { return comm_; }
+  size_t rows_with_halo() const { return (size_t)num_vertices_ + halo_gids_.size(); }
+  size_t num_halo() const { return halo_gids_.size(); }
+  index_t first_global() const { return first_; }
+  index_t size_global() const { return comm_ ? nv_global_ : num_vertices_; }
+  const std::vector<index_t>& halo_global_ids() const { return halo_gids_; }
+  // A matrix some aggregation gathers from holds this rank's master rows; it is registered once (collective, same order on every rank) ...
+  void register_gather_buffer(const float* buf);
+  // ... and before an aggregation reads it, the rows of the halo vertices are fetched from their owners' instances of the same matrix
+  // (barrier - pull - barrier) into a scratch buffer shared by all exchanges of this graph; the returned pointer (row k = halo vertex k,
+  // pitch ld) is what the aggregation reads neighbour ids >= size() from. NULL when there is nothing to exchange.
+  const float* halo_exchange(const float* buf, int F, size_t ld);
+  // The same into a caller-owned buffer of num_halo() x ld floats (halo rows that stay valid across steps: the input features).
+  void halo_exchange_into(const float* buf, int F, size_t ld, float* dst);
+  unsigned long long halo_exchanges = 0, halo_bytes = 0;  // counted per call (measurement)
+
   size_t size() const { return num_vertices_; }
   size_t sizeEdges() const { return num_edges_; }
   bool on_device() const { return is_device; }
@@ -86,6 +115,12 @@ class LearningGraph {
   index_t num_vertices_ = 0, num_edges_ = 0, max_degree = 0;
   std::vector<index_t> rowptr_, colidx_;
   gai_csr_t dev_ = nullptr;
+  gai_host::Comm* comm_ = nullptr;
+  index_t nv_global_ = 0, first_ = 0;
+  std::vector<index_t> halo_gids_;
+  gai_halo_plan_t plan_ = nullptr;
+  float* halo_scratch_ = nullptr;
+  size_t halo_scratch_floats_ = 0;
 };
 
 typedef LearningGraph Graph;

@@ -1,6 +1,7 @@
 // C handles over the host classes, for ctypes callers (tests, bench.py). Not part of the reference boundary: the
 // reference-facing surface is the C++ API in gai_graph.h / gai_layers.h / gai_model.h.
 #include <cstring>
+#include <thread>
 #include "gai_model.h"
 
 namespace {
@@ -15,6 +16,7 @@ struct ModelBase {
   virtual void prefetch(const float* feats) = 0;
   // device pointer + logical element count; cols/ld != 0 for per-vertex tensors stored with a row pitch
   virtual float* tensor(const char* name, int layer, size_t* n, size_t* cols, size_t* ld) = 0;
+  virtual Graph* graph() = 0;
 };
 template <typename L>
 struct Box : ModelBase {
@@ -26,6 +28,7 @@ struct Box : ModelBase {
   float evaluate(const char* which) override { return m.evaluate(which); }
   void refresh(const float* feats) override { m.refresh_inputs_from_host(feats); }
   void prefetch(const float* feats) override { m.prefetch_features_from_host(feats); }
+  Graph* graph() override { return m.graph(); }
   float* extra(GCN_layer&, const std::string&, size_t*) { return nullptr; }
   float* extra(SAGE_layer&, const std::string&, size_t*) { return nullptr; }
   float* extra(GAT_layer& y, const std::string& name, size_t* n) {
@@ -143,6 +146,96 @@ int gai_reader_load(const char* dataset, int single_class, int64_t* meta, uint32
     memcpy(colidx, g.edge_dst_host_ptr(), sizeof(uint32_t) * g.sizeEdges());
     memcpy(feats, f.data(), sizeof(float) * f.size());
     memcpy(labels, lab.data(), lab.size());
+  }
+  return 0;
+}
+// ---- 1D-partitioned training (host/gai_dist.h) --------------------------------------------------------------------------------
+void* gai_comm_new(int rank, int world, gai_allgather_fn allgather, void* ctx) { return new gai_host::Comm(rank, world, allgather, ctx); }
+void gai_comm_free(void* c) { delete (gai_host::Comm*)c; }
+void gai_comm_barrier(void* c) { ((gai_host::Comm*)c)->barrier(); }
+void gai_comm_check(void* c) { ((gai_host::Comm*)c)->check(); }
+
+// One rank's model: its rows of the RAW graph (global column ids, rows_rowptr rebased to 0), its rows of features / labels, the GLOBAL split.
+void* gai_model_new_partitioned(int arch, void* comm, uint32_t nv_global, const int64_t* rows_rowptr, const uint32_t* rows_colidx, int dim_init,
+                                int dim_hid, int num_cls, int num_layers, float lr, const float* feats_local, const uint8_t* labels_local,
+                                const int64_t* split9_global) {
+  gai_host::Comm* c = (gai_host::Comm*)comm;
+  if (arch == 0) { auto* b = new Box<GCN_layer>(); b->m.set_comm(c); b->m.init_partitioned(gnn_arch::GCN, nv_global, rows_rowptr, rows_colidx, dim_init, num_cls, feats_local, labels_local, split9_global, dim_hid, num_layers, lr); b->m.construct_network(); return (ModelBase*)b; }
+  if (arch == 1) { auto* b = new Box<SAGE_layer>(); b->m.set_comm(c); b->m.init_partitioned(gnn_arch::SAGE, nv_global, rows_rowptr, rows_colidx, dim_init, num_cls, feats_local, labels_local, split9_global, dim_hid, num_layers, lr); b->m.construct_network(); return (ModelBase*)b; }
+  return nullptr;  // GAT: single-GPU only
+}
+// out4 = {masters, halo rows, halo exchanges so far, halo bytes received so far}
+void gai_model_halo_stats(void* m, uint64_t* out4) {
+  Graph* g = ((ModelBase*)m)->graph();
+  out4[0] = g->size(); out4[1] = g->num_halo(); out4[2] = g->halo_exchanges; out4[3] = g->halo_bytes;
+}
+
+// The whole partitioned path inside one process: `world` host threads = `world` ranks on the visible devices (rank r on device
+// r mod device count), each taking its slice of the full host graph, training `epochs` epochs. Rank 0's per-epoch loss / accuracy and
+// final weights come back ("W" / "W_self" of layer l at w_out + offsets the caller computes: layers in order, W then W_self).
+int gai_host_train_partitioned(int arch, int world, uint32_t nv, const int64_t* rowptr64, const uint32_t* colidx, int dim_init, int dim_hid,
+                               int num_cls, int num_layers, float lr, const float* feats, const uint8_t* labels, const int64_t* split9, int epochs,
+                               float* losses_out, float* accs_out, float* test_acc_out, float* w_out, uint64_t* halo_stats_out /* world x 4 */) {
+  int ndev = 0;
+  if (gai_device_count(&ndev) != GAI_OK || ndev < 1) return -1;
+  gai_host::ThreadGroup group(world);
+  std::vector<gai_host::ThreadRank> ctx((size_t)world);
+  std::vector<std::thread> threads;
+  for (int r = 0; r < world; r++) {
+    ctx[r] = {&group, r};
+    threads.emplace_back([&, r]() {
+      gai_host::die_on(gai_set_device(r % ndev), "gai_set_device");
+      gai_stream_t st = nullptr;
+      gai_host::die_on(gai_stream_create(&st), "gai_stream_create");
+      gai_host::set_stream(st);
+      gai_host::Comm* comm = new gai_host::Comm(r, world, gai_host::thread_allgather, &ctx[r]);
+      const gai_host::OwnerRange own = gai_host::owner_range(nv, world, r);
+      std::vector<int64_t> rp(own.last - own.first + 1);
+      for (uint32_t v = own.first; v <= own.last; v++) rp[v - own.first] = rowptr64[v] - rowptr64[own.first];
+      ModelBase* m = (ModelBase*)gai_model_new_partitioned(arch, comm, nv, rp.data(), colidx + rowptr64[own.first], dim_init, dim_hid, num_cls, num_layers, lr,
+                                                           feats + (size_t)own.first * dim_init, labels + own.first, split9);
+      for (int ep = 0; ep < epochs; ep++) {
+        float loss = 0.f;
+        const float acc = m->train_epoch(&loss);
+        if (r == 0) { losses_out[ep] = loss; accs_out[ep] = acc; }
+      }
+      const float tacc = m->evaluate("test");
+      comm->check();
+      if (r == 0) {
+        *test_acc_out = tacc;
+        size_t off = 0;
+        for (int l = 0; l < num_layers && w_out; l++) {
+          for (const char* name : {"W", "W_self"}) {
+            size_t n = 0, cols = 0, ld = 0;
+            float* p = m->tensor(name, l, &n, &cols, &ld);
+            if (p && n) { copy_float_to_host(n, p, w_out + off); off += n; }
+          }
+        }
+      }
+      if (halo_stats_out) gai_model_halo_stats(m, halo_stats_out + 4 * r);
+      gai_stream_sync(st);
+    });
+  }
+  for (auto& t : threads) t.join();
+  return 0;
+}
+// Host-only (integer) part of the partition, for tests: this rank's rows (global column ids; self-loops added first if `selfloops`) ->
+// local column ids + the halo list. Two-call protocol: halo_out == NULL returns the sizes only. sizes = {n_halo, nnz_out}.
+int gai_host_partition_rows(int world, int rank, uint32_t nv_global, const int64_t* rows_rowptr, const uint32_t* rows_colidx, int selfloops,
+                            uint64_t* sizes, uint32_t* rowptr_out, uint32_t* colidx_out, uint32_t* halo_out) {
+  const gai_host::OwnerRange own = gai_host::owner_range(nv_global, world, rank);
+  const uint32_t n = own.last - own.first;
+  Graph g(false);
+  g.allocateFrom(n, (index_t)rows_rowptr[n]);
+  for (uint32_t v = 0; v < n; v++) g.fixEndEdge(v, (index_t)rows_rowptr[v + 1]);
+  std::copy(rows_colidx, rows_colidx + rows_rowptr[n], g.edge_dst_host_ptr());
+  if (selfloops) g.add_selfloop_rows(own.first);
+  g.partition_rows(world, rank, nv_global);
+  sizes[0] = g.num_halo(); sizes[1] = g.sizeEdges();
+  if (halo_out) {
+    std::copy(g.row_start_host_ptr(), g.row_start_host_ptr() + n + 1, rowptr_out);
+    std::copy(g.edge_dst_host_ptr(), g.edge_dst_host_ptr() + g.sizeEdges(), colidx_out);
+    std::copy(g.halo_global_ids().begin(), g.halo_global_ids().end(), halo_out);
   }
   return 0;
 }

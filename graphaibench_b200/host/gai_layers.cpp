@@ -1,4 +1,5 @@
 #include "gai_layers.h"
+#include "gai_dist.h"
 #include <cassert>
 #include <cmath>
 #include <cstdlib>
@@ -110,7 +111,7 @@ static void d_relu_rows(size_t rows, int F, float* grad, size_t ldg, const float
 }
 // algorithmic bytes of one aggregation call: gather model of SURVEY.md §8d
 static double spmm_bytes(Graph& g, int F, int extra_per_edge = 0) {
-  const double n = (double)g.size(), nnz = (double)g.sizeEdges();
+  const double n = (double)g.size(), nnz = (double)g.sizeEdges();  // partitioned: this rank's master rows and their edges
   return 4.0 * (nnz * F + n * F + nnz * (1 + extra_per_edge) + (n + 1) + n);
 }
 
@@ -132,36 +133,42 @@ void adam::reset() {
 // ---- aggregators --------------------------------------------------------------------------------------------------
 
 void GCN_Aggregator::init(int len, int, int, float, float) { length = len; }
-void GCN_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend) {
+enum { SPMM_GCN = 0, SPMM_MEAN = 1, SPMM_MEAN_T = 2 };  // gai_spmm_rows_ex modes
+void GCN_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend,
+                                  const float* static_halo) {
+  const float* halo = static_halo ? static_halo : g.halo_exchange(in, len, ld_in);
   gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_gcn(g.device(), len, in, (int)ld_in, out, (int)ld_out, flags, addend, stream()), "gai_spmm_gcn");
+  die_on(gai_spmm_rows_ex(g.device(), SPMM_GCN, 0, (uint32_t)g.size(), len, nullptr, nullptr, in, (int)ld_in, out, (int)ld_out, flags, addend, nullptr, 0,
+                          halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(gcn)");
 }
 // the normalised adjacency is symmetric, so the derivative is the same product (gcn_aggregator.cpp:35-46)
 void GCN_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
                                     const uint32_t* mask_bits) {
   if (!mask_bits) { aggregate_ld(len, g, grad_in, ld_in, grad_out, ld_out, flags, addend); return; }
+  const float* halo = g.halo_exchange(grad_in, len, ld_in);
   gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len) + " bitmask", spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + g.size() * len / 8.0,
                        2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_gcn_masked(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend, mask_bits, (int)bits_pitch(len), stream()),
-         "gai_spmm_gcn_masked");
+  die_on(gai_spmm_rows_ex(g.device(), SPMM_GCN, 0, (uint32_t)g.size(), len, nullptr, nullptr, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend,
+                          mask_bits, (int)bits_pitch(len), halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(gcn, masked)");
 }
 void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) { aggregate(len, g, grad_in, grad_out); }
 
 void SAGE_Aggregator::init(int len, int, int, float, float) { length = len; }
-void SAGE_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend) {
+void SAGE_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend,
+                                   const float* static_halo) {
+  const float* halo = static_halo ? static_halo : g.halo_exchange(in, len, ld_in);
   gai_host::OpScope sc("AGGR", "mean F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_mean(g.device(), len, in, (int)ld_in, out, (int)ld_out, 0, flags, addend, stream()), "gai_spmm_mean");
+  die_on(gai_spmm_rows_ex(g.device(), SPMM_MEAN, 0, (uint32_t)g.size(), len, nullptr, nullptr, in, (int)ld_in, out, (int)ld_out, flags, addend, nullptr, 0,
+                          halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(mean)");
 }
 void SAGE_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
                                      const uint32_t* mask_bits) {
+  const float* halo = g.halo_exchange(grad_in, len, ld_in);
   gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len) + (mask_bits ? " bitmask" : ""),
                        spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + (mask_bits ? g.size() * len / 8.0 : 0), 2.0 * g.sizeEdges() * len);
-  if (mask_bits)
-    die_on(gai_spmm_mean_masked(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, mask_bits, (int)bits_pitch(len), stream()),
-           "gai_spmm_mean_masked(T)");
-  else
-    die_on(gai_spmm_mean(g.device(), len, grad_in, (int)ld_in, grad_out, (int)ld_out, 1, flags, addend, stream()), "gai_spmm_mean(T)");
+  die_on(gai_spmm_rows_ex(g.device(), SPMM_MEAN_T, 0, (uint32_t)g.size(), len, nullptr, nullptr, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend,
+                          mask_bits, mask_bits ? (int)bits_pitch(len) : 0, halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(meanT)");
 }
 void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {
@@ -221,11 +228,28 @@ graph_conv_layer<A>::graph_conv_layer(int id, int nv, int din, int dout, Graph* 
   ld_out = row_pitch(dout);
   // temporaries: only what this layer's schedule touches (the reference allocates all of them unconditionally)
   const bool transform_first = din > dout || std::is_same<A, GAT_Aggregator>::value;  // GAT always transforms first
-  if (transform_first) d_out_temp = float_malloc_device_zero(n * ld_out);
+  transform_first_ = transform_first;
+  // partitioned graph: a matrix an aggregation gathers from is registered with the peer group (same construction order on every rank):
+  // the other ranks read their halo rows out of it (Graph::halo_exchange)
+  const bool part = g->partitioned();
+  if (part && ((size_t)nv != g->size() || std::is_same<A, GAT_Aggregator>::value || feat_drop > 0.f)) {
+    std::cerr << "partitioned training supports GCN / SAGE layers without dropout over the rank's own masters\n";
+    std::exit(EXIT_FAILURE);
+  }
+  auto gathered = [&](size_t pitch) { float* p = float_malloc_device_zero(n * pitch); g->register_gather_buffer(p); return p; };
+  if (transform_first) d_out_temp = gathered(ld_out);                         // forward gathers X·W
   if (!transform_first) d_in_temp1 = float_malloc_device_zero(n * row_pitch(din));
-  if (!transform_first && id > 0) d_in_temp = float_malloc_device_zero(n * row_pitch(din));
-  if (id > 0) feat_in = float_malloc_device_zero(n * ld_in);
-  grad_in = float_malloc_device_zero(n * ld_out);
+  if (!transform_first && id > 0) d_in_temp = gathered(row_pitch(din));      // backward gathers G·W^T
+  if (id > 0) feat_in = transform_first ? float_malloc_device_zero(n * ld_in) : gathered(ld_in);  // forward gathers the input
+  grad_in = transform_first ? gathered(ld_out) : float_malloc_device_zero(n * ld_out);           // backward gathers the output gradient
+  if (part) {  // per-rank partial weight gradients, summed over the ranks into the public ones at the end of backward()
+    d_W_neigh_grad_local = float_malloc_device_zero((size_t)din * dout);
+    g->comm()->register_buffer(d_W_neigh_grad_local);
+    if (concat) { d_W_self_grad_local = float_malloc_device_zero((size_t)din * dout); g->comm()->register_buffer(d_W_self_grad_local); }
+  } else {
+    d_W_neigh_grad_local = d_W_neigh_grad;
+    d_W_self_grad_local = d_W_self_grad;
+  }
   if (feat_dropout_rate > 0.f) {  // dropout_mask + in_temp of the reference (graph_conv_layer.cpp:33-38)
     d_drop_in = float_malloc_device_zero(n * ld_in);
     void* mp = nullptr;
@@ -252,6 +276,14 @@ void graph_conv_layer<A>::backward_dropout(float* grad_out) {
   if (level_ == 0 || !(feat_dropout_rate > 0.f) || grad_out == nullptr) return;
   gai_host::OpScope sc("DROPOUT", "bwd n=" + std::to_string((size_t)num_samples * ld_in), 9.0 * num_samples * ld_in, 0);
   die_on(gai_d_dropout((size_t)num_samples * ld_in, feat_scale, grad_out, d_dropout_mask, grad_out, stream()), "gai_d_dropout");
+}
+
+template <typename A>
+void graph_conv_layer<A>::reduce_weight_grads() {
+  if (!graph->partitioned()) return;
+  gai_host::OpScope sc("ALLREDUCE", "dW " + std::to_string(dim_in) + "x" + std::to_string(dim_out), 4.0 * dim_in * dim_out * graph->comm()->world(), 0);
+  graph->comm()->all_reduce_sum(d_W_neigh_grad_local, (size_t)dim_in * dim_out, d_W_neigh_grad);
+  if (use_concat) graph->comm()->all_reduce_sum(d_W_self_grad_local, (size_t)dim_in * dim_out, d_W_self_grad);
 }
 
 template <typename A>
@@ -313,7 +345,7 @@ void GCN_layer::forward(float* feat_out) {
     mm(x, z, y, in_data, ld_in, d_W_neigh, z, d_out_temp, ld_out);
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, relu, nullptr);
   } else {      // aggregate first; ReLU rides the GEMM epilogue
-    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr, input_static_halo);
     if (is_act && d_relu_bits) mm_relu_bits(x, z, y, d_in_temp1, ldt, d_W_neigh, feat_out, ld_out, d_relu_bits);
     else mm(x, z, y, d_in_temp1, ldt, d_W_neigh, z, feat_out, ld_out, false, false, false, relu);
   }
@@ -328,14 +360,15 @@ void GCN_layer::backward(float* feat_out, float* grad_out) {
       if (mask_grad_out) mm_mask(x, y, z, d_out_temp, ld_out, d_W_neigh, grad_out, ld_in, true, feat_in, ld_in, mask_bits_in);
       else mm(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_out, ld_in, false, true);
     }
-    mm(y, z, x, feat_dropout_rate > 0.f ? d_drop_in : feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad, z, true, false);  // gcn_layer.cpp:48-50
+    mm(y, z, x, feat_dropout_rate > 0.f ? d_drop_in : feat_in, ld_in, d_out_temp, ld_out, d_W_neigh_grad_local, z, true, false);  // gcn_layer.cpp:48-50
   } else {
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
       aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_NONE, nullptr, mask_grad_out ? mask_bits_in : nullptr);
     }
-    mm(y, z, x, d_in_temp1, ldt, grad_in, ld_out, d_W_neigh_grad, z, true, false);
+    mm(y, z, x, d_in_temp1, ldt, grad_in, ld_out, d_W_neigh_grad_local, z, true, false);
   }
+  reduce_weight_grads();
   backward_dropout(grad_out);
 }
 
@@ -361,7 +394,7 @@ void SAGE_layer::forward(float* feat_out) {
     mm_ncat(x, y, in_data, ld_in, z, d_W_neigh, d_out_temp, ld_out, d_W_self, feat_out, ld_out);
     aggr.aggregate_ld((int)z, *graph, d_out_temp, ld_out, feat_out, ld_out, GAI_EPI_ADD | relu, feat_out);
   } else {
-    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr);
+    aggr.aggregate_ld((int)y, *graph, in_data, ld_in, d_in_temp1, ldt, GAI_EPI_NONE, nullptr, input_static_halo);
     mm_kcat(x, z, y, d_in_temp1, ldt, d_W_neigh, y, in_data, ld_in, d_W_self, feat_out, ld_out, false, relu, nullptr, 0, nullptr,
             is_act ? d_relu_bits : nullptr);
   }
@@ -373,18 +406,19 @@ void SAGE_layer::backward(float* feat_out, float* grad_out) {
   const float* in_data = feat_dropout_rate > 0.f ? d_drop_in : feat_in;  // sage_layer.cpp:35-36
   if (y > z) {
     aggr.d_aggregate_ld((int)z, *graph, grad_in, ld_out, d_out_temp, ld_out, GAI_EPI_NONE, nullptr);
-    wgrad_two_b(x, y, in_data, ld_in, z, grad_in, ld_out, d_W_self_grad, d_out_temp, ld_out, d_W_neigh_grad);
+    wgrad_two_b(x, y, in_data, ld_in, z, grad_in, ld_out, d_W_self_grad_local, d_out_temp, ld_out, d_W_neigh_grad_local);
     if (level_ > 0)
       mm_kcat(x, y, z, d_out_temp, ld_out, d_W_neigh, z, grad_in, ld_out, d_W_self, grad_out, ld_in, true, 0,
               (mask_grad_out && !mask_bits_in) ? feat_in : nullptr, ld_in, mask_grad_out ? mask_bits_in : nullptr);
   } else {
-    wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad, in_data, ld_in, d_W_self_grad);
+    wgrad_two_a(x, z, grad_in, ld_out, y, d_in_temp1, ldt, d_W_neigh_grad_local, in_data, ld_in, d_W_self_grad_local);
     if (level_ > 0) {
       mm(x, y, z, grad_in, ld_out, d_W_neigh, z, d_in_temp, ldt, false, true);
       mm(x, y, z, grad_in, ld_out, d_W_self, z, grad_out, ld_in, false, true);
       aggr.d_aggregate_ld((int)y, *graph, d_in_temp, ldt, grad_out, ld_in, GAI_EPI_ADD, grad_out, mask_grad_out ? mask_bits_in : nullptr);
     }
   }
+  reduce_weight_grads();
   backward_dropout(grad_out);
 }
 
@@ -459,7 +493,29 @@ loss_layer::loss_layer(int nv, int ncls, label_t* ptr) : num_samples(nv), num_cl
   d_stats = float_malloc_device_zero(4);
 }
 
+void loss_layer::set_partition(gai_host::Comm* comm) {
+  comm_ = comm;
+  comm->register_buffer(d_stats);
+  d_stats_all = float_malloc_device_zero(4 * (size_t)comm->world());
+}
+
+void loss_layer::combine_stats(float* h) {
+  if (!comm_) { copy_float_to_host(3, d_stats, h); return; }
+  comm_->all_gather(d_stats, 4, d_stats_all);
+  std::vector<float> all(4 * (size_t)comm_->world());
+  copy_float_to_host(all.size(), d_stats_all, all.data());
+  double loss = 0, correct = 0, count = 0;
+  for (int q = 0; q < comm_->world(); q++) {
+    const double c = all[4 * q + 2];
+    if (c > 0) { loss += (double)all[4 * q] * c; correct += (double)all[4 * q + 1] * c; count += c; }
+  }
+  h[0] = count > 0 ? (float)(loss / count) : 0.f;
+  h[1] = count > 0 ? (float)(correct / count) : 0.f;
+  h[2] = (float)count;
+}
+
 void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
+  if (comm_) die_on(gai_memset(d_stats, 0, 4 * sizeof(float), stream()), "gai_memset");  // a rank without rows of the range reports count 0
   // one pass over the logits also yields the loss mean and the accuracy get_prediction_loss() reports (forward_prop calls the two back to back)
   gai_host::OpScope sc("LOSS", "fwd+stats", 4.0 * (end - begin) * (2 * num_cls + 2), 0);
   die_on(gai_softmax_ce_forward_stats_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), feat_out, row_pitch(num_cls), d_losses, d_stats,
@@ -469,21 +525,33 @@ void softmax_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
 void softmax_loss_layer::backward(size_t begin, size_t end, mask_t* masks, float* grad_out) {
   gai_host::OpScope sc("LOSS", "bwd", 8.0 * (end - begin) * num_cls, 0);
   if (begin == end) return;
-  die_on(gai_softmax_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, row_pitch(num_cls), grad_out, row_pitch(num_cls), (uint64_t)(end - begin),
-                                    stream()), "gai_softmax_ce_backward");
+  die_on(gai_softmax_ce_backward_ld(num_cls, begin, end, masks, labels, feat_out, row_pitch(num_cls), grad_out, row_pitch(num_cls),
+                                    (uint64_t)(global_denom ? global_denom : end - begin), stream()), "gai_softmax_ce_backward");
 }
 acc_t softmax_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) {
   if (!(stats_valid && stats_begin == begin && stats_end == end && stats_masks == masks)) {  // not preceded by forward() on the same rows
     gai_host::OpScope sc("LOSS", "reduce", 4.0 * (end - begin) * (num_cls + 1), 0);
-    die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), d_losses, d_stats, stream()),
-           "gai_masked_loss_accuracy");
+    if (comm_) die_on(gai_memset(d_stats, 0, 4 * sizeof(float), stream()), "gai_memset");
+    if (begin != end)
+      die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), d_losses, d_stats, stream()),
+             "gai_masked_loss_accuracy");
   }
   stats_valid = false;
   float h[3] = {0, 0, 0};
-  copy_float_to_host(3, d_stats, h);
+  combine_stats(h);
   (void)count;  // the reference asserts masked-row count == count; the count comes back as a float here
   last_acc = h[1];
   return h[0];
+}
+acc_t softmax_loss_layer::masked_accuracy(size_t begin, size_t end, mask_t* masks) {
+  if (comm_) die_on(gai_memset(d_stats, 0, 4 * sizeof(float), stream()), "gai_memset");
+  if (begin != end)
+    die_on(gai_masked_loss_accuracy_ld(num_cls, begin, end, masks, labels, feat_in, row_pitch(num_cls), d_losses, d_stats, stream()),
+           "gai_masked_loss_accuracy");
+  stats_valid = false;
+  float h[3] = {0, 0, 0};
+  combine_stats(h);
+  return h[1];
 }
 
 void sigmoid_loss_layer::forward(size_t begin, size_t end, mask_t* masks) {
@@ -509,7 +577,7 @@ acc_t sigmoid_loss_layer::get_prediction_loss(size_t begin, size_t end, size_t c
 }
 
 float masked_accuracy_multi(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
-  static float* d_f1 = nullptr;
+  static thread_local float* d_f1 = nullptr;
   if (!d_f1) d_f1 = float_malloc_device_zero(4);
   die_on(gai_masked_f1_micro(num_classes, begin, end, masks, ground_truth, preds, row_pitch(num_classes), d_f1, stream()), "gai_masked_f1_micro");
   float h = 0.f;
@@ -519,8 +587,8 @@ float masked_accuracy_multi(int begin, int end, int, int num_classes, mask_t* ma
 
 // preds: the loss layer's feat_in (rows pitched to 4 floats, as every layer-owned buffer)
 float masked_accuracy_single(int begin, int end, int, int num_classes, mask_t* masks, float* preds, label_t* ground_truth) {
-  static float* scratch = nullptr;
-  static size_t scratch_n = 0;
+  static thread_local float* scratch = nullptr;
+  static thread_local size_t scratch_n = 0;
   if (scratch_n < (size_t)end + 4) {
     if (scratch) gai_free(scratch);
     scratch_n = (size_t)end + 4;

@@ -64,12 +64,16 @@ class aggregator {
   int length = 0;
 };
 
+// On a partitioned graph (Graph::partitioned()) `in` holds the master rows; the *_ld forms fetch the halo vertices' rows from their
+// owners (Graph::halo_exchange) before aggregating the master rows, unless `static_halo` already holds them (layer-0 input features:
+// fetched once by Model).
 class GCN_Aggregator : public aggregator {
  public:
   void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
-  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
+  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend,
+                    const float* static_halo = nullptr);
   void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend,
                       const uint32_t* mask_bits = nullptr);
 };
@@ -79,7 +83,8 @@ class SAGE_Aggregator : public aggregator {
   void init(int len, int nv, int ne = 0, float lr = 0.01f, float drop_rate = 0.f);
   void aggregate(int len, Graph& g, const float* in, float* out);
   void d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out);
-  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend);
+  void aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int epilogue_flags, const float* addend,
+                    const float* static_halo = nullptr);
   void d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int epilogue_flags, const float* addend,
                       const uint32_t* mask_bits = nullptr);
 };
@@ -112,7 +117,7 @@ class graph_conv_layer {
   void set_netphase(net_phase phase) { phase_ = phase; }
   void update_dim_size(size_t sz) { num_samples = (int)sz; }
   void print_layer_info() {
-    std::cout << "GraphConv Layer " << level_ << " with " << num_samples << " samples, dims: [" << dim_in << " x " << dim_out << "]\n";
+    gai_host::out() << "GraphConv Layer " << level_ << " with " << num_samples << " samples, dims: [" << dim_in << " x " << dim_out << "]\n";
   }
   // weight access for parity injection / checkpointing (host <-> device copies)
   int get_dim_in() const { return dim_in; }
@@ -136,6 +141,10 @@ class graph_conv_layer {
   const uint32_t* relu_bits() const { return d_relu_bits; }
   void set_mask_bits(const uint32_t* bits) { mask_bits_in = bits; }
   bool has_activation() const { return is_act; }
+  // Partitioned graphs: matrices an aggregation gathers from are registered with the peer group; weight gradients are summed over the
+  // ranks at the end of backward(). Layer 0's input never changes during training: Model fetches its halo rows once and hands them over.
+  bool input_is_gathered() const { return !transform_first_; }
+  void set_input_halo_static(const float* halo_rows) { input_static_halo = halo_rows; }
 
  protected:
   int level_, num_samples, dim_in, dim_out;
@@ -147,6 +156,10 @@ class graph_conv_layer {
   bool mask_grad_out = false, grad_premasked = false;
   uint32_t* d_relu_bits = nullptr;
   const uint32_t* mask_bits_in = nullptr;
+  bool transform_first_ = false;
+  const float* input_static_halo = nullptr;
+  float *d_W_neigh_grad_local = nullptr, *d_W_self_grad_local = nullptr;  // this rank's partial sums (== the public gradients when not partitioned)
+  void reduce_weight_grads();
   // feature dropout (feat_dropout_rate > 0): the dropped-out input of the last training forward and its mask
   float* d_drop_in = nullptr;
   uint8_t* d_dropout_mask = nullptr;
@@ -229,9 +242,18 @@ class loss_layer {
   void set_labels_ptr(label_t* ptr) { labels = ptr; }
   void set_netphase(net_phase phase) { phase_ = phase; }
   void update_dim_size(int sz) { num_samples = sz; }
-  void print_layer_info() { std::cout << "Output Layer with " << num_samples << " samples and " << num_cls << " classes\n"; }
+  void print_layer_info() { gai_host::out() << "Output Layer with " << num_samples << " samples and " << num_cls << " classes\n"; }
+  // 1D partition: this rank's rows are part of the reference's [begin, end) range. The gradient is scaled by the GLOBAL range length
+  // (softmax_loss_layer.cpp:31) and the loss / accuracy statistics are combined over the ranks (collective: every rank calls).
+  void set_partition(gai_host::Comm* comm);
+  void set_global_denominator(size_t n) { global_denom = n; }
 
  protected:
+  gai_host::Comm* comm_ = nullptr;
+  size_t global_denom = 0;
+  float* d_stats_all = nullptr;  // [world x 4] gathered statistics
+  // {mean loss, accuracy, count} of this rank's rows in d_stats -> the same over all ranks' rows (host, double)
+  void combine_stats(float* h3);
   int num_samples, num_cls;
   net_phase phase_ = net_phase::TRAIN;
   float *feat_in, *feat_out;
@@ -248,6 +270,8 @@ class softmax_loss_layer : public loss_layer {
   acc_t get_prediction_loss(size_t begin, size_t end, size_t count, mask_t* masks) override;
   // masked_accuracy_single (math_functions.cpp:79-92) shares the reduction pass with the loss mean
   acc_t last_accuracy() const { return last_acc; }
+  // accuracy of the current logits over [begin, end) — over every rank's rows when partitioned (Model::evaluate)
+  acc_t masked_accuracy(size_t begin, size_t end, mask_t* masks);
 
  private:
   acc_t last_acc = 0;

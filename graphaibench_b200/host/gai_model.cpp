@@ -52,7 +52,7 @@ void Model<L>::load_data(int argc, char* argv[]) {
   dim_init = (int)reader.bin_read_features(input_features);
   num_cls = reader.bin_read_vlabels(labels, !is_sigmoid);
   if (arch != gnn_arch::SAGE) full_graph->add_selfloop();  // net.cpp:96
-  std::cout << "num_threads = " << num_threads << ", num_vertices = " << num_samples << ", num_edges = " << full_graph->sizeEdges()
+  gai_host::out() << "num_threads = " << num_threads << ", num_vertices = " << num_samples << ", num_edges = " << full_graph->sizeEdges()
             << ", num_layers = " << num_layers << ", \nnum_epochs = " << num_epochs << ", input_length = " << dim_init
             << ", hidden_length = " << dim_hid << ", num_classes = " << num_cls << ", \nfeat_drop = " << feat_drop
             << ", score_drop = " << score_drop << ", subg_size = " << subg_size << ", val_interval = " << val_interval
@@ -60,6 +60,59 @@ void Model<L>::load_data(int argc, char* argv[]) {
   train_count = reader.bin_read_masks("train", num_samples, train_begin, train_end, nullptr);
   val_count = reader.bin_read_masks("val", num_samples, val_begin, val_end, nullptr);
   test_count = reader.bin_read_masks("test", num_samples, test_begin, test_end, nullptr);
+  if (partitioned()) {
+    // every rank read the whole dataset; keep this rank's rows (global column ids, self-loops already in place), features and labels
+    if (is_sigmoid) { std::cerr << "partitioned training supports the softmax loss only\n"; std::exit(1); }
+    const index_t nv_global = (index_t)num_samples;
+    const gai_host::OwnerRange own = gai_host::owner_range(nv_global, comm_->world(), comm_->rank());
+    Graph* mine = new Graph(true);
+    const index_t* rp = full_graph->row_start_host_ptr();
+    const index_t* ci = full_graph->edge_dst_host_ptr();
+    mine->allocateFrom(own.last - own.first, rp[own.last] - rp[own.first]);
+    for (index_t v = own.first; v < own.last; v++) mine->fixEndEdge(v - own.first, rp[v + 1] - rp[own.first]);
+    std::copy(ci + rp[own.first], ci + rp[own.last], mine->edge_dst_host_ptr());
+    delete full_graph;
+    full_graph = mine;
+    const int64_t split9[9] = {(int64_t)train_begin, (int64_t)train_end, (int64_t)train_count, (int64_t)val_begin, (int64_t)val_end, (int64_t)val_count,
+                               (int64_t)test_begin, (int64_t)test_end, (int64_t)test_count};
+    std::vector<float> f(input_features.begin() + (size_t)own.first * dim_init, input_features.begin() + (size_t)own.last * dim_init);
+    input_features.swap(f);
+    std::vector<label_t> l(labels.begin() + own.first, labels.begin() + own.last);
+    labels.swap(l);
+    num_samples = (int)(own.last - own.first);
+    localise_split(split9, own.first, own.last);
+    full_graph->partition_rows(comm_, nv_global);
+  }
+  finish_setup();
+}
+
+template <typename L>
+void Model<L>::localise_split(const int64_t* s, index_t first, index_t last) {
+  // the reference's ranges are global row ranges; this rank keeps their intersection with its masters, as local rows
+  auto clip = [&](int64_t v) { return (size_t)(std::min<int64_t>(std::max<int64_t>(v, first), last) - first); };
+  train_denominator = (size_t)(s[1] - s[0]);
+  train_begin = clip(s[0]); train_end = clip(s[1]); train_count = train_end - train_begin;
+  val_begin = clip(s[3]); val_end = clip(s[4]); val_count = val_end - val_begin;
+  test_begin = clip(s[6]); test_end = clip(s[7]); test_count = test_end - test_begin;
+}
+
+template <typename L>
+void Model<L>::init_partitioned(gnn_arch a, index_t nv_global, const int64_t* rows_rowptr, const uint32_t* rows_colidx, int dinit, int ncls,
+                                const float* feats_local, const label_t* labels_local, const int64_t* split9, int dhid, int nlayers, float lr) {
+  assert(a == arch_of<L>::value && comm_ != nullptr);
+  const gai_host::OwnerRange own = gai_host::owner_range(nv_global, comm_->world(), comm_->rank());
+  const index_t n_loc = own.last - own.first;
+  arch = a; num_samples = (int)n_loc; dim_init = dinit; num_cls = ncls; dim_hid = dhid; num_layers = nlayers; lrate = lr;
+  num_epochs = 0; val_interval = 1 << 30;
+  full_graph = new Graph(true);
+  full_graph->allocateFrom(n_loc, (index_t)rows_rowptr[n_loc]);
+  for (index_t v = 0; v < n_loc; v++) full_graph->fixEndEdge(v, (index_t)rows_rowptr[v + 1]);
+  std::copy(rows_colidx, rows_colidx + rows_rowptr[n_loc], full_graph->edge_dst_host_ptr());
+  input_features.assign(feats_local, feats_local + (size_t)n_loc * dinit);
+  labels.assign(labels_local, labels_local + n_loc);
+  localise_split(split9, own.first, own.last);
+  if (arch != gnn_arch::SAGE) full_graph->add_selfloop_rows(own.first);
+  full_graph->partition_rows(comm_, nv_global);
   finish_setup();
 }
 
@@ -88,6 +141,11 @@ void Model<L>::finish_setup() {
   for (size_t i = val_begin; i < val_end; i++) masks_val[i] = 1;
   for (size_t i = test_begin; i < test_end; i++) masks_test[i] = 1;
   training_graph = full_graph;
+  if (partitioned()) {  // the device graph (and its halo plan) first: the input features carry a halo block that is fetched through it
+    training_graph->copy_to_gpu();
+    transfer_data_to_device();
+    return;
+  }
   transfer_data_to_device();
   training_graph->alloc_on_device();
   training_graph->copy_to_gpu();
@@ -99,6 +157,12 @@ void Model<L>::transfer_data_to_device() {  // net.cpp:207-227
   // input features live on the device with rows of pitch row_pitch(dim_init), like every other per-vertex buffer
   d_input_features = float_malloc_device_zero((size_t)num_samples * row_pitch(dim_init));
   upload_features(d_input_features, input_features.data(), stream());
+  if (partitioned()) {
+    // the input never changes during training: the halo vertices' feature rows are fetched once, into a buffer of their own
+    training_graph->register_gather_buffer(d_input_features);
+    d_input_halo = float_malloc_device_zero(std::max<size_t>(training_graph->num_halo(), 1) * row_pitch(dim_init));
+    training_graph->halo_exchange_into(d_input_features, dim_init, row_pitch(dim_init), d_input_halo);
+  }
   d_labels = upload(labels.data(), labels.size());
   d_masks_train = upload(masks_train.data(), masks_train.size());
   d_masks_test = upload(masks_test.data(), masks_test.size());
@@ -160,10 +224,12 @@ void Model<L>::refresh_inputs_from_host(const float* feats_h) {
   } else {
     upload_features(d_input_features, feature_source(feats_h), stream());
   }
+  if (partitioned()) training_graph->halo_exchange_into(d_input_features, dim_init, row_pitch(dim_init), d_input_halo);  // new features: new halo rows
 }
 
 template <typename L>
 void Model<L>::prefetch_features_from_host(const float* feats_h) {
+  if (partitioned()) return;  // the double-buffered copy stream is a single-GPU path: partitioned steps copy in line (refresh_inputs_from_host)
   if (!copy_stream) {
     die_on(gai_stream_create(&copy_stream), "gai_stream_create");
     die_on(gai_event_create(&ev_ready), "gai_event_create");
@@ -182,7 +248,7 @@ void Model<L>::prefetch_features_from_host(const float* feats_h) {
 
 template <typename L>
 void Model<L>::construct_network() {  // net.cpp:422-453
-  std::cout << "constructing neural network...\n";
+  gai_host::out() << "constructing neural network...\n";
   const int nv = num_samples;
   layer_gconv.reserve(num_layers);
   for (int l = 0; l < num_layers - 1; l++)
@@ -191,6 +257,7 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   if (use_l2norm) layer_l2norm = new l2norm_layer(nv, dim_hid);
   if (use_dense) layer_dense = new dense_layer(nv, dim_hid, num_cls, lrate);
   layer_gconv[0].set_feat_in(d_input_features);
+  if (partitioned()) layer_gconv[0].set_input_halo_static(d_input_halo);
   // d_relu of layer l-1 (gcn_layer.cpp:38-40) rides the epilogue of the transform that produces its grad_in in layer l
   for (int l = 1; l < num_layers; l++) {
     if (layer_gconv[l - 1].has_activation() &&
@@ -202,6 +269,10 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   }
   if (is_sigmoid) layer_loss = new sigmoid_loss_layer(nv, num_cls, d_labels);  // net.cpp:447-451
   else layer_loss = new softmax_loss_layer(nv, num_cls, d_labels);
+  if (partitioned()) {
+    layer_loss->set_partition(comm_);
+    layer_loss->set_global_denominator(train_denominator);
+  }
   opt_ = new adam(lrate);  // net.cpp:362
   sync();
 }
@@ -246,6 +317,11 @@ acc_t Model<L>::evaluate(std::string type) {
     layer_loss->forward(b, e, mk);
     return masked_accuracy_multi((int)b, (int)e, (int)c, num_cls, mk, layer_loss->get_feat_out(), d_labels);
   }
+  if (partitioned()) {
+    const bool test = type == "test";
+    return static_cast<softmax_loss_layer*>(layer_loss)->masked_accuracy(test ? test_begin : val_begin, test ? test_end : val_end,
+                                                                         test ? d_masks_test : d_masks_val);
+  }
   if (type == "test") return masked_accuracy_single((int)test_begin, (int)test_end, (int)test_count, num_cls, d_masks_test, layer_loss->get_feat_in(), d_labels);
   return masked_accuracy_single((int)val_begin, (int)val_end, (int)val_count, num_cls, d_masks_val, layer_loss->get_feat_in(), d_labels);
 }
@@ -276,10 +352,10 @@ acc_t Model<L>::train_epoch(acc_t& loss) {
 
 template <typename L>
 void Model<L>::train() {  // log lines as net.cpp:364-410 so that logs diff cleanly against the reference
-  std::cout << "Start training...\n";
+  gai_host::out() << "Start training...\n";
   double total_train_time = 0.0;
   for (int itr = 0; itr < num_epochs; itr++) {
-    std::cout << "Epoch " << std::setw(3) << itr << " ";
+    gai_host::out() << "Epoch " << std::setw(3) << itr << " ";
     set_netphases(net_phase::TRAIN);
     acc_t train_loss = 0.0;
     const double t0 = now_s();
@@ -291,19 +367,19 @@ void Model<L>::train() {  // log lines as net.cpp:364-410 so that logs diff clea
     const double t2 = now_s();
     const double fw_time = t1 - t0, bw_time = t2 - t1, epoch_time = fw_time + bw_time;
     total_train_time += epoch_time;
-    std::cout << "train_loss " << std::setprecision(3) << std::fixed << train_loss << " train_acc " << train_acc << " ";
+    gai_host::out() << "train_loss " << std::setprecision(3) << std::fixed << train_loss << " train_acc " << train_acc << " ";
     if (itr % val_interval == 0 && itr != 0) {
       const double v0 = now_s();
       acc_t val_acc = evaluate("val");
       const double val_time = now_s() - v0;
-      std::cout << "val_acc " << std::setprecision(3) << std::fixed << val_acc << " ";
-      std::cout << "time " << std::setprecision(3) << std::fixed << epoch_time + val_time << " s (train_time " << epoch_time << " val_time "
+      gai_host::out() << "val_acc " << std::setprecision(3) << std::fixed << val_acc << " ";
+      gai_host::out() << "time " << std::setprecision(3) << std::fixed << epoch_time + val_time << " s (train_time " << epoch_time << " val_time "
                 << val_time << ")\n";
     } else {
-      std::cout << "train_time " << std::fixed << epoch_time << " s (fw " << fw_time << ", bw " << bw_time << ")\n";
+      gai_host::out() << "train_time " << std::fixed << epoch_time << " s (fw " << fw_time << ", bw " << bw_time << ")\n";
     }
   }
-  std::cout << "Average training time per epoch: " << total_train_time / (double)num_epochs << " seconds. Throughput "
+  gai_host::out() << "Average training time per epoch: " << total_train_time / (double)num_epochs << " seconds. Throughput "
             << (double)num_epochs / total_train_time << " epoch/s\n";
 }
 

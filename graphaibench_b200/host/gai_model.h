@@ -4,6 +4,7 @@
 #pragma once
 #include <string>
 #include <vector>
+#include "gai_dist.h"
 #include "gai_layers.h"
 
 #define DEFAULT_NUM_LAYER 2
@@ -30,6 +31,15 @@ class Model {
   // arrays (tests, bench.py through gai_host_capi.cpp). `split9` = train/val/test (begin, end, count).
   void init_from_memory(gnn_arch arch, Graph* g, int dim_init, int num_cls, const float* feats_h, const label_t* labels_h,
                         const int64_t* split9, int dim_hid, int num_layers, float lr, int epochs, int val_interval);
+  // 1D-partitioned training (host/gai_dist.h): call set_comm() before load_data() / init_partitioned(). Every rank builds
+  // the same network over its own masters; aggregations exchange halo rows, weight gradients and loss statistics are combined over the
+  // ranks (csrc/peers.cu), weights and optimiser state are replicated and stay bit-identical on every rank.
+  void set_comm(gai_host::Comm* c) { comm_ = c; gai_host::set_quiet(c && c->rank() != 0); }
+  // This rank's rows of the RAW graph (global column ids, no self-loops; rows_rowptr has n_loc + 1 entries, rebased to 0), its rows of
+  // the feature matrix and label vector, and the GLOBAL split ranges.
+  void init_partitioned(gnn_arch arch, index_t nv_global, const int64_t* rows_rowptr, const uint32_t* rows_colidx, int dim_init, int num_cls,
+                        const float* feats_local, const label_t* labels_local, const int64_t* split9_global, int dim_hid, int num_layers, float lr);
+  Graph* graph() { return training_graph; }
   // One training step exactly as Model::train's loop body (net.cpp:373-383); returns train accuracy.
   acc_t train_epoch(acc_t& loss);
   // Re-upload the epoch's inputs (features, labels, masks, CSR) from host memory: the reference's host->device boundary
@@ -67,6 +77,7 @@ class Model {
   std::vector<label_t> labels;
   std::vector<mask_t> masks_train, masks_test, masks_val;
   float* d_input_features = nullptr;
+  float* d_input_halo = nullptr;  // partitioned: feature rows of the halo vertices (fetched once)
   float* d_feat_buf[2] = {nullptr, nullptr};  // double-buffered input features (prefetch_features_from_host)
   int feat_cur = 0;
   bool prefetch_pending = false;
@@ -79,6 +90,11 @@ class Model {
   label_t* d_labels = nullptr;
   mask_t *d_masks_train = nullptr, *d_masks_test = nullptr, *d_masks_val = nullptr;
 
+  gai_host::Comm* comm_ = nullptr;
+  bool partitioned() const { return comm_ != nullptr; }
+  bool talk() const { return !comm_ || comm_->rank() == 0; }  // only rank 0 logs
+  size_t train_denominator = 0;   // GLOBAL length of the train range (the reference's end - begin, softmax_loss_layer.cpp:31)
+  void localise_split(const int64_t* split9_global, index_t first, index_t last);
   void finish_setup();
   void run_forward_layers();
 };

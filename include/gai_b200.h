@@ -125,10 +125,13 @@ int gai_spmm_gcn_masked(gai_csr_t g, int F, const float* in, int ld_in, float* o
                         const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
 int gai_spmm_mean_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend,
                          const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
-/* Every aggregation form over a row range, in one entry point (what the partitioned layer classes call: rows [0, n_masters) of a local
- * CSR whose column ids run over masters + halo). mode: 0 GCN, 1 mean, 2 transposed mean, 3 edge values, 4 edge values through perm. */
+/* Every aggregation form over a row range, in one entry point (what the layer classes call). mode: 0 GCN, 1 mean, 2 transposed mean,
+ * 3 edge values, 4 edge values through perm. 1D partition: the local CSR's column ids run over [masters | halo]; with in_halo != NULL the
+ * rows of neighbour ids >= n_split are read from in_halo[(id - n_split) * ld_in] (the buffer gai_halo_pull fills) and `in` holds master
+ * rows only, so no matrix carries a halo block of its own. in_halo == NULL: one matrix, n_split ignored. */
 int gai_spmm_rows_ex(gai_csr_t g, int mode, uint32_t row_begin, uint32_t row_end, int F, const float* vals, const uint32_t* perm, const float* in,
-                     int ld_in, float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, gai_stream_t stream);
+                     int ld_in, float* out, int ld_out, int flags, const float* addend, const uint32_t* mask_bits, int ld_bits, const float* in_halo,
+                     uint32_t n_split, gai_stream_t stream);
 /* Row-range variants for the 1D partition (interior rows first, boundary rows after the halo arrives). */
 int gai_spmm_gcn_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
 int gai_spmm_mean_rows(gai_csr_t g, uint32_t row_begin, uint32_t row_end, int F, const float* in, int ld_in, float* out, int ld_out, int transposed, int flags, const float* addend, gai_stream_t stream);
@@ -291,9 +294,9 @@ int gai_peers_error(gai_peers_t p, gai_stream_t stream);
 int gai_halo_plan_create(gai_peers_t p, uint32_t nv_global, uint32_t n_halo, const uint32_t* halo_gids_h, gai_stream_t stream, gai_halo_plan_t* out);
 int gai_halo_plan_destroy(gai_halo_plan_t h);
 enum { GAI_PULL_NO_BARRIER_BEFORE = 1, GAI_PULL_NO_BARRIER_AFTER = 2 };
-/* Rows [dst_row_offset, dst_row_offset + n_halo) of this rank's instance of buffer `buf_id` <- the owners' rows, read through the mapped
- * peer pointers (row pitch ld floats on every rank, F live columns). barrier - pull - barrier unless `flags` drops one. */
-int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld, size_t dst_row_offset, int flags, gai_stream_t stream);
+/* dst[k, 0:F] (pitch ld_dst, a private buffer of this rank) <- row of halo vertex k in its owner's instance of buffer `buf_id` (pitch ld_src
+ * on every rank), read through the mapped peer pointers. barrier - pull - barrier unless `flags` drops one. */
+int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld_src, float* dst, size_t ld_dst, int flags, gai_stream_t stream);
 /* sum = 1: out[i] = sum over ranks (rank order, identical bits everywhere) of buffer `buf_id`[i], i < n   (weight-gradient all-reduce);
  * sum = 0: out[q*n + i] = rank q's buffer[i]                                                              (all-gather of small vectors).
  * `out` is a private buffer, not the registered one. barrier - combine - barrier. */
