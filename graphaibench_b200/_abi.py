@@ -42,6 +42,8 @@ _SIGS = {
     "gai_event_destroy": (C.c_int, [C.c_void_p]),
     "gai_launch_count": (C.c_uint64, []),
     "gai_add_selfloop_h": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gai_coo_to_csr": (C.c_int, [C.c_uint32, C.c_uint64, c_u32p, c_u32p, C.c_int, c_stream, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "gai_add_selfloop_d": (C.c_int, [C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, c_u32p, c_stream]),
     "gai_csr_create": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_csr_create_device": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_csr_destroy": (C.c_int, [C.c_void_p]),
@@ -52,6 +54,8 @@ _SIGS = {
     "gai_csr_vertex_norm": (C.c_void_p, [C.c_void_p]),
     "gai_csr_set_norms": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_stream]),
     "gai_csr_num_hub_rows": (C.c_uint32, [C.c_void_p]),
+    "gai_csr_max_degree": (C.c_uint32, [C.c_void_p]),
+    "gai_triangle_count_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), c_stream]),
     "gai_csr_set_row_segments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_stream]),
     "gai_csr_build_transpose": (C.c_int, [C.c_void_p, c_stream]),
     "gai_csr_transpose_perm": (C.c_void_p, [C.c_void_p]),

@@ -60,13 +60,15 @@ def build_host(force=False):
         return None
     hdrs = glob.glob(os.path.join(HOST, "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
     if force or _newer(HOSTLIB, srcs + hdrs + [LIB]):
-        lib_srcs = [s for s in srcs if not os.path.basename(s).startswith("train")]
+        lib_srcs = [s for s in srcs if not os.path.basename(s).startswith(("train", "convert_main"))]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST,
                                *lib_srcs, "-o", HOSTLIB, "-L", PKG, "-lgai_b200", "-Wl,-rpath,$ORIGIN"])
         for arch, macro in (("gcn", []), ("sage", ["-DUSE_SAGE"]), ("gat", ["-DUSE_GAT"])):
             subprocess.check_call(["g++", "-O2", "-std=c++17", *macro, "-I", os.path.join(ROOT, "include"), "-I", HOST,
                                    os.path.join(HOST, "train.cpp"), "-o", os.path.join(PKG, f"gpu_train_{arch}"),
                                    "-L", PKG, "-lgai_host", "-lgai_b200", "-Wl,-rpath,$ORIGIN"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", HOST, os.path.join(HOST, "convert_main.cpp"),
+                               "-o", os.path.join(PKG, "gpu_converter"), "-L", PKG, "-lgai_host", "-lgai_b200", "-Wl,-rpath,$ORIGIN"])
     return HOSTLIB
 
 

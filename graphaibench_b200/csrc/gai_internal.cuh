@@ -99,6 +99,7 @@ struct gai_csr {
   uint32_t* hub_rows = nullptr;   // == row_order (its first n_hub entries)
   uint32_t n_hub = 0;
   uint32_t hub_degree = 1024;
+  uint32_t max_degree = 0;
   uint32_t* row_order = nullptr;  // all rows, longest first (ties: ascending id); the first n_hub entries are the hub rows
   uint32_t* claim_ptr = nullptr;  // light rows (row_order + n_hub) cut into claims of <= 32 rows / <= 2048 edges: (begin, end) pairs in execution order
   uint32_t n_claims = 0;

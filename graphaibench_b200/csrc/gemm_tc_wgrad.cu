@@ -27,7 +27,11 @@ using namespace tc;
 
 constexpr int WG_BK = 16;                 // rows per k-block (8-row blocks measured 40 % slower: twice the TMA boxes and barrier hand-offs per byte)
 constexpr uint32_t WG_BOX = WG_BK * 128;  // bytes per TMA box
-constexpr size_t WG_MAX_ROWS = 2048;      // rows one TMEM accumulator absorbs before it is written out as a partial sum (accuracy, see launch)
+constexpr uint32_t WG_SEG_KB = 2048 / WG_BK;  // k-blocks (2048 rows) one TMEM accumulator absorbs before it is flushed into the CTA's fp32 partial: the
+                                          // tensor core adds into TMEM with truncation, so the error of one accumulator grows linearly with the k-steps
+                                          // it absorbs. One accumulator per CTA over 2.45 M rows (16.5 K rows each) measured 0.9-1.3e-4 of the result
+                                          // norm against the exact fp64 product — 20x the reference's OpenBLAS sgemm; segments of 2048 rows: 1-2e-5
+                                          // (tests/test_reference_parity_gpu.py). The flushes add round-to-nearest in ordinary fp32.
 constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 splitters + epilogue
 constexpr int WG_SPLIT_WARPS = 8;
 
@@ -45,6 +49,7 @@ struct WgArgs {
   int nbox_b, nbox_b0;  // B boxes; the first nbox_b0 stream from map_b[0], the rest from map_b[1]
   int my0;         // live columns of the first B part (the second starts at tile column 32*nbox_b0)
   int stages, passes;
+  int ldp;         // row pitch of the partial (My rounded up to 4 floats)
   uint32_t a_bytes, b_bytes, stage_bytes;
 };
 
@@ -60,7 +65,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                      const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1, const WgArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[8], conv_bar[8], empty_bar[8], done_bar;
+  __shared__ uint64_t full_bar[8], conv_bar[8], empty_bar[8], done_bar, tfree_bar;
   __shared__ uint32_t tmem_base_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,6 +78,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.stages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&conv_bar[i], WG_SPLIT_WARPS); mbar_init(&empty_bar[i], 1); }
     mbar_init(&done_bar, 1);
+    mbar_init(&tfree_bar, (uint32_t)g.mt * 4u);  // the warps that flush the accumulator
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -117,6 +123,9 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.n_mma >> 3) << 17) | ((128u >> 4) << 24);
       for (uint32_t it = 0; it < nkb; it++) {
         const int s = it % g.stages;
+        const uint32_t seg = it / WG_SEG_KB;
+        const bool seg_start = it % WG_SEG_KB == 0;
+        if (seg_start && seg > 0) mbar_wait(&tfree_bar, (seg - 1) & 1);  // the previous segment's sums have left the accumulator
         mbar_wait(&conv_bar[s], (it / g.stages) & 1);
         tcgen05_fence_after();
         const uint32_t a_hi = smem_u32(smem + (size_t)s * g.stage_bytes);
@@ -129,7 +138,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
           for (int t = 0; t < g.mt; t++) {
             const uint32_t toff = (uint32_t)t * 4u * WG_BOX + koff;
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            const uint32_t first = (it == 0 && kg == 0) ? 0u : 1u;
+            const uint32_t first = (seg_start && kg == 0) ? 0u : 1u;
             if (g.passes == 3) {
               umma_tf32(d_tmem, make_desc_mn128(a_lo + toff), make_desc_mn128(b_hi + koff), idesc, first);
               umma_tf32(d_tmem, make_desc_mn128(a_hi + toff), make_desc_mn128(b_lo + koff), idesc, 1u);
@@ -140,8 +149,8 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
           }
         }
         umma_commit(&empty_bar[s]);
+        if ((it + 1) % WG_SEG_KB == 0 || it + 1 == nkb) umma_commit(&done_bar);  // segment complete
       }
-      umma_commit(&done_bar);
     }
   } else if (warp >= 4) {
     // ---------------- splitters: x -> (rn_tf32(x) in place, rn_tf32(x - hi)) for the A and B boxes ----------------
@@ -181,28 +190,49 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv_bar[s]);
-    }
-    // ---------------- epilogue: TMEM -> this CTA's partial ----------------
-    const int tile = (warp - 4) >> 2;  // warps 4-7: M tile 0, warps 8-11: M tile 1
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    if (tile < g.mt) {
-      mbar_wait(&done_bar, 0);
-      tcgen05_fence_after();
-      const int kl = q * 32 + lane;  // accumulator row within the tile
-      const bool live = kl < g.rows_t[tile];
-      const int kx = (tile ? g.rows_t[0] : 0) + kl;  // row of the concatenated partial
-      float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (live ? kx : 0)) * g.My;
-      for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
-        // tile columns -> concatenated partial columns: part 0 at [0, my0), part 1 from tile column 32*nbox_b0
-        const int part1 = c0 >= 32 * g.nbox_b0;
-        const int pc0 = part1 ? g.my0 + c0 - 32 * g.nbox_b0 : c0;
-        const int lim = part1 ? g.My : g.my0;
-        if (live) {
+      // ---------------- flush: TMEM accumulator -> (+=) this CTA's partial, once per segment ----------------
+      if ((it + 1) % WG_SEG_KB == 0 || it + 1 == nkb) {
+        const uint32_t seg = it / WG_SEG_KB;
+        const int tile = (warp - 4) >> 2;  // warps 4-7: M tile 0, warps 8-11: M tile 1
+        const int q = warp & 3;            // TMEM lane quarter this warp may read
+        if (tile < g.mt) {
+          mbar_wait(&done_bar, seg & 1);
+          tcgen05_fence_after();
+          const int kl = q * 32 + lane;  // accumulator row within the tile
+          const bool live = kl < g.rows_t[tile];
+          const int kx = (tile ? g.rows_t[0] : 0) + kl;  // row of the concatenated partial
+          float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (live ? kx : 0)) * g.ldp;
+          for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
+            // tile columns -> concatenated partial columns: part 0 at [0, my0), part 1 from tile column 32*nbox_b0
+            const int part1 = c0 >= 32 * g.nbox_b0;
+            const int pc0 = part1 ? g.my0 + c0 - 32 * g.nbox_b0 : c0;
+            const int lim = part1 ? g.My : g.my0;
+            if (!live) continue;
+            if ((pc0 & 3) == 0) {  // 16-byte aligned run of this lane's row (rows are pitched to 4 floats): 128-bit read-modify-write
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (pc0 + j < lim) prow[pc0 + j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; j += 4) {
+                if (pc0 + j + 3 < lim) {
+                  float4* dst = reinterpret_cast<float4*>(prow + pc0 + j);
+                  float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                  if (seg) { const float4 o = *dst; v.x = __fadd_rn(v.x, o.x); v.y = __fadd_rn(v.y, o.y); v.z = __fadd_rn(v.z, o.z); v.w = __fadd_rn(v.w, o.w); }
+                  *dst = v;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; k++)
+                    if (pc0 + j + k < lim) prow[pc0 + j + k] = seg ? __fadd_rn(prow[pc0 + j + k], __uint_as_float(r[j + k])) : __uint_as_float(r[j + k]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (pc0 + j < lim) prow[pc0 + j] = seg ? __fadd_rn(prow[pc0 + j], __uint_as_float(r[j])) : __uint_as_float(r[j]);
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tfree_bar);
         }
       }
     }
@@ -219,7 +249,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
 // C = (accum ? C : 0) + sum_p partial[p], p ascending (deterministic). The concatenated partial [Kx x My] is cut back into
 // its destinations: rows >= kx0 belong to C1 (two-A form), columns >= my0 belong to C1 (two-B form).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C0, size_t ldc0, float* __restrict__ C1, size_t ldc1,
-                                    int Kx, int My, int kx0, int my0, int parts, int accum) {
+                                    int Kx, int My, int ldp, int kx0, int my0, int parts, int accum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Kx * My) return;
   int m = i / My, n = i % My;
@@ -228,8 +258,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   else if (n >= my0) dst = C1 + (size_t)m * ldc1 + (n - my0);
   else dst = C0 + (size_t)m * ldc0 + n;
   double r = accum ? (double)*dst : 0.0;
-  const size_t stride = (size_t)Kx * My;
-  for (int p = 0; p < parts; p++) r += (double)partial[(size_t)p * stride + i];
+  const size_t stride = (size_t)Kx * ldp, off = (size_t)m * ldp + n;
+  for (int p = 0; p < parts; p++) r += (double)partial[(size_t)p * stride + off];
   *dst = (float)r;
 }
 
@@ -289,19 +319,15 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   if (g.stages > 8) g.stages = 8;
   if (g.stages < 2) return GAI_ERR_UNSUPPORTED;
 
-  // Rows per partial sum. The tensor core adds into its fp32 TMEM accumulator with truncation, so the error of one accumulator grows
-  // linearly with the number of k-steps it absorbs: one CTA per SM over 2.45 M rows (16.5 K rows per accumulator) measured 0.9-1.3e-4
-  // of the result norm against the exact fp64 product, 20x the reference's OpenBLAS sgemm (tests/test_reference_parity_gpu.py). An
-  // accumulator therefore never sees more than WG_MAX_ROWS rows; the partials are added in double by the reduce kernel.
   const size_t total_kb = (nrows + WG_BK - 1) / WG_BK;
   size_t grid = total_kb < (size_t)sm_count() ? total_kb : (size_t)sm_count();
   g.blocks_per_cta = (total_kb + grid - 1) / grid;
-  if (g.blocks_per_cta > WG_MAX_ROWS / WG_BK) g.blocks_per_cta = WG_MAX_ROWS / WG_BK;
   grid = (total_kb + g.blocks_per_cta - 1) / g.blocks_per_cta;  // every CTA owns at least one k-block
+  g.ldp = (g.My + 3) / 4 * 4;
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
-  int rc = workspace(sizeof(float) * grid * g.Kx * g.My, &ws, st);
+  int rc = workspace(sizeof(float) * grid * g.Kx * g.ldp, &ws, st);
   if (rc != GAI_OK) return rc;
   g.partial = reinterpret_cast<float*>(ws);
   const float* src[4] = {q.A[0], na == 2 ? q.A[1] : q.A[0], q.B[0], nb == 2 ? q.B[1] : q.B[0]};
@@ -346,7 +372,7 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   const int kx0 = na == 2 ? (int)q.Kx[0] : g.Kx, my0 = nb == 2 ? (int)q.My[0] : g.My;
   float* C1 = q.dual ? q.C[1] : q.C[0];
   const size_t ldc1 = q.dual ? q.ldc[1] : q.ldc[0];
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, kx0, my0, (int)grid, q.accum);
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, g.ldp, kx0, my0, (int)grid, q.accum);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

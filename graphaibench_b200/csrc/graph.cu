@@ -132,6 +132,7 @@ int build_work_lists(gai_csr* g, const uint32_t* rowptr_h, cudaStream_t st) {
   rc = build_list(g, rowptr_h, 0, g->nv, &full, st);
   if (rc != GAI_OK) return rc;
   g->row_order = full.row_order; g->claim_ptr = full.claim_ptr; g->n_hub = full.n_hub; g->n_claims = full.n_claims;
+  for (uint32_t v = 0; v < g->nv; v++) g->max_degree = std::max(g->max_degree, rowptr_h[v + 1] - rowptr_h[v]);
   g->hub_rows = g->row_order;
   return GAI_OK;
 }
@@ -227,6 +228,7 @@ const uint32_t* gai_csr_colidx(gai_csr_t g) { return g ? g->colidx : nullptr; }
 const float* gai_csr_vertex_norm(gai_csr_t g) { return g ? g->norm_gcn : nullptr; }
 const float* gai_csr_mean_norm(gai_csr_t g) { return g ? g->norm_mean : nullptr; }
 uint32_t gai_csr_num_hub_rows(gai_csr_t g) { return g ? g->n_hub : 0; }
+uint32_t gai_csr_max_degree(gai_csr_t g) { return g ? g->max_degree : 0; }
 
 int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream) {
   GAI_CHECK_ARG(g != nullptr);

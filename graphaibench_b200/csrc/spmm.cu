@@ -56,8 +56,11 @@ struct SpmmArgs {
   uint32_t n_split;
 };
 
-// base of neighbour row `c` (float4 units)
+// base of neighbour row `c` (float4 units). SPLIT is a template parameter of the kernels: the single-matrix path pays nothing for it
+// (a run-time test per gathered row cost 8 % of the aggregation time).
+template <bool SPLIT>
 __device__ __forceinline__ const float4* row_base(const float4* in4, const float4* halo4, uint32_t n_split, size_t ld4, uint32_t c) {
+  if (!SPLIT) return in4 + (size_t)c * ld4;
   return c < n_split ? in4 + (size_t)c * ld4 : halo4 + (size_t)(c - n_split) * ld4;
 }
 
@@ -171,7 +174,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
-template <int MODE>
+template <int MODE, bool SPLIT>
 __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh) {
   const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,7 +213,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
           const int j = j0 + u * EL + el;
           const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
           ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
-          if (chv && j < cnt) x[u] = __ldg(row_base(in4, halo4, a.n_split, ld4, cc) + cb + cl);
+          if (chv && j < cnt) x[u] = __ldg(row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc) + cb + cl);
         }
 #pragma unroll
         for (int u = 0; u < HI_UB; u++) {
@@ -263,7 +266,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
 
 constexpr int SLOTS = 32;  // work-list entries per claim
 
-template <int MODE, int G, int K>
+template <int MODE, int G, int K, bool SPLIT>
 __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, const uint32_t* __restrict__ order, const uint32_t* __restrict__ claim_ptr,
                                                          unsigned long long n_claims, unsigned long long* __restrict__ counter,
                                                          const uint32_t* __restrict__ hub_rows, unsigned long long n_hub_items, int hub_nsplit) {
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
       const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
       if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
       const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
-      hub_item_cta<MODE>(a, hrow, hs, he, cb, nch, hub_sh);
+      hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh);
       __syncthreads();
       if (threadIdx.x == 0) {
         const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = row_base(in4, halo4, a.n_split, ld4, cc);
+                  const float4* src = row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
                   for (int k = 0; k < K; k++) x[u][k] = gather4(src + ch[k]);
                 }
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = row_base(in4, halo4, a.n_split, ld4, cc);
+                  const float4* src = row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
                   for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
               const int j = j0 + u * EL + el;
               const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j & 31);
               ww[u] = __shfl_sync(0xffffffffu, cur_w, j & 31);
-              if (chv && j < cnt) x[u] = __ldg(row_base(in4, halo4, a.n_split, ld4, cc) + cb + ch);
+              if (chv && j < cnt) x[u] = __ldg(row_base<true>(in4, halo4, a.n_split, ld4, cc) + cb + ch);
             }
 #pragma unroll
             for (int u = 0; u < UB; u++) {
@@ -628,7 +631,11 @@ int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   // launches that overlap on different streams (interior / boundary rows of the 1D partition) from sharing a pair
   unsigned long long* ctr = g->row_counters + 2 * (__atomic_fetch_add(&const_cast<gai_csr*>(g)->counter_seq, 1u, __ATOMIC_RELAXED) % 8u);
   GAI_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
-#define GAI_ROWS_LAUNCH(GG, KK) spmm_rows_kernel<MODE, GG, KK><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit)
+#define GAI_ROWS_LAUNCH(GG, KK)                                                                                                        \
+  do {                                                                                                                                \
+    if (a.in_halo) spmm_rows_kernel<MODE, GG, KK, true><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit); \
+    else spmm_rows_kernel<MODE, GG, KK, false><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit);          \
+  } while (0)
   if (G == 4) GAI_ROWS_LAUNCH(4, 1);
   else if (G == 8) GAI_ROWS_LAUNCH(8, 1);
   else if (G == 16) GAI_ROWS_LAUNCH(16, 1);

@@ -124,10 +124,20 @@ def rmat_csr_torch(n_vertices: int, target_nnz: int, seed: int = 1, abcd=(0.57, 
     if permute:
         perm = torch.randperm(n_vertices, generator=g, device=device)
         lo, hi = perm[lo], perm[hi]
+    first, last = (0, n_vertices) if rows is None else rows
+    if lo.is_cuda and n_vertices < (1 << 31) and os.environ.get("GAI_DATAGEN_TORCH", "0") != "1":
+        # CSR construction on the device (csrc/convert.cu: keys, radix sort, unique, offsets — the reference converter's edge SET), the
+        # same routine gpu_converter uses; the CSR of an edge set is unique, so this returns what the torch construction below does
+        from . import ops
+        rowptr, colidx = ops.coo_to_csr(n_vertices, lo.to(torch.int32), hi.to(torch.int32), symmetrize=True)
+        del lo, hi
+        if rows is not None:
+            b, e = int(rowptr[first]), int(rowptr[last])
+            rowptr, colidx = rowptr[first:last + 1] - b, colidx[b:e]
+        return rowptr, colidx.to(torch.int64)
     s = torch.cat([lo, hi])
     d = torch.cat([hi, lo])
     del lo, hi
-    first, last = (0, n_vertices) if rows is None else rows
     if rows is not None:
         sel = (s >= first) & (s < last)
         s, d = s[sel], d[sel]

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 
 namespace gai_host {
 static thread_local gai_stream_t g_stream = nullptr;
@@ -238,6 +239,115 @@ static void read_exact(const std::string& fname, T* dst, size_t count) {
   std::ifstream in(fname.c_str(), std::ios::binary);
   if (!in.good()) { std::cerr << "Failed to open file: " << fname << "\n"; std::exit(1); }
   in.read(reinterpret_cast<char*>(dst), sizeof(T) * count);
+}
+
+// ---- legacy .csgr / text layout (reader.cpp:16-246) ----------------------------------------------------------------------------
+
+static std::string dataset_root() {
+  const char* root = std::getenv("DATASET_PATH");
+  if (!root) { std::cerr << "DATASET_PATH is not set\n"; std::exit(1); }
+  return std::string(root);
+}
+
+size_t Reader::csgr_read_labels(std::vector<label_t>& labels, bool is_single_class) {  // reader.cpp:16-64
+  const std::string filename = dataset_root() + dataset_str + "/" + dataset_str + "-labels.txt";
+  std::ifstream in(filename.c_str(), std::ios::in);
+  std::string line;
+  size_t m = 0, num_classes = 0;
+  in >> m >> num_classes >> std::ws;
+  gai_host::out() << (is_single_class ? "Using single-class (one-hot) labels\n" : "Using multi-class (multi-hot) labels\n");
+  labels.assign(is_single_class ? m : m * num_classes, 0);
+  gai_host::out() << "Number of classes (unique label counts): " << num_classes << "\n";
+  size_t v = 0;
+  while (std::getline(in, line) && v < m) {
+    std::istringstream label_stream(line);
+    unsigned x = 0;
+    for (size_t idx = 0; idx < num_classes; ++idx) {
+      label_stream >> x;
+      if (is_single_class) {
+        if (x != 0) { labels[v] = (label_t)idx; break; }  // the first non-zero column is the class
+      } else {
+        labels[v * num_classes + idx] = (label_t)x;
+      }
+    }
+    v++;
+  }
+  num_vertex_classes = (int)num_classes;
+  return num_classes;
+}
+
+size_t Reader::csgr_read_features(std::vector<float>& feats, std::string filetype) {  // reader.cpp:68-121
+  size_t m = 0, flen = 0;
+  const std::string base = dataset_root() + dataset_str + "/" + dataset_str;
+  if (filetype == "bin") {
+    std::ifstream dims((base + "-dims.txt").c_str(), std::ios::in);
+    dims >> m >> flen >> std::ws;
+    gai_host::out() << "Reading features ... N x D: " << m << " x " << flen << "\n";
+    feats.assign(m * flen, 0.f);
+    std::ifstream in((base + "-feats.bin").c_str(), std::ios::binary | std::ios::in);
+    if (!feats.empty()) in.read(reinterpret_cast<char*>(feats.data()), sizeof(float) * feats.size());
+  } else {  // "<row> <col> <value>" triples
+    std::ifstream in((base + ".ft").c_str(), std::ios::in);
+    in >> m >> flen >> std::ws;
+    gai_host::out() << "Reading features ... N x D: " << m << " x " << flen << "\n";
+    feats.assign(m * flen, 0.f);
+    std::string line;
+    while (std::getline(in, line)) {
+      std::istringstream s(line);
+      size_t u = 0, v = 0;
+      float w = 0.f;
+      s >> u >> v >> w;
+      if (u < m && v < flen) feats[u * flen + v] = w;
+    }
+  }
+  feat_len = (index_t)flen;
+  return flen;
+}
+
+size_t Reader::csgr_read_masks(std::string mask_type, size_t n, size_t& begin, size_t& end, mask_t* masks) {  // reader.cpp:125-171
+  bool known = false;
+  for (const char* d : kDatasets) known = known || dataset_str == d;
+  if (!known) { std::cout << "Dataset currently not supported\n"; std::exit(1); }
+  const std::string filename = dataset_root() + dataset_str + "/" + dataset_str + "-" + mask_type + "_mask.txt";
+  std::ifstream in(filename.c_str(), std::ios::in);
+  std::string line;
+  in >> begin >> end >> std::ws;
+  size_t i = 0, sample_count = 0;
+  while (std::getline(in, line)) {
+    std::istringstream mask_stream(line);
+    if (i >= begin && i < end) {
+      unsigned mask = 0;
+      mask_stream >> mask;
+      if (mask == 1) { masks[i] = 1; sample_count++; }
+    }
+    i++;
+  }
+  gai_host::out() << mask_type << "_mask range: [" << begin << ", " << end << ") Number of valid samples: " << sample_count << " ("
+                  << (float)sample_count / (float)n * 100.0f << "%)\n";
+  return sample_count;
+}
+
+void Reader::csgr_read_graph(LearningGraph* g) {  // reader.cpp:173-246: Galois .gr v1 — header {version, sizeof(edge data), nv, ne}, u64 row ENDS, u32 columns
+  gai_host::out() << "Reading graph into CPU memory\n";
+  const std::string filename = dataset_root() + dataset_str + "/" + dataset_str + ".csgr";
+  std::ifstream in(filename.c_str(), std::ios::binary);
+  if (!in.good()) { std::cout << "LearningGraph: unable to open " << filename << "\n"; std::exit(1); }
+  uint64_t header[4] = {0, 0, 0, 0};
+  in.read(reinterpret_cast<char*>(header), sizeof(header));
+  assert(header[0] == 1);
+  if (header[1] != 0) { std::cout << "LearningGraph: currently edge data not supported.\n"; std::exit(1); }
+  const uint64_t nv = header[2], ne = header[3];
+  std::vector<uint64_t> ends(nv);
+  in.read(reinterpret_cast<char*>(ends.data()), sizeof(uint64_t) * nv);
+  g->allocateFrom((index_t)nv, (index_t)ne);
+  in.read(reinterpret_cast<char*>(g->edge_dst_host_ptr()), sizeof(uint32_t) * ne);
+  for (uint64_t v = 0; v < nv; v++) g->fixEndEdge((index_t)v, (index_t)ends[v]);
+  const index_t* ci = g->edge_dst_host_ptr();
+  for (uint64_t e = 0; e < ne; e++)
+    if (ci[e] >= nv) { printf("\tinvalid edge to %u at index %llu.\n", ci[e], (unsigned long long)e); std::exit(0); }
+  num_vertices_ = (index_t)nv; num_edges_ = (index_t)ne;
+  g->degree_counting();
+  gai_host::out() << "|V| " << nv << " |E| " << ne << " max_deg " << g->get_max_degree() << "\n";
 }
 
 void Reader::bin_read_graph(LearningGraph* g) {

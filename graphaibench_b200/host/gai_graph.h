@@ -131,6 +131,13 @@ class Reader {
   explicit Reader(std::string dataset) : dataset_str(dataset) {}
   void init(std::string dataset) { dataset_str = dataset; }
 
+  // legacy text / .csgr dataset layout (reader.cpp:16-246): <DATASET_PATH><name>/<name>.csgr, <name>-labels.txt, <name>.ft or
+  // <name>-feats.bin + <name>-dims.txt, <name>-{train,val,test}_mask.txt
+  size_t csgr_read_labels(std::vector<label_t>& labels, bool is_single_class = true);
+  size_t csgr_read_features(std::vector<float>& feats, std::string filetype = "bin");
+  size_t csgr_read_masks(std::string mask_type, size_t n, size_t& begin, size_t& end, mask_t* masks);
+  void csgr_read_graph(LearningGraph* g);
+
   void bin_read_graph(LearningGraph* g);
   size_t bin_read_features(std::vector<float>& feats);
   int bin_read_vlabels(std::vector<label_t>& labels, bool is_single_class = true);

@@ -2,6 +2,7 @@
 // reference-facing surface is the C++ API in gai_graph.h / gai_layers.h / gai_model.h.
 #include <cstring>
 #include <thread>
+#include "gai_converter.h"
 #include "gai_model.h"
 
 namespace {
@@ -236,6 +237,54 @@ int gai_host_partition_rows(int world, int rank, uint32_t nv_global, const int64
     std::copy(g.row_start_host_ptr(), g.row_start_host_ptr() + n + 1, rowptr_out);
     std::copy(g.edge_dst_host_ptr(), g.edge_dst_host_ptr() + g.sizeEdges(), colidx_out);
     std::copy(g.halo_global_ids().begin(), g.halo_global_ids().end(), halo_out);
+  }
+  return 0;
+}
+// Converter (host/gai_converter.h) for ctypes callers: file -> files, and pairs -> CSR (two-call: rowptr_out == NULL returns nv/ne in sizes).
+int gai_convert_file(const char* file_type, const char* infile, const char* out_prefix, int is_bipartite) {
+  Converter c(file_type, infile, is_bipartite != 0);
+  c.generate_binary_graph(out_prefix, true, true, false, false);
+  c.write_meta(out_prefix);
+  return 0;
+}
+int gai_convert_pairs(int64_t nv, const uint32_t* src, const uint32_t* dst, uint64_t n, int symmetrize, int64_t* sizes, int64_t* rowptr_out, uint32_t* colidx_out) {
+  static thread_local Converter* last = nullptr;
+  if (!rowptr_out) {
+    delete last;
+    last = new Converter();
+    last->from_pairs(nv, src, dst, (size_t)n, symmetrize != 0);
+    sizes[0] = last->V(); sizes[1] = last->E();
+    return 0;
+  }
+  if (!last) return -1;
+  std::copy(last->row_offsets().begin(), last->row_offsets().end(), rowptr_out);
+  std::copy(last->column_indices().begin(), last->column_indices().end(), colidx_out);
+  delete last; last = nullptr;
+  return 0;
+}
+// The legacy loader (csgr_* methods) with the same two-call protocol; meta = {nv, ne, feat_len, num_classes, then (begin, end, count) of
+// train / val / test}; masks_out = 3 x nv bytes.
+int gai_reader_load_csgr(const char* dataset, int single_class, int64_t* meta, uint32_t* rowptr, uint32_t* colidx, float* feats, uint8_t* labels,
+                         uint8_t* masks_out) {
+  Reader reader{std::string(dataset)};
+  Graph g(true);
+  reader.csgr_read_graph(&g);
+  std::vector<float> f;
+  const size_t flen = reader.csgr_read_features(f, "bin");
+  std::vector<label_t> lab;
+  const size_t ncls = reader.csgr_read_labels(lab, single_class != 0);
+  std::vector<mask_t> masks(3 * g.size(), 0);
+  size_t b[3], e[3], c[3];
+  const char* kinds[3] = {"train", "val", "test"};
+  for (int i = 0; i < 3; i++) c[i] = reader.csgr_read_masks(kinds[i], g.size(), b[i], e[i], masks.data() + (size_t)i * g.size());
+  meta[0] = (int64_t)g.size(); meta[1] = (int64_t)g.sizeEdges(); meta[2] = (int64_t)flen; meta[3] = (int64_t)ncls;
+  for (int i = 0; i < 3; i++) { meta[4 + 3 * i] = (int64_t)b[i]; meta[5 + 3 * i] = (int64_t)e[i]; meta[6 + 3 * i] = (int64_t)c[i]; }
+  if (rowptr) {
+    memcpy(rowptr, g.row_start_host_ptr(), sizeof(uint32_t) * (g.size() + 1));
+    memcpy(colidx, g.edge_dst_host_ptr(), sizeof(uint32_t) * g.sizeEdges());
+    memcpy(feats, f.data(), sizeof(float) * f.size());
+    memcpy(labels, lab.data(), lab.size());
+    memcpy(masks_out, masks.data(), masks.size());
   }
   return 0;
 }

@@ -102,6 +102,34 @@ def add_selfloop(rowptr, colidx):
     return rpo, cio
 
 
+def coo_to_csr(nv, src, dst, symmetrize=True):
+    """Device CSR construction (csrc/convert.cu): int32/uint32 COO tensors on the GPU -> (rowptr int64[nv+1], colidx int32[nnz]) tensors:
+    self-loops and ids >= nv dropped, mirrors added if `symmetrize`, duplicates removed, rows sorted — the reference converter's edge SET."""
+    assert src.is_cuda and dst.is_cuda and src.numel() == dst.numel() and src.element_size() == 4 and dst.element_size() == 4
+    src, dst = src.contiguous(), dst.contiguous()
+    rp, ci, nnz = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    check(lib().gai_coo_to_csr(nv, src.numel(), src.data_ptr(), dst.data_ptr(), int(symmetrize), _stream(), C.byref(rp), C.byref(ci), C.byref(nnz)),
+          "gai_coo_to_csr")
+    rowptr = torch.empty(nv + 1, dtype=torch.int64, device=src.device)
+    colidx = torch.empty(nnz.value, dtype=torch.int32, device=src.device)
+    check(lib().gai_memcpy_d2d(rowptr.data_ptr(), rp, 8 * (nv + 1), _stream()), "gai_memcpy_d2d")
+    if nnz.value:
+        check(lib().gai_memcpy_d2d(colidx.data_ptr(), ci, 4 * nnz.value, _stream()), "gai_memcpy_d2d")
+    check(lib().gai_stream_sync(_stream()), "gai_stream_sync")
+    lib().gai_free(rp); lib().gai_free(ci)
+    return rowptr, colidx
+
+
+def add_selfloop_device(rowptr, colidx, first_id=0):
+    """LearningGraph::add_selfloop on the device (int32 tensors): row r gains the id first_id + r at its sorted place."""
+    nv = rowptr.numel() - 1
+    rpo = torch.empty(nv + 1, dtype=torch.int32, device=rowptr.device)
+    cio = torch.empty(colidx.numel() + nv, dtype=torch.int32, device=rowptr.device)
+    check(lib().gai_add_selfloop_d(nv, first_id, rowptr.contiguous().data_ptr(), colidx.contiguous().data_ptr(), rpo.data_ptr(), cio.data_ptr(), _stream()),
+          "gai_add_selfloop_d")
+    return rpo, cio
+
+
 def _ld(t):
     return t.stride(0) if t.dim() == 2 else t.numel()
 

@@ -72,6 +72,19 @@ uint64_t gai_launch_count(void); /* kernels launched by this library since load 
 /* LearningGraph::add_selfloop (include/gnn/lgraph.h:185-218). colidx_out_h has nnz+nv entries. */
 int gai_add_selfloop_h(uint32_t nv, const uint32_t* rowptr_h, const uint32_t* colidx_h, uint32_t* rowptr_out_h, uint32_t* colidx_out_h);
 
+/* ---- CSR construction on the device (csrc/convert.cu) ----------------------------------------------------------------
+ * COO pairs -> sorted, de-duplicated CSR: what the reference's text converter builds on the host with one std::set per vertex
+ * (Converter::read_mtx + adjlist2CSR, src/converters/converter.cc:27-60,314-420): self-loops (and ids >= nv) dropped, with
+ * `symmetrize` the reverse of every kept pair added, duplicates removed, rows in ascending neighbour order, int64 row offsets
+ * (eidType, as GraphT::write_to_file stores them, src/common/graph.cc:467-508). Inputs and outputs are DEVICE arrays; the two outputs
+ * are allocated here (release with gai_free). Synchronises `stream` (the edge count comes back to the host). */
+int gai_coo_to_csr(uint32_t nv, uint64_t n_pairs, const uint32_t* src_d, const uint32_t* dst_d, int symmetrize, gai_stream_t stream,
+                   int64_t** rowptr_out_d, uint32_t** colidx_out_d, uint64_t* nnz_out);
+/* LearningGraph::add_selfloop (lgraph.h:185-218) on the device: row i gains the id first_id + i at its sorted place (first_id = 0 for a
+ * whole graph, the first master id for one rank's rows). Out arrays: nv + 1 offsets, nnz + nv columns; must not alias the inputs. */
+int gai_add_selfloop_d(uint32_t nv, uint32_t first_id, const uint32_t* rowptr_d, const uint32_t* colidx_d, uint32_t* rowptr_out_d,
+                       uint32_t* colidx_out_d, gai_stream_t stream);
+
 /* ---- device CSR: replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data/compute_edge_data
  *      (src/gnn/lgraph.cu:51-140) and the role of GraphGPU::init (include/graph_gpu.h:207-243). -------------
  * Uploads rowptr (u32, nv+1) and colidx (u32, nnz), then on the device computes
@@ -92,6 +105,10 @@ const float* gai_csr_mean_norm(gai_csr_t g);   /* 1 / deg (sage_aggregator.cpp:1
 /* Override the per-vertex normalisers with values computed elsewhere (1D partition: norms come from GLOBAL degrees). */
 int gai_csr_set_norms(gai_csr_t g, const float* norm_gcn_d, const float* norm_mean_d, gai_stream_t stream);
 uint32_t gai_csr_num_hub_rows(gai_csr_t g);
+uint32_t gai_csr_max_degree(gai_csr_t g);      /* GraphGPU::get_max_degree (graph_gpu.h:74): longest row */
+/* A consumer of the GraphGPU accessor surface (include/gai_graph_gpu.cuh) on this device CSR: the reference's vertex-parallel triangle
+ * kernel (src/triangle/gpu_kernels/bs_warp_vertex.cuh) over rows [begin, end): *count_h = sum_v sum_{u in N(v)} |N(v) ∩ N(u)|. */
+int gai_triangle_count_rows(gai_csr_t g, uint32_t begin, uint32_t end, uint64_t* count_h, gai_stream_t stream);
 /* Register up to 8 row segments [bounds_h[2i], bounds_h[2i+1]) (1D partition: interior rows, boundary rows, all masters; they
  * may overlap). Each gets its own
  * degree-ordered, edge-budgeted work list, used by the *_rows entry points when called with exactly those bounds; any other

@@ -77,5 +77,15 @@ if [ -f "$HERE/ref_part_harness.cpp" ]; then
     "$R/src/common/VertexSet.cc" "$R/src/common/graph.cc" "$R/src/partitioner/graph_partition.cc" \
     "$HERE/ref_part_harness.cpp" -o "$OUT/libref_part.so"
 fi
+# text -> CSR converter (src/converters/converter.cc + src/common/{graph,VertexSet}.cc, no external deps) behind oracle/ref_conv_harness.cpp.
+#   patch 6  converter.cc: `new Graph(nv, ne)` with two uint64_t arguments is ambiguous between GraphT(vidType, eidType) and
+#            GraphT(bool, bool) under g++ 13 (4 call sites) -> explicit casts to the intended (vidType, eidType) overload
+if [ -f "$HERE/ref_conv_harness.cpp" ]; then
+  mkdir -p "$R/src/converters"
+  cp "$REF/src/converters/converter.cc" "$REF/src/converters/converter.h" "$R/src/converters/"
+  sed -i 's/new Graph(nv, ne)/new Graph((vidType)nv, (eidType)ne)/' "$R/src/converters/converter.cc"
+  g++ -O2 -fopenmp -std=c++17 -w -I"$R/include" -I"$R/src/converters" \
+    "$R/src/common/VertexSet.cc" "$R/src/common/graph.cc" "$R/src/converters/converter.cc" "$HERE/ref_conv_harness.cpp" -o "$OUT/ref_convert"
+fi
 rm -rf "$SCRATCH"
 ls -la "$OUT"

