@@ -31,7 +31,9 @@ constexpr uint32_t WG_SEG_KB = 2048 / WG_BK;  // k-blocks (2048 rows) one TMEM a
                                           // tensor core adds into TMEM with truncation, so the error of one accumulator grows linearly with the k-steps
                                           // it absorbs. One accumulator per CTA over 2.45 M rows (16.5 K rows each) measured 0.9-1.3e-4 of the result
                                           // norm against the exact fp64 product — 20x the reference's OpenBLAS sgemm; segments of 2048 rows: 1-2e-5
-                                          // (tests/test_reference_parity_gpu.py). The flushes add round-to-nearest in ordinary fp32.
+                                          // (tests/test_reference_parity_gpu.py). Every segment is stored as a partial of its own (plain stores:
+                                          // a read-modify-write flush into one partial per CTA measured 35 us per flush — dependent L2 round trips)
+                                          // and the reduce kernel adds the partials in double.
 constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 splitters + epilogue
 constexpr int WG_SPLIT_WARPS = 8;
 
@@ -50,6 +52,7 @@ struct WgArgs {
   int my0;         // live columns of the first B part (the second starts at tile column 32*nbox_b0)
   int stages, passes;
   int ldp;         // row pitch of the partial (My rounded up to 4 floats)
+  int nseg;        // partial slots per CTA (segments of WG_SEG_KB k-blocks)
   uint32_t a_bytes, b_bytes, stage_bytes;
 };
 
@@ -190,7 +193,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv_bar[s]);
-      // ---------------- flush: TMEM accumulator -> (+=) this CTA's partial, once per segment ----------------
+      // ---------------- flush: TMEM accumulator -> the partial slot of this (CTA, segment) ----------------
       if ((it + 1) % WG_SEG_KB == 0 || it + 1 == nkb) {
         const uint32_t seg = it / WG_SEG_KB;
         const int tile = (warp - 4) >> 2;  // warps 4-7: M tile 0, warps 8-11: M tile 1
@@ -201,7 +204,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
           const int kl = q * 32 + lane;  // accumulator row within the tile
           const bool live = kl < g.rows_t[tile];
           const int kx = (tile ? g.rows_t[0] : 0) + kl;  // row of the concatenated partial
-          float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (live ? kx : 0)) * g.ldp;
+          float* prow = g.partial + (((size_t)blockIdx.x * g.nseg + seg) * g.Kx + (live ? kx : 0)) * g.ldp;
           for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
@@ -215,19 +218,17 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
               for (int j = 0; j < 32; j += 4) {
                 if (pc0 + j + 3 < lim) {
                   float4* dst = reinterpret_cast<float4*>(prow + pc0 + j);
-                  float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                  if (seg) { const float4 o = *dst; v.x = __fadd_rn(v.x, o.x); v.y = __fadd_rn(v.y, o.y); v.z = __fadd_rn(v.z, o.z); v.w = __fadd_rn(v.w, o.w); }
-                  *dst = v;
+                  *dst = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                 } else {
 #pragma unroll
                   for (int k = 0; k < 4; k++)
-                    if (pc0 + j + k < lim) prow[pc0 + j + k] = seg ? __fadd_rn(prow[pc0 + j + k], __uint_as_float(r[j + k])) : __uint_as_float(r[j + k]);
+                    if (pc0 + j + k < lim) prow[pc0 + j + k] = __uint_as_float(r[j + k]);
                 }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j++)
-                if (pc0 + j < lim) prow[pc0 + j] = seg ? __fadd_rn(prow[pc0 + j], __uint_as_float(r[j])) : __uint_as_float(r[j]);
+                if (pc0 + j < lim) prow[pc0 + j] = __uint_as_float(r[j]);
             }
           }
           tcgen05_fence_before();
@@ -250,17 +251,25 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
 // its destinations: rows >= kx0 belong to C1 (two-A form), columns >= my0 belong to C1 (two-B form).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C0, size_t ldc0, float* __restrict__ C1, size_t ldc1,
                                     int Kx, int My, int ldp, int kx0, int my0, int parts, int accum) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Kx * My) return;
-  int m = i / My, n = i % My;
+  // 8 lanes per output element, each adding every 8th partial in double; a butterfly over the 8 lanes finishes the sum (fixed order:
+  // the same bits run to run). Slots a short last CTA never wrote are zero (the launch clears the buffer).
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, slice = t & 7;
+  const bool live = i < Kx * My;
+  const int m = live ? i / My : 0, n = live ? i % My : 0;
+  const size_t stride = (size_t)Kx * ldp, off = (size_t)m * ldp + n;
+  double r = 0.0;
+  if (live)
+    for (int p = slice; p < parts; p += 8) r += (double)partial[(size_t)p * stride + off];
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  if (!live || slice != 0) return;
   float* dst;
   if (m >= kx0) dst = C1 + (size_t)(m - kx0) * ldc1 + n;
   else if (n >= my0) dst = C1 + (size_t)m * ldc1 + (n - my0);
   else dst = C0 + (size_t)m * ldc0 + n;
-  double r = accum ? (double)*dst : 0.0;
-  const size_t stride = (size_t)Kx * ldp, off = (size_t)m * ldp + n;
-  for (int p = 0; p < parts; p++) r += (double)partial[(size_t)p * stride + off];
-  *dst = (float)r;
+  *dst = (float)(r + (accum ? (double)*dst : 0.0));
 }
 
 // [n x F] (ld) -> [n x Fp], zero-filled tail columns (operands whose row pitch is not a multiple of 16 bytes)
@@ -324,12 +333,15 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   g.blocks_per_cta = (total_kb + grid - 1) / grid;
   grid = (total_kb + g.blocks_per_cta - 1) / g.blocks_per_cta;  // every CTA owns at least one k-block
   g.ldp = (g.My + 3) / 4 * 4;
+  g.nseg = (int)((g.blocks_per_cta + WG_SEG_KB - 1) / WG_SEG_KB);
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
-  int rc = workspace(sizeof(float) * grid * g.Kx * g.ldp, &ws, st);
+  const size_t partial_bytes = sizeof(float) * grid * g.nseg * g.Kx * g.ldp;
+  int rc = workspace(partial_bytes, &ws, st);
   if (rc != GAI_OK) return rc;
   g.partial = reinterpret_cast<float*>(ws);
+  GAI_CUDA(cudaMemsetAsync(ws, 0, partial_bytes, st));  // the last CTA may own fewer segments than the others
   const float* src[4] = {q.A[0], na == 2 ? q.A[1] : q.A[0], q.B[0], nb == 2 ? q.B[1] : q.B[0]};
   size_t ld[4] = {q.lda[0], na == 2 ? q.lda[1] : q.lda[0], q.ldb[0], nb == 2 ? q.ldb[1] : q.ldb[0]};
   size_t cols[4] = {q.Kx[0], na == 2 ? q.Kx[1] : q.Kx[0], q.My[0], nb == 2 ? q.My[1] : q.My[0]};
@@ -372,7 +384,7 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   const int kx0 = na == 2 ? (int)q.Kx[0] : g.Kx, my0 = nb == 2 ? (int)q.My[0] : g.My;
   float* C1 = q.dual ? q.C[1] : q.C[0];
   const size_t ldc1 = q.dual ? q.ldc[1] : q.ldc[0];
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, g.ldp, kx0, my0, (int)grid, q.accum);
+  wgrad_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, g.ldp, kx0, my0, (int)grid * g.nseg, q.accum);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
