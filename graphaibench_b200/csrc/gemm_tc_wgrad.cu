@@ -31,9 +31,11 @@ constexpr uint32_t WG_SEG_KB = 2048 / WG_BK;  // k-blocks (2048 rows) one TMEM a
                                           // tensor core adds into TMEM with truncation, so the error of one accumulator grows linearly with the k-steps
                                           // it absorbs. One accumulator per CTA over 2.45 M rows (16.5 K rows each) measured 0.9-1.3e-4 of the result
                                           // norm against the exact fp64 product — 20x the reference's OpenBLAS sgemm; segments of 2048 rows: 1-2e-5
-                                          // (tests/test_reference_parity_gpu.py). Every segment is stored as a partial of its own (plain stores:
-                                          // a read-modify-write flush into one partial per CTA measured 35 us per flush — dependent L2 round trips)
-                                          // and the reduce kernel adds the partials in double.
+                                          // (tests/test_reference_parity_gpu.py). Each flush adds the segment into the CTA's L2-resident partial with
+                                          // ordinary round-to-nearest fp32 adds, the old values of a 32-column chunk requested together before the
+                                          // TMEM read-back (one dependent load per value measured 35 us per flush; one partial slot per segment
+                                          // cost as much in memset + write + re-read traffic: 3 x 242 MB per call). The reduce kernel adds the
+                                          // CTAs' partials in double.
 constexpr int WG_THREADS = 384;           // warp 0 TMA, warp 1 MMA, warps 4-11 splitters + epilogue
 constexpr int WG_SPLIT_WARPS = 8;
 
@@ -52,7 +54,6 @@ struct WgArgs {
   int my0;         // live columns of the first B part (the second starts at tile column 32*nbox_b0)
   int stages, passes;
   int ldp;         // row pitch of the partial (My rounded up to 4 floats)
-  int nseg;        // partial slots per CTA (segments of WG_SEG_KB k-blocks)
   uint32_t a_bytes, b_bytes, stage_bytes;
 };
 
@@ -204,31 +205,38 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
           const int kl = q * 32 + lane;  // accumulator row within the tile
           const bool live = kl < g.rows_t[tile];
           const int kx = (tile ? g.rows_t[0] : 0) + kl;  // row of the concatenated partial
-          float* prow = g.partial + (((size_t)blockIdx.x * g.nseg + seg) * g.Kx + (live ? kx : 0)) * g.ldp;
+          float* prow = g.partial + ((size_t)blockIdx.x * g.Kx + (live ? kx : 0)) * g.ldp;
           for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
             // tile columns -> concatenated partial columns: part 0 at [0, my0), part 1 from tile column 32*nbox_b0
             const int part1 = c0 >= 32 * g.nbox_b0;
             const int pc0 = part1 ? g.my0 + c0 - 32 * g.nbox_b0 : c0;
             const int lim = part1 ? g.My : g.my0;
-            if (!live) continue;
-            if ((pc0 & 3) == 0) {  // 16-byte aligned run of this lane's row (rows are pitched to 4 floats): 128-bit read-modify-write
+            const bool vec = (pc0 & 3) == 0;  // 16-byte aligned run of this lane's row (rows are pitched to 4 floats)
+            float4 old[8];
+            if (seg && live && vec) {  // the running sums of this chunk, all eight requests in flight together
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (pc0 + j + 3 < lim) {
-                  float4* dst = reinterpret_cast<float4*>(prow + pc0 + j);
-                  *dst = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              for (int j = 0; j < 8; j++) old[j] = (pc0 + 4 * j + 3 < lim) ? *reinterpret_cast<const float4*>(prow + pc0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tile * 256u + (uint32_t)c0, r);
+            if (!live) continue;
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                if (pc0 + 4 * j + 3 < lim) {
+                  float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                  if (seg) { v.x = __fadd_rn(v.x, old[j].x); v.y = __fadd_rn(v.y, old[j].y); v.z = __fadd_rn(v.z, old[j].z); v.w = __fadd_rn(v.w, old[j].w); }
+                  *reinterpret_cast<float4*>(prow + pc0 + 4 * j) = v;
                 } else {
 #pragma unroll
                   for (int k = 0; k < 4; k++)
-                    if (pc0 + j + k < lim) prow[pc0 + j + k] = __uint_as_float(r[j + k]);
+                    if (pc0 + 4 * j + k < lim) prow[pc0 + 4 * j + k] = seg ? __fadd_rn(prow[pc0 + 4 * j + k], __uint_as_float(r[4 * j + k])) : __uint_as_float(r[4 * j + k]);
                 }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j++)
-                if (pc0 + j < lim) prow[pc0 + j] = __uint_as_float(r[j]);
+                if (pc0 + j < lim) prow[pc0 + j] = seg ? __fadd_rn(prow[pc0 + j], __uint_as_float(r[j])) : __uint_as_float(r[j]);
             }
           }
           tcgen05_fence_before();
@@ -252,7 +260,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C0, size_t ldc0, float* __restrict__ C1, size_t ldc1,
                                     int Kx, int My, int ldp, int kx0, int my0, int parts, int accum) {
   // 8 lanes per output element, each adding every 8th partial in double; a butterfly over the 8 lanes finishes the sum (fixed order:
-  // the same bits run to run). Slots a short last CTA never wrote are zero (the launch clears the buffer).
+  // the same bits run to run).
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = t >> 3, slice = t & 7;
   const bool live = i < Kx * My;
@@ -333,15 +341,12 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   g.blocks_per_cta = (total_kb + grid - 1) / grid;
   grid = (total_kb + g.blocks_per_cta - 1) / g.blocks_per_cta;  // every CTA owns at least one k-block
   g.ldp = (g.My + 3) / 4 * 4;
-  g.nseg = (int)((g.blocks_per_cta + WG_SEG_KB - 1) / WG_SEG_KB);
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
-  const size_t partial_bytes = sizeof(float) * grid * g.nseg * g.Kx * g.ldp;
-  int rc = workspace(partial_bytes, &ws, st);
+  int rc = workspace(sizeof(float) * grid * g.Kx * g.ldp, &ws, st);
   if (rc != GAI_OK) return rc;
   g.partial = reinterpret_cast<float*>(ws);
-  GAI_CUDA(cudaMemsetAsync(ws, 0, partial_bytes, st));  // the last CTA may own fewer segments than the others
   const float* src[4] = {q.A[0], na == 2 ? q.A[1] : q.A[0], q.B[0], nb == 2 ? q.B[1] : q.B[0]};
   size_t ld[4] = {q.lda[0], na == 2 ? q.lda[1] : q.lda[0], q.ldb[0], nb == 2 ? q.ldb[1] : q.ldb[0]};
   size_t cols[4] = {q.Kx[0], na == 2 ? q.Kx[1] : q.Kx[0], q.My[0], nb == 2 ? q.My[1] : q.My[0]};
@@ -384,7 +389,7 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   const int kx0 = na == 2 ? (int)q.Kx[0] : g.Kx, my0 = nb == 2 ? (int)q.My[0] : g.My;
   float* C1 = q.dual ? q.C[1] : q.C[0];
   const size_t ldc1 = q.dual ? q.ldc[1] : q.ldc[0];
-  wgrad_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, g.ldp, kx0, my0, (int)grid * g.nseg, q.accum);
+  wgrad_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(g.partial, q.C[0], q.ldc[0], C1, ldc1, g.Kx, g.My, g.ldp, kx0, my0, (int)grid, q.accum);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

