@@ -53,7 +53,8 @@ struct WgArgs {
   int nbox_b, nbox_b0;  // B boxes; the first nbox_b0 stream from map_b[0], the rest from map_b[1]
   int my0;         // live columns of the first B part (the second starts at tile column 32*nbox_b0)
   int stages, passes;
-  int ldp;         // row pitch of the partial (My rounded up to 4 floats)
+  int ldp;         // row pitch of the partial: each B part's columns padded to 4 floats (part 1 starts at my0p)
+  int my0p;        // my0 rounded up to 4: a lane's 32-column run of either part is then 16-byte aligned
   uint32_t a_bytes, b_bytes, stage_bytes;
 };
 
@@ -209,9 +210,9 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
           for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
             // tile columns -> concatenated partial columns: part 0 at [0, my0), part 1 from tile column 32*nbox_b0
             const int part1 = c0 >= 32 * g.nbox_b0;
-            const int pc0 = part1 ? g.my0 + c0 - 32 * g.nbox_b0 : c0;
-            const int lim = part1 ? g.My : g.my0;
-            const bool vec = (pc0 & 3) == 0;  // 16-byte aligned run of this lane's row (rows are pitched to 4 floats)
+            const int pc0 = part1 ? g.my0p + c0 - 32 * g.nbox_b0 : c0;
+            const int lim = part1 ? g.my0p + (g.My - g.my0) : g.my0;
+            const bool vec = true;  // pc0 is a multiple of 4 by construction (my0p, 32-column chunks) and rows are pitched to 4 floats
             float4 old[8];
             if (seg && live && vec) {  // the running sums of this chunk, all eight requests in flight together
 #pragma unroll
@@ -265,7 +266,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int i = t >> 3, slice = t & 7;
   const bool live = i < Kx * My;
   const int m = live ? i / My : 0, n = live ? i % My : 0;
-  const size_t stride = (size_t)Kx * ldp, off = (size_t)m * ldp + n;
+  const int my0p = (my0 + 3) / 4 * 4;
+  const size_t stride = (size_t)Kx * ldp, off = (size_t)m * ldp + (n >= my0 ? my0p + (n - my0) : n);
   double r = 0.0;
   if (live)
     for (int p = slice; p < parts; p += 8) r += (double)partial[(size_t)p * stride + off];
@@ -340,7 +342,8 @@ int gemm_tc_wgrad_cat(const WgradCat& q, int passes, cudaStream_t st) {
   size_t grid = total_kb < (size_t)sm_count() ? total_kb : (size_t)sm_count();
   g.blocks_per_cta = (total_kb + grid - 1) / grid;
   grid = (total_kb + g.blocks_per_cta - 1) / g.blocks_per_cta;  // every CTA owns at least one k-block
-  g.ldp = (g.My + 3) / 4 * 4;
+  g.my0p = (g.my0 + 3) / 4 * 4;
+  g.ldp = g.my0p + ((g.My - g.my0) + 3) / 4 * 4;
 
   // workspace slot 0: per-CTA partials; slot 2: padded copies of operands TMA cannot address
   void* ws = nullptr;
