@@ -44,6 +44,7 @@ _SIGS = {
     "gai_add_selfloop_h": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gai_coo_to_csr": (C.c_int, [C.c_uint32, C.c_uint64, c_u32p, c_u32p, C.c_int, c_stream, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "gai_add_selfloop_d": (C.c_int, [C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, c_u32p, c_stream]),
+    "gai_induced_subgraph": (C.c_int, [C.c_void_p, C.c_uint32, c_u32p, c_stream, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "gai_csr_create": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_csr_create_device": (C.c_int, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_csr_destroy": (C.c_int, [C.c_void_p]),

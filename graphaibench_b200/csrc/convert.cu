@@ -67,6 +67,35 @@ __global__ void selfloop_kernel(uint32_t nv, uint32_t first, const uint32_t* __r
   if (lane == 0) { o[pos - b] = self; rowptr_out[i] = b + i; }
 }
 
+// ---- induced subgraph, re-indexed (Sampler::generateSubgraph: getMaskedGraph + reindexSubgraph, src/gnn/sampler.cpp:66-158) -----------
+// new_id[v] = rank of v in the ascending keep list, 0xffffffff for vertices outside it
+__global__ void scatter_ids_kernel(uint32_t n_keep, const uint32_t* __restrict__ keep, uint32_t* __restrict__ new_id) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_keep) new_id[keep[i]] = i;
+}
+// one warp per kept vertex. FILL = false: deg[i] = neighbours that are kept; FILL = true: their new ids, in the row's (ascending) order,
+// written from out_rowptr[i] — a ballot prefix keeps the order inside each batch of 32 neighbours
+template <bool FILL>
+__global__ void induced_rows_kernel(uint32_t n_keep, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rowptr,
+                                    const uint32_t* __restrict__ colidx, const uint32_t* __restrict__ new_id, uint32_t* __restrict__ deg,
+                                    const uint32_t* __restrict__ out_rowptr, uint32_t* __restrict__ out_colidx) {
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_keep) return;
+  const uint32_t v = keep[w];
+  const uint32_t b = rowptr[v], e = rowptr[v + 1];
+  uint32_t count = 0;
+  uint32_t* out = FILL ? out_colidx + out_rowptr[w] : nullptr;
+  for (uint32_t k0 = b; k0 < e; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    const uint32_t id = k < e ? new_id[colidx[k]] : 0xffffffffu;
+    const unsigned kept = __ballot_sync(0xffffffffu, id != 0xffffffffu);
+    if (FILL && id != 0xffffffffu) out[count + __popc(kept & ((1u << lane) - 1u))] = id;
+    count += __popc(kept);
+  }
+  if (!FILL && lane == 0) deg[w] = count;
+}
+
 inline unsigned blocks_for(size_t n, int per_block = 256) {
   size_t b = (n + per_block - 1) / per_block;
   const size_t cap = (size_t)gai::sm_count() * 32;
@@ -136,6 +165,46 @@ int gai_coo_to_csr(uint32_t nv, uint64_t n_pairs, const uint32_t* src_d, const u
     rowptr = nullptr;
   } while (0);
   cudaFree(keys); cudaFree(keys_alt); cudaFree(d_num); cudaFree(tmp); cudaFree(rowptr);
+  return rc;
+}
+
+int gai_induced_subgraph(gai_csr_t g, uint32_t n_keep, const uint32_t* keep_ids_d, gai_stream_t stream, uint32_t** rowptr_out_d, uint32_t** colidx_out_d,
+                         uint64_t* nnz_out) {
+  GAI_CHECK_ARG(g != nullptr && rowptr_out_d != nullptr && colidx_out_d != nullptr && nnz_out != nullptr && (keep_ids_d != nullptr || n_keep == 0));
+  cudaStream_t st = gai::S(stream);
+  const uint32_t nv = gai_csr_nv(g);
+  GAI_CHECK_ARG(n_keep <= nv);
+  *rowptr_out_d = nullptr; *colidx_out_d = nullptr; *nnz_out = 0;
+  uint32_t *new_id = nullptr, *deg = nullptr, *rp = nullptr, *ci = nullptr;
+  void* tmp = nullptr;
+  int rc = GAI_OK;
+  do {
+    if (cudaMalloc(&new_id, sizeof(uint32_t) * (nv ? nv : 1)) != cudaSuccess || cudaMalloc(&deg, sizeof(uint32_t) * ((size_t)n_keep + 1)) != cudaSuccess ||
+        cudaMalloc(&rp, sizeof(uint32_t) * ((size_t)n_keep + 1)) != cudaSuccess) { cudaGetLastError(); rc = gai::set_error(GAI_ERR_NOMEM, "gai_induced_subgraph", "scratch"); break; }
+    cudaMemsetAsync(new_id, 0xff, sizeof(uint32_t) * (nv ? nv : 1), st);
+    cudaMemsetAsync(deg, 0, sizeof(uint32_t) * ((size_t)n_keep + 1), st);
+    const unsigned warp_blocks = (unsigned)(((size_t)n_keep * 32 + 255) / 256);
+    if (n_keep) {
+      scatter_ids_kernel<<<(n_keep + 255) / 256, 256, 0, st>>>(n_keep, keep_ids_d, new_id);
+      induced_rows_kernel<false><<<warp_blocks, 256, 0, st>>>(n_keep, keep_ids_d, gai_csr_rowptr(g), gai_csr_colidx(g), new_id, deg, nullptr, nullptr);
+      __atomic_fetch_add(&gai::g_launches, 2ull, __ATOMIC_RELAXED);
+    }
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, rp, (int)n_keep + 1, st);  // n_keep + 1 items: the last output is the total
+    if (cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1) != cudaSuccess) { cudaGetLastError(); rc = gai::set_error(GAI_ERR_NOMEM, "gai_induced_subgraph", "scan workspace"); break; }
+    if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, rp, (int)n_keep + 1, st) != cudaSuccess) { rc = gai::set_error(GAI_ERR_CUDA, "gai_induced_subgraph", "scan"); break; }
+    uint32_t total = 0;
+    if (cudaMemcpyAsync(&total, rp + n_keep, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = gai::set_error(GAI_ERR_CUDA, "gai_induced_subgraph", cudaGetErrorString(cudaGetLastError())); break; }
+    if (cudaMalloc(&ci, sizeof(uint32_t) * (total ? total : 1)) != cudaSuccess) { cudaGetLastError(); rc = gai::set_error(GAI_ERR_NOMEM, "gai_induced_subgraph", "columns"); break; }
+    if (n_keep) {
+      induced_rows_kernel<true><<<warp_blocks, 256, 0, st>>>(n_keep, keep_ids_d, gai_csr_rowptr(g), gai_csr_colidx(g), new_id, nullptr, rp, ci);
+      __atomic_fetch_add(&gai::g_launches, 1ull, __ATOMIC_RELAXED);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = gai::set_error(GAI_ERR_CUDA, "gai_induced_subgraph", cudaGetErrorString(cudaGetLastError())); break; }
+    *rowptr_out_d = rp; *colidx_out_d = ci; *nnz_out = total;
+    rp = nullptr; ci = nullptr;
+  } while (0);
+  cudaFree(new_id); cudaFree(deg); cudaFree(tmp); cudaFree(rp); cudaFree(ci);
   return rc;
 }
 

@@ -4,6 +4,7 @@
 #include <thread>
 #include "gai_converter.h"
 #include "gai_model.h"
+#include "gai_sampler.h"
 
 namespace {
 struct ModelBase {
@@ -287,6 +288,40 @@ int gai_reader_load_csgr(const char* dataset, int single_class, int64_t* meta, u
     memcpy(masks_out, masks.data(), masks.size());
   }
   return 0;
+}
+// Sampler (host/gai_sampler.h) on an in-memory graph, same protocol as the reference-side harness (oracle/ref_harness.cpp:
+// ref_sampler_run). with_subgraph = 0 stops after select_vertices (host only, no device needed).
+int64_t gai_sampler_run(uint32_t nv, const uint32_t* rowptr, const uint32_t* colidx, const uint8_t* masks_train, size_t count, uint32_t n, unsigned seed,
+                        int with_subgraph, int64_t* sizes, uint32_t* set_out, uint32_t* rowptr_out, uint32_t* colidx_out) {
+  Graph full(true);
+  full.allocateFrom(nv, rowptr[nv]);
+  for (uint32_t v = 0; v < nv; v++) full.fixEndEdge(v, rowptr[v + 1]);
+  std::copy(colidx, colidx + rowptr[nv], full.edge_dst_host_ptr());
+  gai_host::set_quiet(true);
+  Graph* tg = full.generate_masked_graph(const_cast<mask_t*>(masks_train));
+  Sampler sampler(&full, tg, const_cast<mask_t*>(masks_train), count);
+  VertexSet st;
+  sampler.select_vertices(n, st, seed);
+  sizes[0] = (int64_t)st.size(); sizes[1] = 0;
+  Graph sg(true);
+  if (with_subgraph) {
+    full.copy_to_gpu();
+    std::vector<mask_t> masks(nv, 0);
+    sampler.generateSubgraph(st, masks.data(), &sg);
+    sizes[1] = (int64_t)sg.sizeEdges();
+  }
+  if (set_out) {
+    size_t i = 0;
+    for (auto v : st) set_out[i++] = v;
+    if (with_subgraph) {
+      std::copy(sg.row_start_host_ptr(), sg.row_start_host_ptr() + sg.size() + 1, rowptr_out);
+      std::copy(sg.edge_dst_host_ptr(), sg.edge_dst_host_ptr() + sg.sizeEdges(), colidx_out);
+    }
+  }
+  full.dealloc();
+  delete tg;
+  gai_host::set_quiet(false);
+  return (int64_t)st.size();
 }
 void gai_model_sync() { gai_stream_sync(gai_host::stream()); }
 }

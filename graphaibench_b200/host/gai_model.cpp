@@ -44,7 +44,7 @@ void Model<L>::load_data(int argc, char* argv[]) {
     inductive = atoi(argv[12]) != 0;
   }
   assert(num_layers >= 2);
-  if (subg_size > 0 || inductive) { std::cerr << "subgraph sampling / inductive training is out of scope of this build\n"; std::exit(1); }
+  if (subg_size > 0) inductive = true;  // net.cpp:157
   full_graph = new Graph(true);
   Reader reader(dataset_name);
   reader.bin_read_graph(full_graph);
@@ -60,6 +60,11 @@ void Model<L>::load_data(int argc, char* argv[]) {
   train_count = reader.bin_read_masks("train", num_samples, train_begin, train_end, nullptr);
   val_count = reader.bin_read_masks("val", num_samples, val_begin, val_end, nullptr);
   test_count = reader.bin_read_masks("test", num_samples, test_begin, test_end, nullptr);
+  if (partitioned() && (subg_size > 0 || inductive)) { std::cerr << "partitioned training runs the full graph only (no sampling / inductive mode)\n"; std::exit(1); }
+  if (subg_size > 0 && val_interval < num_epochs) {  // net.cpp:100-103
+    gai_host::out() << "disabling validation for subgraph sampling on GPU\n";
+    val_interval = num_epochs;
+  }
   if (partitioned()) {
     // every rank read the whole dataset; keep this rank's rows (global column ids, self-loops already in place), features and labels
     if (is_sigmoid) { std::cerr << "partitioned training supports the softmax loss only\n"; std::exit(1); }
@@ -134,13 +139,34 @@ void Model<L>::init_from_memory(gnn_arch a, Graph* g, int dinit, int ncls, const
 template <typename L>
 void Model<L>::finish_setup() {
   // l2norm + dense tail for GAT (net.cpp:67-71); masks from the meta ranges (net.cpp:126-142)
-  use_l2norm = (arch == gnn_arch::GAT);
+  use_l2norm = (arch == gnn_arch::GAT) || subg_size > 0;  // "l2norm+dense layer is useful for sampling and GAT" (net.cpp:67-71)
   use_dense = use_l2norm;
   masks_train.assign(num_samples, 0); masks_val.assign(num_samples, 0); masks_test.assign(num_samples, 0);
   for (size_t i = train_begin; i < train_end; i++) masks_train[i] = 1;
   for (size_t i = val_begin; i < val_end; i++) masks_val[i] = 1;
   for (size_t i = test_begin; i < test_end; i++) masks_test[i] = 1;
   training_graph = full_graph;
+  if (inductive) {
+    // net.cpp:154-172: train on the graph masked to the training vertices, evaluate on the full one; with sampling the masked graph is
+    // what the frontier walk reads and the subgraphs are induced from the full graph
+    assert((size_t)subg_size <= train_count);
+    training_graph = full_graph->generate_masked_graph(masks_train.data());
+    transfer_data_to_device();
+    full_graph->copy_to_gpu();
+    if (subg_size > 0) {
+      num_subgraphs = num_threads > 0 ? num_threads : 1;
+      sampler = new Sampler(full_graph, training_graph, masks_train.data(), train_count);
+      subgs.assign(num_subgraphs, nullptr);
+      subg_masks.assign((size_t)num_subgraphs * num_samples, 0);
+      d_feats_subg = float_malloc_device_zero((size_t)subg_size * row_pitch(dim_init));
+      void* p = nullptr;
+      die_on(gai_malloc(&p, (size_t)subg_size * (is_sigmoid ? num_cls : 1)), "gai_malloc"); d_labels_subg = reinterpret_cast<label_t*>(p);
+      die_on(gai_malloc(&p, sizeof(uint32_t) * (size_t)subg_size), "gai_malloc"); d_subg_ids = reinterpret_cast<uint32_t*>(p);
+    } else {
+      training_graph->copy_to_gpu();
+    }
+    return;
+  }
   if (partitioned()) {  // the device graph (and its halo plan) first: the input features carry a halo block that is fetched through it
     training_graph->copy_to_gpu();
     transfer_data_to_device();
@@ -251,9 +277,12 @@ void Model<L>::construct_network() {  // net.cpp:422-453
   gai_host::out() << "constructing neural network...\n";
   const int nv = num_samples;
   layer_gconv.reserve(num_layers);
+  // inductive / sampling runs evaluate on the full graph: per-edge buffers (GAT) are sized by it; the layers then point at the training graph
+  Graph* sizing_graph = inductive ? full_graph : training_graph;
   for (int l = 0; l < num_layers - 1; l++)
-    layer_gconv.emplace_back(l, nv, l == 0 ? dim_init : dim_hid, dim_hid, training_graph, true, lrate, feat_drop, score_drop);
-  layer_gconv.emplace_back(num_layers - 1, nv, dim_hid, use_dense ? dim_hid : num_cls, training_graph, false, lrate, feat_drop, score_drop);
+    layer_gconv.emplace_back(l, nv, l == 0 ? dim_init : dim_hid, dim_hid, sizing_graph, true, lrate, feat_drop, score_drop);
+  layer_gconv.emplace_back(num_layers - 1, nv, dim_hid, use_dense ? dim_hid : num_cls, sizing_graph, false, lrate, feat_drop, score_drop);
+  if (inductive) for (auto& y : layer_gconv) y.set_graph_ptr(training_graph);
   if (use_l2norm) layer_l2norm = new l2norm_layer(nv, dim_hid);
   if (use_dense) layer_dense = new dense_layer(nv, dim_hid, num_cls, lrate);
   layer_gconv[0].set_feat_in(d_input_features);
@@ -299,16 +328,21 @@ void Model<L>::run_forward_layers() {  // shared by forward_prop and evaluate (n
 template <typename L>
 acc_t Model<L>::forward_prop(acc_t& loss) {
   run_forward_layers();
-  layer_loss->forward(train_begin, train_end, d_masks_train);
-  loss = layer_loss->get_prediction_loss(train_begin, train_end, train_count, d_masks_train);
+  size_t begin = train_begin, end = train_end, count = train_count;
+  mask_t* masks_ptr = d_masks_train;
+  label_t* labels_ptr = d_labels;
+  if (subg_size > 0) { masks_ptr = nullptr; begin = 0; end = (size_t)subg_nv; count = (size_t)subg_nv; labels_ptr = d_labels_subg; }  // net.cpp:477-488
+  layer_loss->forward(begin, end, masks_ptr);
+  loss = layer_loss->get_prediction_loss(begin, end, count, masks_ptr);
   if (is_sigmoid)  // net.cpp:495-497
-    return masked_accuracy_multi((int)train_begin, (int)train_end, (int)train_count, num_cls, d_masks_train, layer_loss->get_feat_out(), d_labels);
+    return masked_accuracy_multi((int)begin, (int)end, (int)count, num_cls, masks_ptr, layer_loss->get_feat_out(), labels_ptr);
   return static_cast<softmax_loss_layer*>(layer_loss)->last_accuracy();  // same reduction pass as the loss mean
 }
 
 template <typename L>
 acc_t Model<L>::evaluate(std::string type) {
   set_netphases(net_phase::TEST);
+  if (subg_size > 0 || inductive) use_full_graph();  // net.cpp:508-535
   run_forward_layers();
   if (is_sigmoid) {  // net.cpp:569-572: the loss layer's forward produces the sigmoid outputs the F1 score thresholds
     const bool test = type == "test";
@@ -328,6 +362,9 @@ acc_t Model<L>::evaluate(std::string type) {
 
 template <typename L>
 void Model<L>::backward_prop() {  // net.cpp:580-615
+  size_t train_begin = this->train_begin, train_end = this->train_end;
+  mask_t* d_masks_train = this->d_masks_train;
+  if (subg_size > 0) { d_masks_train = nullptr; train_begin = 0; train_end = (size_t)subg_nv; }  // net.cpp:586-590
   if (use_dense) {
     layer_loss->backward(train_begin, train_end, d_masks_train, layer_dense->get_grad_in());
     layer_dense->backward(layer_l2norm->get_grad_in());
@@ -343,6 +380,9 @@ void Model<L>::backward_prop() {  // net.cpp:580-615
 
 template <typename L>
 acc_t Model<L>::train_epoch(acc_t& loss) {
+  if (subg_size > 0) subgraph_sampling(epochs_done);
+  else if (inductive) for (auto& y : layer_gconv) y.set_graph_ptr(training_graph);  // back from an evaluation on the full graph
+  epochs_done++;
   set_netphases(net_phase::TRAIN);
   acc_t acc = forward_prop(loss);
   backward_prop();
@@ -355,6 +395,8 @@ void Model<L>::train() {  // log lines as net.cpp:364-410 so that logs diff clea
   gai_host::out() << "Start training...\n";
   double total_train_time = 0.0;
   for (int itr = 0; itr < num_epochs; itr++) {
+    if (subg_size > 0) subgraph_sampling(itr);
+    else if (inductive) for (auto& y : layer_gconv) y.set_graph_ptr(training_graph);
     gai_host::out() << "Epoch " << std::setw(3) << itr << " ";
     set_netphases(net_phase::TRAIN);
     acc_t train_loss = 0.0;
@@ -381,6 +423,65 @@ void Model<L>::train() {  // log lines as net.cpp:364-410 so that logs diff clea
   }
   gai_host::out() << "Average training time per epoch: " << total_train_time / (double)num_epochs << " seconds. Throughput "
             << (double)num_epochs / total_train_time << " epoch/s\n";
+}
+
+// net.cpp:287-358. The frontier walk runs on the host (sequential, rand_r), the induced subgraph is built on the device; the feature rows
+// of the kept vertices are gathered on the device from the resident feature matrix, the labels on the host.
+template <typename L>
+void Model<L>::subgraph_sampling(int) {
+  if (num_subg_remain == 0) {
+    for (int sid = 0; sid < num_subgraphs; sid++) {
+      VertexSet sampled;
+      // the reference seeds each walk with its OpenMP thread id (net.cpp:297-299); num_subgraphs == num_threads, static schedule: seed = sid
+      sampler->select_vertices((index_t)subg_size, sampled, (unsigned)sid);
+      if (subgs[sid]) { subgs[sid]->dealloc(); delete subgs[sid]; }
+      subgs[sid] = new Graph(true);
+      sampler->generateSubgraph(sampled, &subg_masks[(size_t)sid * num_samples], subgs[sid]);
+    }
+    num_subg_remain = num_subgraphs;
+  }
+  num_subg_remain--;
+  const int sg_id = num_subg_remain;
+  Graph* sg = subgs[sg_id];
+  sg->degree_counting();
+  subg_nv = (int)sg->size();
+  // the subgraph is induced from the full graph, which already carries the self-loops of GCN / GAT: none are added (the reference's CPU
+  // path adds none either; its GPU path would add a second one, net.cpp:325-327)
+  if (!sg->device()) sg->copy_to_gpu();
+  for (auto& y : layer_gconv) { y.update_dim_size((size_t)subg_nv); y.set_graph_ptr(sg); }
+  if (use_l2norm) layer_l2norm->update_dim_size(subg_nv);
+  if (use_dense) layer_dense->update_dim_size(subg_nv);
+  layer_loss->update_dim_size(subg_nv);
+  const mask_t* mk = &subg_masks[(size_t)sg_id * num_samples];
+  std::vector<uint32_t> ids;
+  ids.reserve(subg_nv);
+  const size_t lw = is_sigmoid ? (size_t)num_cls : 1;
+  labels_subg.resize((size_t)subg_nv * lw);
+  for (int i = 0; i < num_samples; i++) {
+    if (mk[i] != 1) continue;
+    std::copy(labels.begin() + (size_t)i * lw, labels.begin() + (size_t)(i + 1) * lw, labels_subg.begin() + ids.size() * lw);
+    ids.push_back((uint32_t)i);
+  }
+  assert((int)ids.size() == subg_nv);
+  die_on(gai_memcpy_h2d(d_subg_ids, ids.data(), sizeof(uint32_t) * ids.size(), stream()), "gai_memcpy_h2d");
+  die_on(gai_memcpy_h2d(d_labels_subg, labels_subg.data(), labels_subg.size(), stream()), "gai_memcpy_h2d");
+  sync();  // the staging vectors go out of scope
+  const int ld = (int)row_pitch(dim_init);
+  die_on(gai_gather_rows((size_t)subg_nv, d_subg_ids, dim_init, d_input_features, ld, d_feats_subg, ld, stream()), "gai_gather_rows");
+  layer_gconv[0].set_feat_in(d_feats_subg);
+  layer_loss->set_labels_ptr(d_labels_subg);
+}
+
+template <typename L>
+void Model<L>::use_full_graph() {
+  for (auto& y : layer_gconv) { y.set_graph_ptr(full_graph); if (subg_size > 0) y.update_dim_size((size_t)num_samples); }
+  if (subg_size > 0) {
+    if (use_dense) layer_dense->update_dim_size(num_samples);
+    if (use_l2norm) layer_l2norm->update_dim_size(num_samples);
+    layer_loss->update_dim_size(num_samples);
+    layer_gconv[0].set_feat_in(d_input_features);
+    layer_loss->set_labels_ptr(d_labels);
+  }
 }
 
 template class Model<GCN_layer>;

@@ -1,11 +1,13 @@
 // Host-side mirror of the reference's model driver: Model<L> (include/gnn/net.h:9-83, src/gnn/net.cpp:11-620) over the
-// layer classes in gai_layers.h. Same public methods and argv contract (train.cpp:9-15); subgraph sampling is out of
-// scope (every config runs subg_size = 0) and is rejected at load time.
+// layer classes in gai_layers.h. Same public methods and argv contract (train.cpp:9-15), subgraph sampling (argv subg_size > 0:
+// Sampler + Model::subgraph_sampling, net.cpp:287-358) and inductive training (train on the training-masked graph, evaluate on the full
+// one) included.
 #pragma once
 #include <string>
 #include <vector>
 #include "gai_dist.h"
 #include "gai_layers.h"
+#include "gai_sampler.h"
 
 #define DEFAULT_NUM_LAYER 2
 #define DEFAULT_SIZE_HID 16
@@ -97,4 +99,16 @@ class Model {
   void localise_split(const int64_t* split9_global, index_t first, index_t last);
   void finish_setup();
   void run_forward_layers();
+  // subgraph sampling (net.cpp:64-79,154-186,287-358)
+  int epochs_done = 0;
+  Sampler* sampler = nullptr;
+  int num_subgraphs = 1, subg_nv = 0, num_subg_remain = 0;
+  std::vector<Graph*> subgs;
+  std::vector<mask_t> subg_masks;   // num_subgraphs x num_samples
+  float* d_feats_subg = nullptr;
+  label_t* d_labels_subg = nullptr;
+  uint32_t* d_subg_ids = nullptr;   // kept vertex ids of the subgraph in use (device), for the feature-row gather
+  std::vector<label_t> labels_subg;
+  void subgraph_sampling(int cur_epoch);
+  void use_full_graph();            // evaluate(): back to the full graph, features and labels
 };

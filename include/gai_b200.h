@@ -85,6 +85,11 @@ int gai_coo_to_csr(uint32_t nv, uint64_t n_pairs, const uint32_t* src_d, const u
 int gai_add_selfloop_d(uint32_t nv, uint32_t first_id, const uint32_t* rowptr_d, const uint32_t* colidx_d, uint32_t* rowptr_out_d,
                        uint32_t* colidx_out_d, gai_stream_t stream);
 
+/* The subgraph induced by an ascending list of kept vertices, re-indexed to 0..n_keep-1 (new id = rank in the list), neighbour order kept:
+ * Sampler::generateSubgraph = getMaskedGraph + reindexSubgraph (src/gnn/sampler.cpp:66-158). Outputs are allocated here (gai_free). */
+int gai_induced_subgraph(gai_csr_t g, uint32_t n_keep, const uint32_t* keep_ids_d, gai_stream_t stream, uint32_t** rowptr_out_d, uint32_t** colidx_out_d,
+                         uint64_t* nnz_out);
+
 /* ---- device CSR: replaces LearningGraph::alloc_on_device/copy_to_gpu/compute_vertex_data/compute_edge_data
  *      (src/gnn/lgraph.cu:51-140) and the role of GraphGPU::init (include/graph_gpu.h:207-243). -------------
  * Uploads rowptr (u32, nv+1) and colidx (u32, nnz), then on the device computes

@@ -19,6 +19,7 @@
 #include "softmax_loss_layer.h"
 #include "sigmoid_loss_layer.h"
 #include "reader.h"
+#include "sampler.h"
 
 std::map<char, double> time_ops;  // reference global (defined in train.cpp:3, which is not linked here)
 
@@ -334,6 +335,29 @@ int ref_reader_load_csgr(const char* dataset, int single_class, int64_t* meta, u
     memcpy(masks_out, masks.data(), masks.size());
   }
   return 0;
+}
+
+// The reference's Sampler (src/gnn/sampler.cpp) on an in-memory graph: masked training graph (LearningGraph::generate_masked_graph,
+// lgraph.h:231-272), frontier sampling (select_vertices, :170-294) and the induced, re-indexed subgraph (generateSubgraph, :148-158).
+// Returns the number of selected vertices; set_out (ascending) / rowptr_out / colidx_out are filled when non-NULL; sizes = {n_set, nnz}.
+int64_t ref_sampler_run(void* g_full, const uint8_t* masks_train, size_t count, uint32_t n, unsigned seed, int64_t* sizes, uint32_t* set_out,
+                        uint32_t* rowptr_out, uint32_t* colidx_out) {
+  Graph* full = (Graph*)g_full;
+  Graph* tg = full->generate_masked_graph((mask_t*)masks_train);
+  Sampler sampler(full, tg, (mask_t*)masks_train, count);
+  VertexSet st;
+  sampler.select_vertices(n, st, seed);
+  std::vector<mask_t> masks(full->size(), 0);
+  Graph sg;
+  sampler.generateSubgraph(st, masks.data(), &sg);
+  sizes[0] = (int64_t)st.size(); sizes[1] = (int64_t)sg.sizeEdges();
+  if (set_out) {
+    size_t i = 0;
+    for (auto v : st) set_out[i++] = v;
+    memcpy(rowptr_out, sg.row_start_host_ptr(), sizeof(uint32_t) * (sg.size() + 1));
+    memcpy(colidx_out, sg.edge_dst_host_ptr(), sizeof(uint32_t) * sg.sizeEdges());
+  }
+  return (int64_t)st.size();
 }
 
 }  // extern "C"

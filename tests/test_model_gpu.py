@@ -173,3 +173,32 @@ def test_refresh_inputs_reads_the_callers_buffer_every_call(gm):
     assert m.forward()[0] == la
     m.refresh_inputs(None)                                    # NULL = the model's own copy of its training features
     assert m.forward()[0] == la
+
+
+REF_SAMPLING = {   # the reference's own CPU binary, run in the build container (oracle/_ref/cpu_train_sage cora <epochs> <threads> softmax 16 0 0 0.02 2 ...)
+    # subg_size 100, 1 thread: one subgraph (walk seed 0), reused every epoch; l2norm + dense tail (net.cpp:67-71)
+    ("8", "1", "100", "0"): ([1.989, 1.642, 1.530, 1.438, 1.350, 1.265, 1.181, 1.104], 0.288),
+    # 2 threads: two subgraphs (walk seeds 0 and 1), used in the order 1, 0, 1, 0, ...
+    ("6", "2", "100", "0"): ([2.031, 1.753, 1.585, 1.499, 1.407, 1.324], 0.286),
+    # inductive without sampling: train on the graph masked to the training vertices (42 edges on cora), evaluate on the full graph
+    ("8", "1", "0", "1"): ([1.945, 1.925, 1.903, 1.876, 1.843, 1.803, 1.756, 1.704], 0.202),
+}
+
+
+@pytest.mark.parametrize("key", sorted(REF_SAMPLING))
+def test_cli_subgraph_sampling_and_inductive_match_reference(gm, ref_inputs, key):
+    """SURVEY.md §8 (f)2 end to end: `gpu_train_sage cora E T softmax 16 0 0 0.02 2 <subg_size> 50 <inductive>` (argv as net.cpp:13-64) against the
+    reference's CPU binary on the same arguments: frontier walk (same rand_r stream), induced subgraph built on the device, per-epoch switch of
+    graph / features / labels, evaluation back on the full graph."""
+    epochs, threads, subg, ind = key
+    want_losses, want_test = REF_SAMPLING[key]
+    out = subprocess.run([os.path.join(ROOT, "graphaibench_b200", "gpu_train_sage"), "cora", epochs, threads, "softmax", "16", "0", "0", "0.02", "2", subg, "50", ind],
+                         env=dict(os.environ, DATASET_PATH=ref_inputs), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    lines = out.stdout.splitlines()
+    got = [float(l.split("train_loss")[1].split()[0]) for l in lines if l.startswith("Epoch") and "train_loss" in l]
+    assert len(got) == len(want_losses)
+    for g, w in zip(got, want_losses):
+        assert abs(g - w) <= 0.002, (got, want_losses)
+    test = float([l for l in lines if l.startswith("Test accuracy:")][0].split()[2])
+    assert abs(test - want_test) <= 0.002, (test, want_test)
