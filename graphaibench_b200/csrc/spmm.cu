@@ -58,10 +58,19 @@ struct SpmmArgs {
 
 // base of neighbour row `c` (float4 units). SPLIT is a template parameter of the kernels: the single-matrix path pays nothing for it
 // (a run-time test per gathered row cost 8 % of the aggregation time).
+// Address of a 16-byte chunk of neighbour row `c`: base + c * row_bytes with a 32-bit row pitch, i.e. ONE IMAD.WIDE.U32 per gathered row
+// (`base` already carries the lane's chunk offset). The aggregation is issue-bound enough (70 % of the issue slots at F = 100) for the
+// address arithmetic to matter: a 64-bit pitch cost 5 instructions per edge (13.75 in all), a second address computation for the halo
+// block cost 30 % (N = 8: 5.7 ms vs 4.2 ms for the same rows in one matrix).
+// `halo` is the VIRTUAL base of the halo block (halo_virtual_base: first halo row minus n_split rows), so that both branches of a split
+// (masters | halo) input share the multiply-add and differ in the base pointer only.
 template <bool SPLIT>
-__device__ __forceinline__ const float4* row_base(const float4* in4, const float4* halo4, uint32_t n_split, size_t ld4, uint32_t c) {
-  if (!SPLIT) return in4 + (size_t)c * ld4;
-  return c < n_split ? in4 + (size_t)c * ld4 : halo4 + (size_t)(c - n_split) * ld4;
+__device__ __forceinline__ const float4* row_chunk(const char* base, const char* halo, uint32_t n_split, uint32_t row_bytes, uint32_t c) {
+  const char* b = (SPLIT && c >= n_split) ? halo : base;
+  return reinterpret_cast<const float4*>(b + (unsigned long long)c * row_bytes);
+}
+__device__ __forceinline__ const char* halo_virtual_base(const float* in_halo, uint32_t n_split, uint32_t row_bytes) {
+  return reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(in_halo) - (uintptr_t)n_split * row_bytes);
 }
 
 // out[row, 4*chunk .. 4*chunk+3] = epilogue(acc)
@@ -178,9 +187,9 @@ template <int MODE, bool SPLIT>
 __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh) {
   const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4* in4 = reinterpret_cast<const float4*>(a.in);
-  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
-  const size_t ld4 = (size_t)a.ld_in >> 2;
+  const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
+  const char* inb = reinterpret_cast<const char*>(a.in);
+  const char* halob = halo_virtual_base(a.in_halo, a.n_split, row_bytes);
   if (warp > 0) {
     // ---------------- producers ----------------
     const int pw = warp - 1;
@@ -195,6 +204,9 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     constexpr int EL = 32 / HI_CL;
     const int cl = lane % HI_CL, el = lane / HI_CL;
     const bool chv = cl < nch;
+    const char* inb_c = inb + (size_t)(cb + cl) * 16;
+    const char* halob_c = halob + (size_t)(cb + cl) * 16;
+    asm volatile("" : "+l"(inb_c), "+l"(halob_c));
     for (uint32_t k = pw, r = 0; k < nstages; k += HI_PW, r++) {
       const uint32_t base = s + k * HI_ES;
       const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
@@ -213,7 +225,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
           const int j = j0 + u * EL + el;
           const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
           ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
-          if (chv && j < cnt) x[u] = __ldg(row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc) + cb + cl);
+          if (chv && j < cnt) x[u] = __ldg(row_chunk<SPLIT>(inb_c, halob_c, a.n_split, row_bytes, cc));
         }
 #pragma unroll
         for (int u = 0; u < HI_UB; u++) {
@@ -277,9 +289,9 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gl = lane % G, grp = lane / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-  const float4* in4 = reinterpret_cast<const float4*>(a.in);
-  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
-  const size_t ld4 = (size_t)a.ld_in >> 2;
+  const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
+  const char* inb = reinterpret_cast<const char*>(a.in);
+  const char* halob = halo_virtual_base(a.in_halo, a.n_split, row_bytes);
   // lanes whose chunk lies past the row width re-read chunk 0 (same sectors as lane 0) and store nothing. Predicating them off instead
   // was measured slower (round 2: F = 47 calls +4..9 %): the L1 data pipe is not the limiter and the predicate costs issue slots.
   int chunk[K];
@@ -361,6 +373,13 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
           bool av[K];
 #pragma unroll
           for (int k = 0; k < K; k++) { av[k] = cb == 0 ? act[k] : (cb + gl + G * k) < a.nchunks; ch[k] = cb == 0 ? chunk[k] : (av[k] ? cb + gl + G * k : 0); }
+          const char* bk[K];   // lane's chunk k of row 0 (masters) / of virtual row 0 (halo)
+          const char* hk[K];
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            bk[k] = inb + (size_t)ch[k] * 16; hk[k] = halob + (size_t)ch[k] * 16;
+            asm volatile("" : "+l"(bk[k]), "+l"(hk[k]));  // keep base + chunk offset as ONE 64-bit addend (ptxas otherwise re-associates: +2 instructions per edge)
+          }
           uint32_t c_cur = c_first;
           if (cb != 0 && s + gl < e) c_cur = __ldg(a.colidx + s + gl);
           for (uint32_t b = s; b < e; b += G) {
@@ -376,9 +395,8 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = gather4(src + ch[k]);
+                  for (int k = 0; k < K; k++) x[u][k] = gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc));
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -396,9 +414,9 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
-                  const float4* src = row_base<SPLIT>(in4, halo4, a.n_split, ld4, cc);
 #pragma unroll
-                  for (int k = 0; k < K; k++) x[u][k] = (j + u < cnt) ? gather4(src + ch[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int k = 0; k < K; k++)
+                    x[u][k] = (j + u < cnt) ? gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -455,9 +473,9 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
   const uint32_t s = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
   const uint32_t nstages = (e - s + ES - 1) / ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4* in4 = reinterpret_cast<const float4*>(a.in);
-  const float4* halo4 = reinterpret_cast<const float4*>(a.in_halo);
-  const size_t ld4 = (size_t)a.ld_in >> 2;
+  const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
+  const char* inb = reinterpret_cast<const char*>(a.in);
+  const char* halob = halo_virtual_base(a.in_halo, a.n_split, row_bytes);
   const int cb_begin = (int)blockIdx.y * a.hub_per;
   const int cb_end = a.nchunks < cb_begin + a.hub_per ? a.nchunks : cb_begin + a.hub_per;
   if (cb_begin >= cb_end) return;  // uniform for the CTA
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(HUB_THREADS, HUB_MIN_CTAS) spmm_hub_kernel(con
               const int j = j0 + u * EL + el;
               const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j & 31);
               ww[u] = __shfl_sync(0xffffffffu, cur_w, j & 31);
-              if (chv && j < cnt) x[u] = __ldg(row_base<true>(in4, halo4, a.n_split, ld4, cc) + cb + ch);
+              if (chv && j < cnt) x[u] = __ldg(row_chunk<true>(inb + (size_t)(cb + ch) * 16, halob + (size_t)(cb + ch) * 16, a.n_split, row_bytes, cc));
             }
 #pragma unroll
             for (int u = 0; u < UB; u++) {
@@ -702,7 +720,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   GAI_CHECK_ARG(rb <= re && re <= g->nv);
   if (re == rb) return GAI_OK;  // empty graph / empty row range: nothing to do (buffers may be NULL)
   GAI_CHECK_ARG(in != nullptr && out != nullptr);
-  GAI_CHECK_ARG(F > 0 && ld_in >= F && ld_out >= F);
+  GAI_CHECK_ARG(F > 0 && ld_in >= F && ld_out >= F && ld_in < (1 << 28));  // row pitch in bytes is 32-bit inside the kernels
   GAI_CHECK_ARG(!(flags & GAI_EPI_ADD) || addend != nullptr);
   GAI_CHECK_ARG(mode < M_EDGE || vals != nullptr);
   GAI_CHECK_ARG(in != out);
