@@ -122,10 +122,12 @@ _SIGS = {
     "gai_peers_world": (C.c_int, [C.c_void_p]),
     "gai_peers_register": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "gai_peers_barrier": (C.c_int, [C.c_void_p, c_stream]),
+    "gai_peers_barrier_on": (C.c_int, [C.c_void_p, C.c_int, c_stream]),
     "gai_peers_error": (C.c_int, [C.c_void_p, c_stream]),
     "gai_halo_plan_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, c_stream, C.POINTER(C.c_void_p)]),
     "gai_halo_plan_destroy": (C.c_int, [C.c_void_p]),
     "gai_halo_pull": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, c_f32p, C.c_size_t, C.c_int, c_stream]),
+    "gai_halo_pull_cols": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, c_f32p, C.c_size_t, C.c_int, C.c_int, c_stream]),
     "gai_peers_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_int, c_f32p, c_stream]),
     "gai_spmm_rows_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, c_f32p, c_u32p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int,
                                    c_f32p, C.c_void_p, C.c_int, c_f32p, C.c_uint32, c_stream]),

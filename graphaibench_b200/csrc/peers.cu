@@ -22,6 +22,7 @@
 #include "gai_internal.cuh"
 
 constexpr int GAI_MAX_PEERS = 16;
+constexpr int GAI_BARRIER_CHANNELS = 2;  // one sequence of barriers per stream that issues them (0: the rank's main stream, 1: its pull stream)
 
 struct gai_peers {
   int rank = 0, world = 1, device = 0;
@@ -31,9 +32,9 @@ struct gai_peers {
   std::vector<void*> local;               // local base pointer of buffer id
   std::vector<std::vector<void*>> peer;   // peer[id][q]: buffer id of rank q as seen from this device
   std::vector<void*> opened;              // IPC mappings to close
-  unsigned long long* flags = nullptr;    // [world] this rank's flag row (buffer id 0)
-  unsigned long long** d_flag_rows = nullptr;  // device array [world]: every rank's flag row
-  unsigned long long seq = 0;
+  unsigned long long* flags = nullptr;    // [channels][GAI_MAX_PEERS] this rank's flag rows (buffer id 0)
+  unsigned long long** d_flag_rows = nullptr;  // device array [world]: every rank's flag rows
+  unsigned long long seq[GAI_BARRIER_CHANNELS] = {0, 0};
   int* d_err = nullptr;
   bool host_barrier = false;  // every rank lives in this process
 };
@@ -63,12 +64,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 // Thread q: publish `seq` in rank q's flag row (slot = my rank), then wait until rank q has published it in mine. A rank that never
 // arrives (crashed peer) trips the cycle budget instead of hanging the GPU: *err is set and the caller reports it.
-__global__ void peer_barrier_kernel(unsigned long long* const* __restrict__ flag_rows, int rank, int world, unsigned long long seq, int* err) {
+// Barriers issued on different streams of one rank may execute in either order, and a flag only ever grows within ONE ordered sequence:
+// each issuing stream therefore has its own flag row (`channel`) and sequence counter.
+__global__ void peer_barrier_kernel(unsigned long long* const* __restrict__ flag_rows, int rank, int world, int channel, unsigned long long seq, int* err) {
   const int q = threadIdx.x;
   if (q >= world) return;
   __threadfence_system();
-  st_release_sys(flag_rows[q] + rank, seq);
-  const unsigned long long* mine = flag_rows[rank] + q;
+  st_release_sys(flag_rows[q] + channel * GAI_MAX_PEERS + rank, seq);
+  const unsigned long long* mine = flag_rows[rank] + channel * GAI_MAX_PEERS + q;
   const long long t0 = clock64();
   while (ld_acquire_sys(mine) < seq) {
     if (clock64() - t0 > 40000000000ll) { *err = 1; break; }  // ~20 s at 2 GHz
@@ -99,6 +102,7 @@ __device__ __forceinline__ int owner_of(const PullArgs& a, uint32_t k) {
 // peers and every owner's NVLink egress serves all its readers at once. (Walking the halo block in ascending global id instead made
 // every rank read owner 0 first, then owner 1, ...: seven readers queued on one GPU's egress while the other links idled — 200 GB/s per
 // rank at N = 8 against 580 GB/s at N = 2.)
+template <int UNR>
 __global__ void __launch_bounds__(256) halo_pull_kernel(const PullArgs a, int rank) {
   const int ngroups = a.world - 1;
   const int j = (int)(blockIdx.x % (unsigned)ngroups);
@@ -106,27 +110,30 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const PullArgs a, int ra
   const size_t nb = gridDim.x / (unsigned)ngroups;      // CTAs of this group (the launch rounds the grid to a multiple of ngroups)
   const size_t b = blockIdx.x / (unsigned)ngroups;
   const uint32_t k0 = a.seg[q];
-  const size_t total = (size_t)(a.seg[q + 1] - k0) * a.nch;
+  const uint32_t nch = (uint32_t)a.nch;
+  const size_t total = (size_t)(a.seg[q + 1] - k0) * nch;   // < 2^32 * 2^16
   const size_t stride = nb * blockDim.x;
   const float* __restrict__ src = a.src[q];
   size_t i = b * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < total; i += 4 * stride) {
-    float4 v[4];
-    size_t o[4];
+  for (; i + (UNR - 1) * stride < total; i += UNR * stride) {
+    float4 v[UNR];
+    size_t o[UNR];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < UNR; u++) {
       const size_t idx = i + u * stride;
-      const uint32_t k = k0 + (uint32_t)(idx / a.nch);
-      const int c = (int)(idx % a.nch);
+      const uint32_t kk = (uint32_t)(idx / nch);
+      const uint32_t c = (uint32_t)(idx - (size_t)kk * nch);
+      const uint32_t k = k0 + kk;
       v[u] = __ldcv(reinterpret_cast<const float4*>(src + (size_t)__ldg(a.src_row + k) * a.ld_src) + c);
       o[u] = (size_t)k * a.ld_dst + (size_t)c * 4;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) *reinterpret_cast<float4*>(a.dst + o[u]) = v[u];
+    for (int u = 0; u < UNR; u++) *reinterpret_cast<float4*>(a.dst + o[u]) = v[u];
   }
   for (; i < total; i += stride) {
-    const uint32_t k = k0 + (uint32_t)(i / a.nch);
-    const int c = (int)(i % a.nch);
+    const uint32_t kk = (uint32_t)(i / nch);
+    const uint32_t c = (uint32_t)(i - (size_t)kk * nch);
+    const uint32_t k = k0 + kk;
     *reinterpret_cast<float4*>(a.dst + (size_t)k * a.ld_dst + (size_t)c * 4) =
         __ldcv(reinterpret_cast<const float4*>(src + (size_t)__ldg(a.src_row + k) * a.ld_src) + c);
   }
@@ -159,7 +166,7 @@ __global__ void peer_reduce_kernel(const ReduceArgs a, size_t n, int sum, float*
   }
 }
 
-int launch_barrier(gai_peers* p, cudaStream_t st) {
+int launch_barrier(gai_peers* p, cudaStream_t st, int channel = 0) {
   if (p->world == 1) return GAI_OK;
   if (p->host_barrier) {
     GAI_CUDA(cudaStreamSynchronize(st));
@@ -168,8 +175,8 @@ int launch_barrier(gai_peers* p, cudaStream_t st) {
     p->allgather(p->ctx, &token, 1, all.data());
     return GAI_OK;
   }
-  p->seq++;
-  peer_barrier_kernel<<<1, 32, 0, st>>>(p->d_flag_rows, p->rank, p->world, p->seq, p->d_err);
+  p->seq[channel]++;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(p->d_flag_rows, p->rank, p->world, channel, p->seq[channel], p->d_err);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }
@@ -221,8 +228,8 @@ int gai_peers_create(int rank, int world, gai_allgather_fn allgather, void* ctx,
   p->rank = rank; p->world = world; p->allgather = allgather; p->ctx = ctx; p->pid = (unsigned long long)getpid();
   GAI_CUDA(cudaGetDevice(&p->device));
   cudaStream_t st = gai::S(stream);
-  GAI_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * GAI_MAX_PEERS));
-  GAI_CUDA(cudaMemsetAsync(p->flags, 0, sizeof(unsigned long long) * GAI_MAX_PEERS, st));
+  GAI_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * GAI_MAX_PEERS * GAI_BARRIER_CHANNELS));
+  GAI_CUDA(cudaMemsetAsync(p->flags, 0, sizeof(unsigned long long) * GAI_MAX_PEERS * GAI_BARRIER_CHANNELS, st));
   GAI_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
   GAI_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
   GAI_CUDA(cudaStreamSynchronize(st));  // the flag rows are zero before any peer can see them
@@ -250,6 +257,10 @@ int gai_peers_world(gai_peers_t p) { return p ? p->world : 1; }
 int gai_peers_barrier(gai_peers_t p, gai_stream_t stream) {
   GAI_CHECK_ARG(p != nullptr);
   return launch_barrier(p, gai::S(stream));
+}
+int gai_peers_barrier_on(gai_peers_t p, int channel, gai_stream_t stream) {
+  GAI_CHECK_ARG(p != nullptr && channel >= 0 && channel < GAI_BARRIER_CHANNELS);
+  return launch_barrier(p, gai::S(stream), channel);
 }
 
 int gai_peers_error(gai_peers_t p, gai_stream_t stream) {
@@ -292,30 +303,42 @@ int gai_halo_plan_destroy(gai_halo_plan_t h) {
 }
 
 int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld, float* dst, size_t ld_dst, int flags, gai_stream_t stream) {
-  GAI_CHECK_ARG(p != nullptr && h != nullptr && buf_id > 0 && buf_id < (int)p->local.size() && F > 0 && ld >= (size_t)F && ld_dst >= (size_t)F);
+  return gai_halo_pull_cols(p, h, buf_id, 0, F, ld, dst, ld_dst, flags, 0, stream);
+}
+
+int gai_halo_pull_cols(gai_peers_t p, gai_halo_plan_t h, int buf_id, int col0, int F, size_t ld, float* dst, size_t ld_dst, int flags, int channel,
+                       gai_stream_t stream) {
+  GAI_CHECK_ARG(p != nullptr && h != nullptr && buf_id > 0 && buf_id < (int)p->local.size() && F > 0 && col0 >= 0);
+  GAI_CHECK_ARG(ld >= (size_t)col0 + (size_t)F && ld_dst >= (size_t)col0 + (size_t)F && channel >= 0 && channel < GAI_BARRIER_CHANNELS);
   GAI_CHECK_ARG(dst != nullptr || h->n_halo == 0);
   cudaStream_t st = gai::S(stream);
   if (p->world == 1) return GAI_OK;
   int rc = GAI_OK;
-  if (!(flags & GAI_PULL_NO_BARRIER_BEFORE)) { rc = launch_barrier(p, st); if (rc != GAI_OK) return rc; }  // every owner's matrix is complete
+  if (!(flags & GAI_PULL_NO_BARRIER_BEFORE)) { rc = launch_barrier(p, st, channel); if (rc != GAI_OK) return rc; }  // every owner's matrix is complete
   if (h->n_halo) {
     PullArgs a;
     memset(&a, 0, sizeof(a));
-    for (int q = 0; q < p->world; q++) a.src[q] = reinterpret_cast<const float*>(p->peer[buf_id][q]);
+    for (int q = 0; q < p->world; q++) a.src[q] = reinterpret_cast<const float*>(p->peer[buf_id][q]) + col0;
     for (int q = 0; q <= GAI_MAX_PEERS; q++) a.seg[q] = h->seg[q];
     a.src_row = h->d_src_row;
-    a.dst = dst;
+    a.dst = dst + col0;
     a.ld_src = ld; a.ld_dst = ld_dst; a.n_halo = h->n_halo; a.world = p->world; a.F = F;
-    const bool vec = ld % 4 == 0 && ld_dst % 4 == 0 && reinterpret_cast<uintptr_t>(p->local[buf_id]) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+    const bool vec = ld % 4 == 0 && ld_dst % 4 == 0 && col0 % 4 == 0 && reinterpret_cast<uintptr_t>(p->local[buf_id]) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(dst) % 16 == 0;
     if (vec) {
       a.nch = (F + 3) / 4;
       const size_t total = (size_t)h->n_halo * a.nch;
       const size_t ngroups = (size_t)p->world - 1;
-      size_t per_group = (total / ngroups + 256 * 4 - 1) / (256 * 4);
-      const size_t cap = ((size_t)gai::sm_count() * 8 + ngroups - 1) / ngroups;
+      // GAI_PULL_SMALL_GRID: the pull shares the SMs with an aggregation kernel (pipelined exchange): about one CTA per SM with eight
+      // 16-byte loads in flight per thread (4.8 MB in flight: NVLink's bandwidth-delay product is ~2.5 MB) instead of filling the machine
+      const bool small = (flags & GAI_PULL_SMALL_GRID) != 0;
+      const int unr = small ? 8 : 4;
+      size_t per_group = (total / ngroups + 256 * unr - 1) / (256 * unr);
+      const size_t cap = ((size_t)gai::sm_count() * (small ? 1 : 8) + ngroups - 1) / ngroups;
       if (per_group > cap) per_group = cap;
       if (per_group < 1) per_group = 1;
-      halo_pull_kernel<<<(unsigned)(per_group * ngroups), 256, 0, st>>>(a, p->rank);
+      if (small) halo_pull_kernel<8><<<(unsigned)(per_group * ngroups), 256, 0, st>>>(a, p->rank);
+      else halo_pull_kernel<4><<<(unsigned)(per_group * ngroups), 256, 0, st>>>(a, p->rank);
     } else {
       const size_t total = (size_t)h->n_halo * F;
       size_t blocks = (total + 255) / 256;
@@ -325,7 +348,7 @@ int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld
     }
     GAI_LAUNCH_CHECK();
   }
-  if (!(flags & GAI_PULL_NO_BARRIER_AFTER)) rc = launch_barrier(p, st);  // the owners may overwrite their matrices again
+  if (!(flags & GAI_PULL_NO_BARRIER_AFTER)) rc = launch_barrier(p, st, channel);  // the owners may overwrite their matrices again
   return rc;
 }
 

@@ -11,6 +11,11 @@
 //     traffic for F = 100 against a measured 19 TB/s L2 streaming rate, DRAM at 49 %, occupancy 48 % at 64 registers, long_scoreboard the
 //     top stall: the bytes in flight per SM are capped by the registers that hold them. It is NOT the L1 data pipe: 128-byte-aligned row
 //     pitches cut its wavefronts by a third and changed nothing (the larger footprint cost the hit rates), predicated lanes likewise.
+//     Landing the gathers in shared memory instead of registers (a private 16-slot cp.async FIFO per lane, 8..16 row chunks in flight
+//     per lane at all times, no barrier or second warp role; bit-exact, round 2) was measured at 5.05 ms against 2.81 ms for F = 100:
+//     every gathered byte then crosses the shared-memory pipe twice (LDGSTS write + LDS read, 128 B/clk/SM), which costs more than the
+//     extra bytes in flight buy. Together with the earlier per-row cp.async.bulk and producer/consumer LDGSTS-ring attempts this rules
+//     out shared-memory staging for the light rows: the register file is the cheapest landing zone this gather has.
 //   * one persistent kernel (4 CTAs x 148 SMs), two kinds of work items taken from global counters:
 //       light rows (deg <= hub_degree): rows in DEGREE order, cut into claims of <= 32 rows / <= 2048 edges. A group of
 //         G lanes (G = 4..32, from the feature width) owns one output row in registers; the group loads G column
@@ -25,6 +30,7 @@
 //     scale()+vadd() (math_functions.cpp:266,336): results are bit-identical for every row length, hub rows included.
 //   * fused: zero-init (no memset pass), optional "+ addend", ReLU and sign-bit d_relu mask epilogues, leading
 //     dimensions, row ranges (1D partition: interior vs boundary rows).
+#include <cstdlib>
 #include "gai_internal.cuh"
 
 namespace {
@@ -160,8 +166,9 @@ constexpr int HI_PW = 7;    // producer warps
 constexpr int HI_ES = 32;   // edges per stage
 constexpr int HI_CL = 8;    // chunk lanes per gather instruction
 constexpr int HI_UB = 4;    // gathers in flight per lane (64-register budget of the persistent kernel)
+constexpr int HI_RING_F4 = HI_PW * HI_ES * HI_CL;   // float4 entries of the ring (28 KB)
 struct HubShared {
-  float4 ring[HI_PW][HI_ES * HI_CL];
+  float4* ring;   // [HI_PW][HI_ES * HI_CL] in the caller's shared memory
   uint64_t full_bar[HI_PW], empty_bar[HI_PW];
   uint32_t round0[HI_PW];  // uses of each slot by the items this CTA has already processed (mbarrier phase bookkeeping)
   unsigned long long item;
@@ -194,7 +201,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     // ---------------- producers ----------------
     const int pw = warp - 1;
     const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-    float4* slot = sh.ring[pw];
+    float4* slot = sh.ring + pw * (HI_ES * HI_CL);
     const uint32_t round0 = sh.round0[pw];
     uint32_t c = 0; float w = 0.0f;
     {
@@ -250,7 +257,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
       const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
       mbar_wait(&sh.full_bar[pw], (sh.round0[pw] + r) & 1);
       if (lane < nch) {
-        const float4* tile = sh.ring[pw] + lane;
+        const float4* tile = sh.ring + pw * (HI_ES * HI_CL) + lane;
         if (cnt == HI_ES) {
           constexpr int SB = 8;
           float4 p[2][SB];
@@ -274,6 +281,36 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     }
     if (lane < nch) store_chunk(a, row, cb + lane, acc);
   }
+}
+
+// All hub items, one at a time per CTA (work counter counter[1]); returns when the list is exhausted.
+template <int MODE, bool SPLIT>
+__device__ __forceinline__ void hub_phase(const SpmmArgs& a, HubShared& hub_sh, float4* ring, unsigned long long* __restrict__ counter,
+                                          const uint32_t* __restrict__ hub_rows, unsigned long long n_hub_items, int hub_nsplit) {
+  if (threadIdx.x == 0) {
+    hub_sh.ring = ring;
+    for (int i = 0; i < HI_PW; i++) { mbar_init(&hub_sh.full_bar[i], 1); mbar_init(&hub_sh.empty_bar[i], 1); hub_sh.round0[i] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (;;) {
+    __syncthreads();  // previous item fully drained (ring, round0) / barriers initialised
+    if (threadIdx.x == 0) hub_sh.item = atomicAdd(counter + 1, 1ull);
+    __syncthreads();
+    const unsigned long long item = hub_sh.item;
+    if (item >= n_hub_items) break;  // uniform
+    const uint32_t hrow = __ldg(hub_rows + item / (unsigned)hub_nsplit);
+    const int cb = (int)(item % (unsigned)hub_nsplit) * a.hub_per;
+    const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
+    if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
+    const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
+    hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
+      for (int i = 0; i < HI_PW; i++) hub_sh.round0[i] += (nst + HI_PW - 1 - i) / HI_PW;
+    }
+  }
+  __syncthreads();   // the ring may be reused by the caller
 }
 
 constexpr int SLOTS = 32;  // work-list entries per claim
@@ -302,28 +339,8 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
   // ---- hub items first (counter[1]), CTA-wide ----
   if (n_hub_items != 0) {
     __shared__ HubShared hub_sh;
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < HI_PW; i++) { mbar_init(&hub_sh.full_bar[i], 1); mbar_init(&hub_sh.empty_bar[i], 1); hub_sh.round0[i] = 0; }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (;;) {
-      __syncthreads();  // previous item fully drained (ring, round0) / barriers initialised
-      if (threadIdx.x == 0) hub_sh.item = atomicAdd(counter + 1, 1ull);
-      __syncthreads();
-      const unsigned long long item = hub_sh.item;
-      if (item >= n_hub_items) break;  // uniform
-      const uint32_t hrow = __ldg(hub_rows + item / (unsigned)hub_nsplit);
-      const int cb = (int)(item % (unsigned)hub_nsplit) * a.hub_per;
-      const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
-      if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
-      const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
-      hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
-        for (int i = 0; i < HI_PW; i++) hub_sh.round0[i] += (nst + HI_PW - 1 - i) / HI_PW;
-      }
-    }
+    __shared__ float4 hub_ring[HI_RING_F4];
+    hub_phase<MODE, SPLIT>(a, hub_sh, hub_ring, counter, hub_rows, n_hub_items, hub_nsplit);
   }
 
   for (;;) {
@@ -642,7 +659,8 @@ int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   if (G == 32) { K = (a.nchunks + 31) / 32; K = K <= 1 ? 1 : (K <= 2 ? 2 : 4); }
   unsigned long long ctas = (claims + 7) / 8;
   if (ctas < hub_items) ctas = hub_items;
-  const unsigned long long persistent = (unsigned long long)gai::sm_count() * 4;
+  const bool share = (a.flags & GAI_SPMM_SHARE_SMS) != 0;   // leave registers / threads for one foreign CTA per SM
+  const unsigned long long persistent = (unsigned long long)gai::sm_count() * (share ? 3 : 4);
   if (ctas > persistent) ctas = persistent;
   const unsigned grid = (unsigned)ctas;
   // rotating work-counter pairs {light-row claims, hub items}: launches on one stream are ordered; the rotation keeps up to 8

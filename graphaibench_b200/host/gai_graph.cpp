@@ -194,16 +194,79 @@ const float* LearningGraph::halo_exchange(const float* buf, int F, size_t ld) {
     if (comm_ && comm_->world() > 1) halo_exchange_into(buf, F, ld, nullptr);  // a rank without halo still takes part in the barriers
     return nullptr;
   }
-  const size_t need = halo_gids_.size() * ld;
-  if (need > halo_scratch_floats_) {  // grown on the first epoch only (widest exchanged matrix)
-    if (halo_scratch_) { die_on(gai_stream_sync(gai_host::stream()), "gai_stream_sync"); gai_free(halo_scratch_); }
-    void* p = nullptr;
-    die_on(gai_malloc(&p, sizeof(float) * need), "gai_malloc(halo scratch)");
-    halo_scratch_ = reinterpret_cast<float*>(p);
-    halo_scratch_floats_ = need;
-  }
+  ensure_halo_scratch(halo_gids_.size() * ld);
   halo_exchange_into(buf, F, ld, halo_scratch_);
   return halo_scratch_;
+}
+
+void LearningGraph::ensure_halo_scratch(size_t need) {
+  if (need <= halo_scratch_floats_) return;  // grown on the first epoch only (widest exchanged matrix)
+  if (halo_scratch_) {
+    die_on(gai_stream_sync(gai_host::stream()), "gai_stream_sync");
+    if (pull_stream_) die_on(gai_stream_sync(pull_stream_), "gai_stream_sync");
+    gai_free(halo_scratch_);
+  }
+  void* p = nullptr;
+  die_on(gai_malloc(&p, sizeof(float) * need), "gai_malloc(halo scratch)");
+  halo_scratch_ = reinterpret_cast<float*>(p);
+  halo_scratch_floats_ = need;
+}
+
+int LearningGraph::halo_block_count(int F) {
+  const char* e = std::getenv("GAI_HALO_BLOCKS");   // read per call: the tests switch it between runs of one process
+  int n = e ? std::atoi(e) : 4;
+  n = n < 1 ? 1 : (n > 8 ? 8 : n);
+  while (n > 1 && (F + n - 1) / n < 64) n--;   // narrower blocks waste gather lanes in the aggregation
+  return n;
+}
+
+LearningGraph::HaloBlocks LearningGraph::halo_exchange_begin(const float* buf, int F, size_t ld) {
+  HaloBlocks hb;
+  if (!comm_ || comm_->world() == 1) return hb;
+  const int id = comm_->id_of(buf);
+  if (id < 0) { std::cerr << "halo_exchange: the gathered matrix was never registered with the peer group\n"; std::exit(EXIT_FAILURE); }
+  hb.n = halo_block_count(F);
+  const int w = ((F + hb.n - 1) / hb.n + 31) / 32 * 32;   // block width: a multiple of 32 columns (whole sign-bit words, 128-byte segments)
+  hb.n = (F + w - 1) / w;
+  for (int k = 0; k < hb.n; k++) { hb.col0[k] = k * w; hb.ncol[k] = (k + 1) * w <= F ? w : F - k * w; }
+  if (!pull_stream_) {
+    die_on(gai_stream_create(&pull_stream_), "gai_stream_create");
+    die_on(gai_event_create(&ev_fork_), "gai_event_create");
+    die_on(gai_event_create(&ev_done_), "gai_event_create");
+    for (auto& e : ev_block_) die_on(gai_event_create(&e), "gai_event_create");
+  }
+  const bool have = !halo_gids_.empty();
+  if (have) ensure_halo_scratch(halo_gids_.size() * ld);
+  gai_stream_t main = gai_host::stream();
+  {
+    gai_host::OpScope sc("HALO", "barrier + fork W=" + std::to_string(F), 0, 0);
+    die_on(gai_peers_barrier_on(comm_->peers(), 0, main), "gai_peers_barrier_on");   // every owner's matrix is complete
+    die_on(gai_event_record(ev_fork_, main), "gai_event_record");
+  }
+  die_on(gai_stream_wait_event(pull_stream_, ev_fork_), "gai_stream_wait_event");
+  for (int k = 0; k < hb.n; k++) {
+    die_on(gai_halo_pull_cols(comm_->peers(), plan_, id, hb.col0[k], hb.ncol[k], ld, have ? halo_scratch_ : nullptr, ld,
+                              GAI_PULL_NO_BARRIER_BEFORE | GAI_PULL_NO_BARRIER_AFTER | GAI_PULL_SMALL_GRID, 1, pull_stream_), "gai_halo_pull_cols");
+    die_on(gai_event_record(ev_block_[k], pull_stream_), "gai_event_record");
+  }
+  die_on(gai_peers_barrier_on(comm_->peers(), 1, pull_stream_), "gai_peers_barrier_on");   // every rank has read what it needs
+  die_on(gai_event_record(ev_done_, pull_stream_), "gai_event_record");
+  halo_exchanges++;
+  halo_bytes += 4ull * (unsigned long long)F * halo_gids_.size();
+  hb.halo = have ? halo_scratch_ : nullptr;
+  return hb;
+}
+
+void LearningGraph::halo_wait_block(int k) {
+  if (!pull_stream_) return;
+  gai_host::OpScope sc("HALO", "wait block", 0, 0);
+  die_on(gai_stream_wait_event(gai_host::stream(), ev_block_[k]), "gai_stream_wait_event");
+}
+
+void LearningGraph::halo_exchange_end() {
+  if (!pull_stream_) return;
+  gai_host::OpScope sc("HALO", "wait closing barrier", 0, 0);
+  die_on(gai_stream_wait_event(gai_host::stream(), ev_done_), "gai_stream_wait_event");
 }
 
 void LearningGraph::halo_exchange_into(const float* buf, int F, size_t ld, float* dst) {
@@ -225,6 +288,13 @@ void LearningGraph::dealloc() {
   if (dev_) { gai_csr_destroy(dev_); dev_ = nullptr; }
   if (plan_) { gai_halo_plan_destroy(plan_); plan_ = nullptr; }
   if (halo_scratch_) { gai_free(halo_scratch_); halo_scratch_ = nullptr; halo_scratch_floats_ = 0; }
+  if (pull_stream_) {
+    gai_stream_sync(pull_stream_);
+    gai_event_destroy(ev_fork_); gai_event_destroy(ev_done_);
+    for (auto& e : ev_block_) { gai_event_destroy(e); e = nullptr; }
+    gai_stream_destroy(pull_stream_);
+    pull_stream_ = nullptr; ev_fork_ = ev_done_ = nullptr;
+  }
   rowptr_.clear(); rowptr_.shrink_to_fit();
   colidx_.clear(); colidx_.shrink_to_fit();
 }

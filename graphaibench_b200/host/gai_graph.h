@@ -88,6 +88,20 @@ class LearningGraph {
   // The same into a caller-owned buffer of num_halo() x ld floats (halo rows that stay valid across steps: the input features).
   void halo_exchange_into(const float* buf, int F, size_t ld, float* dst);
   unsigned long long halo_exchanges = 0, halo_bytes = 0;  // counted per call (measurement)
+  // Pipelined form: aggregation is independent per feature column, so the exchange is cut into column blocks (multiples of 32 columns)
+  // that cross NVLink on a second stream while the blocks already here are aggregated on the main one: only the first block's transfer
+  // is exposed. begin() issues barrier (main stream) -> all block pulls + closing barrier (pull stream); wait_block(k) makes the main
+  // stream wait for block k; end() makes it wait for the closing barrier (the owners may overwrite the matrix again). Every rank calls
+  // the same sequence (a rank without halo takes part in the barriers). Results are bit-identical to the one-piece exchange.
+  struct HaloBlocks {
+    int n = 1;
+    int col0[8] = {0}, ncol[8] = {0};
+    const float* halo = nullptr;
+  };
+  static int halo_block_count(int F);   // GAI_HALO_BLOCKS (default 4) capped so that a block keeps >= 64 columns; 1 = not pipelined
+  HaloBlocks halo_exchange_begin(const float* buf, int F, size_t ld);
+  void halo_wait_block(int k);
+  void halo_exchange_end();
 
   size_t size() const { return num_vertices_; }
   size_t sizeEdges() const { return num_edges_; }
@@ -121,6 +135,11 @@ class LearningGraph {
   gai_halo_plan_t plan_ = nullptr;
   float* halo_scratch_ = nullptr;
   size_t halo_scratch_floats_ = 0;
+  void ensure_halo_scratch(size_t floats);
+  gai_stream_t pull_stream_ = nullptr;
+  void* ev_fork_ = nullptr;
+  void* ev_done_ = nullptr;
+  void* ev_block_[8] = {nullptr};
 };
 
 typedef LearningGraph Graph;

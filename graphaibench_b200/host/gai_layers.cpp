@@ -134,22 +134,45 @@ void adam::reset() {
 
 void GCN_Aggregator::init(int len, int, int, float, float) { length = len; }
 enum { SPMM_GCN = 0, SPMM_MEAN = 1, SPMM_MEAN_T = 2 };  // gai_spmm_rows_ex modes
+// One aggregation call of any GCN / SAGE form. Partitioned graphs: the halo rows of `in` are fetched from their owners first — in one
+// piece, or (wide matrices) in column blocks on the pull stream while the blocks already here are aggregated (Graph::halo_exchange_begin;
+// columns are independent, so the result is bit-identical).
+static void spmm_any(Graph& g, int mode, const char* name, int len, const float* in, size_t ld_in, float* out, size_t ld_out, int flags,
+                     const float* addend, const uint32_t* mask_bits, const float* static_halo) {
+  const uint32_t n = (uint32_t)g.size();
+  const bool exchange = g.partitioned() && g.comm()->world() > 1 && !static_halo;
+  const int nblk = exchange ? Graph::halo_block_count(len) : 1;
+  const std::string tag = std::string(name) + " F=" + std::to_string(len) + (mask_bits ? " bitmask" : "");
+  if (nblk <= 1) {
+    const float* halo = static_halo ? static_halo : g.halo_exchange(in, len, ld_in);
+    gai_host::OpScope sc("AGGR", tag, spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + (mask_bits ? g.size() * len / 8.0 : 0),
+                         2.0 * g.sizeEdges() * len);
+    die_on(gai_spmm_rows_ex(g.device(), mode, 0, n, len, nullptr, nullptr, in, (int)ld_in, out, (int)ld_out, flags, addend, mask_bits,
+                            mask_bits ? (int)bits_pitch(len) : 0, halo, n, stream()), "gai_spmm_rows_ex");
+    return;
+  }
+  const Graph::HaloBlocks hb = g.halo_exchange_begin(in, len, ld_in);
+  for (int k = 0; k < hb.n; k++) {
+    g.halo_wait_block(k);
+    const int c0 = hb.col0[k], w = hb.ncol[k];
+    gai_host::OpScope sc("AGGR", tag + " /" + std::to_string(hb.n),
+                         spmm_bytes(g, w) + (addend ? 4.0 * g.size() * w : 0) + (mask_bits ? g.size() * w / 8.0 : 0), 2.0 * g.sizeEdges() * w);
+    die_on(gai_spmm_rows_ex(g.device(), mode, 0, n, w, nullptr, nullptr, in + c0, (int)ld_in, out + c0, (int)ld_out,
+                            flags | (k + 1 < hb.n ? GAI_SPMM_SHARE_SMS : 0) /* the next block's pull runs next to this kernel */, addend ? addend + c0 : nullptr,
+                            mask_bits ? mask_bits + c0 / 32 : nullptr, mask_bits ? (int)bits_pitch(len) : 0, hb.halo ? hb.halo + c0 : nullptr, n, stream()),
+           "gai_spmm_rows_ex(column block)");
+  }
+  g.halo_exchange_end();
+}
+
 void GCN_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend,
                                   const float* static_halo) {
-  const float* halo = static_halo ? static_halo : g.halo_exchange(in, len, ld_in);
-  gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_rows_ex(g.device(), SPMM_GCN, 0, (uint32_t)g.size(), len, nullptr, nullptr, in, (int)ld_in, out, (int)ld_out, flags, addend, nullptr, 0,
-                          halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(gcn)");
+  spmm_any(g, SPMM_GCN, "gcn", len, in, ld_in, out, ld_out, flags, addend, nullptr, static_halo);
 }
 // the normalised adjacency is symmetric, so the derivative is the same product (gcn_aggregator.cpp:35-46)
 void GCN_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
                                     const uint32_t* mask_bits) {
-  if (!mask_bits) { aggregate_ld(len, g, grad_in, ld_in, grad_out, ld_out, flags, addend); return; }
-  const float* halo = g.halo_exchange(grad_in, len, ld_in);
-  gai_host::OpScope sc("AGGR", "gcn F=" + std::to_string(len) + " bitmask", spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + g.size() * len / 8.0,
-                       2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_rows_ex(g.device(), SPMM_GCN, 0, (uint32_t)g.size(), len, nullptr, nullptr, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend,
-                          mask_bits, (int)bits_pitch(len), halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(gcn, masked)");
+  spmm_any(g, SPMM_GCN, "gcn", len, grad_in, ld_in, grad_out, ld_out, flags, addend, mask_bits, nullptr);
 }
 void GCN_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) { aggregate(len, g, grad_in, grad_out); }
@@ -157,18 +180,11 @@ void GCN_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* g
 void SAGE_Aggregator::init(int len, int, int, float, float) { length = len; }
 void SAGE_Aggregator::aggregate_ld(int len, Graph& g, const float* in, size_t ld_in, float* out, size_t ld_out, int flags, const float* addend,
                                    const float* static_halo) {
-  const float* halo = static_halo ? static_halo : g.halo_exchange(in, len, ld_in);
-  gai_host::OpScope sc("AGGR", "mean F=" + std::to_string(len), spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_rows_ex(g.device(), SPMM_MEAN, 0, (uint32_t)g.size(), len, nullptr, nullptr, in, (int)ld_in, out, (int)ld_out, flags, addend, nullptr, 0,
-                          halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(mean)");
+  spmm_any(g, SPMM_MEAN, "mean", len, in, ld_in, out, ld_out, flags, addend, nullptr, static_halo);
 }
 void SAGE_Aggregator::d_aggregate_ld(int len, Graph& g, const float* grad_in, size_t ld_in, float* grad_out, size_t ld_out, int flags, const float* addend,
                                      const uint32_t* mask_bits) {
-  const float* halo = g.halo_exchange(grad_in, len, ld_in);
-  gai_host::OpScope sc("AGGR", "meanT F=" + std::to_string(len) + (mask_bits ? " bitmask" : ""),
-                       spmm_bytes(g, len) + (addend ? 4.0 * g.size() * len : 0) + (mask_bits ? g.size() * len / 8.0 : 0), 2.0 * g.sizeEdges() * len);
-  die_on(gai_spmm_rows_ex(g.device(), SPMM_MEAN_T, 0, (uint32_t)g.size(), len, nullptr, nullptr, grad_in, (int)ld_in, grad_out, (int)ld_out, flags, addend,
-                          mask_bits, mask_bits ? (int)bits_pitch(len) : 0, halo, (uint32_t)g.size(), stream()), "gai_spmm_rows_ex(meanT)");
+  spmm_any(g, SPMM_MEAN_T, "meanT", len, grad_in, ld_in, grad_out, ld_out, flags, addend, mask_bits, nullptr);
 }
 void SAGE_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_ld(len, g, in, len, out, len, GAI_EPI_NONE, nullptr); }
 void SAGE_Aggregator::d_aggregate(int len, Graph& g, const float*, const float* grad_in, float* grad_out) {

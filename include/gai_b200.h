@@ -127,6 +127,8 @@ const uint32_t* gai_csr_transpose_perm(gai_csr_t g);
 /* ---- neighbour aggregation (SpMM) -------------------------------------------------------------------
  * out[i, 0:F] = epilogue( sum_{e in row i} w_e * in[col_e, 0:F] ), i in [row_begin, row_end).
  * flags: GAI_EPI_ADD  -> add `addend[i, :]` (ld = ld_out) after the sum;  GAI_EPI_RELU -> max(.,0) last. */
+enum { GAI_SPMM_SHARE_SMS = 64 /* aggregations only: size the persistent grid so that one 256-thread CTA of another kernel (the halo pull
+                                  of the next column block) fits on every SM next to it */ };
 enum { GAI_EPI_NONE = 0, GAI_EPI_RELU = 1, GAI_EPI_ADD = 2, GAI_EPI_MASK = 4 /* dense transforms only: see gai_matmul_kcat */,
        GAI_EPI_BITMASK = 16 /* with GAI_EPI_MASK: `mask` points to uint32 sign-bit words, one per row and 32-column chunk (bit c % 32 of
                                word c / 32 = activation[row, c] > 0), ldmask in words — written by the ReLU epilogue of the layer below */,
@@ -310,15 +312,24 @@ int gai_peers_world(gai_peers_t p);
 int gai_peers_register(gai_peers_t p, void* dptr, int* id_out);
 /* Flag barrier in peer memory, enqueued on `stream`: everything this rank enqueued before it is visible to every rank's work behind it. */
 int gai_peers_barrier(gai_peers_t p, gai_stream_t stream);
+/* The same on barrier channel `channel` (0 or 1). Barriers of one channel must be issued in one order on every rank; a rank that issues
+ * barriers from two streams (main stream / pull stream of a pipelined halo exchange) gives each stream its own channel. */
+int gai_peers_barrier_on(gai_peers_t p, int channel, gai_stream_t stream);
 /* Synchronises `stream`; GAI_ERR_CUDA if a barrier gave up waiting for a peer (a rank died). */
 int gai_peers_error(gai_peers_t p, gai_stream_t stream);
 /* halo_gids_h: this rank's distinct remote neighbours, strictly ascending global ids (grouped by owner as a consequence). */
 int gai_halo_plan_create(gai_peers_t p, uint32_t nv_global, uint32_t n_halo, const uint32_t* halo_gids_h, gai_stream_t stream, gai_halo_plan_t* out);
 int gai_halo_plan_destroy(gai_halo_plan_t h);
-enum { GAI_PULL_NO_BARRIER_BEFORE = 1, GAI_PULL_NO_BARRIER_AFTER = 2 };
+enum { GAI_PULL_NO_BARRIER_BEFORE = 1, GAI_PULL_NO_BARRIER_AFTER = 2,
+       GAI_PULL_SMALL_GRID = 4 /* the pull runs next to another kernel: ~1 CTA per SM, deeper per-thread pipelining */ };
 /* dst[k, 0:F] (pitch ld_dst, a private buffer of this rank) <- row of halo vertex k in its owner's instance of buffer `buf_id` (pitch ld_src
  * on every rank), read through the mapped peer pointers. barrier - pull - barrier unless `flags` drops one. */
 int gai_halo_pull(gai_peers_t p, gai_halo_plan_t h, int buf_id, int F, size_t ld_src, float* dst, size_t ld_dst, int flags, gai_stream_t stream);
+/* Columns [col0, col0 + F) of the same rows (dst still names column 0 of halo row 0); its barriers, if any, run on `channel`. Aggregation
+ * is independent per feature column, so an exchange cut into column blocks lets block k be aggregated while block k + 1 crosses NVLink
+ * (host/gai_graph.cpp halo_exchange_begin). No reference counterpart (the reference's GNN path is single-GPU). */
+int gai_halo_pull_cols(gai_peers_t p, gai_halo_plan_t h, int buf_id, int col0, int F, size_t ld_src, float* dst, size_t ld_dst, int flags, int channel,
+                       gai_stream_t stream);
 /* sum = 1: out[i] = sum over ranks (rank order, identical bits everywhere) of buffer `buf_id`[i], i < n   (weight-gradient all-reduce);
  * sum = 0: out[q*n + i] = rank q's buffer[i]                                                              (all-gather of small vectors).
  * `out` is a private buffer, not the registered one. barrier - combine - barrier. */

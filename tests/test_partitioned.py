@@ -170,3 +170,23 @@ def test_partitioned_training_matches_single_gpu(gm, arch, world, dims, layers):
     assert np.quantile(d, 0.9) <= 5e-4 and np.quantile(d, 0.99) <= 2e-3, (float(np.quantile(d, 0.9)), float(np.quantile(d, 0.99)))
     assert d.max() <= 4 * epochs * 0.01 / np.abs(w_single).max(), float(d.max())
     assert int(got["halo"][:, 0].sum()) == nv and (got["halo"][:, 2] > 0).all() == (world > 1)
+
+
+@pytest.mark.gpu
+def test_pipelined_halo_exchange_is_bit_identical_to_one_piece(gm, monkeypatch):
+    """Column-block pipelining of the halo exchange (Graph::halo_exchange_begin: blocks cross NVLink on a pull stream while the blocks
+    already here are aggregated) changes the schedule, not one bit of the result: aggregation is independent per feature column."""
+    require_cuda()
+    from graphaibench_b200 import datagen
+    nv, F, hid, ncls = 7000, 128, 256, 172
+    rp64, ci = datagen.rmat_csr(nv, 110000, seed=61)
+    feats = datagen.features(nv, F, seed=62)
+    labels = np.random.default_rng(63).integers(0, ncls, nv).astype(np.uint8)
+    split = datagen.split_ranges(nv)
+    runs = {}
+    for blocks in ("1", "2", "4"):
+        monkeypatch.setenv("GAI_HALO_BLOCKS", blocks)
+        runs[blocks] = gm.train_partitioned_inprocess("gcn", 3, rp64, ci, feats, labels, split, hid, ncls, num_layers=3, lr=0.01, epochs=3)
+    for blocks in ("2", "4"):
+        assert np.array_equal(runs[blocks]["losses"], runs["1"]["losses"])
+        assert np.array_equal(runs[blocks]["weights"], runs["1"]["weights"])
