@@ -65,6 +65,14 @@ struct TcArgs {
                    // 4 = no hi/lo split, 8 = no MMA issue
 };
 
+// PAIR: the two CTAs of a cluster (one TPC) work on 256 consecutive rows with ONE cta_group::2 MMA per k-step (M = 256): each CTA stages
+// its own 128 rows of A (TMA + hi/lo split as before) and only HALF of the weight tile (its N/2 rows of the K-major B_hi / B_lo), the
+// tensor cores of both SMs read both halves. A stage shrinks from 96 KB to 64 KB at N = 256 — three stages instead of two — and the
+// L2 -> SM traffic per k-block from 80 KB to 48 KB per SM (the re-streamed weights were 4/5 of it). Protocol: both CTAs' splitter warps
+// arrive on the LEADER's conv barrier (count 8, remote mbarrier arrive), the leader's elected thread issues the MMAs and commits with
+// multicast onto the empty / accumulator-full barriers of both CTAs, each CTA's epilogue drains its own TMEM half and arrives on the
+// leader's accumulator-empty barrier (count 8).
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const TcArgs g) {
@@ -74,26 +82,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t num_tiles = (g.M + BM - 1) / BM;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const size_t num_rb = (g.M + BM - 1) / BM;                  // 128-row blocks
+  const size_t num_tiles = PAIR ? (num_rb + 1) / 2 : num_rb;  // work items: a row block, or a pair of them
+  const size_t tile0 = PAIR ? blockIdx.x / 2 : blockIdx.x, tile_step = PAIR ? gridDim.x / 2 : gridDim.x;
   constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < g.stages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&conv_bar[i], 4); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < g.stages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&conv_bar[i], PAIR ? 8 : 4); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 512 columns = two fp32 accumulators of up to 256 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (PAIR) cluster_sync_all();  // both CTAs resident, barriers initialised, before anything touches the peer
+  if (warp == 1) {  // TMEM: 512 columns = two fp32 accumulators of up to 256 columns (the same warp of both CTAs for a pair)
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
   // N >> 3 in bits [17,23), M >> 4 in bits [24,29)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
+  auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc_flag) {
+    if (PAIR) umma_tf32_pair(d, da, db, idesc, acc_flag); else umma_tf32(d, da, db, idesc, acc_flag);
+  };
+  auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
   // MMAs of one k-block into accumulator `acc` (one thread), then the commits that release the stage / publish the accumulator
   auto issue_kblock = [&](int kb, int s, int acc) {
     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
@@ -107,47 +128,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes along the swizzled 128-byte row
       const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
       if (g.passes == 3) {
-        umma_tf32(d_tmem, make_desc_k128(a_lo + koff), make_desc_k128(b_hi + koff), idesc, first);
-        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_lo + koff), idesc, 1u);
-        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, 1u);
+        mma(d_tmem, make_desc_k128(a_lo + koff), make_desc_k128(b_hi + koff), first);
+        mma(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_lo + koff), 1u);
+        mma(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), 1u);
       } else {
-        umma_tf32(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), idesc, first);
+        mma(d_tmem, make_desc_k128(a_hi + koff), make_desc_k128(b_hi + koff), first);
       }
     }
-    umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
-    if (kb == g.num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+    commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it (both CTAs of a pair)
+    if (kb == g.num_kb - 1) commit(&tfull_bar[acc]);  // accumulator complete
   };
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b_row = PAIR ? (int)crank * (g.n_mma / 2) : 0;  // this CTA's half of the weight tile
+      for (size_t tile = tile0; tile < num_tiles; tile += tile_step) {
+        const size_t rb = PAIR ? tile * 2 + crank : tile;       // a row block past the end loads zeros (TMA out-of-bounds fill)
         for (int kb = 0; kb < g.num_kb; kb++, it++) {
           const int s = it % g.stages;
           mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
           uint8_t* st = smem + (size_t)s * g.stage_bytes;
           const bool load_b = !(g.debug & 1) || it < (uint32_t)g.stages;
           mbar_arrive_expect_tx(&full_bar[s], A_BYTES + (load_b ? (g.passes == 3 ? 2 : 1) * g.b_tile_bytes : 0u));
-          if (kb < g.nkb0) tma_load_2d(st, &map_a0, kb * BK, (int)(tile * BM), &full_bar[s]);
-          else             tma_load_2d(st, &map_a1, (kb - g.nkb0) * BK, (int)(tile * BM), &full_bar[s]);
+          if (kb < g.nkb0) tma_load_2d(st, &map_a0, kb * BK, (int)(rb * BM), &full_bar[s]);
+          else             tma_load_2d(st, &map_a1, (kb - g.nkb0) * BK, (int)(rb * BM), &full_bar[s]);
           if (load_b) {
-            tma_load_2d(st + 2 * A_BYTES, &map_bhi, kb * BK, 0, &full_bar[s]);
-            if (g.passes == 3) tma_load_2d(st + 2 * A_BYTES + g.b_tile_bytes, &map_blo, kb * BK, 0, &full_bar[s]);
+            tma_load_2d(st + 2 * A_BYTES, &map_bhi, kb * BK, b_row, &full_bar[s]);
+            if (g.passes == 3) tma_load_2d(st + 2 * A_BYTES + g.b_tile_bytes, &map_blo, kb * BK, b_row, &full_bar[s]);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    if (lane == 0 && crank == 0) {
       uint32_t it = 0, tcount = 0;
-      for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+      for (size_t tile = tile0; tile < num_tiles; tile += tile_step, tcount++) {
         const int acc = tcount & 1;
-        mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        // epilogue(s) have drained this accumulator
+        if (PAIR) mbar_wait_cluster(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1); else mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         for (int kb = 0; kb < g.num_kb; kb++, it++) {
           const int s = it % g.stages;
-          mbar_wait(&conv_bar[s], (it / g.stages) & 1);
+          if (PAIR) mbar_wait_cluster(&conv_bar[s], (it / g.stages) & 1); else mbar_wait(&conv_bar[s], (it / g.stages) & 1);
           tcgen05_fence_after();
           issue_kblock(kb, s, acc);
         }
@@ -157,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ---------------- splitter: A -> (A_hi in place, A_lo) ----------------
     const int t = threadIdx.x - 256;  // 0..127
     uint32_t it = 0;
-    for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (size_t tile = tile0; tile < num_tiles; tile += tile_step) {
       for (int kb = 0; kb < g.num_kb; kb++, it++) {
         const int s = it % g.stages;
         mbar_wait(&full_bar[s], (it / g.stages) & 1);
@@ -176,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&conv_bar[s]);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(&conv_bar[s], 0); else mbar_arrive(&conv_bar[s]); }  // the MMA issuer's barrier
       }
     }
   } else if (warp >= 4) {
@@ -187,12 +211,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const bool relu = (g.flags & GAI_EPI_RELU) != 0;
     const bool mask_ok = g.mask == nullptr || (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
     uint32_t tcount = 0;
-    for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+    for (size_t tile = tile0; tile < num_tiles; tile += tile_step, tcount++) {
       const int acc = tcount & 1;
       mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1);
       tcgen05_fence_after();
-      const size_t row0 = tile * BM + (size_t)q * 32;
-      const bool tile_full = tile * BM + BM <= g.M;
+      const size_t rb = PAIR ? tile * 2 + crank : tile;
+      const size_t row0 = rb * BM + (size_t)q * 32;
+      const bool tile_full = rb * BM + BM <= g.M;
       const int nrows = tile_full ? 32 : (g.M > row0 ? (int)(g.M - row0 < 32 ? g.M - row0 : 32) : 0);  // live rows of this warp's quarter
       for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
         const int j = (g.nouts > 1 && c0 >= g.noff1) ? 1 : 0;
@@ -343,15 +368,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // a pair: neither CTA leaves while the other may still signal it or read its operands
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -401,7 +427,14 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   const size_t n_tile = q.nn > 1 ? (size_t)noff1 + q.N[1] : q.N[0];
   if (n_tile > 256) return GAI_ERR_UNSUPPORTED;
   if (!encode_fn()) return GAI_ERR_UNSUPPORTED;
-  const int n_mma = (int)((n_tile + 15) / 16 * 16);
+  // CTA pairs for wide outputs (three 64 KB stages instead of two 96 KB ones, 48 instead of 80 KB of L2 -> SM traffic per k-block).
+  // OPT-IN (GAI_TC_PAIR=1): correct on every transform test, but measured SLOWER than the single-CTA kernel on the C2 epoch (K-concatenated
+  // forward 1.77 vs 1.65 ms, masked input gradient 1.17 vs 1.13 ms; profiles/r2_gemm_pair_ab.json) — the depth of the operand ring and the
+  // weight re-streaming are therefore NOT what holds these transforms at 0.42 of the HBM roofline.
+  const char* pair_env = getenv("GAI_TC_PAIR");   // read per call (the tests switch it)
+  const bool allow_pair = pair_env != nullptr && atoi(pair_env) != 0;
+  const bool pair = allow_pair && n_tile > 128;
+  const int n_mma = pair ? (int)((n_tile + 31) / 32 * 32) : (int)((n_tile + 15) / 16 * 16);
   int nkb[2] = {0, 0}, last_steps[2] = {BK / 8, BK / 8};
   for (int p = 0; p < q.nk; p++) {
     nkb[p] = (int)((q.K[p] + BK - 1) / BK);
@@ -410,7 +443,8 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   if (q.nk == 1) last_steps[1] = last_steps[0];  // num_kb - 1 == nkb0 - 1: both tests name the same block
   const int num_kb = nkb[0] + nkb[1];
   const int k_pad = num_kb * BK;
-  const uint32_t b_tile_bytes = (uint32_t)n_mma * BK * 4;
+  const uint32_t b_rows = pair ? (uint32_t)n_mma / 2 : (uint32_t)n_mma;  // rows of the K-major weight tile one CTA stages
+  const uint32_t b_tile_bytes = b_rows * BK * 4;
   const uint32_t stage_bytes = 2 * BM * BK * 4 + 2 * b_tile_bytes;  // A_hi | A_lo | B_hi | B_lo   (all multiples of 1024)
   int stages = (int)((204u * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
@@ -460,8 +494,8 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
     }
     if (!make_map_f32(&map_a[p], a_src, M, a_cols, a_ld, BM, true)) return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed (A)");
   }
-  if (!make_map_f32(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false) ||
-      !make_map_f32(&map_blo, blo, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)n_mma, false))
+  if (!make_map_f32(&map_bhi, bhi, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, b_rows, false) ||
+      !make_map_f32(&map_blo, blo, (uint64_t)n_mma, (uint64_t)k_pad, (uint64_t)k_pad, b_rows, false))
     return set_error(GAI_ERR_CUDA, "gemm_tc", "cuTensorMapEncodeTiled failed (B)");
 
   TcArgs g;
@@ -491,12 +525,29 @@ int gemm_tc_cat(const GemmCat& q, int passes, cudaStream_t st) {
   const size_t smem = (size_t)stages * stage_bytes + EPI_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    GAI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    GAI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    GAI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     configured = true;
   }
   const size_t tiles = (M + BM - 1) / BM;
+  if (pair) {
+    // one cluster of two CTAs per TPC; a pair walks 256-row tiles
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2), 1, 1);
+    cfg.blockDim = dim3(THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GAI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, map_a[0], map_a[1], map_bhi, map_blo, g));
+    GAI_LAUNCH_CHECK();
+    return GAI_OK;
+  }
   const unsigned grid = (unsigned)(tiles < (size_t)sm_count() ? tiles : (size_t)sm_count());
-  gemm_tc_kernel<<<grid, THREADS, smem, st>>>(map_a[0], map_a[1], map_bhi, map_blo, g);
+  gemm_tc_kernel<false><<<grid, THREADS, smem, st>>>(map_a[0], map_a[1], map_bhi, map_blo, g);
   GAI_LAUNCH_CHECK();
   return GAI_OK;
 }

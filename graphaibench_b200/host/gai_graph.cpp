@@ -214,7 +214,7 @@ void LearningGraph::ensure_halo_scratch(size_t need) {
 
 int LearningGraph::halo_block_count(int F) {
   const char* e = std::getenv("GAI_HALO_BLOCKS");   // read per call: the tests switch it between runs of one process
-  int n = e ? std::atoi(e) : 4;
+  int n = e ? std::atoi(e) : 1;
   n = n < 1 ? 1 : (n > 8 ? 8 : n);
   while (n > 1 && (F + n - 1) / n < 64) n--;   // narrower blocks waste gather lanes in the aggregation
   return n;

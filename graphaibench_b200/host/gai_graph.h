@@ -88,9 +88,11 @@ class LearningGraph {
   // The same into a caller-owned buffer of num_halo() x ld floats (halo rows that stay valid across steps: the input features).
   void halo_exchange_into(const float* buf, int F, size_t ld, float* dst);
   unsigned long long halo_exchanges = 0, halo_bytes = 0;  // counted per call (measurement)
-  // Pipelined form: aggregation is independent per feature column, so the exchange is cut into column blocks (multiples of 32 columns)
-  // that cross NVLink on a second stream while the blocks already here are aggregated on the main one: only the first block's transfer
-  // is exposed. begin() issues barrier (main stream) -> all block pulls + closing barrier (pull stream); wait_block(k) makes the main
+  // Pipelined form (opt-in, GAI_HALO_BLOCKS > 1): aggregation is independent per feature column, so the exchange is cut into column
+  // blocks (multiples of 32 columns) that cross NVLink on a second stream while the blocks already here are aggregated on the main one:
+  // only the first block's transfer is exposed. Measured on the papers100M-shaped GCN (round 2, 2 and 8 GPUs): the exchange hides as
+  // designed (HALO 14.5 -> 6.5 ms per epoch at N = 2) but the aggregation pays more than that for walking the CSR once per block
+  // (75.7 -> 107.6 ms: at average degree 14 the per-row work, not the bytes, bounds it), so the one-piece exchange stays the default. begin() issues barrier (main stream) -> all block pulls + closing barrier (pull stream); wait_block(k) makes the main
   // stream wait for block k; end() makes it wait for the closing barrier (the owners may overwrite the matrix again). Every rank calls
   // the same sequence (a rank without halo takes part in the barriers). Results are bit-identical to the one-piece exchange.
   struct HaloBlocks {
@@ -98,7 +100,7 @@ class LearningGraph {
     int col0[8] = {0}, ncol[8] = {0};
     const float* halo = nullptr;
   };
-  static int halo_block_count(int F);   // GAI_HALO_BLOCKS (default 4) capped so that a block keeps >= 64 columns; 1 = not pipelined
+  static int halo_block_count(int F);   // GAI_HALO_BLOCKS (default 1 = one piece) capped so that a block keeps >= 64 columns
   HaloBlocks halo_exchange_begin(const float* buf, int F, size_t ld);
   void halo_wait_block(int k);
   void halo_exchange_end();

@@ -245,11 +245,17 @@ def test_gather_rows(T, ops):
 
 @pytest.mark.parametrize("shape", [(5000, 256, 100, 0), (8192, 47, 256, 0), (6000, 256, 47, 1), (4096, 16, 1433, 0), (20000, 100, 256, 1),
                                    (4500, 7, 16, 0), (33000, 172, 128, 0)])
-def test_matmul_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape):
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_matmul_tcgen05_3xtf32_vs_oracle(T, ops, liborc, shape, pair, monkeypatch):
     """tcgen05/TMEM path (mode 2 = forced, 3xTF32): fp32-level accuracy (norm-wise 1e-5) on aligned and unaligned widths,
-    ragged row counts, transposed weights, accumulate and ReLU epilogues. Mode 3 (single TF32 pass) is ~1e-3 by design."""
+    ragged row counts, transposed weights, accumulate and ReLU epilogues. Mode 3 (single TF32 pass) is ~1e-3 by design.
+    pair = 1: the opt-in cta_group::2 kernel (two CTAs of a cluster on one M = 256 MMA; outputs wider than 128 columns only), including
+    odd row-block counts whose last pair has one out-of-bounds half."""
     from graphaibench_b200._abi import lib
+    monkeypatch.setenv("GAI_TC_PAIR", pair)
     x, y, z, tb = shape
+    if pair == "1" and y <= 128:
+        pytest.skip("the pair kernel takes outputs wider than 128 columns")
     rng = np.random.default_rng(x + 3 * y + z)
     A = rng.standard_normal((x, z), dtype=np.float32)
     B = rng.standard_normal((y, z) if tb else (z, y), dtype=np.float32)
