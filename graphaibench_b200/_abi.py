@@ -69,6 +69,11 @@ _SIGS = {
     "gai_spmm_mean_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
     "gai_gat_forward": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_stream]),
     "gai_gat_backward": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "gai_spmm_edge_heads": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f32p, c_u32p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
+    "gai_gat_forward_heads_ld": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, C.c_size_t,
+                                           C.c_int, c_stream]),
+    "gai_gat_backward_heads_ld": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p,
+                                            c_f32p, c_f32p, C.c_size_t, c_stream]),
     "gai_gat_forward_ld": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_size_t, c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, C.c_size_t, C.c_int, c_stream]),
     "gai_gat_backward_ld": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_size_t, c_f32p, C.c_size_t, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                       c_f32p, C.c_size_t, c_stream]),

@@ -25,6 +25,42 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Per-head reductions over the lanes of a warp: with H heads (a power of two <= 32) lane l works on head l % H, so a butterfly over the
+// offsets 16 .. H leaves every lane with the total of its own head. H = 1: the plain warp reduction.
+__device__ __forceinline__ float head_sum(float v, int H) {
+  for (int o = 16; o >= H; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float head_max(float v, int H) {
+  for (int o = 16; o >= H; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Row-cooperative per-head reductions: a warp (light rows) or a whole CTA (hub rows; red holds 32 floats per warp).
+template <bool CTA>
+__device__ __forceinline__ float coop_hsum(float v, int H, float* red) {
+  v = head_sum(v, H);
+  if (!CTA) return v;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane < H) red[w * 32 + lane] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; i++) t += red[i * 32 + (lane & (H - 1))];
+  return t;
+}
+template <bool CTA>
+__device__ __forceinline__ float coop_hmax(float v, int H, float* red) {
+  v = head_max(v, H);
+  if (!CTA) return v;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane < H) red[w * 32 + lane] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < nw; i++) t = fmaxf(t, red[i * 32 + (lane & (H - 1))]);
+  return t;
+}
+
 // Row-cooperative reductions: a warp (light rows) or a whole CTA (hub rows).
 template <bool CTA>
 __device__ __forceinline__ float coop_sum(float v, float* red) {
@@ -75,45 +111,52 @@ __device__ __forceinline__ bool pick_row(const RowSel& r, uint32_t& row, uint32_
   return true;
 }
 
-// el/er per vertex: one warp per row, coalesced.
-__global__ void el_er_kernel(uint32_t nv, int F, const float* __restrict__ z, size_t ld, const float* __restrict__ al, const float* __restrict__ ar,
+// el/er per vertex (and head): one warp per row, coalesced. H heads of D = F / H columns each: el[i * H + h] = <alpha_l[hD..], z_i[hD..]>.
+__global__ void el_er_kernel(uint32_t nv, int F, int H, const float* __restrict__ z, size_t ld, const float* __restrict__ al, const float* __restrict__ ar,
                              float* __restrict__ el, float* __restrict__ er) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nv) return;
   const float* x = z + (size_t)w * ld;
-  float a = 0.f, b = 0.f;
-  for (int k = lane; k < F; k += 32) { const float v = x[k]; a += __ldg(al + k) * v; b += __ldg(ar + k) * v; }
-  a = warp_sum(a); b = warp_sum(b);
-  if (lane == 0) { el[w] = a; er[w] = b; }
+  const int D = F / H;
+  for (int h = 0; h < H; h++) {
+    float a = 0.f, b = 0.f;
+    for (int k = h * D + lane; k < (h + 1) * D; k += 32) { const float v = x[k]; a += __ldg(al + k) * v; b += __ldg(ar + k) * v; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { el[w * H + h] = a; er[w * H + h] = b; }
+  }
 }
 
 // temp_scores[e] = el_i + er_j; norm_scores = softmax_row(LeakyReLU(temp_scores))   (gat_aggregator.cpp:62-77)
+// Score arrays are edge-major with H entries per edge: item i = e * H + h. The items of a row are the contiguous range [s*H, e*H); thread
+// `tid` walks them with a stride that is a multiple of H, so it only ever sees head tid % H and the per-head reductions are butterflies.
 template <bool CTA>
-__global__ void scores_kernel(const RowSel r, const uint32_t* __restrict__ colidx, const float* __restrict__ el, const float* __restrict__ er,
+__global__ void scores_kernel(const RowSel r, int H, const uint32_t* __restrict__ colidx, const float* __restrict__ el, const float* __restrict__ er,
                               float slope, float* __restrict__ temp_scores, float* __restrict__ norm_scores) {
-  __shared__ float red[32];
+  __shared__ float red[32 * 8];
   uint32_t row, s, e; int tid, nthr;
   if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
-  const float eli = __ldg(el + row);
+  const int h = tid & (H - 1), hs = __ffs(H) - 1;
+  const uint64_t i0 = (uint64_t)s * H, i1 = (uint64_t)e * H;
+  const float eli = __ldg(el + (size_t)row * H + h);
   float mx = -INFINITY;
-  for (uint32_t k = s + tid; k < e; k += nthr) {
-    const float t = eli + __ldg(er + __ldg(colidx + k));
-    temp_scores[k] = t;
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) {
+    const float t = eli + __ldg(er + (size_t)__ldg(colidx + (i >> hs)) * H + h);
+    temp_scores[i] = t;
     const float sc = t > 0.f ? t : slope * t;
     mx = fmaxf(mx, sc);
   }
-  mx = coop_max<CTA>(mx, red);
+  mx = coop_hmax<CTA>(mx, H, red);
   float sum = 0.f;
-  for (uint32_t k = s + tid; k < e; k += nthr) {
-    const float t = temp_scores[k];
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) {
+    const float t = temp_scores[i];
     const float sc = t > 0.f ? t : slope * t;
     const float p = expf(sc - mx);
-    norm_scores[k] = p;
+    norm_scores[i] = p;
     sum += p;
   }
-  sum = coop_sum<CTA>(sum, red);
-  for (uint32_t k = s + tid; k < e; k += nthr) norm_scores[k] = norm_scores[k] / sum;
+  sum = coop_hsum<CTA>(sum, H, red);
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) norm_scores[i] = norm_scores[i] / sum;
 }
 
 // SDDMM dS[e] = <g_i, z_j>. One warp per edge-slice: light rows = one warp per row; hub rows = CTA per row, warps split the edges.
@@ -240,42 +283,109 @@ __global__ void __launch_bounds__(256, 4) sddmm_edges_kernel(uint32_t nv, uint64
   }
 }
 
+// Multi-head SDDMM: dS[e * H + h] = <g_row(e)[head h], z_col(e)[head h]>. Same flat edge chunks as above; a head owns `cph` consecutive
+// float4 chunks (a power of two <= 32), i.e. `cph` consecutive lanes of a 32-chunk slab, so its dot product is a segmented butterfly
+// (log2(cph) shuffles) and the 32 / cph heads of a slab are stored by their first lanes as one contiguous run.
+template <int KCH>
+__global__ void __launch_bounds__(256, 4) sddmm_heads_kernel(uint32_t nv, uint64_t nnz, const uint32_t* __restrict__ rowptr,
+                                                             const uint32_t* __restrict__ colidx, int nch, int cph, int H, size_t ld4,
+                                                             const float4* __restrict__ grad4, const float4* __restrict__ z4, float* __restrict__ ds) {
+  constexpr int EC = 1024;
+  constexpr int U = KCH == 1 ? 8 : (KCH == 2 ? 4 : 2);
+  const int lane = threadIdx.x & 31;
+  const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t nchunks = (nnz + EC - 1) / EC;
+  bool act[KCH];
+  int head[KCH];
+#pragma unroll
+  for (int k = 0; k < KCH; k++) { act[k] = lane + 32 * k < nch; head[k] = (lane + 32 * k) / cph; }
+  const bool writer = (lane & (cph - 1)) == 0;
+  for (uint64_t chunk = gwarp; chunk < nchunks; chunk += nwarps) {
+    const uint64_t e0 = chunk * EC;
+    const uint64_t e1 = e0 + EC < nnz ? e0 + EC : nnz;
+    uint32_t lo = 0, hi = nv;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if ((uint64_t)__ldg(rowptr + mid) <= e0) lo = mid; else hi = mid;
+    }
+    uint32_t row = lo;
+    uint64_t re = __ldg(rowptr + row + 1);
+    while (re <= e0) { row++; re = __ldg(rowptr + row + 1); }
+    float4 gq[KCH];
+#pragma unroll
+    for (int k = 0; k < KCH; k++) gq[k] = act[k] ? __ldg(grad4 + (size_t)row * ld4 + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint64_t b = e0; b < e1; b += 32) {
+      const uint32_t c = (b + lane < e1) ? __ldg(colidx + b + lane) : 0u;
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += U) {
+        if (b + j0 >= e1) break;
+        float4 x[U][KCH];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t cc = __shfl_sync(0xffffffffu, c, j0 + u);
+#pragma unroll
+          for (int k = 0; k < KCH; k++) x[u][k] = (act[k] && b + j0 + u < e1) ? __ldg(z4 + (size_t)cc * ld4 + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint64_t edge = b + j0 + u;
+          if (edge < e1 && edge >= re) {  // warp-uniform: the edge starts a new row
+            do { row++; re = __ldg(rowptr + row + 1); } while (edge >= re);
+#pragma unroll
+            for (int k = 0; k < KCH; k++) gq[k] = act[k] ? __ldg(grad4 + (size_t)row * ld4 + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < KCH; k++) {
+            float d = gq[k].x * x[u][k].x + gq[k].y * x[u][k].y + gq[k].z * x[u][k].z + gq[k].w * x[u][k].w;
+            for (int o = cph >> 1; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (writer && act[k] && edge < e1) ds[edge * H + head[k]] = d;
+          }
+        }
+      }
+    }
+  }
+}
+
 // In place on ds: softmax backward (closed form of math_functions.cpp:496-514), LeakyReLU backward
 // (gat_aggregator.cpp:144); rowsum[i] = sum_e ds_e (the reference's src_score_grad, :149).
 template <bool CTA>
-__global__ void softmax_bwd_kernel(const RowSel r, float slope, const float* __restrict__ temp_scores, const float* __restrict__ p,
+__global__ void softmax_bwd_kernel(const RowSel r, int H, float slope, const float* __restrict__ temp_scores, const float* __restrict__ p,
                                    float* __restrict__ ds, float* __restrict__ rowsum) {
-  __shared__ float red[32];
+  __shared__ float red[32 * 8];
   uint32_t row, s, e; int tid, nthr;
   if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const uint64_t i0 = (uint64_t)s * H, i1 = (uint64_t)e * H;
   float dot = 0.f;
-  for (uint32_t k = s + tid; k < e; k += nthr) dot += p[k] * ds[k];
-  dot = coop_sum<CTA>(dot, red);
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) dot += p[i] * ds[i];
+  dot = coop_hsum<CTA>(dot, H, red);
   float rs = 0.f;
-  for (uint32_t k = s + tid; k < e; k += nthr) {
-    const float dy = p[k] * (ds[k] - dot);
-    const float v = dy * (temp_scores[k] > 0.f ? 1.0f : slope);
-    ds[k] = v;
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) {
+    const float dy = p[i] * (ds[i] - dot);
+    const float v = dy * (temp_scores[i] > 0.f ? 1.0f : slope);
+    ds[i] = v;
     rs += v;
   }
-  rs = coop_sum<CTA>(rs, red);
-  if (tid == 0) rowsum[row] = rs;
+  rs = coop_hsum<CTA>(rs, H, red);
+  if (tid < H) rowsum[(size_t)row * H + tid] = rs;
 }
 
 // colsum[j] = sum over edges e' pointing at j of ds[e'] = sum_{e in row j} ds[perm[e]]  (symmetric pattern)
 template <bool CTA>
-__global__ void colsum_kernel(const RowSel r, const uint32_t* __restrict__ perm, const float* __restrict__ ds, float* __restrict__ colsum) {
-  __shared__ float red[32];
+__global__ void colsum_kernel(const RowSel r, int H, const uint32_t* __restrict__ perm, const float* __restrict__ ds, float* __restrict__ colsum) {
+  __shared__ float red[32 * 8];
   uint32_t row, s, e; int tid, nthr;
   if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const int h = tid & (H - 1), hs = __ffs(H) - 1;
+  const uint64_t i0 = (uint64_t)s * H, i1 = (uint64_t)e * H;
   float cs = 0.f;
-  for (uint32_t k = s + tid; k < e; k += nthr) cs += __ldg(ds + __ldg(perm + k));
-  cs = coop_sum<CTA>(cs, red);
-  if (tid == 0) colsum[row] = cs;
+  for (uint64_t i = i0 + tid; i < i1; i += nthr) cs += __ldg(ds + (size_t)__ldg(perm + (i >> hs)) * H + h);
+  cs = coop_hsum<CTA>(cs, H, red);
+  if (tid < H) colsum[(size_t)row * H + tid] = cs;
 }
 
 // Stage 1 of d_alpha = Z^T·[rowsum colsum]: each CTA reduces a slab of rows; thread (tx, ty): column tx (+CW*q), rows ty, ty+RH, ...
-__global__ void alpha_grad_stage1(uint32_t nv, int F, size_t ld, const float* __restrict__ z, const float* __restrict__ rowsum, const float* __restrict__ colsum,
+__global__ void alpha_grad_stage1(uint32_t nv, int F, int H, size_t ld, const float* __restrict__ z, const float* __restrict__ rowsum, const float* __restrict__ colsum,
                                   uint32_t rows_per_cta, int CW, float* __restrict__ partial /*[grid][2][F]*/) {
   extern __shared__ float sm[];  // [RH][2][CW]
   const int tx = threadIdx.x % CW, ty = threadIdx.x / CW, RH = blockDim.x / CW;
@@ -285,10 +395,11 @@ __global__ void alpha_grad_stage1(uint32_t nv, int F, size_t ld, const float* __
     const int c = c0 + tx;
     float al = 0.f, ar = 0.f;
     if (c < F) {
+      const int h = c / (F / H);   // the head this column belongs to
       for (uint32_t i = r0 + ty; i < r1; i += RH) {
         const float v = __ldg(z + (size_t)i * ld + c);
-        al += __ldg(rowsum + i) * v;
-        ar += __ldg(colsum + i) * v;
+        al += __ldg(rowsum + (size_t)i * H + h) * v;
+        ar += __ldg(colsum + (size_t)i * H + h) * v;
       }
     }
     sm[(ty * 2 + 0) * CW + tx] = al;
@@ -324,32 +435,54 @@ inline unsigned warp_grid(uint32_t nv) { return (unsigned)(((uint64_t)nv * 32 + 
 
 extern "C" {
 
-int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
-                       float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream) {
+static bool heads_ok(int F, int H) {
+  // a power-of-two number of heads <= 32; for H > 1 whole float4 chunks per head, a power-of-two number (<= 32) of them
+  if (H < 1 || H > 32 || (H & (H - 1)) != 0 || F % H != 0) return false;
+  if (H == 1) return true;
+  const int D = F / H;
+  return D % 4 == 0 && ((D / 4) & (D / 4 - 1)) == 0 && D / 4 <= 32 && F <= 512;
+}
+
+int gai_gat_forward_heads_ld(gai_csr_t g, int F, int H, const float* z, size_t ld, const float* alpha_l, const float* alpha_r, float slope,
+                             float* temp_scores, float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream) {
   GAI_CHECK_ARG(g && z && alpha_l && alpha_r && temp_scores && norm_scores && out && F > 0 && ld >= (size_t)F && ld_out >= (size_t)F);
+  GAI_CHECK_ARG(heads_ok(F, H));
   if (g->nv == 0) return GAI_OK;
   cudaStream_t st = gai::S(stream);
   void* ws = nullptr;
-  int rc = gai::workspace(sizeof(float) * 2 * (size_t)g->nv, &ws, st);
+  int rc = gai::workspace(sizeof(float) * 2 * (size_t)g->nv * H, &ws, st);
   if (rc != GAI_OK) return rc;
   float* el = reinterpret_cast<float*>(ws);
-  float* er = el + g->nv;
-  el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, z, ld, alpha_l, alpha_r, el, er);
+  float* er = el + (size_t)g->nv * H;
+  el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, H, z, ld, alpha_l, alpha_r, el, er);
   GAI_LAUNCH_CHECK();
   const RowSel r = make_sel(g);
-  scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
+  scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
   GAI_LAUNCH_CHECK();
   if (g->n_hub) {
-    scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, el, er, slope, temp_scores, norm_scores);
+    scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
     GAI_LAUNCH_CHECK();
   }
-  return gai_spmm_edge(g, F, norm_scores, nullptr, z, (int)ld, out, (int)ld_out, flags, nullptr, stream);
+  if (H == 1) return gai_spmm_edge(g, F, norm_scores, nullptr, z, (int)ld, out, (int)ld_out, flags, nullptr, stream);
+  return gai_spmm_edge_heads(g, F, H, norm_scores, nullptr, z, (int)ld, out, (int)ld_out, flags, nullptr, stream);
+}
+
+int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,
+                       float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream) {
+  return gai_gat_forward_heads_ld(g, F, 1, z, ld, alpha_l, alpha_r, slope, temp_scores, norm_scores, out, ld_out, flags, stream);
 }
 
 int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld, const float* grad_in, size_t ld_grad, float slope, const float* temp_scores,
                         const float* norm_scores, float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, size_t ld_dz, gai_stream_t stream) {
+  return gai_gat_backward_heads_ld(g, F, 1, z, ld, grad_in, ld_grad, slope, temp_scores, norm_scores, ds, d_alpha_l, d_alpha_r, dz, ld_dz, stream);
+}
+
+int gai_gat_backward_heads_ld(gai_csr_t g, int F, int H, const float* z, size_t ld, const float* grad_in, size_t ld_grad, float slope,
+                              const float* temp_scores, const float* norm_scores, float* ds, float* d_alpha_l, float* d_alpha_r, float* dz, size_t ld_dz,
+                              gai_stream_t stream) {
   GAI_CHECK_ARG(g && z && grad_in && temp_scores && norm_scores && ds && d_alpha_l && d_alpha_r && dz && F > 0);
   GAI_CHECK_ARG(ld >= (size_t)F && ld_grad >= (size_t)F && ld_dz >= (size_t)F);
+  GAI_CHECK_ARG(heads_ok(F, H));
   if (g->nv == 0) return GAI_OK;
   int rc = gai_csr_build_transpose(g, stream);
   if (rc != GAI_OK) return rc;
@@ -357,17 +490,30 @@ int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld, const flo
   const int sms = gai::sm_count();
   const int nparts = (int)((g->nv + 255) / 256 < (uint32_t)(4 * sms) ? (g->nv + 255) / 256 : (uint32_t)(4 * sms));
   void* ws = nullptr;
-  rc = gai::workspace(sizeof(float) * (2 * (size_t)g->nv + (size_t)nparts * 2 * F), &ws, st);
+  rc = gai::workspace(sizeof(float) * (2 * (size_t)g->nv * H + (size_t)nparts * 2 * F), &ws, st);
   if (rc != GAI_OK) return rc;
   float* rowsum = reinterpret_cast<float*>(ws);
-  float* colsum = rowsum + g->nv;
-  float* partial = colsum + g->nv;
+  float* colsum = rowsum + (size_t)g->nv * H;
+  float* partial = colsum + (size_t)g->nv * H;
   const RowSel r = make_sel(g);
   // 128-bit path: both gathered matrices share one pitch that is a multiple of 4 floats (the tail chunk of a width that is not reads
   // padding columns, which the layer classes keep at zero on both sides: 0 * 0 adds nothing to the dot product)
   const bool vec_ok = ld == ld_grad && ld % 4 == 0 && ld >= (size_t)((F + 3) / 4 * 4) && reinterpret_cast<uintptr_t>(z) % 16 == 0 &&
                       reinterpret_cast<uintptr_t>(grad_in) % 16 == 0;
-  if (vec_ok && F <= 512 && g->nnz > 0) {
+  if (H > 1) {
+    // multi-head: both gathered matrices must be 128-bit loadable with one pitch (the layer classes' pitched buffers are)
+    if (!vec_ok) return gai::set_error(GAI_ERR_ARG, "gai_gat_backward_heads", "H > 1 needs 16-byte aligned rows with one pitch that is a multiple of 4 floats");
+    if (g->nnz > 0) {
+      const int nch = F / 4, cph = F / H / 4;
+      const unsigned grid = (unsigned)(sms * 4);
+      const float4* g4 = reinterpret_cast<const float4*>(grad_in);
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      if (nch <= 32) sddmm_heads_kernel<1><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, cph, H, ld / 4, g4, z4, ds);
+      else if (nch <= 64) sddmm_heads_kernel<2><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, cph, H, ld / 4, g4, z4, ds);
+      else sddmm_heads_kernel<4><<<grid, 256, 0, st>>>(g->nv, g->nnz, g->rowptr, g->colidx, nch, cph, H, ld / 4, g4, z4, ds);
+      GAI_LAUNCH_CHECK();
+    }
+  } else if (vec_ok && F <= 512 && g->nnz > 0) {
     const int nch = (F + 3) / 4;
     const unsigned grid = (unsigned)(sms * 4);
     const float4* g4 = reinterpret_cast<const float4*>(grad_in);
@@ -384,21 +530,22 @@ int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld, const flo
     GAI_LAUNCH_CHECK();
     if (g->n_hub) { sddmm_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, F, ldc, grad_in, z, ds, vec); GAI_LAUNCH_CHECK(); }
   }
-  softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, slope, temp_scores, norm_scores, ds, rowsum);
+  softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
   GAI_LAUNCH_CHECK();
-  if (g->n_hub) { softmax_bwd_kernel<true><<<g->n_hub, 256, 0, st>>>(r, slope, temp_scores, norm_scores, ds, rowsum); GAI_LAUNCH_CHECK(); }
-  colsum_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, g->tperm, ds, colsum);
+  if (g->n_hub) { softmax_bwd_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum); GAI_LAUNCH_CHECK(); }
+  colsum_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->tperm, ds, colsum);
   GAI_LAUNCH_CHECK();
-  if (g->n_hub) { colsum_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->tperm, ds, colsum); GAI_LAUNCH_CHECK(); }
+  if (g->n_hub) { colsum_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->tperm, ds, colsum); GAI_LAUNCH_CHECK(); }
   int CW = 1;
   while (CW < F && CW < 256) CW <<= 1;
   const uint32_t rows_per_cta = (g->nv + nparts - 1) / nparts;
-  alpha_grad_stage1<<<nparts, 256, sizeof(float) * 2 * 256, st>>>(g->nv, F, ld, z, rowsum, colsum, rows_per_cta, CW, partial);
+  alpha_grad_stage1<<<nparts, 256, sizeof(float) * 2 * 256, st>>>(g->nv, F, H, ld, z, rowsum, colsum, rows_per_cta, CW, partial);
   GAI_LAUNCH_CHECK();
   alpha_grad_stage2<<<(2 * F + 255) / 256, 256, 0, st>>>(F, nparts, partial, d_alpha_l, d_alpha_r);
   GAI_LAUNCH_CHECK();
   // dZ = P^T · G  (update_all with transposed scores, gat_aggregator.cpp:175-199); z is dead from here on, dz may alias it
-  return gai_spmm_edge(g, F, norm_scores, g->tperm, grad_in, (int)ld_grad, dz, (int)ld_dz, GAI_EPI_NONE, nullptr, stream);
+  if (H == 1) return gai_spmm_edge(g, F, norm_scores, g->tperm, grad_in, (int)ld_grad, dz, (int)ld_dz, GAI_EPI_NONE, nullptr, stream);
+  return gai_spmm_edge_heads(g, F, H, norm_scores, g->tperm, grad_in, (int)ld_grad, dz, (int)ld_dz, GAI_EPI_NONE, nullptr, stream);
 }
 
 int gai_gat_forward(gai_csr_t g, int F, const float* z, const float* alpha_l, const float* alpha_r, float slope, float* temp_scores,

@@ -35,7 +35,8 @@
 
 namespace {
 
-enum Mode { M_GCN = 0, M_MEAN = 1, M_MEAN_T = 2, M_EDGE = 3, M_EDGE_PERM = 4 };
+// M_EDGE_H / M_EDGE_PERM_H: multi-head edge values, vals[e * heads + h] with h = the head the output column belongs to (GAT extension)
+enum Mode { M_GCN = 0, M_MEAN = 1, M_MEAN_T = 2, M_EDGE = 3, M_EDGE_PERM = 4, M_EDGE_H = 5, M_EDGE_PERM_H = 6 };
 
 struct SpmmArgs {
   const uint32_t* rowptr;
@@ -60,6 +61,7 @@ struct SpmmArgs {
   // the owners' rows land there (gai_halo_pull) and the matrix itself carries master rows only. n_split = 0xffffffff: one matrix.
   const float* in_halo;
   uint32_t n_split;
+  int heads, hshift;   // multi-head edge values: head of float4 chunk c = c >> hshift (columns per head = 4 << hshift)
 };
 
 // base of neighbour row `c` (float4 units). SPLIT is a template parameter of the kernels: the single-matrix path pays nothing for it
@@ -153,8 +155,12 @@ __device__ __forceinline__ float edge_weight_t(const SpmmArgs& a, float wrow, ui
   if (MODE == M_MEAN) return wrow;                               // 1/deg_i (sage_aggregator.cpp:17)
   if (MODE == M_MEAN_T) return __ldg(a.norm + c);                // 1/deg_j (sage_aggregator.cpp:41)
   if (MODE == M_EDGE) return __ldg(a.vals + idx);
+  if (MODE == M_EDGE_H) return 0.0f;                                               // weights are fetched per (edge, head) at the gather
+  if (MODE == M_EDGE_PERM_H) return __uint_as_float(__ldg(a.perm + idx));          // the reverse edge's index, carried as bits
   return __ldg(a.vals + __ldg(a.perm + idx));
 }
+template <int MODE>
+__host__ __device__ constexpr bool mode_has_heads() { return MODE == M_EDGE_H || MODE == M_EDGE_PERM_H; }
 
 // ---- hub rows inside the persistent light-row kernel --------------------------------------------------------------------
 // A hub item = (hub row, column block of <= 8 float4 chunks). A whole 256-thread CTA of the persistent kernel takes one item at a
@@ -211,6 +217,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     constexpr int EL = 32 / HI_CL;
     const int cl = lane % HI_CL, el = lane / HI_CL;
     const bool chv = cl < nch;
+    const int hd = (cb + cl) >> a.hshift;   // multi-head modes: the head of this lane's chunk
     const char* inb_c = inb + (size_t)(cb + cl) * 16;
     const char* halob_c = halob + (size_t)(cb + cl) * 16;
     asm volatile("" : "+l"(inb_c), "+l"(halob_c));
@@ -233,6 +240,10 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
           const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
           ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
           if (chv && j < cnt) x[u] = __ldg(row_chunk<SPLIT>(inb_c, halob_c, a.n_split, row_bytes, cc));
+          if (mode_has_heads<MODE>() && chv && j < cnt) {
+            const uint32_t eidx = MODE == M_EDGE_H ? base + (uint32_t)j : __float_as_uint(ww[u]);
+            ww[u] = __ldg(a.vals + (size_t)eidx * a.heads + hd);
+          }
         }
 #pragma unroll
         for (int u = 0; u < HI_UB; u++) {
@@ -390,6 +401,9 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
           bool av[K];
 #pragma unroll
           for (int k = 0; k < K; k++) { av[k] = cb == 0 ? act[k] : (cb + gl + G * k) < a.nchunks; ch[k] = cb == 0 ? chunk[k] : (av[k] ? cb + gl + G * k : 0); }
+          int hd[K];           // multi-head modes: the head of the lane's chunk k
+#pragma unroll
+          for (int k = 0; k < K; k++) hd[k] = ch[k] >> a.hshift;
           const char* bk[K];   // lane's chunk k of row 0 (masters) / of virtual row 0 (halo)
           const char* hk[K];
 #pragma unroll
@@ -409,18 +423,24 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
               for (int j = 0; j < G; j += U) {
                 float4 x[U][K];
+                float wv[mode_has_heads<MODE>() ? U : 1][mode_has_heads<MODE>() ? K : 1];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
 #pragma unroll
                   for (int k = 0; k < K; k++) x[u][k] = gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc));
+                  if (mode_has_heads<MODE>()) {   // per-(edge, head) weights, requested with the gathers
+                    const uint32_t eidx = MODE == M_EDGE_H ? b + (uint32_t)(j + u) : __float_as_uint(__shfl_sync(gmask, w, j + u, G));
+#pragma unroll
+                    for (int k = 0; k < K; k++) wv[u][k] = __ldg(a.vals + (size_t)eidx * a.heads + hd[k]);
+                  }
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   // mean aggregation: every edge of the row carries the same 1/deg_i — no broadcast needed
-                  const float ww = MODE == M_MEAN ? wrow : __shfl_sync(gmask, w, j + u, G);
+                  const float ww = (MODE == M_MEAN || mode_has_heads<MODE>()) ? wrow : __shfl_sync(gmask, w, j + u, G);
 #pragma unroll
-                  for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }
+                  for (int k = 0; k < K; k++) { float4 p; mul_w_f4(mode_has_heads<MODE>() ? wv[u][k] : ww, x[u][k], p); acc_add(acc[k], p); }
                 }
               }
             } else {
@@ -428,19 +448,25 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
               for (int j = 0; j < G; j += U) {
                 if (j >= cnt) break;
                 float4 x[U][K];
+                float wv[mode_has_heads<MODE>() ? U : 1][mode_has_heads<MODE>() ? K : 1];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
 #pragma unroll
                   for (int k = 0; k < K; k++)
                     x[u][k] = (j + u < cnt) ? gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (mode_has_heads<MODE>()) {
+                    const uint32_t eidx = MODE == M_EDGE_H ? b + (uint32_t)(j + u) : __float_as_uint(__shfl_sync(gmask, w, j + u, G));
+#pragma unroll
+                    for (int k = 0; k < K; k++) wv[u][k] = (j + u < cnt) ? __ldg(a.vals + (size_t)eidx * a.heads + hd[k]) : 0.0f;
+                  }
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                  const float ww = MODE == M_MEAN ? wrow : __shfl_sync(gmask, w, j + u, G);
+                  const float ww = (MODE == M_MEAN || mode_has_heads<MODE>()) ? wrow : __shfl_sync(gmask, w, j + u, G);
                   if (j + u < cnt) {
 #pragma unroll
-                    for (int k = 0; k < K; k++) { float4 p; mul_w_f4(ww, x[u][k], p); acc_add(acc[k], p); }
+                    for (int k = 0; k < K; k++) { float4 p; mul_w_f4(mode_has_heads<MODE>() ? wv[u][k] : ww, x[u][k], p); acc_add(acc[k], p); }
                   }
                 }
               }
@@ -689,6 +715,8 @@ int launch_rows(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
     case M_MEAN: return launch_rows_mode<M_MEAN>(a, g, st);
     case M_MEAN_T: return launch_rows_mode<M_MEAN_T>(a, g, st);
     case M_EDGE: return launch_rows_mode<M_EDGE>(a, g, st);
+    case M_EDGE_H: return launch_rows_mode<M_EDGE_H>(a, g, st);
+    case M_EDGE_PERM_H: return launch_rows_mode<M_EDGE_PERM_H>(a, g, st);
     default: return launch_rows_mode<M_EDGE_PERM>(a, g, st);
   }
 }
@@ -733,7 +761,7 @@ int launch_hub(const SpmmArgs& a, const gai_csr* g, cudaStream_t st) {
 
 int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const float* vals, const uint32_t* perm, const float* in,
                   int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream, const uint32_t* mask_bits = nullptr,
-                  int ld_bits = 0, const float* in_halo = nullptr, uint32_t n_split = 0xffffffffu) {
+                  int ld_bits = 0, const float* in_halo = nullptr, uint32_t n_split = 0xffffffffu, int heads = 1) {
   GAI_CHECK_ARG(g != nullptr);
   GAI_CHECK_ARG(rb <= re && re <= g->nv);
   if (re == rb) return GAI_OK;  // empty graph / empty row range: nothing to do (buffers may be NULL)
@@ -741,6 +769,12 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   GAI_CHECK_ARG(F > 0 && ld_in >= F && ld_out >= F && ld_in < (1 << 28));  // row pitch in bytes is 32-bit inside the kernels
   GAI_CHECK_ARG(!(flags & GAI_EPI_ADD) || addend != nullptr);
   GAI_CHECK_ARG(mode < M_EDGE || vals != nullptr);
+  if (heads > 1) {
+    // multi-head edge values: a power-of-two number of heads, whole float4 chunks per head, a power-of-two number of them
+    const int cols = F / heads;
+    GAI_CHECK_ARG((mode == M_EDGE || mode == M_EDGE_PERM) && F % heads == 0 && cols % 4 == 0 && ((cols / 4) & (cols / 4 - 1)) == 0 && F <= 512);
+    mode = mode == M_EDGE ? M_EDGE_H : M_EDGE_PERM_H;
+  }
   GAI_CHECK_ARG(in != out);
   cudaStream_t st = gai::S(stream);
   SpmmArgs a;
@@ -753,6 +787,8 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.hub_per = a.nchunks;
   a.mask_bits = mask_bits; a.ld_bits = ld_bits;
   a.in_halo = in_halo; a.n_split = in_halo ? n_split : 0xffffffffu;
+  a.heads = heads; a.hshift = 0;
+  if (heads > 1) { int cph = F / heads / 4; while (cph > 1) { a.hshift++; cph >>= 1; } }
   a.out_vec = (F % 4 == 0) && (ld_out % 4 == 0) && aligned16(out) && aligned16(addend);
   if (in_halo && !((ld_in % 4 == 0) && aligned16(in) && aligned16(in_halo) && ld_in >= a.nchunks * 4))
     return gai::set_error(GAI_ERR_ARG, "spmm", "a split (masters | halo) input needs 16-byte aligned rows whose pitch is a multiple of 4 floats");
@@ -812,6 +848,12 @@ int gai_spmm_mean(gai_csr_t g, int F, const float* in, int ld_in, float* out, in
 int gai_spmm_edge(gai_csr_t g, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream) {
   GAI_CHECK_ARG(g != nullptr);
   return spmm_dispatch(g, perm ? M_EDGE_PERM : M_EDGE, 0, g->nv, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream);
+}
+int gai_spmm_edge_heads(gai_csr_t g, int F, int heads, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags,
+                        const float* addend, gai_stream_t stream) {
+  GAI_CHECK_ARG(g != nullptr && heads >= 1);
+  return spmm_dispatch(g, perm ? M_EDGE_PERM : M_EDGE, 0, g->nv, F, vals, perm, in, ld_in, out, ld_out, flags, addend, stream, nullptr, 0, nullptr,
+                       0xffffffffu, heads);
 }
 int gai_spmm_gcn_masked(gai_csr_t g, int F, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend,
                         const uint32_t* mask_bits, int ld_bits, gai_stream_t stream) {

@@ -198,25 +198,36 @@ void GAT_Aggregator::init(int len, int, int ne, float lr, float drop_rate) {
   // the reference accepts the rate and ignores it on its CPU path (the attention-dropout lines of gat_aggregator.cpp:78-79,138-139 are
   // commented out): same here, with a note
   if (attn_drop > 0.f) std::cerr << "note: score_drop = " << attn_drop << " is accepted and ignored (as the reference CPU path does)\n";
+  // Multi-head attention is an extension (the reference has one head, gat_layer.cpp:3-42; BASELINE.json configs[2] names 8): the row is
+  // cut into `heads` blocks, the attention vectors keep their length (head h uses its block of them), scores become nnz x heads.
+  if (const char* e = std::getenv("GAI_GAT_HEADS")) heads = std::atoi(e);
+  if (heads < 1 || heads > 32 || (heads & (heads - 1)) != 0 || len % heads != 0 ||
+      (heads > 1 && ((len / heads) % 4 != 0 || (((len / heads) / 4) & ((len / heads) / 4 - 1)) != 0 || len / heads > 128 || len > 512))) {
+    std::cerr << "GAT_Aggregator: GAI_GAT_HEADS = " << heads << " does not divide a width of " << len
+              << " into blocks the kernels take (power-of-two head count, 4 / 8 / 16 / ... / 128 columns per head, width <= 512)\n";
+    std::exit(EXIT_FAILURE);
+  }
   d_alpha_l = upload_glorot(len, 1, 2);  // seeds 2 / 3: gat_aggregator.cpp:11-12
   d_alpha_r = upload_glorot(len, 1, 3);
   d_alpha_lgrad = float_malloc_device_zero(len);
   d_alpha_rgrad = float_malloc_device_zero(len);
-  d_temp_scores = float_malloc_device_zero(ne);
-  d_norm_scores = float_malloc_device_zero(ne);
-  d_scores_grad = float_malloc_device_zero(ne);
+  d_temp_scores = float_malloc_device_zero((size_t)ne * heads);
+  d_norm_scores = float_malloc_device_zero((size_t)ne * heads);
+  d_scores_grad = float_malloc_device_zero((size_t)ne * heads);
   alpha_opt = new adam(lr);
 }
 void GAT_Aggregator::aggregate_fused(int len, Graph& g, const float* in, float* out, int flags, const float*) {
-  gai_host::OpScope sc("ATTN_FWD", "gat F=" + std::to_string(len), spmm_bytes(g, len, 2) + 4.0 * g.size() * len, 2.0 * g.sizeEdges() * len);
-  die_on(gai_gat_forward_ld(g.device(), len, in, row_pitch(len), d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out, row_pitch(len), flags,
-                            stream()), "gai_gat_forward");
+  gai_host::OpScope sc("ATTN_FWD", "gat F=" + std::to_string(len) + (heads > 1 ? " H=" + std::to_string(heads) : ""),
+                       spmm_bytes(g, len, 2) + 4.0 * g.size() * len + 8.0 * g.sizeEdges() * (heads - 1), 2.0 * g.sizeEdges() * len);
+  die_on(gai_gat_forward_heads_ld(g.device(), len, heads, in, row_pitch(len), d_alpha_l, d_alpha_r, epsilon, d_temp_scores, d_norm_scores, out,
+                                  row_pitch(len), flags, stream()), "gai_gat_forward");
 }
 void GAT_Aggregator::aggregate(int len, Graph& g, const float* in, float* out) { aggregate_fused(len, g, in, out, GAI_EPI_NONE, nullptr); }
 void GAT_Aggregator::d_aggregate(int len, Graph& g, const float* feat_in, const float* grad_in, float* grad_out) {
-  gai_host::OpScope sc("ATTN_BWD", "gat F=" + std::to_string(len), 2.0 * spmm_bytes(g, len, 3) + 4.0 * g.size() * len, 4.0 * g.sizeEdges() * len);
-  die_on(gai_gat_backward_ld(g.device(), len, feat_in, row_pitch(len), grad_in, row_pitch(len), epsilon, d_temp_scores, d_norm_scores, d_scores_grad,
-                             d_alpha_lgrad, d_alpha_rgrad, grad_out, row_pitch(len), stream()), "gai_gat_backward");
+  gai_host::OpScope sc("ATTN_BWD", "gat F=" + std::to_string(len) + (heads > 1 ? " H=" + std::to_string(heads) : ""),
+                       2.0 * spmm_bytes(g, len, 3) + 4.0 * g.size() * len + 12.0 * g.sizeEdges() * (heads - 1), 4.0 * g.sizeEdges() * len);
+  die_on(gai_gat_backward_heads_ld(g.device(), len, heads, feat_in, row_pitch(len), grad_in, row_pitch(len), epsilon, d_temp_scores, d_norm_scores,
+                                   d_scores_grad, d_alpha_lgrad, d_alpha_rgrad, grad_out, row_pitch(len), stream()), "gai_gat_backward");
 }
 void GAT_Aggregator::update_weights(optimizer*) {  // own optimiser, two calls (gat_aggregator.cpp:202-205)
   alpha_opt->update_gpu(length, d_alpha_lgrad, d_alpha_l);

@@ -102,7 +102,10 @@ class GAT_Aggregator : public aggregator {
  private:
   float epsilon = 0.2f;  // LeakyReLU slope (gat_aggregator.cpp:22)
   float attn_drop = 0.f;
+  int heads = 1;         // attention heads (GAI_GAT_HEADS; 1 = the reference, which has no multi-head path)
   optimizer* alpha_opt = nullptr;
+ public:
+  int num_heads() const { return heads; }
 };
 
 // ---- graph convolution layers -------------------------------------------------------------------------------------

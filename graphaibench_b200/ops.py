@@ -355,6 +355,28 @@ def gat_forward(g, z, alpha_l, alpha_r, slope=0.2, flags=0):
     return out, temp, norm
 
 
+def gat_forward_heads(g, z, heads, alpha_l, alpha_r, slope=0.2, flags=0):
+    """Multi-head attention forward (extension; heads == 1 is gat_forward). Score arrays are edge-major [nnz x heads]."""
+    F = z.shape[1]
+    temp = torch.empty(max(g.nnz, 1) * heads, dtype=torch.float32, device=z.device)
+    norm = torch.empty(max(g.nnz, 1) * heads, dtype=torch.float32, device=z.device)
+    out = torch.empty(g.nv, F, dtype=torch.float32, device=z.device)
+    check(lib().gai_gat_forward_heads_ld(g.handle, F, heads, _f32(z), z.stride(0), _f32(alpha_l), _f32(alpha_r), slope, _f32(temp), _f32(norm), _f32(out),
+                                         out.stride(0), flags, _stream()), "gai_gat_forward_heads_ld")
+    return out, temp, norm
+
+
+def gat_backward_heads(g, z, heads, grad_in, temp, norm, slope=0.2):
+    F = z.shape[1]
+    ds = torch.empty(max(g.nnz, 1) * heads, dtype=torch.float32, device=z.device)
+    dal = torch.empty(F, dtype=torch.float32, device=z.device)
+    dar = torch.empty(F, dtype=torch.float32, device=z.device)
+    dz = torch.empty_like(z)
+    check(lib().gai_gat_backward_heads_ld(g.handle, F, heads, _f32(z), z.stride(0), _f32(grad_in), grad_in.stride(0), slope, _f32(temp), _f32(norm),
+                                          _f32(ds), _f32(dal), _f32(dar), _f32(dz), dz.stride(0), _stream()), "gai_gat_backward_heads_ld")
+    return dz, dal, dar, ds
+
+
 def gat_backward(g, z, grad_in, temp, norm, slope=0.2, dz=None):
     F = z.shape[1]
     ds = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=z.device)

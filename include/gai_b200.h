@@ -142,6 +142,10 @@ int gai_spmm_mean(gai_csr_t g, int F, const float* in, int ld_in, float* out, in
 /* update_all with explicit per-edge values (src/gnn/gconv/gat_aggregator.cpp:26-45; spmm(), math_functions.cpp:206-219).
  * If perm != NULL the value used for edge e is vals[perm[e]] (transposed attention without materialising it). */
 int gai_spmm_edge(gai_csr_t g, int F, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out, int flags, const float* addend, gai_stream_t stream);
+/* Multi-head edge values (GAT extension, no reference counterpart: the reference has one head): vals[e * heads + h] weighs the columns of
+ * head h = column / (F / heads). heads must be a power of two, F / heads a multiple of 4 with a power-of-two number of float4 chunks. */
+int gai_spmm_edge_heads(gai_csr_t g, int F, int heads, const float* vals, const uint32_t* perm, const float* in, int ld_in, float* out, int ld_out,
+                        int flags, const float* addend, gai_stream_t stream);
 /* Aggregation whose epilogue also applies the d_relu of the layer below (out = bit ? out : 0) from sign-bit words written by that
  * layer's ReLU epilogue (GAI_EPI_BITMASK layout): the last op of an aggregate-first layer's backward (gcn_layer.cpp:55-58 followed by
  * gcn_layer.cpp:38-40 of the layer below). */
@@ -177,6 +181,16 @@ int gai_gat_forward_ld(gai_csr_t g, int F, const float* z, size_t ld_z, const fl
 int gai_gat_backward_ld(gai_csr_t g, int F, const float* z, size_t ld_z, const float* grad_in, size_t ld_grad, float slope, const float* temp_scores,
                         const float* norm_scores, float* scores_grad_ws, float* d_alpha_l, float* d_alpha_r, float* dz, size_t ld_dz,
                         gai_stream_t stream);
+/* Multi-head attention (EXTENSION: the reference has one head everywhere, gat_layer.cpp:3-42; BASELINE.json configs[2] names 8). The
+ * feature row is cut into `heads` blocks of F / heads columns; head h uses alpha_l / alpha_r entries of its block, has its own scores and
+ * row softmax and aggregates its own columns. Score arrays are edge-major, nnz * heads floats: x[e * heads + h]. heads == 1 is the
+ * reference path (the *_ld entry points above). heads: a power of two <= 32; heads > 1 needs F / heads % 4 == 0 with a power-of-two
+ * number (<= 32) of float4 chunks per head, F <= 512 and 16-byte aligned rows sharing one pitch in the backward pass. */
+int gai_gat_forward_heads_ld(gai_csr_t g, int F, int heads, const float* z, size_t ld_z, const float* alpha_l, const float* alpha_r, float slope,
+                             float* temp_scores, float* norm_scores, float* out, size_t ld_out, int flags, gai_stream_t stream);
+int gai_gat_backward_heads_ld(gai_csr_t g, int F, int heads, const float* z, size_t ld_z, const float* grad_in, size_t ld_grad, float slope,
+                              const float* temp_scores, const float* norm_scores, float* scores_grad_ws, float* d_alpha_l, float* d_alpha_r,
+                              float* dz, size_t ld_dz, gai_stream_t stream);
 
 /* ---- dense transform: matmul(x,y,z,A,B,C,transA,transB,accum) (src/utilities/math_functions.cpp:142-171;
  *      GPU twin cublasSgemm, math_functions.cu:321-343).  C[x×y] = op(A)[x×z] · op(B)[z×y] (+ C if accum).

@@ -79,6 +79,9 @@ def liborc():
         L.orc_d_l2norm.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p]
         L.orc_gat_forward.argtypes = [C.c_uint32, u32p, u32p, C.c_int, f32p, f32p, C.c_float, f32p, f32p, f32p, f32p, f32p]
         L.orc_gat_backward.argtypes = [C.c_uint32, u32p, u32p, C.c_int, C.c_float, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int]
+        L.orc_gat_forward_heads.argtypes = [C.c_uint32, u32p, u32p, C.c_int, C.c_int, f32p, f32p, C.c_float, f32p, f32p, f32p, f32p, f32p]
+        L.orc_gat_backward_heads.argtypes = [C.c_uint32, u32p, u32p, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                             C.c_int]
         L.orc_partition1d.argtypes = [C.c_uint32, i64p, u32p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_partition1d.restype = C.c_int64
     return _liborc

@@ -385,6 +385,99 @@ void orc_gat_backward(index_t nv, const index_t* rowptr, const index_t* colidx, 
   free(st);
 }
 
+/* ---- Multi-head attention: an EXTENSION the reference does not have (single head everywhere, gat_layer.cpp:3-42); BASELINE.json
+ * configs[2] names 8 heads. Defined so that heads == 1 is the reference path above, operation for operation (tests pin that bit for
+ * bit): the feature row is cut into `heads` blocks of D = len / heads columns, head h uses alpha_l / alpha_r entries [hD, (h+1)D)
+ * (same parameter count), has its own scores / row softmax, and aggregates its own block of columns (heads concatenated).
+ * Score arrays are edge-major: x[e * heads + h]. */
+void orc_gat_forward_heads(index_t nv, const index_t* rowptr, const index_t* colidx, int len, int heads, const float* alpha_l,
+                           const float* alpha_r, float slope, const float* z, float* temp_scores, float* scores, float* norm_scores, float* out) {
+  const int D = len / heads;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (index_t src = 0; src < nv; src++) {
+    index_t b = rowptr[src], e_end = rowptr[src + 1];
+    size_t n = e_end - b;
+    float* col = (float*)malloc(sizeof(float) * 2 * (n ? n : 1));
+    for (int h = 0; h < heads; h++) {
+      float ss = orc_dot(D, alpha_l + h * D, z + (size_t)src * len + h * D);
+      for (index_t e = b; e != e_end; e++) {
+        float ds = orc_dot(D, alpha_r + h * D, z + (size_t)colidx[e] * len + h * D);
+        float t = ss + ds;
+        temp_scores[(size_t)e * heads + h] = t;
+        col[e - b] = scores[(size_t)e * heads + h] = t > 0.0f ? t : slope * t;
+      }
+      if (n) {
+        orc_softmax(n, col, col + n);
+        for (index_t e = b; e != e_end; e++) norm_scores[(size_t)e * heads + h] = col[n + (e - b)];
+      }
+    }
+    free(col);
+    float* o = out + (size_t)src * len;
+    for (int k = 0; k < len; k++) o[k] = 0.0f;
+    for (index_t e = b; e != e_end; e++) {
+      const float* x = z + (size_t)colidx[e] * len;
+      for (int k = 0; k < len; k++) { float t = norm_scores[(size_t)e * heads + k / D] * x[k]; o[k] = o[k] + t; }
+    }
+  }
+}
+
+void orc_gat_backward_heads(index_t nv, const index_t* rowptr, const index_t* colidx, int len, int heads, float slope, const float* z,
+                            const float* grad_in, const float* temp_scores, const float* norm_scores, float* scores, float* norm_scores_grad,
+                            float* alpha_lgrad, float* alpha_rgrad, float* grad_out, int closed_form) {
+  const int D = len / heads;
+  index_t nnz = rowptr[nv];
+#pragma omp parallel for schedule(dynamic, 64)
+  for (index_t src = 0; src < nv; src++)
+    for (index_t e = rowptr[src]; e != rowptr[src + 1]; e++)
+      for (int h = 0; h < heads; h++)
+        norm_scores_grad[(size_t)e * heads + h] = orc_dot(D, grad_in + (size_t)src * len + h * D, z + (size_t)colidx[e] * len + h * D);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (index_t src = 0; src < nv; src++) {
+    index_t b = rowptr[src], n = rowptr[src + 1] - b;
+    if (n == 0) continue;
+    float* col = (float*)malloc(sizeof(float) * 3 * n);
+    for (int h = 0; h < heads; h++) {
+      for (index_t i = 0; i < n; i++) { col[i] = norm_scores[(size_t)(b + i) * heads + h]; col[n + i] = norm_scores_grad[(size_t)(b + i) * heads + h]; }
+      if (closed_form) orc_d_softmax_closed((int)n, col, col + n, col + 2 * n);
+      else orc_d_softmax((int)n, col, col + n, col + 2 * n);
+      for (index_t i = 0; i < n; i++) scores[(size_t)(b + i) * heads + h] = col[2 * n + i];
+    }
+    free(col);
+  }
+  float* sum_l = (float*)calloc(len, sizeof(float));
+  float* sum_r = (float*)calloc(len, sizeof(float));
+  float* ssg = (float*)malloc(sizeof(float) * heads);
+  for (index_t src = 0; src < nv; src++) {
+    for (int h = 0; h < heads; h++) ssg[h] = 0.0f;
+    for (index_t e = rowptr[src]; e != rowptr[src + 1]; e++) {
+      const float* x = z + (size_t)colidx[e] * len;
+      for (int h = 0; h < heads; h++) {
+        float tsg = scores[(size_t)e * heads + h] * (temp_scores[(size_t)e * heads + h] > 0.0f ? 1.0f : slope);
+        for (int k = h * D; k < (h + 1) * D; k++) { float t = tsg * x[k]; sum_r[k] = t + sum_r[k]; }
+        ssg[h] += tsg;
+      }
+    }
+    const float* x = z + (size_t)src * len;
+    for (int k = 0; k < len; k++) { float t = ssg[k / D] * x[k]; sum_l[k] = t + sum_l[k]; }
+  }
+  for (int k = 0; k < len; k++) { alpha_lgrad[k] = 0.0f + sum_l[k]; alpha_rgrad[k] = 0.0f + sum_r[k]; }
+  free(sum_l); free(sum_r); free(ssg);
+  /* dZ = P^T·G per head: transpose each head's scores on the symmetric pattern */
+  index_t* perm = (index_t*)malloc(sizeof(index_t) * (nnz ? nnz : 1));
+  orc_symmetric_transpose(nv, rowptr, colidx, NULL, NULL, perm);   /* perm[e] = position of the reverse edge (an involution) */
+#pragma omp parallel for schedule(dynamic, 64)
+  for (index_t src = 0; src < nv; src++) {
+    float* o = grad_out + (size_t)src * len;
+    for (int k = 0; k < len; k++) o[k] = 0.0f;
+    for (index_t e = rowptr[src]; e != rowptr[src + 1]; e++) {
+      const float* x = grad_in + (size_t)colidx[e] * len;
+      const float* w = norm_scores + (size_t)perm[e] * heads;
+      for (int k = 0; k < len; k++) { float t = w[k / D] * x[k]; o[k] = o[k] + t; }
+    }
+  }
+  free(perm);
+}
+
 /* ---- PartitionedGraph::edgecut_induced_partition1D + generate_induced_subgraph:
  *      src/partitioner/graph_partition.cc:70-178 (rowptr is int64 there: include/common.h eidType) -----
  * Partition `part` of `nparts`: masters [S*part, min(S*(part+1), nv)), S = ceil(nv/nparts); vertex set =

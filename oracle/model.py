@@ -86,8 +86,9 @@ def matmul(x, y, z, A, B, Cm, ta=False, tb=False, accum=False):
 class ConvLayer:
     """graph_conv_layer<A> (include/layers/graph_conv_layer.h:6-61, src/gnn/graph_conv_layer.cpp:4-51)."""
 
-    def __init__(self, arch, level, nv, din, dout, graph, act, lr):
+    def __init__(self, arch, level, nv, din, dout, graph, act, lr, heads=1):
         self.arch, self.level, self.nv, self.din, self.dout, self.g, self.act = arch, level, nv, din, dout, graph, act
+        self.heads = heads  # GAT extension (the reference has one head): see orc_gat_forward_heads
         self.W = glorot(din, dout, 1)
         self.W_grad = np.zeros(din * dout, np.float32)
         if arch == "sage":
@@ -103,8 +104,8 @@ class ConvLayer:
             ne = graph.ne
             self.alpha_l, self.alpha_r = glorot(dout, 1, 2), glorot(dout, 1, 3)
             self.alpha_lgrad, self.alpha_rgrad = np.zeros(dout, np.float32), np.zeros(dout, np.float32)
-            self.scores, self.temp_scores = np.zeros(ne, np.float32), np.zeros(ne, np.float32)
-            self.norm_scores, self.norm_scores_grad = np.zeros(ne, np.float32), np.zeros(ne, np.float32)
+            self.scores, self.temp_scores = np.zeros(ne * heads, np.float32), np.zeros(ne * heads, np.float32)
+            self.norm_scores, self.norm_scores_grad = np.zeros(ne * heads, np.float32), np.zeros(ne * heads, np.float32)
             self.alpha_opt = Adam(lr)
             self.closed_form = False
 
@@ -123,8 +124,12 @@ class ConvLayer:
         if self.arch == "gat":  # gat_layer.cpp:3-22
             matmul(x, z, y, self.feat_in, self.W, self.out_temp)
             g = self.g
-            L.orc_gat_forward(g.nv, g.rowptr, g.colidx, z, self.alpha_l, self.alpha_r, 0.2, self.out_temp,
-                              self.temp_scores, self.scores, self.norm_scores, feat_out)
+            if self.heads == 1:
+                L.orc_gat_forward(g.nv, g.rowptr, g.colidx, z, self.alpha_l, self.alpha_r, 0.2, self.out_temp,
+                                  self.temp_scores, self.scores, self.norm_scores, feat_out)
+            else:
+                L.orc_gat_forward_heads(g.nv, g.rowptr, g.colidx, z, self.heads, self.alpha_l, self.alpha_r, 0.2, self.out_temp,
+                                        self.temp_scores, self.scores, self.norm_scores, feat_out)
         else:  # gcn_layer.cpp:5-28, sage_layer.cpp:5-26
             if y > z:
                 matmul(x, z, y, self.feat_in, self.W, self.out_temp)
@@ -146,8 +151,13 @@ class ConvLayer:
         if self.arch == "gat":  # gat_layer.cpp:24-42 (d_aggregate writes dZ over out_temp)
             g = self.g
             dz = np.zeros(x * z, np.float32)
-            L.orc_gat_backward(g.nv, g.rowptr, g.colidx, z, 0.2, self.out_temp, self.grad_in, self.temp_scores, self.norm_scores,
-                               self.scores, self.norm_scores_grad, self.alpha_lgrad, self.alpha_rgrad, dz, int(self.closed_form))
+            if self.heads == 1:
+                L.orc_gat_backward(g.nv, g.rowptr, g.colidx, z, 0.2, self.out_temp, self.grad_in, self.temp_scores, self.norm_scores,
+                                   self.scores, self.norm_scores_grad, self.alpha_lgrad, self.alpha_rgrad, dz, int(self.closed_form))
+            else:
+                L.orc_gat_backward_heads(g.nv, g.rowptr, g.colidx, z, self.heads, 0.2, self.out_temp, self.grad_in, self.temp_scores,
+                                         self.norm_scores, self.scores, self.norm_scores_grad, self.alpha_lgrad, self.alpha_rgrad, dz,
+                                         int(self.closed_form))
             self.out_temp[:] = dz
             if self.level != 0:
                 matmul(x, y, z, self.out_temp, self.W, grad_out, False, True)
@@ -183,7 +193,7 @@ class ConvLayer:
 class OracleModel:
     """Model<L> for subg_size == 0, softmax loss (src/gnn/net.cpp)."""
 
-    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02, sigmoid=False):
+    def __init__(self, arch, rowptr, colidx, feats, labels, split9, dim_hid, num_cls, num_layers=2, lr=0.02, sigmoid=False, heads=1):
         self.arch = arch
         self.sigmoid = sigmoid  # argv[4] == "sigmoid": multi-hot labels, sigmoid_loss_layer, micro-F1 as accuracy (net.cpp:20,447-451)
         self.g = Graph(rowptr, colidx)
@@ -207,9 +217,9 @@ class OracleModel:
         self.use_dense = self.use_l2norm = arch == "gat"  # net.cpp:67-71
         self.layers = []
         for l in range(num_layers - 1):  # net.cpp:426-430
-            self.layers.append(ConvLayer(arch, l, nv, dim_init if l == 0 else dim_hid, dim_hid, self.g, True, lr))
+            self.layers.append(ConvLayer(arch, l, nv, dim_init if l == 0 else dim_hid, dim_hid, self.g, True, lr, heads))
         dim_out = dim_hid if self.use_dense else num_cls
-        self.layers.append(ConvLayer(arch, num_layers - 1, nv, dim_hid, dim_out, self.g, False, lr))
+        self.layers.append(ConvLayer(arch, num_layers - 1, nv, dim_hid, dim_out, self.g, False, lr, heads))
         self.layers[0].feat_in = self.feats
         if self.use_l2norm:
             self.l2_feat_in = np.zeros(nv * dim_hid, np.float32); self.l2_grad_in = np.zeros(nv * dim_hid, np.float32)

@@ -107,6 +107,35 @@ def test_medium_graph_layers_match_oracle(gm, arch, dims, layers):
         close(m.get("W", k), o.layers[k].W, 2e-3)
 
 
+@pytest.mark.parametrize("heads,hid", [(8, 64), (4, 32)])
+def test_multi_head_gat_model_matches_oracle(gm, heads, hid, monkeypatch):
+    """Model<GAT_layer> with GAI_GAT_HEADS attention heads (the extension BASELINE.json configs[2] names; the reference has one head)
+    against the restated model with the same head count: first-step tensors 2e-5, three epochs of losses 1e-4."""
+    from graphaibench_b200 import datagen
+    from oracle import model as om
+    monkeypatch.setenv("GAI_GAT_HEADS", str(heads))
+    nv, F, ncls, layers = 6000, 40, 6, 2
+    rp64, ci = datagen.rmat_csr(nv, 90000, seed=21)
+    rp = rp64.astype(np.uint32)
+    feats = datagen.features(nv, F, seed=22)
+    labels = np.random.default_rng(23).integers(0, ncls, nv).astype(np.uint8)
+    split = datagen.split_ranges(nv)
+    m = gm.GnnModel("gat", rp, ci, feats, labels, split, hid, ncls, num_layers=layers, lr=0.01)
+    o = om.OracleModel("gat", rp, ci, feats, labels, split, hid, ncls, num_layers=layers, lr=0.01, heads=heads)
+    l, a = m.forward(); lo, ao = o.forward()
+    assert abs(l - lo) <= 2e-5 * abs(lo) and abs(a - ao) < 1e-6
+    m.backward(); o.backward()
+    for k in range(layers):
+        if k > 0:
+            close(m.get("feat_in", k), o.layers[k].feat_in, 2e-5)
+        close(m.get("grad_in", k), o.layers[k].grad_in, 2e-5)
+        close(m.get("W_grad", k), o.layers[k].W_grad, 2e-5)
+    m.update(); o.update()
+    for ep in range(3):
+        l, a = m.train_epoch(); lo, ao = o.train_epoch()
+        assert abs(l - lo) <= 1e-4 * abs(lo), (ep, l, lo)
+
+
 def test_cli_sigmoid_loss_on_cora(gm, ref_inputs):
     """`gpu_train_gcn cora 60 1 sigmoid` (multi-hot labels, sigmoid cross-entropy, micro-F1 as accuracy; net.cpp:20,447-451,495-497,569-572)
     against the reference's own CPU binary run in the build container:

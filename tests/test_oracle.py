@@ -78,6 +78,43 @@ def test_gat_aggregator_matches_reference(golden, small_graph, liborc):
     np.testing.assert_allclose(dal, golden["gat_dal"], rtol=2e-5, atol=1e-6)
 
 
+def test_multi_head_attention_with_one_head_is_the_reference_path(golden, small_graph, liborc):
+    """The multi-head extension (BASELINE.json configs[2] names 8 heads; the reference has one) is defined so that heads == 1 reproduces
+    the pinned single-head restatement bit for bit, forward and backward; with H > 1 every head must equal a single-head run on its own
+    block of columns (same graph, that block's attention vectors)."""
+    g = om.Graph(small_graph["rowptr"], small_graph["colidx"]); g.add_selfloop()
+    n, F = g.nv, 16
+    z, gin, al, ar = golden["gat_z"], golden["gat_gin"], golden["gat_al"], golden["gat_ar"]
+
+    def run(heads, fn_fwd, fn_bwd, zz, gg, aal, aar, width):
+        ts, sc, ns, nsg = (np.zeros(g.ne * (heads or 1), np.float32) for _ in range(4))
+        out, gout = np.zeros((n, width), np.float32), np.zeros((n, width), np.float32)
+        dal, dar = np.zeros(width, np.float32), np.zeros(width, np.float32)
+        zz, gg = np.ascontiguousarray(zz), np.ascontiguousarray(gg)
+        if heads is None:
+            liborc.orc_gat_forward(n, g.rowptr, g.colidx, width, aal, aar, 0.2, zz.reshape(-1), ts, sc, ns, out.reshape(-1))
+            liborc.orc_gat_backward(n, g.rowptr, g.colidx, width, 0.2, zz.reshape(-1), gg.reshape(-1), ts, ns, sc, nsg, dal, dar, gout.reshape(-1), 0)
+        else:
+            liborc.orc_gat_forward_heads(n, g.rowptr, g.colidx, width, heads, aal, aar, 0.2, zz.reshape(-1), ts, sc, ns, out.reshape(-1))
+            liborc.orc_gat_backward_heads(n, g.rowptr, g.colidx, width, heads, 0.2, zz.reshape(-1), gg.reshape(-1), ts, ns, sc, nsg, dal, dar,
+                                          gout.reshape(-1), 0)
+        return ns, out, gout, dal, dar
+
+    ref = run(None, None, None, z, gin, al, ar, F)
+    one = run(1, None, None, z, gin, al, ar, F)
+    for a, b in zip(ref, one):
+        assert np.array_equal(a, b)
+    assert np.array_equal(ref[1], golden["gat_out"]) and np.array_equal(ref[2], golden["gat_gout"])
+    H, D = 4, F // 4
+    multi = run(H, None, None, z, gin, al, ar, F)
+    for h in range(H):
+        blk = slice(h * D, (h + 1) * D)
+        single = run(None, None, None, z[:, blk], gin[:, blk], np.ascontiguousarray(al[blk]), np.ascontiguousarray(ar[blk]), D)
+        assert np.array_equal(multi[0].reshape(-1, H)[:, h], single[0])          # per-head softmax
+        assert np.array_equal(multi[1][:, blk], single[1]) and np.array_equal(multi[2][:, blk], single[2])
+        assert np.array_equal(multi[3][blk], single[3]) and np.array_equal(multi[4][blk], single[4])
+
+
 def test_loss_and_adam_bit_exact(golden, liborc):
     logits, labs, masks = golden["loss_logits"], golden["loss_labels"], golden["loss_masks"]
     nv, ncls = logits.shape

@@ -3,6 +3,8 @@
 
     c3   GAT 2-layer, hidden 256 (one head of width 256 = reference semantics, gat_layer.cpp), + l2norm + dense tail, on a synthetic
          Reddit-shaped R-MAT graph (232 965 vertices, ~114.6 M CSR edges, 602 features, 41 classes)
+    c3h8 the same with 8 attention heads of 32 columns (GAI_GAT_HEADS=8: configs[2] as named; multi-head attention is an extension the
+         reference does not have, restated in oracle/gnn_oracle.c orc_gat_*_heads)
     c4s  GCN 3-layer hidden 256 on ONE GPU's share of the papers100M shape at P = 8 (13.9 M vertices, ~202 M CSR edges, 128 features,
          172 classes) without the halo exchange: the per-GPU compute of configs[3]
     c2g  GCN 2-layer hidden 256 on the configs[1] graph (the GCN line of the headline metric)
@@ -23,6 +25,8 @@ import bench  # noqa: E402
 CONFIGS = {
     "c3": dict(arch="gat", nv=232_965, nnz=114_600_000, feat=602, hid=256, ncls=41, layers=2, lr=0.01,
                name="GAT 2-layer hidden 256 (1 head) + l2norm + dense, Reddit-shaped R-MAT (BASELINE.json configs[2])"),
+    "c3h8": dict(arch="gat", nv=232_965, nnz=114_600_000, feat=602, hid=256, ncls=41, layers=2, lr=0.01, heads=8,
+                 name="GAT 2-layer hidden 256 = 8 heads x 32 + l2norm + dense, Reddit-shaped R-MAT (BASELINE.json configs[2] as named)"),
     "c4s": dict(arch="gcn", nv=13_882_495, nnz=202_000_000, feat=128, hid=256, ncls=172, layers=3, lr=0.01,
                 name="GCN 3-layer hidden 256, one GPU's 1/8 share of the papers100M shape, no halo (BASELINE.json configs[3], per-GPU compute)"),
     "c2g": dict(arch="gcn", nv=2_449_029, nnz=62_000_000, feat=100, hid=256, ncls=47, layers=2, lr=0.01,
@@ -36,6 +40,8 @@ def run(key, scale, steps, warmup):
     import torch
     from graphaibench_b200 import _abi, datagen, model as gmodel
     c = CONFIGS[key]
+    if c.get("heads", 1) > 1:
+        os.environ["GAI_GAT_HEADS"] = str(c["heads"])   # read by GAT_Aggregator::init when the model is built
     nv, nnz = c["nv"] // scale, c["nnz"] // scale
     dev = "cuda"
     rp, ci = datagen.rmat_csr_torch(nv, nnz, seed=1, device=dev)
@@ -74,7 +80,7 @@ def run(key, scale, steps, warmup):
     roof, breakdown, per_shape = bench.roofline_from_profile(prof, bench.load_peaks(), n_prof)
     edges = real_nnz + (nv if c["arch"] != "sage" else 0)  # GCN / GAT train on the self-looped graph (net.cpp:96)
     print(json.dumps({"config": key, "workload": c["name"], "arch": c["arch"], "vertices": nv, "csr_edges": real_nnz, "edges_trained": edges,
-                      "features": c["feat"], "hidden": c["hid"], "classes": c["ncls"], "layers": c["layers"], "scale_div": scale, "steps": steps,
+                      "features": c["feat"], "hidden": c["hid"], "heads": c.get("heads", 1), "classes": c["ncls"], "layers": c["layers"], "scale_div": scale, "steps": steps,
                       "warmup": warmup, "epoch_ms": ms, "Medges_per_s": edges / ms / 1e3, "gpu_launches": int(launches), "roofline": roof,
                       "breakdown_ms_per_step": breakdown, "ops": per_shape[:16], "final": {"train_loss": loss, "train_acc": acc}}), flush=True)
 
