@@ -90,6 +90,7 @@ __device__ __forceinline__ float coop_max(float v, float* red) {
 struct RowSel {
   const uint32_t* rowptr;
   const uint32_t* hub_rows;
+  const uint32_t* order;   // rows by degree, longest first (hub rows at its head); NULL: natural order
   uint32_t nv, n_hub, hub_threshold;
 };
 
@@ -101,9 +102,12 @@ __device__ __forceinline__ bool pick_row(const RowSel& r, uint32_t& row, uint32_
     row = r.hub_rows[blockIdx.x];
     tid = threadIdx.x; nthr = blockDim.x;
   } else {
+    // warp-per-row kernels walk the rows in DEGREE order: the eight warps of a CTA then own rows of (nearly) equal length. In natural
+    // order a CTA stays resident until its longest row is done with one warp active — on the Reddit-shaped graph that held the score
+    // kernels at a quarter of an item per clock and SM (13 ms per call with 8 heads).
     const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= r.nv) return false;
-    row = (uint32_t)w;
+    row = r.order ? __ldg(r.order + w) : (uint32_t)w;
     tid = threadIdx.x & 31; nthr = 32;
   }
   s = __ldg(r.rowptr + row); e = __ldg(r.rowptr + row + 1);
@@ -140,23 +144,179 @@ __global__ void scores_kernel(const RowSel r, int H, const uint32_t* __restrict_
   const uint64_t i0 = (uint64_t)s * H, i1 = (uint64_t)e * H;
   const float eli = __ldg(el + (size_t)row * H + h);
   float mx = -INFINITY;
-  for (uint64_t i = i0 + tid; i < i1; i += nthr) {
+  // four independent (index -> er) load chains per thread and iteration
+  uint64_t i = i0 + tid;
+  for (; i + 3ull * nthr < i1; i += 4ull * nthr) {
+    uint32_t c[4]; float t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) c[u] = __ldg(colidx + ((i + (uint64_t)u * nthr) >> hs));
+#pragma unroll
+    for (int u = 0; u < 4; u++) t[u] = eli + __ldg(er + (size_t)c[u] * H + h);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { temp_scores[i + (uint64_t)u * nthr] = t[u]; mx = fmaxf(mx, t[u] > 0.f ? t[u] : slope * t[u]); }
+  }
+  for (; i < i1; i += nthr) {
     const float t = eli + __ldg(er + (size_t)__ldg(colidx + (i >> hs)) * H + h);
     temp_scores[i] = t;
-    const float sc = t > 0.f ? t : slope * t;
-    mx = fmaxf(mx, sc);
+    mx = fmaxf(mx, t > 0.f ? t : slope * t);
   }
   mx = coop_hmax<CTA>(mx, H, red);
+  // the thread re-reads only what it wrote itself: no barrier between the passes. The unnormalised exponentials are stored once and
+  // rescaled in place (the reference's softmax: exp, sum, divide — math_functions.cpp:485-494).
   float sum = 0.f;
-  for (uint64_t i = i0 + tid; i < i1; i += nthr) {
-    const float t = temp_scores[i];
-    const float sc = t > 0.f ? t : slope * t;
-    const float p = expf(sc - mx);
-    norm_scores[i] = p;
+#pragma unroll 4
+  for (uint64_t k = i0 + tid; k < i1; k += nthr) {
+    const float t = temp_scores[k];
+    const float p = expf((t > 0.f ? t : slope * t) - mx);
+    norm_scores[k] = p;
     sum += p;
   }
   sum = coop_hsum<CTA>(sum, H, red);
-  for (uint64_t i = i0 + tid; i < i1; i += nthr) norm_scores[i] = norm_scores[i] / sum;
+#pragma unroll 4
+  for (uint64_t k = i0 + tid; k < i1; k += nthr) norm_scores[k] = norm_scores[k] / sum;
+}
+
+// ---- 128-bit forms of the three per-(edge, head) passes for H % 4 == 0 ----------------------------------------------------------------
+// A thread owns a float4 of four consecutive heads of one edge: 16 bytes per load instead of 4 quadruple the bytes a warp keeps in
+// flight, which is what bounds these streaming passes (one warp per row: with 4-byte items the scalar kernels moved 1.4 TB/s on the
+// Reddit-shaped graph with 8 heads). G4 = H / 4 float4 groups per edge; thread tid always sees group tid % G4, so the per-head reductions
+// are butterflies over the offsets 16 .. G4 applied to each component.
+__device__ __forceinline__ float4 f4_set(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ float4 head_sum4(float4 v, int G4) {
+  for (int o = 16; o >= G4; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  return v;
+}
+__device__ __forceinline__ float4 head_max4(float4 v, int G4) {
+  for (int o = 16; o >= G4; o >>= 1) {
+    v.x = fmaxf(v.x, __shfl_xor_sync(0xffffffffu, v.x, o)); v.y = fmaxf(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
+    v.z = fmaxf(v.z, __shfl_xor_sync(0xffffffffu, v.z, o)); v.w = fmaxf(v.w, __shfl_xor_sync(0xffffffffu, v.w, o));
+  }
+  return v;
+}
+template <bool CTA, bool MAX>
+__device__ __forceinline__ float4 coop_h4(float4 v, int G4, float4* red) {
+  v = MAX ? head_max4(v, G4) : head_sum4(v, G4);
+  if (!CTA) return v;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane < G4) red[w * 8 + lane] = v;
+  __syncthreads();
+  float4 t = MAX ? f4_set(-INFINITY) : f4_set(0.f);
+  for (int i = 0; i < nw; i++) {
+    const float4 q = red[i * 8 + (lane & (G4 - 1))];
+    if (MAX) { t.x = fmaxf(t.x, q.x); t.y = fmaxf(t.y, q.y); t.z = fmaxf(t.z, q.z); t.w = fmaxf(t.w, q.w); }
+    else { t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+  }
+  return t;
+}
+__device__ __forceinline__ float lrelu(float t, float slope) { return t > 0.f ? t : slope * t; }
+
+template <bool CTA>
+__global__ void scores_kernel_v4(const RowSel r, int H, const uint32_t* __restrict__ colidx, const float* __restrict__ el, const float* __restrict__ er,
+                                 float slope, float* __restrict__ temp_scores, float* __restrict__ norm_scores) {
+  __shared__ float4 red[8 * 8];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const int G4 = H >> 2, gs = __ffs(G4) - 1, hg = tid & (G4 - 1);
+  const uint64_t q0 = (uint64_t)s * G4, q1 = (uint64_t)e * G4;
+  float4* t4 = reinterpret_cast<float4*>(temp_scores);
+  float4* n4 = reinterpret_cast<float4*>(norm_scores);
+  const float4* er4 = reinterpret_cast<const float4*>(er);
+  const float4 eli = __ldg(reinterpret_cast<const float4*>(el) + (size_t)row * G4 + hg);
+  float4 mx = f4_set(-INFINITY);
+  uint64_t q = q0 + tid;
+  for (; q + 3ull * nthr < q1; q += 4ull * nthr) {
+    uint32_t c[4]; float4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) c[u] = __ldg(colidx + ((q + (uint64_t)u * nthr) >> gs));
+#pragma unroll
+    for (int u = 0; u < 4; u++) t[u] = __ldg(er4 + (size_t)c[u] * G4 + hg);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      t[u].x += eli.x; t[u].y += eli.y; t[u].z += eli.z; t[u].w += eli.w;
+      t4[q + (uint64_t)u * nthr] = t[u];
+      mx.x = fmaxf(mx.x, lrelu(t[u].x, slope)); mx.y = fmaxf(mx.y, lrelu(t[u].y, slope));
+      mx.z = fmaxf(mx.z, lrelu(t[u].z, slope)); mx.w = fmaxf(mx.w, lrelu(t[u].w, slope));
+    }
+  }
+  for (; q < q1; q += nthr) {
+    float4 t = __ldg(er4 + (size_t)__ldg(colidx + (q >> gs)) * G4 + hg);
+    t.x += eli.x; t.y += eli.y; t.z += eli.z; t.w += eli.w;
+    t4[q] = t;
+    mx.x = fmaxf(mx.x, lrelu(t.x, slope)); mx.y = fmaxf(mx.y, lrelu(t.y, slope));
+    mx.z = fmaxf(mx.z, lrelu(t.z, slope)); mx.w = fmaxf(mx.w, lrelu(t.w, slope));
+  }
+  mx = coop_h4<CTA, true>(mx, G4, red);
+  float4 sum = f4_set(0.f);
+#pragma unroll 4
+  for (uint64_t k = q0 + tid; k < q1; k += nthr) {
+    const float4 t = t4[k];
+    float4 p;
+    p.x = expf(lrelu(t.x, slope) - mx.x); p.y = expf(lrelu(t.y, slope) - mx.y);
+    p.z = expf(lrelu(t.z, slope) - mx.z); p.w = expf(lrelu(t.w, slope) - mx.w);
+    n4[k] = p;
+    sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+  }
+  sum = coop_h4<CTA, false>(sum, G4, red);
+#pragma unroll 4
+  for (uint64_t k = q0 + tid; k < q1; k += nthr) {
+    float4 p = n4[k];
+    p.x = p.x / sum.x; p.y = p.y / sum.y; p.z = p.z / sum.z; p.w = p.w / sum.w;
+    n4[k] = p;
+  }
+}
+
+template <bool CTA>
+__global__ void softmax_bwd_kernel_v4(const RowSel r, int H, float slope, const float* __restrict__ temp_scores, const float* __restrict__ p,
+                                      float* __restrict__ ds, float* __restrict__ rowsum) {
+  __shared__ float4 red[8 * 8];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const int G4 = H >> 2;
+  const uint64_t q0 = (uint64_t)s * G4, q1 = (uint64_t)e * G4;
+  const float4* t4 = reinterpret_cast<const float4*>(temp_scores);
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  float4* d4 = reinterpret_cast<float4*>(ds);
+  float4 dot = f4_set(0.f);
+#pragma unroll 4
+  for (uint64_t k = q0 + tid; k < q1; k += nthr) {
+    const float4 a = p4[k], b = d4[k];
+    dot.x += a.x * b.x; dot.y += a.y * b.y; dot.z += a.z * b.z; dot.w += a.w * b.w;
+  }
+  dot = coop_h4<CTA, false>(dot, G4, red);
+  float4 rs = f4_set(0.f);
+#pragma unroll 4
+  for (uint64_t k = q0 + tid; k < q1; k += nthr) {
+    const float4 a = p4[k], b = d4[k], t = t4[k];
+    float4 v;
+    v.x = a.x * (b.x - dot.x) * (t.x > 0.f ? 1.0f : slope); v.y = a.y * (b.y - dot.y) * (t.y > 0.f ? 1.0f : slope);
+    v.z = a.z * (b.z - dot.z) * (t.z > 0.f ? 1.0f : slope); v.w = a.w * (b.w - dot.w) * (t.w > 0.f ? 1.0f : slope);
+    d4[k] = v;
+    rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+  }
+  rs = coop_h4<CTA, false>(rs, G4, red);
+  if (tid < G4) reinterpret_cast<float4*>(rowsum)[(size_t)row * G4 + tid] = rs;
+}
+
+template <bool CTA>
+__global__ void colsum_kernel_v4(const RowSel r, int H, const uint32_t* __restrict__ perm, const float* __restrict__ ds, float* __restrict__ colsum) {
+  __shared__ float4 red[8 * 8];
+  uint32_t row, s, e; int tid, nthr;
+  if (!pick_row<CTA>(r, row, s, e, tid, nthr)) return;
+  const int G4 = H >> 2, gs = __ffs(G4) - 1, hg = tid & (G4 - 1);
+  const uint64_t q0 = (uint64_t)s * G4, q1 = (uint64_t)e * G4;
+  const float4* d4 = reinterpret_cast<const float4*>(ds);
+  float4 cs = f4_set(0.f);
+#pragma unroll 4
+  for (uint64_t k = q0 + tid; k < q1; k += nthr) {
+    const float4 v = __ldg(d4 + (size_t)__ldg(perm + (k >> gs)) * G4 + hg);
+    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+  }
+  cs = coop_h4<CTA, false>(cs, G4, red);
+  if (tid < G4) reinterpret_cast<float4*>(colsum)[(size_t)row * G4 + tid] = cs;
 }
 
 // SDDMM dS[e] = <g_i, z_j>. One warp per edge-slice: light rows = one warp per row; hub rows = CTA per row, warps split the edges.
@@ -327,6 +487,7 @@ __global__ void __launch_bounds__(256, 4) sddmm_heads_kernel(uint32_t nv, uint64
 #pragma unroll
           for (int k = 0; k < KCH; k++) x[u][k] = (act[k] && b + j0 + u < e1) ? __ldg(z4 + (size_t)cc * ld4 + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        float d[U][KCH];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const uint64_t edge = b + j0 + u;
@@ -336,11 +497,21 @@ __global__ void __launch_bounds__(256, 4) sddmm_heads_kernel(uint32_t nv, uint64
             for (int k = 0; k < KCH; k++) gq[k] = act[k] ? __ldg(grad4 + (size_t)row * ld4 + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int k = 0; k < KCH; k++) {
-            float d = gq[k].x * x[u][k].x + gq[k].y * x[u][k].y + gq[k].z * x[u][k].z + gq[k].w * x[u][k].w;
-            for (int o = cph >> 1; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            if (writer && act[k] && edge < e1) ds[edge * H + head[k]] = d;
-          }
+          for (int k = 0; k < KCH; k++) d[u][k] = gq[k].x * x[u][k].x + gq[k].y * x[u][k].y + gq[k].z * x[u][k].z + gq[k].w * x[u][k].w;
+        }
+        // segmented butterflies of the U x KCH partial sums, round by round (independent shuffles in flight instead of one chain per value)
+        for (int o = cph >> 1; o >= 1; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < KCH; k++) d[u][k] += __shfl_xor_sync(0xffffffffu, d[u][k], o);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint64_t edge = b + j0 + u;
+#pragma unroll
+          for (int k = 0; k < KCH; k++)
+            if (writer && act[k] && edge < e1) ds[edge * H + head[k]] = d[u][k];
         }
       }
     }
@@ -425,7 +596,7 @@ __global__ void alpha_grad_stage2(int F, int nparts, const float* __restrict__ p
 
 RowSel make_sel(gai_csr_t g) {
   RowSel r;
-  r.rowptr = g->rowptr; r.hub_rows = g->hub_rows; r.nv = g->nv; r.n_hub = g->n_hub;
+  r.rowptr = g->rowptr; r.hub_rows = g->hub_rows; r.order = g->row_order; r.nv = g->nv; r.n_hub = g->n_hub;
   r.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
   return r;
 }
@@ -457,10 +628,13 @@ int gai_gat_forward_heads_ld(gai_csr_t g, int F, int H, const float* z, size_t l
   el_er_kernel<<<warp_grid(g->nv), 256, 0, st>>>(g->nv, F, H, z, ld, alpha_l, alpha_r, el, er);
   GAI_LAUNCH_CHECK();
   const RowSel r = make_sel(g);
-  scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
+  const bool v4 = H % 4 == 0 && reinterpret_cast<uintptr_t>(temp_scores) % 16 == 0 && reinterpret_cast<uintptr_t>(norm_scores) % 16 == 0;
+  if (v4) scores_kernel_v4<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
+  else scores_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
   GAI_LAUNCH_CHECK();
   if (g->n_hub) {
-    scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
+    if (v4) scores_kernel_v4<true><<<g->n_hub, 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
+    else scores_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->colidx, el, er, slope, temp_scores, norm_scores);
     GAI_LAUNCH_CHECK();
   }
   if (H == 1) return gai_spmm_edge(g, F, norm_scores, nullptr, z, (int)ld, out, (int)ld_out, flags, nullptr, stream);
@@ -530,12 +704,24 @@ int gai_gat_backward_heads_ld(gai_csr_t g, int F, int H, const float* z, size_t 
     GAI_LAUNCH_CHECK();
     if (g->n_hub) { sddmm_kernel<true><<<g->n_hub, 256, 0, st>>>(r, g->colidx, F, ldc, grad_in, z, ds, vec); GAI_LAUNCH_CHECK(); }
   }
-  softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
+  const bool v4 = H % 4 == 0 && reinterpret_cast<uintptr_t>(temp_scores) % 16 == 0 && reinterpret_cast<uintptr_t>(norm_scores) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(ds) % 16 == 0;
+  if (v4) softmax_bwd_kernel_v4<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
+  else softmax_bwd_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
   GAI_LAUNCH_CHECK();
-  if (g->n_hub) { softmax_bwd_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum); GAI_LAUNCH_CHECK(); }
-  colsum_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->tperm, ds, colsum);
+  if (g->n_hub) {
+    if (v4) softmax_bwd_kernel_v4<true><<<g->n_hub, 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
+    else softmax_bwd_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, slope, temp_scores, norm_scores, ds, rowsum);
+    GAI_LAUNCH_CHECK();
+  }
+  if (v4) colsum_kernel_v4<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->tperm, ds, colsum);
+  else colsum_kernel<false><<<warp_grid(g->nv), 256, 0, st>>>(r, H, g->tperm, ds, colsum);
   GAI_LAUNCH_CHECK();
-  if (g->n_hub) { colsum_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->tperm, ds, colsum); GAI_LAUNCH_CHECK(); }
+  if (g->n_hub) {
+    if (v4) colsum_kernel_v4<true><<<g->n_hub, 256, 0, st>>>(r, H, g->tperm, ds, colsum);
+    else colsum_kernel<true><<<g->n_hub, 256, 0, st>>>(r, H, g->tperm, ds, colsum);
+    GAI_LAUNCH_CHECK();
+  }
   int CW = 1;
   while (CW < F && CW < 256) CW <<= 1;
   const uint32_t rows_per_cta = (g->nv + nparts - 1) / nparts;
