@@ -327,7 +327,8 @@ __device__ __forceinline__ void hub_phase(const SpmmArgs& a, HubShared& hub_sh, 
 constexpr int SLOTS = 32;  // work-list entries per claim
 
 template <int MODE, int G, int K, bool SPLIT>
-__global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, const uint32_t* __restrict__ order, const uint32_t* __restrict__ claim_ptr,
+__global__ void __launch_bounds__(256, MODE == M_EDGE_PERM_H ? 3 : 4) spmm_rows_kernel(  // the transposed multi-head mode carries 8 more registers of weights
+const SpmmArgs a, const uint32_t* __restrict__ order, const uint32_t* __restrict__ claim_ptr,
                                                          unsigned long long n_claims, unsigned long long* __restrict__ counter,
                                                          const uint32_t* __restrict__ hub_rows, unsigned long long n_hub_items, int hub_nsplit) {
   constexpr int RPW = 32 / G;                                  // rows in flight per warp
@@ -419,6 +420,26 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
             if (idx + G < e) c_nb = __ldg(a.colidx + idx + G);  // next batch of this row
             const float w = idx < e ? edge_weight_t<MODE>(a, wrow, idx, c_cur) : 0.0f;
             const int cnt = (e - b) < (uint32_t)G ? (int)(e - b) : G;
+            // Multi-head modes with 8 heads (the configs[2] shape): the G x 8 weights of the batch live in 8 registers per lane, register r of
+            // group lane l holding flat entry r * G + l = (edge, head) = ((r * G + l) / 8, l % 8). They are loaded with 8 requests per
+            // BATCH (coalesced when the edge values are in edge order, 32-byte runs through the transpose permutation) and handed out by
+            // one shuffle per edge and chunk, instead of one 4-byte load per lane, edge and chunk (measured 17.4 vs 9.3 ms per call for the
+            // transposed aggregation of the Reddit-shaped graph against the single-head kernel).
+            // Only through the transpose permutation: edge-ordered weights are sequential 32-byte runs that the per-lane loads already fetch
+            // well (10.7 ms; the register form at three CTAs per SM measured 11.7), the permuted ones are random (17.4 -> 12.6 ms).
+            constexpr bool H8 = MODE == M_EDGE_PERM_H && G >= 8;
+            constexpr int EPR = G >= 8 ? G / 8 : 1;   // edges per register row
+            const bool h8 = H8 && a.heads == 8;       // warp-uniform
+            float wreg[H8 ? 8 : 1];
+            if (h8) {
+#pragma unroll
+              for (int r = 0; r < 8; r++) {
+                const int je = r * EPR + gl / 8;      // edge of the batch this lane fetches a weight of
+                uint32_t eidx = b + (uint32_t)je;
+                if (MODE == M_EDGE_PERM_H) eidx = __float_as_uint(__shfl_sync(gmask, w, je, G));
+                wreg[r] = je < cnt ? __ldg(a.vals + (size_t)eidx * 8 + (gl & 7)) : 0.0f;
+              }
+            }
             if (cnt == G) {
 #pragma unroll
               for (int j = 0; j < G; j += U) {
@@ -429,11 +450,17 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
                   const uint32_t cc = __shfl_sync(gmask, c_cur, j + u, G);
 #pragma unroll
                   for (int k = 0; k < K; k++) x[u][k] = gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc));
-                  if (mode_has_heads<MODE>()) {   // per-(edge, head) weights, requested with the gathers
+                  if (mode_has_heads<MODE>() && !h8) {   // per-(edge, head) weights, requested with the gathers
                     const uint32_t eidx = MODE == M_EDGE_H ? b + (uint32_t)(j + u) : __float_as_uint(__shfl_sync(gmask, w, j + u, G));
 #pragma unroll
                     for (int k = 0; k < K; k++) wv[u][k] = __ldg(a.vals + (size_t)eidx * a.heads + hd[k]);
                   }
+                }
+                if (H8 && h8) {
+#pragma unroll
+                  for (int u = 0; u < U; u++)
+#pragma unroll
+                    for (int k = 0; k < K; k++) wv[u][k] = __shfl_sync(gmask, wreg[(j + u) / EPR], ((j + u) % EPR) * 8 + hd[k], G);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -455,11 +482,17 @@ __global__ void __launch_bounds__(256, 4) spmm_rows_kernel(const SpmmArgs a, con
 #pragma unroll
                   for (int k = 0; k < K; k++)
                     x[u][k] = (j + u < cnt) ? gather4(row_chunk<SPLIT>(bk[k], hk[k], a.n_split, row_bytes, cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (mode_has_heads<MODE>()) {
+                  if (mode_has_heads<MODE>() && !h8) {
                     const uint32_t eidx = MODE == M_EDGE_H ? b + (uint32_t)(j + u) : __float_as_uint(__shfl_sync(gmask, w, j + u, G));
 #pragma unroll
                     for (int k = 0; k < K; k++) wv[u][k] = (j + u < cnt) ? __ldg(a.vals + (size_t)eidx * a.heads + hd[k]) : 0.0f;
                   }
+                }
+                if (H8 && h8) {
+#pragma unroll
+                  for (int u = 0; u < U; u++)
+#pragma unroll
+                    for (int k = 0; k < K; k++) wv[u][k] = __shfl_sync(gmask, wreg[(j + u) / EPR], ((j + u) % EPR) * 8 + hd[k], G);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -686,7 +719,8 @@ int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   unsigned long long ctas = (claims + 7) / 8;
   if (ctas < hub_items) ctas = hub_items;
   const bool share = (a.flags & GAI_SPMM_SHARE_SMS) != 0;   // leave registers / threads for one foreign CTA per SM
-  const unsigned long long persistent = (unsigned long long)gai::sm_count() * (share ? 3 : 4);
+  const int resident = MODE == M_EDGE_PERM_H ? 3 : 4;   // CTAs per SM (launch bounds of the kernel)
+  const unsigned long long persistent = (unsigned long long)gai::sm_count() * (share ? resident - 1 : resident);
   if (ctas > persistent) ctas = persistent;
   const unsigned grid = (unsigned)ctas;
   // rotating work-counter pairs {light-row claims, hub items}: launches on one stream are ordered; the rotation keeps up to 8
