@@ -174,7 +174,6 @@ constexpr int HI_CL = 8;    // chunk lanes per gather instruction
 constexpr int HI_UB = 4;    // gathers in flight per lane (64-register budget of the persistent kernel)
 constexpr int HI_RING_F4 = HI_PW * HI_ES * HI_CL;   // float4 entries of the ring (28 KB)
 struct HubShared {
-  float4* ring;   // [HI_PW][HI_ES * HI_CL] in the caller's shared memory
   uint64_t full_bar[HI_PW], empty_bar[HI_PW];
   uint32_t round0[HI_PW];  // uses of each slot by the items this CTA has already processed (mbarrier phase bookkeeping)
   unsigned long long item;
@@ -197,7 +196,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 
 template <int MODE, bool SPLIT>
-__device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh) {
+__device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh,
+                                             float4* __restrict__ ring /* in a register: read through `sh` it cost the in-order consumer a
+                                             shared-memory load per stage, and on partitioned graphs (rows of 10^5..10^6 edges) that add
+                                             chain is the kernel's critical path: +70 % on the F = 47 calls at N = 4 */) {
   const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
@@ -207,7 +209,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     // ---------------- producers ----------------
     const int pw = warp - 1;
     const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-    float4* slot = sh.ring + pw * (HI_ES * HI_CL);
+    float4* slot = ring + pw * (HI_ES * HI_CL);
     const uint32_t round0 = sh.round0[pw];
     uint32_t c = 0; float w = 0.0f;
     {
@@ -268,7 +270,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
       const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
       mbar_wait(&sh.full_bar[pw], (sh.round0[pw] + r) & 1);
       if (lane < nch) {
-        const float4* tile = sh.ring + pw * (HI_ES * HI_CL) + lane;
+        const float4* tile = ring + pw * (HI_ES * HI_CL) + lane;
         if (cnt == HI_ES) {
           constexpr int SB = 8;
           float4 p[2][SB];
@@ -299,7 +301,6 @@ template <int MODE, bool SPLIT>
 __device__ __forceinline__ void hub_phase(const SpmmArgs& a, HubShared& hub_sh, float4* ring, unsigned long long* __restrict__ counter,
                                           const uint32_t* __restrict__ hub_rows, unsigned long long n_hub_items, int hub_nsplit) {
   if (threadIdx.x == 0) {
-    hub_sh.ring = ring;
     for (int i = 0; i < HI_PW; i++) { mbar_init(&hub_sh.full_bar[i], 1); mbar_init(&hub_sh.empty_bar[i], 1); hub_sh.round0[i] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -314,7 +315,7 @@ __device__ __forceinline__ void hub_phase(const SpmmArgs& a, HubShared& hub_sh, 
     const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
     if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
     const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
-    hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh);
+    hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh, ring);
     __syncthreads();
     if (threadIdx.x == 0) {
       const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
