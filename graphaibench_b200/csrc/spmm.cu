@@ -171,7 +171,10 @@ __host__ __device__ constexpr bool mode_has_heads() { return MODE == M_EDGE_H ||
 constexpr int HI_PW = 7;    // producer warps
 constexpr int HI_ES = 32;   // edges per stage
 constexpr int HI_CL = 8;    // chunk lanes per gather instruction
-constexpr int HI_UB = 4;    // gathers in flight per lane (64-register budget of the persistent kernel)
+#ifndef GAI_HI_UB
+#define GAI_HI_UB 4
+#endif
+constexpr int HI_UB = GAI_HI_UB;   // gathers in flight per producer lane: 4 = half a stage per round (64-register budget of the persistent kernel)
 constexpr int HI_RING_F4 = HI_PW * HI_ES * HI_CL;   // float4 entries of the ring (28 KB)
 struct HubShared {
   uint64_t full_bar[HI_PW], empty_bar[HI_PW];
