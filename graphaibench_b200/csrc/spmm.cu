@@ -22,7 +22,7 @@
 //         indices with one coalesced request, broadcasts them by shuffle, and keeps U independent 128-bit
 //         neighbour-row loads in flight per lane, with a two-deep index pipeline across rows and batches.
 //       hub rows (deg > hub_degree, a per-graph threshold = a warp's fair share of the edges): item = (row, column block
-//         of <= 8 float4 chunks). A whole CTA takes one item: 7 producer warps gather + scale stages of 32 edges into a
+//         of <= 4 float4 chunks). A whole CTA takes one item: 7 producer warps fetch (cp.async) + scale stages of 64 edges into a
 //         shared-memory ring (mbarrier full/empty pairs); warp 0 adds the staged products IN EDGE ORDER. The longest
 //         rows are listed first, so their add chains run underneath the light rows.
 //       (widths beyond 512 floats keep the older CTA-per-row kernel spmm_hub_kernel, forked onto a side stream.)
@@ -61,6 +61,7 @@ struct SpmmArgs {
   // the owners' rows land there (gai_halo_pull) and the matrix itself carries master rows only. n_split = 0xffffffff: one matrix.
   const float* in_halo;
   uint32_t n_split;
+  int hub_cl;          // float4 chunks per hub column block (8 or 4): launch_rows_mode
   int heads, hshift;   // multi-head edge values: head of float4 chunk c = c >> hshift (columns per head = 4 << hshift)
 };
 
@@ -163,19 +164,20 @@ template <int MODE>
 __host__ __device__ constexpr bool mode_has_heads() { return MODE == M_EDGE_H || MODE == M_EDGE_PERM_H; }
 
 // ---- hub rows inside the persistent light-row kernel --------------------------------------------------------------------
-// A hub item = (hub row, column block of <= 8 float4 chunks). A whole 256-thread CTA of the persistent kernel takes one item at a
-// time before it turns to the light-row claims: warp 0 adds in edge order (one lane per chunk), warps 1..7 gather + scale stages
-// of 32 edges into a 7-slot shared-memory ring (mbarrier full/empty pairs), four edges per gather instruction so that every lane
-// carries a 128-bit load. The longest rows come first in the item list, so their sequential add chains start at t = 0 and run
+// A hub item = (hub row, column block of <= 4 float4 chunks). A whole 256-thread CTA of the persistent kernel takes one item at a
+// time before it turns to the light-row claims: warp 0 adds in edge order (one lane per chunk), warps 1..7 fetch + scale stages
+// of 64 edges into a 7-slot shared-memory ring (mbarrier full/empty pairs), eight edges per cp.async instruction so that every lane
+// carries a 128-bit request. The longest rows come first in the item list, so their sequential add chains start at t = 0 and run
 // underneath the rest of the kernel; no second kernel, stream or event is involved and no SM is ever reserved for hub rows.
-constexpr int HI_PW = 7;    // producer warps
-constexpr int HI_ES = 32;   // edges per stage
-constexpr int HI_CL = 8;    // chunk lanes per gather instruction
-#ifndef GAI_HI_UB
-#define GAI_HI_UB 4
-#endif
-constexpr int HI_UB = GAI_HI_UB;   // gathers in flight per producer lane: 4 = half a stage per round (64-register budget of the persistent kernel)
-constexpr int HI_RING_F4 = HI_PW * HI_ES * HI_CL;   // float4 entries of the ring (28 KB)
+// A hub row is a latency-bound pipeline — ring bytes / (memory round trip of a stage) — and on partitioned graphs, whose rows reach
+// 10^5..10^6 edges, the longest row IS the kernel (tools/shard_probe.py, GAI_SPMM_DEBUG=2: 3.1 ms of a 3.3 ms call). What counts is
+// therefore EDGES in flight per ring byte: column blocks of 4 chunks (64 bytes per neighbour row) put 448 edges in flight per CTA
+// where blocks of 8 chunks put 224, at the price of twice as many items.
+// The block width is chosen per call (hub_block_chunks): 8 chunks while the longest row stays below 128 K edges (fewer items: on one GPU
+// the hub chains hide under the light rows and narrower blocks only add items, +3..5 %), 4 chunks beyond (partitioned graphs).
+constexpr int HI_PW = 7;            // producer warps = ring slots
+constexpr int HI_SLOT_F4 = 256;     // float4 entries per ring slot = (edges per stage) x (chunks per column block): 32 x 8 or 64 x 4
+constexpr int HI_RING_F4 = HI_PW * HI_SLOT_F4;   // float4 entries of the ring (28 KB)
 struct HubShared {
   uint64_t full_bar[HI_PW], empty_bar[HI_PW];
   uint32_t round0[HI_PW];  // uses of each slot by the items this CTA has already processed (mbarrier phase bookkeeping)
@@ -198,11 +200,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
-template <int MODE, bool SPLIT>
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int MODE, bool SPLIT, int HI_CL>
 __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, uint32_t s, uint32_t e, int cb, int nch, HubShared& sh,
                                              float4* __restrict__ ring /* in a register: read through `sh` it cost the in-order consumer a
                                              shared-memory load per stage, and on partitioned graphs (rows of 10^5..10^6 edges) that add
                                              chain is the kernel's critical path: +70 % on the F = 47 calls at N = 4 */) {
+  constexpr int HI_ES = HI_SLOT_F4 / HI_CL;   // edges per stage
+  constexpr int NR = HI_ES / 32;              // index registers per producer lane
   const uint32_t nstages = (e - s + HI_ES - 1) / HI_ES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
@@ -212,12 +222,15 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     // ---------------- producers ----------------
     const int pw = warp - 1;
     const float wrow = (MODE == M_GCN || MODE == M_MEAN) ? __ldg(a.norm + row) : 0.0f;
-    float4* slot = ring + pw * (HI_ES * HI_CL);
+    float4* slot = ring + pw * HI_SLOT_F4;
     const uint32_t round0 = sh.round0[pw];
-    uint32_t c = 0; float w = 0.0f;
-    {
-      const uint32_t idx = s + (uint32_t)pw * HI_ES + lane;
-      if (idx < e) { c = __ldg(a.colidx + idx); w = edge_weight_t<MODE>(a, wrow, idx, c); }
+    // lane l holds the column index / weight of edges l, l + 32, ... of the stage
+    uint32_t c[NR]; float w[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h++) {
+      c[h] = 0; w[h] = 0.0f;
+      const uint64_t idx = (uint64_t)s + (uint64_t)pw * HI_ES + 32 * h + lane;
+      if (idx < e) { c[h] = __ldg(a.colidx + idx); w[h] = edge_weight_t<MODE>(a, wrow, (uint32_t)idx, c[h]); }
     }
     constexpr int EL = 32 / HI_CL;
     const int cl = lane % HI_CL, el = lane / HI_CL;
@@ -229,35 +242,41 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
     for (uint32_t k = pw, r = 0; k < nstages; k += HI_PW, r++) {
       const uint32_t base = s + k * HI_ES;
       const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
-      const uint32_t cur_c = c; const float cur_w = w;
-      c = 0; w = 0.0f;
-      {
-        const uint64_t nidx = (uint64_t)base + (uint64_t)HI_PW * HI_ES + lane;
-        if (nidx < e) { c = __ldg(a.colidx + nidx); w = edge_weight_t<MODE>(a, wrow, (uint32_t)nidx, c); }
+      uint32_t cur_c[NR]; float cur_w[NR];
+#pragma unroll
+      for (int h = 0; h < NR; h++) { cur_c[h] = c[h]; cur_w[h] = w[h]; }
+#pragma unroll
+      for (int h = 0; h < NR; h++) {
+        c[h] = 0; w[h] = 0.0f;
+        const uint64_t nidx = (uint64_t)base + (uint64_t)HI_PW * HI_ES + 32 * h + lane;
+        if (nidx < e) { c[h] = __ldg(a.colidx + nidx); w[h] = edge_weight_t<MODE>(a, wrow, (uint32_t)nidx, c[h]); }
       }
       mbar_wait(&sh.empty_bar[pw], ((round0 + r) & 1) ^ 1);
+      // The neighbour-row chunks of the whole stage are requested at once and land straight in the ring slot (cp.async: no register holds
+      // them), then every lane scales the entries it requested itself, in place: one memory round trip per stage.
+      constexpr int NI = HI_ES / EL;
+      float ww[NI];
 #pragma unroll
-      for (int j0 = 0; j0 < HI_ES; j0 += HI_UB * EL) {
-        float4 x[HI_UB]; float ww[HI_UB];
-#pragma unroll
-        for (int u = 0; u < HI_UB; u++) {
-          const int j = j0 + u * EL + el;
-          const uint32_t cc = __shfl_sync(0xffffffffu, cur_c, j);
-          ww[u] = __shfl_sync(0xffffffffu, cur_w, j);
-          if (chv && j < cnt) x[u] = __ldg(row_chunk<SPLIT>(inb_c, halob_c, a.n_split, row_bytes, cc));
-          if (mode_has_heads<MODE>() && chv && j < cnt) {
-            const uint32_t eidx = MODE == M_EDGE_H ? base + (uint32_t)j : __float_as_uint(ww[u]);
-            ww[u] = __ldg(a.vals + (size_t)eidx * a.heads + hd);
-          }
+      for (int u = 0; u < NI; u++) {
+        const int j = u * EL + el;
+        const uint32_t cc = __shfl_sync(0xffffffffu, cur_c[(u * EL) >> 5], j & 31);
+        ww[u] = __shfl_sync(0xffffffffu, cur_w[(u * EL) >> 5], j & 31);
+        if (chv && j < cnt) cp_async16(smem_u32(slot + j * HI_CL + cl), row_chunk<SPLIT>(inb_c, halob_c, a.n_split, row_bytes, cc));
+        if (mode_has_heads<MODE>() && chv && j < cnt) {
+          const uint32_t eidx = MODE == M_EDGE_H ? base + (uint32_t)j : __float_as_uint(ww[u]);
+          ww[u] = __ldg(a.vals + (size_t)eidx * a.heads + hd);
         }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
 #pragma unroll
-        for (int u = 0; u < HI_UB; u++) {
-          const int j = j0 + u * EL + el;
-          if (chv && j < cnt) {
-            float4 p;
-            p.x = __fmul_rn(ww[u], x[u].x); p.y = __fmul_rn(ww[u], x[u].y); p.z = __fmul_rn(ww[u], x[u].z); p.w = __fmul_rn(ww[u], x[u].w);
-            slot[j * HI_CL + cl] = p;
-          }
+      for (int u = 0; u < NI; u++) {
+        const int j = u * EL + el;
+        if (chv && j < cnt) {
+          const float4 x = slot[j * HI_CL + cl];
+          float4 p;
+          p.x = __fmul_rn(ww[u], x.x); p.y = __fmul_rn(ww[u], x.y); p.z = __fmul_rn(ww[u], x.z); p.w = __fmul_rn(ww[u], x.w);
+          slot[j * HI_CL + cl] = p;
         }
       }
       __syncwarp();
@@ -273,7 +292,7 @@ __device__ __forceinline__ void hub_item_cta(const SpmmArgs& a, uint32_t row, ui
       const int cnt = (e - base) < (uint32_t)HI_ES ? (int)(e - base) : HI_ES;
       mbar_wait(&sh.full_bar[pw], (sh.round0[pw] + r) & 1);
       if (lane < nch) {
-        const float4* tile = ring + pw * (HI_ES * HI_CL) + lane;
+        const float4* tile = ring + pw * HI_SLOT_F4 + lane;
         if (cnt == HI_ES) {
           constexpr int SB = 8;
           float4 p[2][SB];
@@ -318,10 +337,12 @@ __device__ __forceinline__ void hub_phase(const SpmmArgs& a, HubShared& hub_sh, 
     const int nch = (a.nchunks - cb) < a.hub_per ? (a.nchunks - cb) : a.hub_per;
     if (hrow < a.row_begin || hrow >= a.row_end || nch <= 0) continue;  // uniform
     const uint32_t hs = __ldg(a.rowptr + hrow), he = __ldg(a.rowptr + hrow + 1);
-    hub_item_cta<MODE, SPLIT>(a, hrow, hs, he, cb, nch, hub_sh, ring);
+    if (a.hub_cl == 4) hub_item_cta<MODE, SPLIT, 4>(a, hrow, hs, he, cb, nch, hub_sh, ring);
+    else hub_item_cta<MODE, SPLIT, 8>(a, hrow, hs, he, cb, nch, hub_sh, ring);
     __syncthreads();
     if (threadIdx.x == 0) {
-      const uint32_t nst = (he - hs + HI_ES - 1) / HI_ES;
+      const uint32_t es = (uint32_t)(HI_SLOT_F4 / a.hub_cl);
+      const uint32_t nst = (he - hs + es - 1) / es;
       for (int i = 0; i < HI_PW; i++) hub_sh.round0[i] += (nst + HI_PW - 1 - i) / HI_PW;
     }
   }
@@ -697,7 +718,14 @@ ListSel select_list(const SpmmArgs& a, const gai_csr* g) {
   return {nullptr, nullptr, g->hub_rows, g->n_hub, (n_rows + SLOTS - 1) / SLOTS, false};
 }
 
-// widths whose hub rows are handled inside the persistent kernel (column blocks of <= 8 chunks, up to 16 blocks)
+// float4 chunks per hub column block: 4 once the longest row passes 128 K edges (its add chain then bounds the kernel and edges in flight
+// per ring byte are what shortens it: N = 8 shard of configs[1], F = 47: 3.27 -> 2.84 ms), else 8. GAI_HUB_CL=4|8 overrides (experiments).
+inline int hub_block_chunks(const gai_csr* g) {
+  static const int forced = [] { const char* e = getenv("GAI_HUB_CL"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 8) ? v : 0; }();
+  if (forced) return forced;
+  return g->max_degree > 131072u ? 4 : 8;
+}
+// widths whose hub rows are handled inside the persistent kernel (column blocks of <= 4 chunks, up to 32 blocks)
 inline bool hub_fused(const SpmmArgs& a) { return a.nchunks <= 128; }
 
 template <int MODE>
@@ -710,11 +738,22 @@ int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   unsigned long long hub_items = 0;
   int nsplit = 1;
   if (sel.n_hub != 0 && hub_fused(a)) {
-    nsplit = (a.nchunks + 7) / 8;
+    a.hub_cl = hub_block_chunks(g);
+    nsplit = (a.nchunks + a.hub_cl - 1) / a.hub_cl;
     a.hub_per = (a.nchunks + nsplit - 1) / nsplit;
     hub_items = (unsigned long long)sel.n_hub * (unsigned)nsplit;
   }
-  if (claims == 0 && hub_items == 0) return GAI_OK;
+  // GAI_SPMM_DEBUG (timing experiments only, results are wrong): 1 = skip the hub items, 2 = skip the light rows — what each half of the
+  // persistent kernel costs on a given graph (tools/shard_probe.py)
+  static const int debug_knob = [] {
+    const int k = getenv("GAI_SPMM_DEBUG") ? atoi(getenv("GAI_SPMM_DEBUG")) : 0;
+    if (k) fprintf(stderr, "libgai_b200: GAI_SPMM_DEBUG=%d — timing experiment, aggregation RESULTS ARE WRONG\n", k);
+    return k;
+  }();
+  unsigned long long claims_run = claims;
+  if (debug_knob == 1) hub_items = 0;
+  if (debug_knob == 2) claims_run = 0;
+  if (claims_run == 0 && hub_items == 0) return GAI_OK;
   const uint32_t* claim_ptr = sel.claim_ptr;
   int G = 4;
   while (G < 32 && G < a.nchunks) G <<= 1;
@@ -733,8 +772,8 @@ int launch_rows_mode(SpmmArgs a, const gai_csr* g, cudaStream_t st) {
   GAI_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
 #define GAI_ROWS_LAUNCH(GG, KK)                                                                                                        \
   do {                                                                                                                                \
-    if (a.in_halo) spmm_rows_kernel<MODE, GG, KK, true><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit); \
-    else spmm_rows_kernel<MODE, GG, KK, false><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims, ctr, sel.hub_rows, hub_items, nsplit);          \
+    if (a.in_halo) spmm_rows_kernel<MODE, GG, KK, true><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims_run, ctr, sel.hub_rows, hub_items, nsplit); \
+    else spmm_rows_kernel<MODE, GG, KK, false><<<grid, 256, 0, st>>>(a, order, claim_ptr, claims_run, ctr, sel.hub_rows, hub_items, nsplit);          \
   } while (0)
   if (G == 4) GAI_ROWS_LAUNCH(4, 1);
   else if (G == 8) GAI_ROWS_LAUNCH(8, 1);
@@ -822,7 +861,7 @@ int spmm_dispatch(gai_csr_t g, int mode, uint32_t rb, uint32_t re, int F, const 
   a.F = F; a.nchunks = (F + 3) / 4; a.ld_out = ld_out; a.row_begin = rb; a.row_end = re;
   a.mode = mode; a.flags = flags;
   a.hub_threshold = g->n_hub ? g->hub_degree : 0xffffffffu;
-  a.hub_per = a.nchunks;
+  a.hub_per = a.nchunks; a.hub_cl = 8;
   a.mask_bits = mask_bits; a.ld_bits = ld_bits;
   a.in_halo = in_halo; a.n_split = in_halo ? n_split : 0xffffffffu;
   a.heads = heads; a.hshift = 0;
