@@ -19,12 +19,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 // Per-head reductions over the lanes of a warp: with H heads (a power of two <= 32) lane l works on head l % H, so a butterfly over the
 // offsets 16 .. H leaves every lane with the total of its own head. H = 1: the plain warp reduction.
 __device__ __forceinline__ float head_sum(float v, int H) {
@@ -58,32 +52,6 @@ __device__ __forceinline__ float coop_hmax(float v, int H, float* red) {
   __syncthreads();
   float t = -INFINITY;
   for (int i = 0; i < nw; i++) t = fmaxf(t, red[i * 32 + (lane & (H - 1))]);
-  return t;
-}
-
-// Row-cooperative reductions: a warp (light rows) or a whole CTA (hub rows).
-template <bool CTA>
-__device__ __forceinline__ float coop_sum(float v, float* red) {
-  v = warp_sum(v);
-  if (!CTA) return v;
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[w] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nw; i++) t += red[i];
-  return t;
-}
-template <bool CTA>
-__device__ __forceinline__ float coop_max(float v, float* red) {
-  v = warp_max(v);
-  if (!CTA) return v;
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[w] = v;
-  __syncthreads();
-  float t = -INFINITY;
-  for (int i = 0; i < nw; i++) t = fmaxf(t, red[i]);
   return t;
 }
 
