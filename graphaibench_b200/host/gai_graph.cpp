@@ -174,14 +174,21 @@ void LearningGraph::partition_rows(int world, int rank, index_t nv_global) {
     std::exit(EXIT_FAILURE);
   }
   nv_global_ = nv_global; first_ = own.first;
-  halo_gids_.clear();
+  // Distinct remote neighbours in ascending global id, and each edge's rank in that list. A bitmap over the global id space (14 MB for
+  // the papers100M shape) + per-word prefix counts gives both in O(nnz + N/64): the sort / unique / binary-search form of the same
+  // result took 30 s per rank at that size (88 M remote column ids), all of it set-up wall clock.
+  const size_t words = ((size_t)nv_global + 63) / 64;
+  std::vector<uint64_t> bits(words, 0);
   for (index_t c : colidx_)
-    if (c < own.first || c >= own.last) halo_gids_.push_back(c);
-  std::sort(halo_gids_.begin(), halo_gids_.end());
-  halo_gids_.erase(std::unique(halo_gids_.begin(), halo_gids_.end()), halo_gids_.end());
+    if (c < own.first || c >= own.last) bits[c >> 6] |= 1ull << (c & 63);
+  std::vector<index_t> before(words + 1, 0);   // halo vertices with an id below word w
+  for (size_t w = 0; w < words; w++) before[w + 1] = before[w] + (index_t)__builtin_popcountll(bits[w]);
+  halo_gids_.assign(before[words], 0);
+  for (size_t w = 0, k = 0; w < words; w++)
+    for (uint64_t b = bits[w]; b; b &= b - 1) halo_gids_[k++] = (index_t)(w * 64 + (size_t)__builtin_ctzll(b));
   for (index_t& c : colidx_) {
     if (c >= own.first && c < own.last) c -= own.first;
-    else c = num_vertices_ + (index_t)(std::lower_bound(halo_gids_.begin(), halo_gids_.end(), c) - halo_gids_.begin());
+    else c = num_vertices_ + before[c >> 6] + (index_t)__builtin_popcountll(bits[c >> 6] & ((1ull << (c & 63)) - 1));
   }
 }
 
