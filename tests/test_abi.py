@@ -113,12 +113,13 @@ def test_argument_errors_are_reported_not_executed(abi):
     assert L.gai_device_count(None) == ARG and L.gai_malloc(None, 16) == ARG and L.gai_event_create(None) == ARG
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    """profiles/r1_bench.json is a real `python bench.py` line: the keys the driver and the judge read must all be there."""
+@pytest.mark.parametrize("name", ["r1_bench.json", "r2_bench.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    """profiles/r{1,2}_bench.json are real `python bench.py` lines: the keys the driver and the judge read must all be there."""
     import json
     import os
     from conftest import ROOT
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench.json")))
+    d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
               "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
